@@ -1,0 +1,47 @@
+// calico_b200 — device-side data layout shared by the host driver and the kernels.
+//
+// HBM layout (all FP64 unless noted; one allocation per array, resident for the lifetime of the uploaded problem):
+//   ctrl[2][n_cp*6]            spline control points, current (x) and candidate point
+//   state[2][n_sensors]        SensorState (intrinsics, extrinsics, latency, sigma, loss), current and candidate
+//   knots[n_cp+6], basis[n_seg*36]   knot vector and per-segment 6x6 basis matrices (bspline.hpp:192-244)
+//   pw[n_points*3]             world-frame model points R_wm p_m + t_wm (world model is constant: world_model.cpp:40-77)
+//   per sensor, observations SORTED BY SPLINE SEGMENT: stamp[n], meas[n*m], seg[n] (i32), pt[n] (i32, camera),
+//                              seg_start[n_seg+1] (CSR), r[n*m], J[n*m*jw]  (jw = 36 + enabled calibration columns)
+//   normal equations           see cb2_normal.cu / cb2_schur.cu
+#pragma once
+#include "cb2_functors.cuh"
+
+namespace cb2 {
+
+constexpr int kTile = 128;          // observations per CTA in the residual/Jacobian sweep
+constexpr int kMaxCalib = 20;       // max calibration unknowns of one sensor: 12 intrinsics + 3 + 3 + 1
+constexpr int kCpCols = 6 * kK;     // 36 control-point columns per residual block
+
+struct SensorDesc {
+  int kind, model, ni, m;
+  int n_obs;                    // active (non-outlier) observations
+  int calib_off, n_calib;       // slice of the calibration unknown vector owned by this sensor (tangent dims)
+  int jw;                       // Jacobian columns stored per residual row: 36 + n_jcal
+  int n_jcal;
+  int jcanon[kMaxCalib];        // canonical column (see jac_entry) of stored calibration column j
+  int junk[kMaxCalib];          // calibration-local unknown index of stored calibration column j
+  int u_intr, u_rot, u_trans, u_lat;   // calibration-local unknown offsets, -1 when the block is constant
+  const double* stamp; const double* meas; const int* seg; const int* pt;
+  const int* seg_start;
+  double* r; double* J; unsigned char* valid;
+};
+
+struct EvalTile { int sensor, start, count; };
+
+// Scalars exchanged with the host once per LM iteration (device array of doubles).
+enum Scal {
+  kScCost = 0, kScInvalid = 1,            // cost at x (1/2 sum rho), number of residual blocks that failed to evaluate
+  kScCandCost = 2, kScCandInvalid = 3,    // same at the candidate point
+  kScGradMax = 4, kScGradNorm = 5,        // |x - Plus(x, -g)|_inf and _2  (trust_region_minimizer.cc, Ceres external)
+  kScSolveFail = 6,                       // > 0 when a Cholesky pivot was not positive / step not finite
+  kScModelChange = 7,                     // model cost change of the computed step
+  kScStepNorm2 = 8, kScXNorm2 = 9, kScCandXNorm2 = 10,
+  kScCount = 16
+};
+
+}  // namespace cb2

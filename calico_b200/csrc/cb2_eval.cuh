@@ -1,0 +1,127 @@
+// calico_b200 — K1/K2/K3 (residual + analytic Jacobian sweep), K8 (cost only) and K9 (final residuals).
+//
+// Replaces, for every residual block at once, what Ceres does per block through
+// DynamicAutoDiffCostFunction::Evaluate -> {Camera,Gyroscope,Accelerometer}CostFunctor::operator()<Jet>
+// (reference calico/sensors/camera_cost_functor.h:72-147, gyroscope_cost_functor.h:59-118,
+// accelerometer_cost_functor.h:63-147), the loss corrector (Ceres external; for Huber/Cauchy rho'' <= 0 so residual and
+// Jacobian are both scaled by sqrt(rho'), SURVEY §8 trap 6) and, in kModeResiduals, Sensor::UpdateResiduals
+// (camera.cpp:70-80).
+//
+// One CTA = one tile of kTile consecutive observations of one sensor (observations are sorted by spline segment, so a
+// tile touches one or two segments' control points). Phase 1: one thread per residual block evaluates the functor and
+// leaves a compact derivative record in shared memory, field-major ([field][tile lane] — conflict free). Phase 2: one
+// warp per residual block expands the record into the m x jw Jacobian rows and streams them to HBM with fully
+// coalesced 8-byte stores (consecutive lanes -> consecutive doubles of one row).
+#pragma once
+#include "cb2_device.cuh"
+
+namespace cb2 {
+
+enum { kModeCost = 0, kModeResiduals = 1, kModeJacobian = 2 };
+
+template <int KIND, int MODE>
+__global__ void __launch_bounds__(kTile) eval_kernel(const SensorDesc* __restrict__ sensors, const SensorState* __restrict__ states,
+                                                     const EvalTile* __restrict__ tiles, const double* __restrict__ ctrl,
+                                                     const double* __restrict__ knots, const double* __restrict__ basis,
+                                                     const double* __restrict__ pw, double gx, double gy, double gz,
+                                                     double* __restrict__ cost_partial, int* __restrict__ invalid_partial, int apply_loss) {
+  double* rec = dyn_smem<double>();
+  __shared__ double s_red[kTile / 32];
+  __shared__ int s_bad[kTile / 32];
+  __shared__ unsigned char s_ok[kTile];
+  constexpr int m = (KIND == kCamera) ? 2 : 3;
+  const EvalTile tl = tiles[blockIdx.x];
+  const SensorDesc& sd = sensors[tl.sensor];
+  const int t = threadIdx.x;
+  const bool active = t < tl.count;
+  double cost = 0.0;
+  int bad = 0;
+  bool ok = false;
+  if (active) {
+    const SensorState S = states[tl.sensor];
+    const long o = long(tl.start) + t;
+    const double stamp = sd.stamp[o];
+    const int seg = sd.seg[o];
+    const double knot0 = knots[seg + kK - 1], knot1 = knots[seg + kK];
+    const double* M = basis + size_t(seg) * (kK * kK);
+    const double* cp = ctrl + size_t(seg) * 6;
+    const Rec rc{rec + t, kTile};
+    if (KIND == kCamera) {
+      const int p = sd.pt[o];
+      ok = camera_block<MODE == kModeJacobian>(S, M, knot0, knot1, cp, stamp, sd.meas[2 * o], sd.meas[2 * o + 1],
+                                               v3(pw[3 * p], pw[3 * p + 1], pw[3 * p + 2]), rc);
+    } else if (KIND == kGyroscope) {
+      ok = gyro_block<MODE == kModeJacobian>(S, M, knot0, knot1, cp, stamp, v3(sd.meas[3 * o], sd.meas[3 * o + 1], sd.meas[3 * o + 2]), rc);
+    } else {
+      ok = accel_block<MODE == kModeJacobian>(S, v3(gx, gy, gz), M, knot0, knot1, cp, stamp,
+                                              v3(sd.meas[3 * o], sd.meas[3 * o + 1], sd.meas[3 * o + 2]), rc);
+    }
+    if (ok) {
+      double sq = 0.0;
+      for (int q = 0; q < m; ++q) { const double v = rc.get(q); sq += v * v; }
+      double rho0, rho1;
+      loss_eval(S.loss_type, S.loss_scale, sq, &rho0, &rho1);
+      cost = 0.5 * rho0;
+      if (MODE == kModeJacobian) rc.put(rec_rs(KIND), apply_loss ? sqrt(rho1) : 1.0);
+    } else {
+      bad = 1;
+    }
+    if (MODE == kModeResiduals) {
+      for (int q = 0; q < m; ++q) sd.r[o * m + q] = ok ? rc.get(q) : 0.0;
+      sd.valid[o] = ok ? 1 : 0;
+    }
+  }
+  s_ok[t] = ok ? 1 : 0;
+  // Deterministic block reduction of the cost and of the failure count.
+  for (int off = 16; off > 0; off >>= 1) {
+    cost += __shfl_down_sync(0xffffffffu, cost, off);
+    bad += __shfl_down_sync(0xffffffffu, bad, off);
+  }
+  if ((t & 31) == 0) { s_red[t >> 5] = cost; s_bad[t >> 5] = bad; }
+  __syncthreads();
+  if (t == 0) {
+    double c = 0.0; int b = 0;
+    for (int w = 0; w < kTile / 32; ++w) { c += s_red[w]; b += s_bad[w]; }
+    cost_partial[blockIdx.x] = c;
+    invalid_partial[blockIdx.x] = b;
+  }
+  if (MODE == kModeJacobian) {
+    const int warp = t >> 5, lane = t & 31;
+    const int jw = sd.jw, ni = sd.ni;
+    const int rowlen = m * jw;
+    for (int oo = 0; oo < 32; ++oo) {
+      const int lt = warp * 32 + oo;
+      if (lt >= tl.count) break;
+      const long o = long(tl.start) + lt;
+      const bool okb = s_ok[lt] != 0;
+      const Rec rc{rec + lt, kTile};
+      const double rs = okb ? rc.get(rec_rs(KIND)) : 0.0;
+      double* __restrict__ Jrow = sd.J + size_t(o) * rowlen;
+      for (int idx = lane; idx < rowlen; idx += 32) {
+        const int row = idx / jw, j = idx - row * jw;
+        const int canon = j < kCpCols ? j : kCpCols + sd.jcanon[j - kCpCols];
+        Jrow[idx] = okb ? rs * jac_entry(KIND, ni, rc, row, canon) : 0.0;
+      }
+      if (lane < m) sd.r[o * m + lane] = okb ? rs * rc.get(lane) : 0.0;
+    }
+  }
+}
+
+// Sums the per-tile partials in a fixed order: scal[slot] = cost, scal[slot+1] = number of failed blocks.
+__global__ void __launch_bounds__(256) reduce_cost_kernel(const double* __restrict__ cost_partial, const int* __restrict__ invalid_partial,
+                                                          int n, double* __restrict__ scal, int slot) {
+  __shared__ double sc[256];
+  __shared__ int sb[256];
+  const int t = threadIdx.x;
+  double c = 0.0; int b = 0;
+  for (int i = t; i < n; i += 256) { c += cost_partial[i]; b += invalid_partial[i]; }
+  sc[t] = c; sb[t] = b;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (t < s) { sc[t] += sc[t + s]; sb[t] += sb[t + s]; }
+    __syncthreads();
+  }
+  if (t == 0) { scal[slot] = sc[0]; scal[slot + 1] = double(sb[0]); }
+}
+
+}  // namespace cb2

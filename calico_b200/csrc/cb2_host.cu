@@ -1,0 +1,1031 @@
+// calico_b200 — host driver behind the C ABI (include/calico_b200.h).
+//
+// Mirrors, for ONE path of the reference, calico::BatchOptimizer::Optimize (calico/batch_optimizer.cpp:53-81):
+//   problem assembly      world_model.cpp:40-77, bspline.hpp:10-17, camera.cpp:92-153, gyroscope.cpp:10-54,
+//                         accelerometer.cpp:10-56  -> one SoA pack + upload (Problem::upload)
+//   ceres::Solve          batch_optimizer.cpp:73 with DefaultSolverOptions (batch_optimizer.cpp:10-17): trust-region
+//                         Levenberg-Marquardt (Ceres external: trust_region_minimizer.cc, levenberg_marquardt_strategy.cc)
+//                         -> Problem::minimize, every numerical step a CUDA kernel, the host reading one small scalar
+//                         block per iteration
+//   Sensor::UpdateResiduals  camera.cpp:70-80 -> Problem::refresh_residuals
+// There is no CPU fallback: without a CUDA device every device entry point returns CB2_INTERNAL.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/calico_b200.h"
+#include "cb2_eval.cuh"
+#include "cb2_lmkernels.cuh"
+#include "cb2_normal.cuh"
+#include "cb2_schur.cuh"
+
+namespace cb2 {
+
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+struct CudaFail { std::string msg; };
+#define CB2_CUDA(expr)                                                                                              \
+  do {                                                                                                              \
+    cudaError_t e_ = (expr);                                                                                        \
+    if (e_ != cudaSuccess) throw CudaFail{std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #expr};      \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+  ~DevBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void alloc(size_t count) {
+    release();
+    n = count;
+    if (count) CB2_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), std::max<size_t>(count, 1) * sizeof(T)));
+  }
+  void zero(cudaStream_t s) { if (n) CB2_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+  void upload(const std::vector<T>& h, int64_t* counter = nullptr) {
+    alloc(h.size());
+    if (!h.empty()) { CB2_CUDA(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice)); if (counter) *counter += int64_t(h.size() * sizeof(T)); }
+  }
+  void download(std::vector<T>& h, int64_t* counter = nullptr) const {
+    h.resize(n);
+    if (n) { CB2_CUDA(cudaMemcpy(h.data(), p, n * sizeof(T), cudaMemcpyDeviceToHost)); if (counter) *counter += int64_t(n * sizeof(T)); }
+  }
+};
+
+struct HostBody {
+  int id = 0;
+  double q[4] = {0, 0, 0, 1}, t[3] = {0, 0, 0};
+  bool pose_const = true, model_const = true;
+  std::vector<int> feature_ids;
+  std::vector<double> pts;
+  std::unordered_map<int, int> slot;
+  int pw0 = 0;   // first index of this body's points in the world-point table
+};
+
+struct HostSensor {
+  int kind = 0, model = 0;
+  std::string name;
+  std::vector<double> intr;
+  double q[4] = {0, 0, 0, 1}, t[3] = {0, 0, 0};
+  double latency = 0, sigma = 1;
+  int loss_type = 0;
+  double loss_scale = 1;
+  bool en_intr = false, en_extr = false, en_lat = false;
+  std::vector<double> stamp, meas;
+  std::vector<int> body_slot, feat_slot;
+  std::vector<uint8_t> outlier;
+  std::vector<double> residuals;
+  std::vector<uint8_t> residual_valid;
+  int m() const { return kind == kCamera ? 2 : 3; }
+  int n_obs() const { return int(stamp.size()); }
+  // device-side bookkeeping
+  std::vector<int> perm;      // sorted position -> original observation index
+  int n_active = 0;
+  DevBuf<double> d_stamp, d_meas, d_r, d_J;
+  DevBuf<int> d_seg, d_pt, d_seg_start;
+  DevBuf<unsigned char> d_valid;
+};
+
+struct ChunkPlan { int a, b; };   // interior control points [a, b)
+
+}  // namespace cb2
+
+using namespace cb2;
+
+struct cb2_problem {
+  // ---- host-side description (what the reference keeps in Trajectory / WorldModel / Sensor objects) ----
+  int k = 6;
+  std::vector<double> knots, ctrl;
+  double gravity[3] = {0, 0, -9.80665};   // world_model.h:78
+  std::vector<HostBody> bodies;
+  std::unordered_map<int, int> body_slot;
+  std::vector<HostSensor> sensors;
+  std::string error;
+
+  // ---- device state ----
+  bool uploaded = false;
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  int n_cp = 0, n_seg = 0, N_c = 0, csz = 0, n_tiles = 0;
+  long n_a = 0, n_tot = 0;
+  std::vector<SensorDesc> h_desc;
+  std::vector<SensorState> h_state;
+  std::vector<int> tile_off = std::vector<int>(4, 0);   // per kind offsets into the tile table
+  DevBuf<SensorDesc> d_desc;
+  DevBuf<SensorState> d_state[2], d_state0;
+  DevBuf<double> d_ctrl[2], d_ctrl0, d_knots, d_basis, d_pw;
+  DevBuf<EvalTile> d_tiles;
+  DevBuf<double> d_cost_partial;
+  DevBuf<int> d_invalid_partial;
+  DevBuf<double> d_scal;
+  DevBuf<unsigned char> d_cp_ref;
+  // normal equations
+  DevBuf<int> d_c2off;
+  DevBuf<CalibEntry> d_centries;
+  DevBuf<double> d_segA, d_segG, d_segB, d_segC, d_segGc, d_Aband, d_Bmat, d_Cmat, d_grad, d_diag, d_scaling, d_dtil2, d_ytil;
+  // Schur
+  std::vector<ChunkPlan> chunks;
+  std::vector<BandSys> h_l1;
+  BandSys h_l2;
+  DevBuf<BandSys> d_l1;
+  DevBuf<BandSys> d_l2;
+  DevBuf<int> d_chunk_sys, d_rowidx, d_colidx;
+  DevBuf<double> d_L1, d_W1, d_T1, d_L2, d_W2, d_T2, d_Cw, d_rawdiag;
+  int cur = 0;   // which of the two parameter buffers holds x
+  size_t smem_eval[3] = {0, 0, 0};
+  int max_tilepairs1 = 0, max_ksplit1 = 1;
+  double* h_scal = nullptr;   // pinned
+  cb2_stats stats{};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  bool scaling_set = false;
+
+  ~cb2_problem() {
+    if (h_scal) cudaFreeHost(h_scal);
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  int fail(int code, const std::string& msg) { error = msg; return code; }
+
+  // ------------------------------------------------------------------------------------------------------------
+  // Spline bookkeeping (host): BSpline::GetSplineIndex bspline.hpp:139-151, basis matrices bspline.hpp:192-244.
+  // ------------------------------------------------------------------------------------------------------------
+  static void basis_matrix(const std::vector<double>& kn, int i, double* M /*36*/) {
+    // Qin's recursion, built bottom-up: M_1 = [1]; M_j = [M_{j-1}; 0] A_j + [0; M_{j-1}] B_j.
+    std::vector<double> cur(1, 1.0);
+    for (int j = 2; j <= kK; ++j) {
+      const int n = j - 1;
+      std::vector<double> nxt(size_t(j) * j, 0.0);
+      for (int idx = 0; idx < n; ++idx) {
+        const int jj = i - j + 2 + idx;
+        const double den = kn[jj + j - 1] - kn[jj];
+        const double d0 = den <= 0.0 ? 0.0 : (kn[i] - kn[jj]) / den;
+        const double d1 = den <= 0.0 ? 0.0 : (kn[i + 1] - kn[i]) / den;
+        // column idx and idx+1 of the new matrix receive contributions from column idx of the old one
+        for (int r = 0; r < n; ++r) {
+          const double v = cur[size_t(r) * n + idx];
+          nxt[size_t(r) * j + idx] += v * (1.0 - d0);
+          nxt[size_t(r) * j + idx + 1] += v * d0;
+          nxt[size_t(r + 1) * j + idx] += v * (-d1);
+          nxt[size_t(r + 1) * j + idx + 1] += v * d1;
+        }
+      }
+      cur.swap(nxt);
+    }
+    std::memcpy(M, cur.data(), sizeof(double) * kK * kK);
+  }
+  int spline_index(double t) const {
+    const double* vk = knots.data() + (kK - 1);
+    const int nv = int(knots.size()) - 2 * (kK - 1);
+    if (t == vk[nv - 1]) return nv - 2;
+    if (t < vk[nv - 1]) return int(std::upper_bound(vk, vk + nv, t) - vk) - 1;
+    return -1;
+  }
+
+  // ------------------------------------------------------------------------------------------------------------
+  // Upload: validate, pack SoA (observations sorted by spline segment), allocate every device array.
+  // ------------------------------------------------------------------------------------------------------------
+  int upload() {
+    try {
+      return upload_impl();
+    } catch (const CudaFail& f) {
+      return fail(CB2_INTERNAL, f.msg);
+    }
+  }
+
+  int ensure_device() {
+    if (stream) return CB2_OK;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0)
+      return fail(CB2_INTERNAL, "No CUDA device available: calico_b200 has no CPU fallback.");
+    if (device >= 0) CB2_CUDA(cudaSetDevice(device));
+    CB2_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CB2_CUDA(cudaEventCreate(&ev[0]));
+    CB2_CUDA(cudaEventCreate(&ev[1]));
+    CB2_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_scal), sizeof(double) * kScCount));
+    return CB2_OK;
+  }
+
+  int upload_impl() {
+    uploaded = false;
+    if (knots.empty() || ctrl.empty()) return fail(CB2_FAILED_PRECONDITION, "Trajectory has not been set.");
+    if (k != kK) return fail(CB2_UNIMPLEMENTED, "Only spline order 6 (calico::Trajectory::kSplineOrder, trajectory.h:28) is supported.");
+    for (const auto& b : bodies)
+      if (!b.pose_const || !b.model_const)
+        return fail(CB2_UNIMPLEMENTED, "Estimating rigid-body poses or model definitions is not supported on the device path yet.");
+    int rc = ensure_device();
+    if (rc != CB2_OK) return rc;
+    n_cp = int(ctrl.size() / 6);
+    n_seg = n_cp - (kK - 1);
+    if (n_seg < 1) return fail(CB2_INVALID_ARGUMENT, "Trajectory has too few control points.");
+    n_a = 6L * n_cp;
+    // World points p_w = q_wm * p_m + t_wm.
+    std::vector<double> pw;
+    for (auto& b : bodies) {
+      b.pw0 = int(pw.size() / 3);
+      const M3 R = quat_matrix(Q4{b.q[0], b.q[1], b.q[2], b.q[3]});
+      for (size_t f = 0; f < b.feature_ids.size(); ++f) {
+        const V3 p = R * v3(b.pts[3 * f], b.pts[3 * f + 1], b.pts[3 * f + 2]);
+        pw.push_back(p.x + b.t[0]); pw.push_back(p.y + b.t[1]); pw.push_back(p.z + b.t[2]);
+      }
+    }
+    std::vector<double> basis(size_t(n_seg) * 36);
+    for (int s = 0; s < n_seg; ++s) basis_matrix(knots, s + kK - 1, &basis[size_t(s) * 36]);
+    // Sensors.
+    const int ns = int(sensors.size());
+    h_desc.assign(ns, SensorDesc{});
+    h_state.assign(ns, SensorState{});
+    std::vector<unsigned char> cp_ref(n_cp, 0);
+    N_c = 0; csz = 0;
+    std::vector<int> c2off(std::max(ns, 1), 0);
+    std::vector<EvalTile> tiles;
+    std::vector<std::vector<EvalTile>> tiles_by_kind(3);
+    int64_t* h2d = &stats.h2d_bytes;
+    for (int si = 0; si < ns; ++si) {
+      HostSensor& s = sensors[si];
+      const int want = s.kind == kCamera ? camera_num_params(s.model) : imu_num_params(s.model);
+      if (want < 0) return fail(CB2_FAILED_PRECONDITION, "Cannot add sensor parameters. Model is not yet defined.");   // camera.cpp:95
+      if (int(s.intr.size()) != want) return fail(CB2_INVALID_ARGUMENT, "Invalid number of intrinsics parameters.");
+      const int m = s.m(), n = s.n_obs();
+      // segment of each active observation; stable counting sort by segment
+      std::vector<int> seg_of(n, -1);
+      std::vector<int> count(n_seg + 1, 0);
+      int n_active = 0;
+      for (int o = 0; o < n; ++o) {
+        if (s.kind == kCamera && !s.outlier.empty() && s.outlier[o]) continue;   // camera.cpp:121-124
+        if (s.kind == kCamera && s.body_slot[o] < 0)
+          return fail(CB2_FAILED_PRECONDITION, "Attempted to create cost function from an observation for a rigidbody that does not exist in the world model.");   // camera.cpp:125-131
+        const int sg = spline_index(s.stamp[o]);
+        if (sg < 0 || sg >= n_seg) return fail(CB2_INVALID_ARGUMENT, "Observation stamp is outside the valid knots of the trajectory.");
+        seg_of[o] = sg;
+        ++count[sg + 1];
+        ++n_active;
+      }
+      for (int g = 0; g < n_seg; ++g) count[g + 1] += count[g];
+      std::vector<int> seg_start(count);
+      s.perm.assign(n_active, 0);
+      {
+        std::vector<int> cursor(count.begin(), count.end() - 1);
+        for (int o = 0; o < n; ++o) if (seg_of[o] >= 0) s.perm[cursor[seg_of[o]]++] = o;
+      }
+      s.n_active = n_active;
+      std::vector<double> stamp(n_active), meas(size_t(n_active) * m);
+      std::vector<int> seg(n_active), pt(s.kind == kCamera ? n_active : 0);
+      for (int i = 0; i < n_active; ++i) {
+        const int o = s.perm[i];
+        stamp[i] = s.stamp[o];
+        seg[i] = seg_of[o];
+        for (int q = 0; q < m; ++q) meas[size_t(i) * m + q] = s.meas[size_t(o) * m + q];
+        if (s.kind == kCamera) pt[i] = bodies[s.body_slot[o]].pw0 + s.feat_slot[o];
+        for (int c = 0; c < kK; ++c) cp_ref[seg_of[o] + c] = 1;
+      }
+      s.d_stamp.upload(stamp, h2d); s.d_meas.upload(meas, h2d); s.d_seg.upload(seg, h2d); s.d_pt.upload(pt, h2d);
+      s.d_seg_start.upload(seg_start, h2d);
+      // Unknown layout of this sensor (constant or unreferenced blocks drop out, as in Ceres's reduced program).
+      SensorDesc& d = h_desc[si];
+      d.kind = s.kind; d.model = s.model; d.ni = want; d.m = m; d.n_obs = n_active;
+      const bool ref = n_active > 0;
+      int u = 0;
+      d.u_intr = (ref && s.en_intr) ? u : -1; if (d.u_intr >= 0) u += want;
+      d.u_rot = (ref && s.en_extr) ? u : -1; if (d.u_rot >= 0) u += 3;
+      d.u_trans = (ref && s.en_extr) ? u : -1; if (d.u_trans >= 0) u += 3;
+      d.u_lat = (ref && s.en_lat) ? u : -1; if (d.u_lat >= 0) u += 1;
+      d.n_calib = u; d.calib_off = N_c; N_c += u;
+      c2off[si] = csz; csz += u * u;
+      // Stored Jacobian columns: canonical order [intr | rot | trans | lat]; the gyroscope's translation columns are
+      // structurally zero (gyroscope_cost_functor.h:59-118 never reads t) and are not stored.
+      int nj = 0;
+      if (d.u_intr >= 0) for (int j = 0; j < want; ++j) { d.jcanon[nj] = j; d.junk[nj] = d.u_intr + j; ++nj; }
+      if (d.u_rot >= 0) for (int j = 0; j < 3; ++j) { d.jcanon[nj] = want + j; d.junk[nj] = d.u_rot + j; ++nj; }
+      if (d.u_trans >= 0 && s.kind != kGyroscope) for (int j = 0; j < 3; ++j) { d.jcanon[nj] = want + 3 + j; d.junk[nj] = d.u_trans + j; ++nj; }
+      if (d.u_lat >= 0) { d.jcanon[nj] = want + 6; d.junk[nj] = d.u_lat; ++nj; }
+      d.n_jcal = nj; d.jw = kCpCols + nj;
+      s.d_r.alloc(size_t(n_active) * m);
+      s.d_J.alloc(size_t(n_active) * m * d.jw);
+      s.d_valid.alloc(n_active);
+      d.stamp = s.d_stamp.p; d.meas = s.d_meas.p; d.seg = s.d_seg.p; d.pt = s.d_pt.p; d.seg_start = s.d_seg_start.p;
+      d.r = s.d_r.p; d.J = s.d_J.p; d.valid = s.d_valid.p;
+      for (int o0 = 0; o0 < n_active; o0 += kTile) tiles_by_kind[s.kind].push_back(EvalTile{si, o0, std::min(kTile, n_active - o0)});
+      // state
+      SensorState& st = h_state[si];
+      st.kind = s.kind; st.model = s.model; st.ni = want;
+      for (int j = 0; j < kMaxIntrinsics; ++j) st.intr[j] = j < want ? s.intr[j] : 0.0;
+      st.q = Q4{s.q[0], s.q[1], s.q[2], s.q[3]}; st.t = v3(s.t[0], s.t[1], s.t[2]);
+      st.latency = s.latency; st.inv_sigma = 1.0 / s.sigma; st.loss_type = s.loss_type; st.loss_scale = s.loss_scale;
+      smem_eval[s.kind] = std::max(smem_eval[s.kind], size_t(rec_size(s.kind, want)) * kTile * sizeof(double));
+    }
+    n_tot = n_a + N_c;
+    if (N_c > kRedThreads) return fail(CB2_UNIMPLEMENTED, "More than 512 calibration unknowns are not supported.");
+    tile_off[0] = 0;
+    for (int kd = 0; kd < 3; ++kd) { tiles.insert(tiles.end(), tiles_by_kind[kd].begin(), tiles_by_kind[kd].end()); tile_off[kd + 1] = int(tiles.size()); }
+    n_tiles = int(tiles.size());
+    d_tiles.upload(tiles, h2d);
+    d_cost_partial.alloc(std::max(n_tiles, 1)); d_invalid_partial.alloc(std::max(n_tiles, 1));
+    d_desc.upload(h_desc, h2d);
+    for (int b = 0; b < 2; ++b) d_state[b].upload(h_state, h2d);
+    d_state0.upload(h_state, h2d);
+    for (int b = 0; b < 2; ++b) d_ctrl[b].upload(ctrl, h2d);
+    d_ctrl0.upload(ctrl, h2d);
+    d_knots.upload(knots, h2d); d_basis.upload(basis, h2d); d_pw.upload(pw, h2d);
+    d_cp_ref.upload(cp_ref, h2d);
+    d_scal.alloc(kScCount);
+    cur = 0;
+    // Normal-equation storage.
+    d_c2off.upload(c2off, h2d);
+    std::vector<CalibEntry> ce;
+    for (int si = 0; si < ns; ++si) {
+      const SensorDesc& d = h_desc[si];
+      for (int li = 0; li < d.n_calib; ++li) for (int lj = 0; lj <= li; ++lj) ce.push_back(CalibEntry{c2off[si] + li * d.n_calib + lj, d.calib_off + li, d.calib_off + lj});
+      for (int li = 0; li < d.n_calib; ++li) ce.push_back(CalibEntry{d.calib_off + li, d.calib_off + li, -1});
+    }
+    d_centries.upload(ce, h2d);
+    d_segA.alloc(size_t(n_seg) * 36 * 36); d_segG.alloc(size_t(n_seg) * 36);
+    d_segB.alloc(size_t(n_seg) * 36 * std::max(N_c, 1)); d_segC.alloc(size_t(n_seg) * std::max(csz, 1)); d_segGc.alloc(size_t(n_seg) * std::max(N_c, 1));
+    d_Aband.alloc(size_t(n_a) * 36); d_Bmat.alloc(size_t(n_a) * std::max(N_c, 1)); d_Cmat.alloc(size_t(std::max(N_c, 1)) * std::max(N_c, 1));
+    d_grad.alloc(n_tot); d_diag.alloc(n_tot); d_scaling.alloc(n_tot); d_dtil2.alloc(n_tot); d_ytil.alloc(n_tot);
+    rc = plan_schur();
+    if (rc != CB2_OK) return rc;
+    set_kernel_attributes();
+    CB2_CUDA(cudaDeviceSynchronize());
+    uploaded = true;
+    scaling_set = false;
+    return CB2_OK;
+  }
+
+  // ------------------------------------------------------------------------------------------------------------
+  // Chunk plan for the substructured Schur elimination (cb2_schur.cuh).
+  // ------------------------------------------------------------------------------------------------------------
+  int plan_schur() {
+    int target = 48;   // interior control points per chunk
+    if (const char* e = std::getenv("CB2_CHUNK_CPS")) target = std::max(6, std::atoi(e));
+    int P = std::max(1, (n_cp + 5) / (target + 5));
+    while (P > 1 && (n_cp - 5 * (P - 1)) / P < 6) --P;
+    const int interior = n_cp - 5 * (P - 1);
+    chunks.clear();
+    int a = 0;
+    for (int p = 0; p < P; ++p) {
+      const int len = interior / P + (p < interior % P ? 1 : 0);
+      chunks.push_back(ChunkPlan{a, a + len});
+      a += len + 5;
+    }
+    const int nbw1 = 2 * kSepDim + N_c + 1, nbw2 = N_c + 1;
+    const int n2 = kSepDim * (P - 1);
+    // index tables
+    std::vector<int> rowidx, colidx;
+    std::vector<size_t> row_off(P + 1), col_off(P + 1);
+    size_t Lsz = 0, Wsz = 0, Tsz = 0;
+    h_l1.assign(P, BandSys{});
+    const int nt1 = (nbw1 + 63) / 64;
+    max_tilepairs1 = nt1 * (nt1 + 1) / 2;
+    max_ksplit1 = 1;
+    std::vector<size_t> Loff(P), Woff(P), Toff(P);
+    for (int p = 0; p < P; ++p) {
+      BandSys& sy = h_l1[p];
+      sy.n = 6 * (chunks[p].b - chunks[p].a); sy.hb = 35; sy.nbw = nbw1;
+      sy.ksplit = std::max(1, std::min((sy.n + 63) / 64, (296 + P * max_tilepairs1 - 1) / (P * max_tilepairs1)));
+      max_ksplit1 = std::max(max_ksplit1, sy.ksplit);
+      row_off[p] = rowidx.size();
+      for (int i = 0; i < sy.n; ++i) rowidx.push_back(6 * chunks[p].a + i);
+      col_off[p] = colidx.size();
+      for (int j = 0; j < kSepDim; ++j) colidx.push_back(p > 0 ? 6 * (chunks[p].a - 5) + j : -1);
+      for (int j = 0; j < kSepDim; ++j) colidx.push_back(p < P - 1 ? 6 * chunks[p].b + j : -1);
+      for (int c = 0; c < N_c; ++c) colidx.push_back(int(n_a) + c);
+      Loff[p] = Lsz; Woff[p] = Wsz; Toff[p] = Tsz;
+      Lsz += size_t(sy.n) * 36; Wsz += size_t(sy.n) * nbw1; Tsz += size_t(sy.ksplit) * nbw1 * nbw1;
+      if (size_t(sy.n + nbw1) * sizeof(double) > 200 * 1024) return fail(CB2_INTERNAL, "Schur chunk too large for shared memory; lower CB2_CHUNK_CPS.");
+    }
+    const size_t row_off2 = rowidx.size();
+    for (int p = 0; p + 1 < P; ++p) for (int j = 0; j < kSepDim; ++j) rowidx.push_back(6 * chunks[p].b + j);
+    const size_t col_off2 = colidx.size();
+    for (int c = 0; c < N_c; ++c) colidx.push_back(int(n_a) + c);
+    d_rowidx.upload(rowidx); d_colidx.upload(colidx);
+    d_L1.alloc(Lsz); d_W1.alloc(Wsz); d_T1.alloc(Tsz);
+    for (int p = 0; p < P; ++p) {
+      BandSys& sy = h_l1[p];
+      sy.row_gidx = d_rowidx.p + row_off[p]; sy.col_gidx = d_colidx.p + col_off[p];
+      sy.L = d_L1.p + Loff[p]; sy.W = d_W1.p + Woff[p]; sy.T = d_T1.p + Toff[p];
+    }
+    d_l1.upload(h_l1);
+    h_l2 = BandSys{};
+    h_l2.n = n2; h_l2.hb = 59; h_l2.nbw = nbw2;
+    const int nt2 = (nbw2 + 63) / 64;
+    h_l2.ksplit = std::max(1, std::min((n2 + 63) / 64, (148 + nt2 * (nt2 + 1) / 2 - 1) / (nt2 * (nt2 + 1) / 2)));
+    d_L2.alloc(size_t(std::max(n2, 1)) * 60); d_W2.alloc(size_t(std::max(n2, 1)) * nbw2); d_T2.alloc(size_t(h_l2.ksplit) * nbw2 * nbw2);
+    h_l2.row_gidx = d_rowidx.p + row_off2; h_l2.col_gidx = d_colidx.p + col_off2;
+    h_l2.L = d_L2.p; h_l2.W = d_W2.p; h_l2.T = d_T2.p;
+    d_l2.upload(std::vector<BandSys>(1, h_l2));
+    std::vector<int> chunk_sys(P);
+    for (int p = 0; p < P; ++p) chunk_sys[p] = p;
+    d_chunk_sys.upload(chunk_sys);
+    d_Cw.alloc(size_t(N_c + 1) * (N_c + 1));
+    d_rawdiag.alloc(size_t(std::max(n2, 1)) + std::max(N_c, 1));
+    const size_t smem_f1 = (36 * 36 + 36 * size_t(nbw1)) * sizeof(double), smem_f2 = (60 * 60 + 60 * size_t(nbw2)) * sizeof(double);
+    if (smem_f1 > 227 * 1024 || smem_f2 > 227 * 1024) return fail(CB2_UNIMPLEMENTED, "Too many calibration unknowns for the shared-memory Schur kernels.");
+    return CB2_OK;
+  }
+
+  void set_kernel_attributes() {
+#ifndef CB2_EMUL
+    const int big = 227 * 1024;
+    cudaFuncSetAttribute(eval_kernel<kCamera, kModeCost>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(eval_kernel<kCamera, kModeResiduals>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(eval_kernel<kCamera, kModeJacobian>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(eval_kernel<kGyroscope, kModeCost>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(eval_kernel<kGyroscope, kModeResiduals>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(eval_kernel<kGyroscope, kModeJacobian>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(eval_kernel<kAccelerometer, kModeCost>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(eval_kernel<kAccelerometer, kModeResiduals>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(eval_kernel<kAccelerometer, kModeJacobian>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(band_factor_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(band_factor_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(reduced_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(band_backsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaGetLastError();
+#endif
+  }
+
+  // ------------------------------------------------------------------------------------------------------------
+  // Kernel launches.
+  // ------------------------------------------------------------------------------------------------------------
+#define CB2_K(...) do { CB2_LAUNCH(__VA_ARGS__); ++stats.kernel_launches; } while (0)
+
+  // Residual sweep over every sensor at parameter buffer `which`; scalars land in d_scal[slot], d_scal[slot + 1].
+  template <int MODE>
+  void launch_eval(int which, int slot) {
+    const SensorDesc* desc = d_desc.p;
+    const SensorState* st = d_state[which].p;
+    const double* c = d_ctrl[which].p;
+    const int nt[3] = {tile_off[1] - tile_off[0], tile_off[2] - tile_off[1], tile_off[3] - tile_off[2]};
+    if (nt[0]) CB2_K((eval_kernel<kCamera, MODE>), nt[0], kTile, smem_eval[0], stream, desc, st, d_tiles.p + tile_off[0], c, d_knots.p, d_basis.p, d_pw.p,
+                     gravity[0], gravity[1], gravity[2], d_cost_partial.p + tile_off[0], d_invalid_partial.p + tile_off[0], 1);
+    if (nt[1]) CB2_K((eval_kernel<kGyroscope, MODE>), nt[1], kTile, smem_eval[1], stream, desc, st, d_tiles.p + tile_off[1], c, d_knots.p, d_basis.p, d_pw.p,
+                     gravity[0], gravity[1], gravity[2], d_cost_partial.p + tile_off[1], d_invalid_partial.p + tile_off[1], 1);
+    if (nt[2]) CB2_K((eval_kernel<kAccelerometer, MODE>), nt[2], kTile, smem_eval[2], stream, desc, st, d_tiles.p + tile_off[2], c, d_knots.p, d_basis.p, d_pw.p,
+                     gravity[0], gravity[1], gravity[2], d_cost_partial.p + tile_off[2], d_invalid_partial.p + tile_off[2], 1);
+    CB2_K(reduce_cost_kernel, 1, 256, 0, stream, d_cost_partial.p, d_invalid_partial.p, n_tiles, d_scal.p, slot);
+  }
+
+  // K1-K3 at x, then K4: normal equations, Hessian diagonal, gradient norms.
+  void launch_jacobian_and_normal_equations() {
+    CB2_CUDA(cudaEventRecord(ev[0], stream));
+    launch_eval<kModeJacobian>(cur, kScCost);
+    CB2_CUDA(cudaEventRecord(ev[1], stream));
+    const int ns = int(sensors.size());
+    CB2_K(accumulate_kernel, n_seg, kAccThreads, 0, stream, d_desc.p, ns, N_c, d_c2off.p, csz, d_segA.p, d_segG.p, d_segB.p, d_segC.p, d_segGc.p);
+    const long total = n_a * 36 + n_a * N_c + n_a;
+    CB2_K(assemble_band_kernel, int(std::min<long>((total + 255) / 256, 148 * 16)), 256, 0, stream, n_cp, n_seg, N_c, d_segA.p, d_segG.p, d_segB.p,
+          d_Aband.p, d_Bmat.p, d_grad.p);
+    if (N_c > 0) {
+      d_Cmat.zero(stream);
+      const int ne = int(d_centries.n);
+      CB2_K(assemble_calib_kernel, (ne + 31) / 32, dim3(32, 8), 0, stream, n_seg, N_c, csz, ne, d_centries.p, d_segC.p, d_segGc.p, d_Cmat.p, d_grad.p + n_a);
+    }
+    CB2_K(hess_diag_kernel, int(std::min<long>((n_tot + 255) / 256, 1024)), 256, 0, stream, n_a, N_c, d_Aband.p, d_Cmat.p, d_diag.p);
+    CB2_K(gradient_norm_kernel, 1, kLmThreads, 0, stream, n_a, d_grad.p, d_desc.p, d_state[cur].p, ns, d_scal.p);
+    ++stats.jacobian_sweeps;
+  }
+
+  // One LM linear solve + candidate point + candidate cost. Everything is enqueued; the caller syncs once.
+  void launch_step(double radius, const cb2_options& opt) {
+    const int P = int(chunks.size());
+    const int ns = int(sensors.size());
+    const int blocks = int(std::min<long>((n_tot + 255) / 256, 1024));
+    CB2_K(damping_kernel, blocks, 256, 0, stream, n_tot, d_diag.p, d_scaling.p, radius, opt.min_lm_diagonal, opt.max_lm_diagonal, d_dtil2.p);
+    CB2_CUDA(cudaMemsetAsync(d_scal.p + kScSolveFail, 0, sizeof(double), stream));
+    const int nbw1 = h_l1[0].nbw;
+    int max_n1 = 0;
+    for (const auto& sy : h_l1) max_n1 = std::max(max_n1, sy.n);
+    CB2_K(gather_level1_kernel, dim3(std::max(1, std::min(64, (max_n1 * (36 + nbw1) + 255) / 256)), P), 256, 0, stream, d_l1.p, n_a, N_c, d_Aband.p,
+          d_Bmat.p, d_Cmat.p, d_grad.p, d_dtil2.p);
+    const size_t smem_f1 = (36 * 36 + 36 * size_t(nbw1)) * sizeof(double);
+    CB2_K((band_factor_kernel<6>), P, kFacThreads, smem_f1, stream, d_l1.p, d_scal.p);
+    CB2_K(border_gram_kernel, dim3(max_tilepairs1, P, max_ksplit1), dim3(16, 16), 0, stream, d_l1.p);
+    if (h_l2.n > 0) {
+      const long tot2 = long(h_l2.n) * (60 + h_l2.nbw);
+      CB2_K(level2_build_kernel, int(std::min<long>((tot2 + 255) / 256, 1024)), 256, 0, stream, h_l2, d_l1.p, d_chunk_sys.p, P, n_a, N_c, d_Aband.p,
+            d_Bmat.p, d_Cmat.p, d_grad.p, d_rawdiag.p);
+      CB2_K(level2_damp_kernel, (h_l2.n + 255) / 256, 256, 0, stream, h_l2, d_dtil2.p);
+      const size_t smem_f2 = (60 * 60 + 60 * size_t(h_l2.nbw)) * sizeof(double);
+      CB2_K((band_factor_kernel<10>), 1, kFacThreads, smem_f2, stream, d_l2.p, d_scal.p);
+      const int nt2 = (h_l2.nbw + 63) / 64;
+      CB2_K(border_gram_kernel, dim3(nt2 * (nt2 + 1) / 2, 1, h_l2.ksplit), dim3(16, 16), 0, stream, d_l2.p);
+    }
+    if (N_c > 0) {
+      const long tot3 = long(N_c + 1) * (N_c + 1);
+      CB2_K(level3_build_kernel, int(std::min<long>((tot3 + 255) / 256, 1024)), 256, 0, stream, d_l1.p, P, n_a, N_c, d_Cmat.p, d_grad.p, d_Cw.p,
+            d_rawdiag.p + std::max(h_l2.n, 1));
+      CB2_K(reduced_solve_kernel, 1, kRedThreads, size_t(N_c + 1) * (kRedPanel + 1) * sizeof(double), stream, h_l2, N_c, n_a, d_Cw.p, d_dtil2.p,
+            d_ytil.p, d_scal.p);
+    }
+    if (h_l2.n > 0) CB2_K(band_backsolve_kernel, 1, kBackThreads, size_t(h_l2.n + h_l2.nbw) * sizeof(double), stream, d_l2.p, d_ytil.p);
+    CB2_K(band_backsolve_kernel, P, kBackThreads, size_t(max_n1 + nbw1) * sizeof(double), stream, d_l1.p, d_ytil.p);
+    CB2_K(apply_step_kernel, 1, kLmThreads, 0, stream, n_a, d_ytil.p, d_grad.p, d_dtil2.p, d_cp_ref.p, d_ctrl[cur].p, d_ctrl[cur ^ 1].p, d_desc.p,
+          d_state[cur].p, d_state[cur ^ 1].p, ns, N_c, d_scal.p);
+    launch_eval<kModeCost>(cur ^ 1, kScCandCost);
+  }
+
+  void sync_scalars() {
+    CB2_CUDA(cudaMemcpyAsync(h_scal, d_scal.p, sizeof(double) * kScCount, cudaMemcpyDeviceToHost, stream));
+    CB2_CUDA(cudaStreamSynchronize(stream));
+    CB2_CUDA(cudaGetLastError());
+    stats.d2h_bytes += sizeof(double) * kScCount;
+  }
+
+  double jacobian_bytes_per_sweep() const {   // obs_read + 8 m w + 8 m per residual block
+    double total = 0.0;
+    for (size_t si = 0; si < sensors.size(); ++si) {
+      const SensorDesc& d = h_desc[si];
+      const double obs = d.kind == kCamera ? 32.0 : 40.0;
+      total += double(d.n_obs) * (obs + 8.0 * d.m * d.jw + 8.0 * d.m);
+    }
+    return total;
+  }
+  long num_active_blocks() const { long n = 0; for (const auto& d : h_desc) n += d.n_obs; return n; }
+
+  // ------------------------------------------------------------------------------------------------------------
+  // Trust-region Levenberg-Marquardt loop: TrustRegionMinimizer::Minimize (Ceres external), same control flow as the
+  // reference's ceres::Solve call (batch_optimizer.cpp:73).
+  // ------------------------------------------------------------------------------------------------------------
+  void fill_summary_counts(cb2_summary& S) const {
+    int nblocks = 0, nparams = 0, neff = 0;
+    for (const auto& b : bodies) { nblocks += int(b.feature_ids.size()) + 2; nparams += 3 * int(b.feature_ids.size()) + 7; neff += 3 * int(b.feature_ids.size()) + 6; }
+    nblocks += 1; nparams += 3; neff += 3;            // gravity
+    nblocks += n_cp; nparams += 6 * n_cp; neff += 6 * n_cp;
+    for (const auto& s : sensors) { nblocks += 4; nparams += int(s.intr.size()) + 8; neff += int(s.intr.size()) + 7; }
+    S.num_parameter_blocks = nblocks; S.num_parameters = nparams; S.num_effective_parameters = neff;
+    int rb = 0, rr = 0, pbr = 0, pr = 0, per = 0;
+    for (const auto& d : h_desc) {
+      rb += d.n_obs; rr += d.n_obs * d.m;
+      if (d.u_intr >= 0) { ++pbr; pr += d.ni; per += d.ni; }
+      if (d.u_rot >= 0) { pbr += 2; pr += 7; per += 6; }
+      if (d.u_lat >= 0) { ++pbr; ++pr; ++per; }
+    }
+    const int ncp_ref = n_cp_referenced;
+    pbr += ncp_ref; pr += 6 * ncp_ref; per += 6 * ncp_ref;
+    S.num_residual_blocks = rb; S.num_residuals = rr;
+    S.num_residual_blocks_reduced = rb; S.num_residuals_reduced = rr;
+    S.num_parameter_blocks_reduced = pbr; S.num_parameters_reduced = pr; S.num_effective_parameters_reduced = per;
+  }
+  int n_cp_referenced = 0;
+
+  int minimize(const cb2_options& opt, cb2_summary& S, std::vector<cb2_iteration>& L) {
+    const double t_start = now_s();
+    std::memset(&S, 0, sizeof(S));
+    S.termination_type = CB2_FAILURE;
+    {
+      std::vector<unsigned char> ref;
+      d_cp_ref.download(ref);
+      n_cp_referenced = 0;
+      for (auto v : ref) n_cp_referenced += v;
+    }
+    fill_summary_counts(S);
+    auto msg = [&](const char* fmt, double a = 0, double b = 0) { std::snprintf(S.message, sizeof S.message, fmt, a, b); };
+    L.clear();
+    if (num_active_blocks() == 0 || n_cp_referenced == 0) {
+      S.termination_type = CB2_CONVERGENCE;
+      msg("Function tolerance reached. No non-constant parameter blocks found.");
+      S.total_time = now_s() - t_start;
+      return CB2_OK;
+    }
+    double radius = opt.initial_trust_region_radius, decrease_factor = 2.0;
+    double x_cost = 0, x_norm = 0, candidate_cost = 0, model_cost_change = 0, reference_cost = 0;
+    int num_consecutive_invalid_steps = 0;
+    bool atleast_one_successful_step = false;
+    cb2_iteration it{};
+    float ms = 0;
+    const int blocks_tot = int(std::min<long>((n_tot + 255) / 256, 1024));
+
+    auto evaluate_gradient_and_jacobian = [&](bool first) -> bool {
+      const double t0 = now_s();
+      launch_jacobian_and_normal_equations();
+      if (first) CB2_K(jacobi_scaling_kernel, blocks_tot, 256, 0, stream, n_tot, d_diag.p, opt.jacobi_scaling, d_scaling.p);
+      sync_scalars();
+      cudaEventElapsedTime(&ms, ev[0], ev[1]);
+      stats.jacobian_kernel_ms += ms;
+      stats.jacobian_blocks += num_active_blocks();
+      stats.jacobian_bytes += jacobian_bytes_per_sweep();
+      S.jacobian_time += now_s() - t0;
+      if (h_scal[kScInvalid] > 0) return false;
+      x_cost = h_scal[kScCost];
+      it.cost = x_cost;
+      it.gradient_max_norm = h_scal[kScGradMax];
+      it.gradient_norm = h_scal[kScGradNorm];
+      return true;
+    };
+
+    double t_iter = now_s();
+    it.iteration = 0; it.trust_region_radius = radius;
+    if (!evaluate_gradient_and_jacobian(true)) {
+      msg("Initial residual and Jacobian evaluation failed.");
+      S.total_time = now_s() - t_start;
+      return CB2_OK;
+    }
+    scaling_set = true;
+    S.initial_cost = x_cost;
+    it.step_is_valid = 1; it.step_is_successful = 1;
+    reference_cost = x_cost;
+    bool have_x_norm = false;
+    if (opt.minimizer_progress_to_stdout)
+      std::printf("iter      cost      cost_change  |gradient|   |step|    tr_ratio  tr_radius  ls_iter  iter_time  total_time\n");
+
+    for (;;) {
+      it.trust_region_radius = radius;
+      it.iteration_time = now_s() - t_iter;
+      L.push_back(it);
+      if (opt.minimizer_progress_to_stdout)
+        std::printf("% 4d % 8e   % 3.2e   % 3.2e  % 3.2e  % 3.2e % 3.2e     % 4d   % 3.2e   % 3.2e\n", it.iteration, it.cost, it.cost_change,
+                    it.gradient_max_norm, it.step_norm, it.relative_decrease, it.trust_region_radius, 1, it.iteration_time, now_s() - t_start);
+      if (it.iteration >= opt.max_num_iterations) { S.termination_type = CB2_NO_CONVERGENCE; msg("Maximum number of iterations reached. Number of iterations: %.0f.", it.iteration); break; }
+      if (it.step_is_successful && it.gradient_max_norm <= opt.gradient_tolerance) {
+        S.termination_type = CB2_CONVERGENCE; msg("Gradient tolerance reached. Gradient max norm: %e <= %e", it.gradient_max_norm, opt.gradient_tolerance); break;
+      }
+      if (radius <= opt.min_trust_region_radius) {
+        S.termination_type = CB2_CONVERGENCE; msg("Minimum trust region radius reached. Trust region radius: %e <= %e", radius, opt.min_trust_region_radius); break;
+      }
+      t_iter = now_s();
+      const double prev_gmax = it.gradient_max_norm, prev_gnorm = it.gradient_norm;
+      const int next_iter = it.iteration + 1;
+      it = cb2_iteration{};
+      it.iteration = next_iter; it.gradient_max_norm = prev_gmax; it.gradient_norm = prev_gnorm;
+
+      // LevenbergMarquardtStrategy::ComputeStep + candidate evaluation, one device round trip.
+      const double t_ls = now_s();
+      launch_step(radius, opt);
+      sync_scalars();
+      S.linear_solver_time += now_s() - t_ls;
+      const bool solved = !(h_scal[kScSolveFail] > 0);
+      it.step_is_valid = 0;
+      if (solved) {
+        model_cost_change = h_scal[kScModelChange];
+        it.step_is_valid = model_cost_change > 0.0;
+        if (it.step_is_valid) num_consecutive_invalid_steps = 0;
+      }
+      if (!have_x_norm) { x_norm = std::sqrt(h_scal[kScXNorm2]); have_x_norm = true; }
+      if (!it.step_is_valid) {
+        if (++num_consecutive_invalid_steps >= opt.max_num_consecutive_invalid_steps) {
+          S.termination_type = CB2_FAILURE;
+          msg("Number of consecutive invalid steps more than Solver::Options::max_num_consecutive_invalid_steps: %.0f", opt.max_num_consecutive_invalid_steps);
+          break;
+        }
+        radius *= 0.5;
+        it.cost = x_cost; it.cost_change = 0.0; it.step_norm = 0.0; it.relative_decrease = 0.0;
+        continue;
+      }
+      candidate_cost = h_scal[kScCandInvalid] > 0 ? std::numeric_limits<double>::max() : h_scal[kScCandCost];   // "Step failed to evaluate."
+      it.step_norm = std::sqrt(h_scal[kScStepNorm2]);
+      if (atleast_one_successful_step && it.step_norm <= opt.parameter_tolerance * (x_norm + opt.parameter_tolerance)) {
+        S.termination_type = CB2_CONVERGENCE;
+        msg("Parameter tolerance reached. Relative step_norm: %e <= %e.", it.step_norm / (x_norm + opt.parameter_tolerance), opt.parameter_tolerance);
+        break;
+      }
+      it.cost_change = x_cost - candidate_cost;
+      if (atleast_one_successful_step && std::fabs(it.cost_change) <= opt.function_tolerance * x_cost) {
+        S.termination_type = CB2_CONVERGENCE;
+        msg("Function tolerance reached. |cost_change|/cost: %e <= %e", std::fabs(it.cost_change) / x_cost, opt.function_tolerance);
+        break;
+      }
+      if (candidate_cost >= std::numeric_limits<double>::max()) it.relative_decrease = std::numeric_limits<double>::lowest();
+      else it.relative_decrease = std::max((x_cost - candidate_cost) / model_cost_change, (reference_cost - candidate_cost) / model_cost_change);
+      if (it.relative_decrease > opt.min_relative_decrease) {
+        x_norm = std::sqrt(h_scal[kScCandXNorm2]);
+        cur ^= 1;   // x = candidate_x
+        if (!evaluate_gradient_and_jacobian(false)) { S.termination_type = CB2_FAILURE; msg("Residual and Jacobian evaluation failed."); break; }
+        it.step_is_successful = 1;
+        radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * it.relative_decrease - 1.0, 3));
+        radius = std::min(opt.max_trust_region_radius, radius);
+        decrease_factor = 2.0;
+        reference_cost = x_cost;
+        atleast_one_successful_step = true;
+        ++S.num_successful_steps;
+      } else {
+        it.step_is_successful = 0;
+        it.cost = candidate_cost;
+        radius = radius / decrease_factor; decrease_factor *= 2.0;
+        ++S.num_unsuccessful_steps;
+      }
+    }
+    S.final_cost = S.initial_cost;
+    for (const auto& e : L) S.final_cost = std::min(S.final_cost, e.cost);
+    S.num_iterations = int(L.size());
+    S.total_time = now_s() - t_start;
+    return CB2_OK;
+  }
+
+  // Device -> host write-back of the optimised parameters (the reference mutates the user's objects in place).
+  void download_parameters() {
+    d_ctrl[cur].download(ctrl, &stats.d2h_bytes);
+    d_state[cur].download(h_state, &stats.d2h_bytes);
+    for (size_t si = 0; si < sensors.size(); ++si) {
+      HostSensor& s = sensors[si];
+      const SensorState& st = h_state[si];
+      for (size_t j = 0; j < s.intr.size(); ++j) s.intr[j] = st.intr[j];
+      s.q[0] = st.q.x; s.q[1] = st.q.y; s.q[2] = st.q.z; s.q[3] = st.q.w;
+      s.t[0] = st.t.x; s.t[1] = st.t.y; s.t[2] = st.t.z;
+      s.latency = st.latency;
+    }
+  }
+
+  // Sensor::UpdateResiduals (camera.cpp:70-80, gyroscope.cpp:171-182, accelerometer.cpp:58-69).
+  int refresh_residuals() {
+    launch_eval<kModeResiduals>(cur, kScCost);
+    sync_scalars();
+    int rc = CB2_OK;
+    for (auto& s : sensors) {
+      const int m = s.m();
+      s.residuals.assign(size_t(s.n_obs()) * m, 0.0);
+      s.residual_valid.assign(s.n_obs(), 0);
+      std::vector<double> r;
+      std::vector<unsigned char> valid;
+      s.d_r.download(r, &stats.d2h_bytes);
+      s.d_valid.download(valid, &stats.d2h_bytes);
+      bool bad = false;
+      for (int i = 0; i < s.n_active; ++i) {
+        const int o = s.perm[i];
+        for (int q = 0; q < m; ++q) s.residuals[size_t(o) * m + q] = r[size_t(i) * m + q];
+        s.residual_valid[o] = valid[i];
+        bad |= !valid[i];
+      }
+      if (bad && rc == CB2_OK) {
+        const char* kind = s.kind == kCamera ? "camera " : (s.kind == kGyroscope ? "gyroscope " : "accelerometer ");
+        rc = fail(CB2_INTERNAL, std::string("Failed to update residual for ") + kind + s.name);
+      }
+    }
+    return rc;
+  }
+};
+
+// ================================================================================================================
+// C ABI
+// ================================================================================================================
+extern "C" {
+
+const char* cb2_version(void) {
+#ifdef CB2_EMUL
+  return "calico_b200 0.1 (SIMT-emulation test build)";
+#else
+  return "calico_b200 0.1 (sm_100a)";
+#endif
+}
+
+void cb2_default_options(cb2_options* o) {
+  o->max_num_iterations = 50;
+  o->function_tolerance = 1e-8;
+  o->gradient_tolerance = 1e-10;
+  o->parameter_tolerance = 1e-10;
+  o->initial_trust_region_radius = 1e4;
+  o->max_trust_region_radius = 1e16;
+  o->min_trust_region_radius = 1e-32;
+  o->min_relative_decrease = 1e-3;
+  o->min_lm_diagonal = 1e-6;
+  o->max_lm_diagonal = 1e32;
+  o->max_num_consecutive_invalid_steps = 5;
+  o->jacobi_scaling = 1;
+  o->num_threads = 1;
+  o->minimizer_progress_to_stdout = 1;
+  o->linear_solver = 0;
+  o->use_cuda_graph = 0;
+}
+
+int cb2_problem_create(cb2_problem** out) { *out = new cb2_problem(); return CB2_OK; }
+void cb2_problem_destroy(cb2_problem* p) { delete p; }
+const char* cb2_last_error(cb2_problem* p) { return p ? p->error.c_str() : ""; }
+
+int cb2_set_device(int device) { return cudaSetDevice(device) == cudaSuccess ? CB2_OK : CB2_INTERNAL; }
+
+int cb2_set_trajectory(cb2_problem* p, int spline_order, int n_knots, const double* knots, int n_cp, const double* ctrl) {
+  if (spline_order < 2) return p->fail(CB2_INVALID_ARGUMENT, "Spline order must be greater than 2.");   // bspline.hpp:27-30
+  if (n_knots != n_cp + spline_order) return p->fail(CB2_INVALID_ARGUMENT, "Knot vector size must equal control points + spline order.");
+  p->k = spline_order;
+  p->knots.assign(knots, knots + n_knots);
+  p->ctrl.assign(ctrl, ctrl + size_t(n_cp) * 6);
+  p->uploaded = false;
+  return CB2_OK;
+}
+int cb2_set_gravity(cb2_problem* p, const double* g) { std::memcpy(p->gravity, g, 24); p->uploaded = false; return CB2_OK; }
+
+int cb2_add_rigid_body(cb2_problem* p, int id, const double* q, const double* t, int n_pts, const int* feature_ids, const double* pts,
+                       int pose_const, int model_const) {
+  if (p->body_slot.count(id)) return p->fail(CB2_INVALID_ARGUMENT, "Rigid body with id " + std::to_string(id) + " already exists in world model.");   // world_model.cpp:32-35
+  HostBody b;
+  b.id = id; std::memcpy(b.q, q, 32); std::memcpy(b.t, t, 24);
+  b.pose_const = pose_const != 0; b.model_const = model_const != 0;
+  b.feature_ids.assign(feature_ids, feature_ids + n_pts);
+  b.pts.assign(pts, pts + size_t(n_pts) * 3);
+  for (int i = 0; i < n_pts; ++i) b.slot[feature_ids[i]] = i;
+  p->body_slot[id] = int(p->bodies.size());
+  p->bodies.push_back(std::move(b));
+  p->uploaded = false;
+  return CB2_OK;
+}
+
+int cb2_add_sensor(cb2_problem* p, int kind, int model, const char* name, int n_intr, const double* intr, const double* q, const double* t,
+                   double latency, double sigma, int loss_type, double loss_scale, int en_intr, int en_extr, int en_lat, int* sensor_id) {
+  if (kind < 0 || kind > 2) return p->fail(CB2_INVALID_ARGUMENT, "Unknown sensor kind.");
+  if (sigma <= 0.0) return p->fail(CB2_INVALID_ARGUMENT, "Sigma must be greater than 0.");   // camera.cpp:62-65
+  p->sensors.emplace_back();
+  HostSensor& s = p->sensors.back();
+  s.kind = kind; s.model = model; s.name = name ? name : "";
+  s.intr.assign(intr, intr + n_intr);
+  std::memcpy(s.q, q, 32); std::memcpy(s.t, t, 24);
+  s.latency = latency; s.sigma = sigma; s.loss_type = loss_type; s.loss_scale = loss_scale;
+  s.en_intr = en_intr != 0; s.en_extr = en_extr != 0; s.en_lat = en_lat != 0;
+  *sensor_id = int(p->sensors.size()) - 1;
+  p->uploaded = false;
+  return CB2_OK;
+}
+
+int cb2_add_camera_observations(cb2_problem* p, int sid, int n, const double* stamp, const int* image_id, const int* model_id,
+                                const int* feature_id, const double* pixel, const uint8_t* outlier) {
+  (void)image_id;
+  if (sid < 0 || sid >= int(p->sensors.size()) || p->sensors[sid].kind != kCamera) return p->fail(CB2_INVALID_ARGUMENT, "Not a camera sensor id.");
+  HostSensor& s = p->sensors[sid];
+  for (int i = 0; i < n; ++i) {
+    int bs = -1, fs = -1;
+    auto it = p->body_slot.find(model_id[i]);
+    if (it != p->body_slot.end()) {
+      bs = it->second;
+      auto f = p->bodies[bs].slot.find(feature_id[i]);
+      if (f == p->bodies[bs].slot.end()) return p->fail(CB2_INVALID_ARGUMENT, "Feature id not in rigid body model definition.");
+      fs = f->second;
+    }
+    s.stamp.push_back(stamp[i]);
+    s.body_slot.push_back(bs); s.feat_slot.push_back(fs);
+    s.meas.push_back(pixel[2 * i]); s.meas.push_back(pixel[2 * i + 1]);
+    s.outlier.push_back(outlier ? outlier[i] : 0);
+  }
+  p->uploaded = false;
+  return CB2_OK;
+}
+
+int cb2_add_imu_observations(cb2_problem* p, int sid, int n, const double* stamp, const int* seq, const double* xyz) {
+  (void)seq;
+  if (sid < 0 || sid >= int(p->sensors.size()) || p->sensors[sid].kind == kCamera) return p->fail(CB2_INVALID_ARGUMENT, "Not an IMU sensor id.");
+  HostSensor& s = p->sensors[sid];
+  s.stamp.insert(s.stamp.end(), stamp, stamp + n);
+  s.meas.insert(s.meas.end(), xyz, xyz + size_t(n) * 3);
+  s.outlier.insert(s.outlier.end(), n, 0);
+  p->uploaded = false;
+  return CB2_OK;
+}
+
+int cb2_upload(cb2_problem* p) { return p->uploaded ? CB2_OK : p->upload(); }
+
+int cb2_optimize(cb2_problem* p, const cb2_options* opts, cb2_summary* summary, cb2_iteration* log, int log_cap, int* n_log) {
+  cb2_options o;
+  if (opts) o = *opts; else cb2_default_options(&o);
+  try {
+    if (!p->uploaded) { const int rc = p->upload(); if (rc != CB2_OK) return rc; }
+    std::vector<cb2_iteration> L;
+    cb2_summary S;
+    int rc = p->minimize(o, S, L);
+    if (summary) *summary = S;
+    if (n_log) *n_log = int(L.size());
+    if (log) for (int i = 0; i < int(L.size()) && i < log_cap; ++i) log[i] = L[i];
+    if (rc != CB2_OK) return rc;
+    p->download_parameters();
+    return p->refresh_residuals();
+  } catch (const CudaFail& f) {
+    return p->fail(CB2_INTERNAL, f.msg);
+  }
+}
+
+int cb2_evaluate_sensor(cb2_problem* p, int sid, double* residuals, double* jacobians, uint8_t* valid) {
+  try {
+    if (!p->uploaded) { const int rc = p->upload(); if (rc != CB2_OK) return rc; }
+    if (sid < 0 || sid >= int(p->sensors.size())) return p->fail(CB2_INVALID_ARGUMENT, "Unknown sensor id.");
+    HostSensor& s = p->sensors[sid];
+    const SensorDesc& d0 = p->h_desc[sid];
+    const int m = s.m(), ni = d0.ni, W = kCpCols + ni + 7, na = s.n_active;
+    if (na == 0) return CB2_OK;
+    // Temporary descriptor storing every canonical column, un-robustified.
+    SensorDesc d = d0;
+    d.n_jcal = ni + 7; d.jw = W;
+    for (int j = 0; j < ni + 7; ++j) { d.jcanon[j] = j; d.junk[j] = j; }
+    DevBuf<double> J, r;
+    DevBuf<unsigned char> v;
+    DevBuf<SensorDesc> dd;
+    DevBuf<EvalTile> dt;
+    DevBuf<double> cpart;
+    DevBuf<int> ipart;
+    if (jacobians) J.alloc(size_t(na) * m * W);
+    r.alloc(size_t(na) * m); v.alloc(na);
+    d.J = J.p; d.r = r.p; d.valid = v.p;
+    dd.upload(std::vector<SensorDesc>(1, d));
+    std::vector<EvalTile> tiles;
+    for (int o0 = 0; o0 < na; o0 += kTile) tiles.push_back(EvalTile{0, o0, std::min(kTile, na - o0)});
+    dt.upload(tiles);
+    cpart.alloc(tiles.size()); ipart.alloc(tiles.size());
+    const SensorState* st = p->d_state[p->cur].p + sid;
+    const double* c = p->d_ctrl[p->cur].p;
+    const size_t smem = size_t(rec_size(s.kind, ni)) * kTile * sizeof(double);
+    const int nt = int(tiles.size());
+    cudaStream_t stream = p->stream;
+    cb2_stats& stats = p->stats;
+#define CB2_EVAL(KIND, MODE)                                                                                                             \
+  CB2_K((eval_kernel<KIND, MODE>), nt, kTile, smem, stream, dd.p, st, dt.p, c, p->d_knots.p, p->d_basis.p, p->d_pw.p, p->gravity[0], \
+        p->gravity[1], p->gravity[2], cpart.p, ipart.p, 0)
+    // residuals + validity (un-robustified), then the Jacobian pass if requested
+    if (s.kind == kCamera) CB2_EVAL(kCamera, kModeResiduals); else if (s.kind == kGyroscope) CB2_EVAL(kGyroscope, kModeResiduals); else CB2_EVAL(kAccelerometer, kModeResiduals);
+    CB2_CUDA(cudaStreamSynchronize(stream));
+    std::vector<double> hr; std::vector<unsigned char> hv;
+    r.download(hr); v.download(hv);
+    std::vector<double> hJ;
+    if (jacobians) {
+      if (s.kind == kCamera) CB2_EVAL(kCamera, kModeJacobian); else if (s.kind == kGyroscope) CB2_EVAL(kGyroscope, kModeJacobian); else CB2_EVAL(kAccelerometer, kModeJacobian);
+      CB2_CUDA(cudaStreamSynchronize(stream));
+      J.download(hJ);
+    }
+#undef CB2_EVAL
+    CB2_CUDA(cudaGetLastError());
+    for (int i = 0; i < na; ++i) {
+      const int o = s.perm[i];
+      if (valid) valid[o] = hv[i];
+      if (!hv[i]) continue;
+      if (residuals) for (int q = 0; q < m; ++q) residuals[size_t(o) * m + q] = hr[size_t(i) * m + q];
+      if (jacobians) std::memcpy(jacobians + size_t(o) * m * W, hJ.data() + size_t(i) * m * W, sizeof(double) * m * W);
+    }
+    return CB2_OK;
+  } catch (const CudaFail& f) {
+    return p->fail(CB2_INTERNAL, f.msg);
+  }
+}
+
+int cb2_cost(cb2_problem* p, double* cost, int* ok) {
+  try {
+    if (!p->uploaded) { const int rc = p->upload(); if (rc != CB2_OK) return rc; }
+    p->launch_eval<kModeCost>(p->cur, kScCost);
+    p->sync_scalars();
+    *cost = p->h_scal[kScCost];
+    *ok = p->h_scal[kScInvalid] > 0 ? 0 : 1;
+    return CB2_OK;
+  } catch (const CudaFail& f) {
+    return p->fail(CB2_INTERNAL, f.msg);
+  }
+}
+
+int cb2_get_sensor(cb2_problem* p, int sid, double* intr, double* q, double* t, double* latency) {
+  if (sid < 0 || sid >= int(p->sensors.size())) return p->fail(CB2_INVALID_ARGUMENT, "Unknown sensor id.");
+  const HostSensor& s = p->sensors[sid];
+  if (intr) std::memcpy(intr, s.intr.data(), s.intr.size() * 8);
+  if (q) std::memcpy(q, s.q, 32);
+  if (t) std::memcpy(t, s.t, 24);
+  if (latency) *latency = s.latency;
+  return CB2_OK;
+}
+int cb2_set_sensor(cb2_problem* p, int sid, const double* intr, const double* q, const double* t, double latency) {
+  if (sid < 0 || sid >= int(p->sensors.size())) return p->fail(CB2_INVALID_ARGUMENT, "Unknown sensor id.");
+  HostSensor& s = p->sensors[sid];
+  if (intr) std::memcpy(s.intr.data(), intr, s.intr.size() * 8);
+  if (q) std::memcpy(s.q, q, 32);
+  if (t) std::memcpy(s.t, t, 24);
+  s.latency = latency;
+  p->uploaded = false;
+  return CB2_OK;
+}
+int cb2_get_trajectory(cb2_problem* p, double* ctrl) { std::memcpy(ctrl, p->ctrl.data(), p->ctrl.size() * 8); return CB2_OK; }
+int cb2_get_residuals(cb2_problem* p, int sid, double* out, uint8_t* valid) {
+  if (sid < 0 || sid >= int(p->sensors.size())) return p->fail(CB2_INVALID_ARGUMENT, "Unknown sensor id.");
+  const HostSensor& s = p->sensors[sid];
+  if (s.residuals.empty() && s.n_obs() > 0) return p->fail(CB2_FAILED_PRECONDITION, "Residuals have not been computed.");
+  if (out) std::memcpy(out, s.residuals.data(), s.residuals.size() * 8);
+  if (valid) std::memcpy(valid, s.residual_valid.data(), s.residual_valid.size());
+  return CB2_OK;
+}
+
+int cb2_reset_parameters(cb2_problem* p) {
+  if (!p->uploaded) return p->fail(CB2_FAILED_PRECONDITION, "Problem has not been uploaded.");
+  try {
+    p->cur = 0;
+    CB2_CUDA(cudaMemcpyAsync(p->d_ctrl[0].p, p->d_ctrl0.p, p->d_ctrl0.n * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    CB2_CUDA(cudaMemcpyAsync(p->d_state[0].p, p->d_state0.p, p->d_state0.n * sizeof(SensorState), cudaMemcpyDeviceToDevice, p->stream));
+    CB2_CUDA(cudaStreamSynchronize(p->stream));
+    return CB2_OK;
+  } catch (const CudaFail& f) {
+    return p->fail(CB2_INTERNAL, f.msg);
+  }
+}
+
+int cb2_stats_reset(cb2_problem* p) { p->stats = cb2_stats{}; return CB2_OK; }
+int cb2_stats_get(cb2_problem* p, cb2_stats* out) { *out = p->stats; return CB2_OK; }
+
+// Multi-GPU entry points are provided by cb2_comm.cu when built with NCCL support.
+int cb2_comm_unique_id(uint8_t* id128) { (void)id128; return CB2_UNIMPLEMENTED; }
+int cb2_comm_init(cb2_problem* p, int world_size, int rank, const uint8_t* id128) {
+  (void)id128;
+  if (world_size == 1 && rank == 0) return CB2_OK;
+  return p->fail(CB2_UNIMPLEMENTED, "Multi-GPU sharding is not built into this library yet.");
+}
+
+}  // extern "C"

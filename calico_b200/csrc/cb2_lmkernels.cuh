@@ -1,0 +1,137 @@
+// calico_b200 — small per-iteration kernels of the Levenberg-Marquardt loop (Ceres external semantics:
+// trust_region_minimizer.cc, levenberg_marquardt_strategy.cc, manifold.h), all single-CTA with fixed reduction order.
+#pragma once
+#include "cb2_device.cuh"
+
+namespace cb2 {
+
+constexpr int kLmThreads = 1024;
+
+// diag[j] = H(j, j): control points from the band, calibration from C.
+__global__ void __launch_bounds__(256) hess_diag_kernel(long n_a, int N_c, const double* __restrict__ Aband, const double* __restrict__ Cmat,
+                                                        double* __restrict__ diag) {
+  const long n = n_a + N_c;
+  for (long j = long(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += long(gridDim.x) * blockDim.x)
+    diag[j] = j < n_a ? Aband[j * kCpCols + (kCpCols - 1)] : Cmat[(j - n_a) * N_c + (j - n_a)];
+}
+
+// Jacobi scaling fixed at iteration 0: s_j = 1 / (1 + sqrt(diag_j))  (TrustRegionMinimizer::EvaluateGradientAndJacobian).
+__global__ void __launch_bounds__(256) jacobi_scaling_kernel(long n, const double* __restrict__ diag, int enable, double* __restrict__ scaling) {
+  for (long j = long(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += long(gridDim.x) * blockDim.x)
+    scaling[j] = enable ? 1.0 / (1.0 + sqrt(diag[j])) : 1.0;
+}
+
+// LM damping in unscaled coordinates. Ceres solves (S H S + D^2) y = S g with D^2 = clamp(diag(S H S), lo, hi) / radius and
+// applies delta = -S y. With ytil = S y this is (H + Dtil^2) ytil = g, Dtil^2_j = clamp(s_j^2 H_jj, lo, hi) / (radius s_j^2).
+__global__ void __launch_bounds__(256) damping_kernel(long n, const double* __restrict__ diag, const double* __restrict__ scaling,
+                                                      double radius, double lo, double hi, double* __restrict__ dtil2) {
+  for (long j = long(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += long(gridDim.x) * blockDim.x) {
+    const double s2 = scaling[j] * scaling[j];
+    dtil2[j] = fmin(fmax(diag[j] * s2, lo), hi) / (radius * s2);
+  }
+}
+
+CB2_D double block_sum(double v, double* sh) {   // all threads must call; returns the total to every thread
+  const int t = threadIdx.x;
+  __syncthreads();
+  sh[t] = v;
+  __syncthreads();
+  for (int s = kLmThreads / 2; s > 0; s >>= 1) { if (t < s) sh[t] += sh[t + s]; __syncthreads(); }
+  return sh[0];
+}
+CB2_D double block_max(double v, double* sh) {
+  const int t = threadIdx.x;
+  __syncthreads();
+  sh[t] = v;
+  __syncthreads();
+  for (int s = kLmThreads / 2; s > 0; s >>= 1) { if (t < s) sh[t] = fmax(sh[t], sh[t + s]); __syncthreads(); }
+  return sh[0];
+}
+
+// gradient_max_norm / gradient_norm = |x - Plus(x, -g)|_inf / _2 over the reduced parameter vector (ambient coordinates).
+__global__ void __launch_bounds__(kLmThreads) gradient_norm_kernel(long n_a, const double* __restrict__ grad, const SensorDesc* __restrict__ sensors,
+                                                                   const SensorState* __restrict__ states, int n_sensors, double* __restrict__ scal) {
+  __shared__ double sh[kLmThreads];
+  const int t = threadIdx.x;
+  double mx = 0.0, sq = 0.0;
+  for (long i = t; i < n_a; i += kLmThreads) { const double g = grad[i]; mx = fmax(mx, fabs(g)); sq += g * g; }
+  for (int s = t; s < n_sensors; s += kLmThreads) {
+    const SensorDesc& sd = sensors[s];
+    const double* gc = grad + n_a + sd.calib_off;
+    for (int j = 0; j < sd.n_calib; ++j) {
+      if (sd.u_rot >= 0 && j >= sd.u_rot && j < sd.u_rot + 3) continue;
+      mx = fmax(mx, fabs(gc[j])); sq += gc[j] * gc[j];
+    }
+    if (sd.u_rot >= 0) {
+      const Q4 q = states[s].q;
+      const Q4 p = quat_plus(q, v3(-gc[sd.u_rot], -gc[sd.u_rot + 1], -gc[sd.u_rot + 2]));
+      const double d[4] = {q.x - p.x, q.y - p.y, q.z - p.z, q.w - p.w};
+      for (int k = 0; k < 4; ++k) { mx = fmax(mx, fabs(d[k])); sq += d[k] * d[k]; }
+    }
+  }
+  const double tot = block_sum(sq, sh);
+  const double m = block_max(mx, sh);
+  if (t == 0) { scal[kScGradMax] = m; scal[kScGradNorm] = sqrt(tot); }
+}
+
+// Candidate point x_cand = Plus(x, -ytil) (ctrl and every non-constant sensor block), with
+//   step_norm^2 = |x - x_cand|^2, x_norm^2 = |x|^2, cand_x_norm^2 (ambient, reduced program only: cp_ref marks control
+//   points referenced by at least one residual block), the model cost change 1/2 ytil.(g + Dtil^2 ytil)
+//   (== -(J step)^T (r + J step / 2) for the exact solution of the damped system) and a finiteness check of the step.
+__global__ void __launch_bounds__(kLmThreads) apply_step_kernel(long n_a, const double* __restrict__ ytil, const double* __restrict__ grad,
+                                                                const double* __restrict__ dtil2, const unsigned char* __restrict__ cp_ref,
+                                                                const double* __restrict__ ctrl, double* __restrict__ ctrl_cand,
+                                                                const SensorDesc* __restrict__ sensors, const SensorState* __restrict__ states,
+                                                                SensorState* __restrict__ states_cand, int n_sensors, int N_c,
+                                                                double* __restrict__ scal) {
+  __shared__ double sh[kLmThreads];
+  const int t = threadIdx.x;
+  double step2 = 0.0, x2 = 0.0, c2 = 0.0, model = 0.0, bad = 0.0;
+  for (long i = t; i < n_a; i += kLmThreads) {
+    const double y = ytil[i], x = ctrl[i];
+    const double xn = x - y;
+    ctrl_cand[i] = xn;
+    if (!isfinite(y)) bad = 1.0;
+    model += y * (grad[i] + dtil2[i] * y);
+    if (cp_ref[i / 6]) { step2 += (x - xn) * (x - xn); x2 += x * x; c2 += xn * xn; }
+  }
+  for (long j = t; j < N_c; j += kLmThreads) {
+    const double y = ytil[n_a + j];
+    if (!isfinite(y)) bad = 1.0;
+    model += y * (grad[n_a + j] + dtil2[n_a + j] * y);
+  }
+  for (int s = t; s < n_sensors; s += kLmThreads) {
+    const SensorDesc& sd = sensors[s];
+    SensorState S = states[s];
+    const double* y = ytil + n_a + sd.calib_off;
+    if (sd.u_intr >= 0) for (int j = 0; j < sd.ni; ++j) {
+      const double x = S.intr[j], xn = x - y[sd.u_intr + j];
+      S.intr[j] = xn; step2 += (x - xn) * (x - xn); x2 += x * x; c2 += xn * xn;
+    }
+    if (sd.u_rot >= 0) {
+      const Q4 q = S.q;
+      const Q4 p = quat_plus(q, v3(-y[sd.u_rot], -y[sd.u_rot + 1], -y[sd.u_rot + 2]));
+      S.q = p;
+      step2 += (q.x - p.x) * (q.x - p.x) + (q.y - p.y) * (q.y - p.y) + (q.z - p.z) * (q.z - p.z) + (q.w - p.w) * (q.w - p.w);
+      x2 += q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+      c2 += p.x * p.x + p.y * p.y + p.z * p.z + p.w * p.w;
+    }
+    if (sd.u_trans >= 0) {
+      const V3 x = S.t;
+      const V3 xn = v3(x.x - y[sd.u_trans], x.y - y[sd.u_trans + 1], x.z - y[sd.u_trans + 2]);
+      S.t = xn; step2 += dot(x - xn, x - xn); x2 += dot(x, x); c2 += dot(xn, xn);
+    }
+    if (sd.u_lat >= 0) {
+      const double x = S.latency, xn = x - y[sd.u_lat];
+      S.latency = xn; step2 += (x - xn) * (x - xn); x2 += x * x; c2 += xn * xn;
+    }
+    states_cand[s] = S;
+  }
+  const double a = block_sum(step2, sh), b = block_sum(x2, sh), c = block_sum(c2, sh), d = block_sum(model, sh), e = block_sum(bad, sh);
+  if (t == 0) {
+    scal[kScStepNorm2] = a; scal[kScXNorm2] = b; scal[kScCandXNorm2] = c; scal[kScModelChange] = 0.5 * d;
+    if (e > 0.0) scal[kScSolveFail] += 1.0;
+  }
+}
+
+}  // namespace cb2

@@ -1,0 +1,452 @@
+// calico_b200 — K5/K6/K7: Schur elimination of the block-banded control-point system and the dense reduced solve.
+//
+// Replaces Ceres's DENSE_SCHUR linear solver (Ceres external; batch_optimizer.cpp:12) for the LM step
+//     (H + D^2) y = g,   unknowns [control points | calibration].
+// Ceres's automatic ordering eliminates only every k-th control point and factors a DENSE reduced system of
+// ~5 n_cp + N_c unknowns. Here the band the reference notes but does not exploit
+// (bspline.hpp:287-289) is used, with time substructuring so the sequential band factorisation parallelises:
+//   level 1: the control points are cut into P chunks separated by k-1 = 5 "separator" control points. Chunk interiors
+//            do not couple to each other; each chunk is one banded SPD system (half bandwidth 35) with a dense border
+//            [left separator 30 | right separator 30 | calibration N_c | rhs 1]. One CTA per chunk factors the band
+//            (right-looking, 6 columns per step, window in shared memory) and forward-substitutes the border in the
+//            same sweep (W = L^-1 border); a tiled Gram kernel forms T = W^T W.
+//   level 2: the separators (30 unknowns each) form a block-tridiagonal system = banded with half bandwidth 59, border
+//            [calibration | rhs], built from H minus the level-1 Schur terms; same factor + Gram kernels.
+//   level 3: dense Cholesky of the N_c x N_c calibration system; then back-substitution level 2, level 1.
+// The same chunk boundaries are the multi-GPU shard boundaries.
+#pragma once
+#include "cb2_device.cuh"
+
+namespace cb2 {
+
+struct BandSys {
+  int n, hb, nbw;           // rows (multiple of 6), half bandwidth (hb + 1 = window size), border width (last column = rhs)
+  int ksplit;               // row splits of the Gram product
+  const int* row_gidx;      // [n] global unknown index of each row
+  const int* col_gidx;      // [nbw - 1] global unknown index of each border column, -1 = absent (zero column)
+  double* L;                // [n][hb+1]: A on entry, Cholesky factor on exit; (i, j) at L[i*(hb+1) + hb - (i-j)]
+  double* W;                // [n][nbw]: border on entry, L^-1 border on exit
+  double* T;                // [ksplit][nbw][nbw] partial Gram matrices W^T W
+};
+
+constexpr int kSepDim = 30;   // (k-1) control points * 6
+constexpr int kFacThreads = 256;
+
+// H(gi, gj) from the assembled normal equations; gi, gj are global unknown indices.
+CB2_D double hess_lookup(long gi, long gj, long n_a, int N_c, const double* __restrict__ Aband, const double* __restrict__ Bmat,
+                         const double* __restrict__ Cmat) {
+  if (gi < gj) { const long tmp = gi; gi = gj; gj = tmp; }
+  if (gi < n_a) { const long d = gi - gj; return d < kCpCols ? Aband[gi * kCpCols + (kCpCols - 1 - d)] : 0.0; }
+  if (gj < n_a) return Bmat[gj * N_c + (gi - n_a)];
+  return Cmat[(gi - n_a) * N_c + (gj - n_a)];
+}
+
+// Fills L (band) and W (border) of every level-1 system from the normal equations, adding the LM damping dtil2 to the diagonal.
+// grid = (row blocks, systems)
+__global__ void __launch_bounds__(256) gather_level1_kernel(const BandSys* __restrict__ systems, long n_a, int N_c,
+                                                            const double* __restrict__ Aband, const double* __restrict__ Bmat,
+                                                            const double* __restrict__ Cmat, const double* __restrict__ grad,
+                                                            const double* __restrict__ dtil2) {
+  const BandSys sy = systems[blockIdx.y];
+  const int S = sy.hb + 1;
+  const long per_row = S + sy.nbw;
+  const long total = long(sy.n) * per_row;
+  for (long idx = long(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += long(gridDim.x) * blockDim.x) {
+    const int row = int(idx / per_row), e = int(idx % per_row);
+    const long gi = sy.row_gidx[row];
+    if (e < S) {
+      const int col = row - (sy.hb - e);
+      double v = 0.0;
+      if (col >= 0) {
+        const long gj = sy.row_gidx[col];
+        v = hess_lookup(gi, gj, n_a, N_c, Aband, Bmat, Cmat);
+        if (col == row) v += dtil2[gi];
+      }
+      sy.L[size_t(row) * S + e] = v;
+    } else {
+      const int c = e - S;
+      double v;
+      if (c == sy.nbw - 1) v = grad[gi];
+      else { const long gj = sy.col_gidx[c]; v = gj >= 0 ? hess_lookup(gi, gj, n_a, N_c, Aband, Bmat, Cmat) : 0.0; }
+      sy.W[size_t(row) * sy.nbw + c] = v;
+    }
+  }
+}
+
+// In-place banded Cholesky (right-looking, 6 columns per step) fused with the forward substitution of the border.
+// Shared memory: Wd[S][S] circular window of the band, Wr[S][nbw] ring of partially updated border rows.
+// Requires n % 6 == 0 and the block structure described in the header (entries beyond the block band are structurally zero).
+template <int NBLK>
+__global__ void __launch_bounds__(kFacThreads) band_factor_kernel(const BandSys* __restrict__ systems, double* __restrict__ scal) {
+  constexpr int S = 6 * NBLK;
+  const BandSys sy = systems[blockIdx.x];
+  const int n = sy.n, nbw = sy.nbw, t = threadIdx.x;
+  double* Wd = dyn_smem<double>();
+  double* Wr = Wd + S * S;
+  __shared__ double Ld[36];
+  __shared__ double Linv[6];
+  __shared__ int s_fail;
+  if (t == 0) s_fail = 0;
+  // Initial window: rows 0..min(S,n)-1.
+  const int n0 = min(S, n);
+  for (int e = t; e < n0 * S; e += kFacThreads) {
+    const int i = e / S, d = e % S;
+    const int j = i - (S - 1 - d);
+    if (j >= 0) Wd[i * S + j] = sy.L[size_t(i) * S + d];
+  }
+  for (int e = t; e < n0 * nbw; e += kFacThreads) Wr[e] = sy.W[e];
+  __syncthreads();
+  for (int j0 = 0; j0 < n; j0 += 6) {
+    const int jm = j0 % S;                       // window position of column/row j0 (6 consecutive, never wraps)
+    const int r_end = min(j0 + S, n);            // rows j0+6 .. r_end-1 form the panel / trailing window
+    // P1: factor the 6x6 diagonal block.
+    if (t == 0) {
+      double a[6][6];
+      for (int r = 0; r < 6; ++r) for (int c = 0; c <= r; ++c) a[r][c] = Wd[(jm + r) * S + jm + c];
+      int fail = 0;
+      for (int c = 0; c < 6; ++c) {
+        double d = a[c][c];
+        for (int k = 0; k < c; ++k) d -= a[c][k] * a[c][k];
+        if (!(d > 0.0) || !isfinite(d)) { fail = 1; d = 1.0; }
+        d = sqrt(d);
+        a[c][c] = d;
+        const double inv = 1.0 / d;
+        Linv[c] = inv;
+        for (int r = c + 1; r < 6; ++r) {
+          double s = a[r][c];
+          for (int k = 0; k < c; ++k) s -= a[r][k] * a[c][k];
+          a[r][c] = s * inv;
+        }
+      }
+      for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) Ld[r * 6 + c] = c <= r ? a[r][c] : 0.0;
+      if (fail) s_fail = 1;
+    }
+    __syncthreads();
+    // P2a: panel rows r: L(r, j0+c) = (A(r, j0+c) - sum_{k<c} L(r, j0+k) Ld[c][k]) / Ld[c][c]
+    for (int r = j0 + 6 + t; r < r_end; r += kFacThreads) {
+      double* pr = Wd + (r % S) * S + jm;
+      double x[6];
+      for (int c = 0; c < 6; ++c) {
+        double s = pr[c];
+        for (int k = 0; k < c; ++k) s -= x[k] * Ld[c * 6 + k];
+        x[c] = s * Linv[c];
+      }
+      for (int c = 0; c < 6; ++c) pr[c] = x[c];
+    }
+    // P2b: border rows j0..j0+5: forward-solve with the diagonal block, in place, and emit the finished rows.
+    for (int c = t; c < nbw; c += kFacThreads) {
+      double x[6];
+      for (int k = 0; k < 6; ++k) {
+        double s = Wr[(jm + k) * nbw + c];
+        for (int q = 0; q < k; ++q) s -= Ld[k * 6 + q] * x[q];
+        x[k] = s * Linv[k];
+      }
+      for (int k = 0; k < 6; ++k) { Wr[(jm + k) * nbw + c] = x[k]; sy.W[size_t(j0 + k) * nbw + c] = x[k]; }
+    }
+    __syncthreads();
+    // P3a: trailing update of the band window: A(r, c) -= sum_k L(r, j0+k) L(c, j0+k) for j0+6 <= c <= r < r_end.
+    {
+      const int nt = r_end - (j0 + 6);
+      for (int e = t; e < nt * nt; e += kFacThreads) {
+        const int rr = e / nt, cc = e % nt;
+        if (cc > rr) continue;
+        const int r = j0 + 6 + rr, c = j0 + 6 + cc;
+        const double* lr = Wd + (r % S) * S + jm;
+        const double* lc = Wd + (c % S) * S + jm;
+        double s = 0.0;
+        for (int k = 0; k < 6; ++k) s += lr[k] * lc[k];
+        Wd[(r % S) * S + (c % S)] -= s;
+      }
+      // P3b: border update: Wr(r, :) -= sum_k L(r, j0+k) w_k
+      for (int c = t; c < nbw; c += kFacThreads) {
+        double w6[6];
+        for (int k = 0; k < 6; ++k) w6[k] = Wr[(jm + k) * nbw + c];
+        for (int r = j0 + 6; r < r_end; ++r) {
+          const double* lr = Wd + (r % S) * S + jm;
+          double s = 0.0;
+          for (int k = 0; k < 6; ++k) s += lr[k] * w6[k];
+          Wr[(r % S) * nbw + c] -= s;
+        }
+      }
+      // P3c: emit the finished factor columns j0..j0+5 (diagonal block from Ld, panel from the window).
+      for (int e = t; e < (r_end - j0) * 6; e += kFacThreads) {
+        const int r = j0 + e / 6, k = e % 6;
+        const int col = j0 + k;
+        if (col > r) continue;
+        const double v = r < j0 + 6 ? Ld[(r - j0) * 6 + k] : Wd[(r % S) * S + jm + k];
+        sy.L[size_t(r) * S + (S - 1 - (r - col))] = v;
+      }
+    }
+    __syncthreads();
+    // P4: rows j0+S .. j0+S+5 enter the window (they reuse the slots of the retired rows j0..j0+5).
+    {
+      const int i0 = j0 + S;
+      if (i0 < n) {
+        for (int e = t; e < 6 * S; e += kFacThreads) {
+          const int i = i0 + e / S, d = e % S;
+          const int j = i - (S - 1 - d);
+          Wd[(i % S) * S + (j % S)] = sy.L[size_t(i) * S + d];
+        }
+        for (int e = t; e < 6 * nbw; e += kFacThreads) {
+          const int i = i0 + e / nbw, c = e % nbw;
+          Wr[(i % S) * nbw + c] = sy.W[size_t(i) * nbw + c];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (t == 0 && s_fail) atomicAdd(&scal[kScSolveFail], 1.0);
+}
+
+// T[sys][k] = W[rows of split k]^T W[rows of split k]  (nbw x nbw, full symmetric storage).
+// grid = (lower tile pairs of 64x64 tiles, systems, ksplit); block = (16, 16), 4x4 outputs per thread.
+__global__ void __launch_bounds__(256) border_gram_kernel(const BandSys* __restrict__ systems) {
+  __shared__ double As[16][65];
+  __shared__ double Bs[16][65];
+  const BandSys sy = systems[blockIdx.y];
+  const int nbw = sy.nbw;
+  const int nt = (nbw + 63) / 64;
+  if (int(blockIdx.z) >= sy.ksplit) return;
+  // decode the lower-triangular tile pair
+  int ta = 0, tb = 0;
+  { int rem = blockIdx.x; while (rem > ta) { rem -= ta + 1; ++ta; } tb = rem; }
+  if (ta >= nt) return;
+  const int rows_per = ((sy.n + sy.ksplit - 1) / sy.ksplit + 15) / 16 * 16;
+  const int r_begin = blockIdx.z * rows_per, r_end = min(sy.n, r_begin + rows_per);
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 16 + tx;
+  double acc[4][4];
+  for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+  for (int r0 = r_begin; r0 < r_end; r0 += 16) {
+    __syncthreads();
+    for (int e = tid; e < 16 * 64; e += 256) {
+      const int rr = e / 64, cc = e % 64;
+      const int r = r0 + rr;
+      const int ca = ta * 64 + cc, cb = tb * 64 + cc;
+      As[rr][cc] = (r < r_end && ca < nbw) ? sy.W[size_t(r) * nbw + ca] : 0.0;
+      Bs[rr][cc] = (r < r_end && cb < nbw) ? sy.W[size_t(r) * nbw + cb] : 0.0;
+    }
+    __syncthreads();
+    for (int rr = 0; rr < 16; ++rr) {
+      double a4[4], b4[4];
+      for (int a = 0; a < 4; ++a) { a4[a] = As[rr][ty * 4 + a]; b4[a] = Bs[rr][tx * 4 + a]; }
+      for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) acc[a][b] += a4[a] * b4[b];
+    }
+  }
+  double* T = sy.T + size_t(blockIdx.z) * nbw * nbw;
+  for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) {
+    const int ia = ta * 64 + ty * 4 + a, ib = tb * 64 + tx * 4 + b;
+    if (ia < nbw && ib < nbw) {
+      T[size_t(ia) * nbw + ib] = acc[a][b];
+      if (ta != tb) T[size_t(ib) * nbw + ia] = acc[a][b];
+    }
+  }
+}
+
+// Sum over the row splits of a system's Gram matrix.
+CB2_D double gram_at(const BandSys& sy, int a, int b) {
+  double s = 0.0;
+  const size_t stride = size_t(sy.nbw) * sy.nbw;
+  for (int k = 0; k < sy.ksplit; ++k) s += sy.T[k * stride + size_t(a) * sy.nbw + b];
+  return s;
+}
+
+// Level-2 system (separators) = H restricted to the separators minus the level-1 Schur terms of the owned chunks.
+// Separator s sits between chunk s (its right border, columns 30..59) and chunk s+1 (its left border, columns 0..29).
+// chunk_sys[c] = index of chunk c in `chunks`, or -1 if the chunk is not owned by this rank (multi-GPU) or has no rows.
+// rawdiag receives the undamped H diagonal of the separator rows (for the LM damping added after a cross-rank reduction).
+__global__ void __launch_bounds__(256) level2_build_kernel(BandSys l2, const BandSys* __restrict__ chunks, const int* __restrict__ chunk_sys,
+                                                           int n_chunks, long n_a, int N_c, const double* __restrict__ Aband,
+                                                           const double* __restrict__ Bmat, const double* __restrict__ Cmat,
+                                                           const double* __restrict__ grad, double* __restrict__ rawdiag) {
+  const int S = l2.hb + 1;   // 60
+  const long per_row = S + l2.nbw;
+  const long total = long(l2.n) * per_row;
+  for (long idx = long(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += long(gridDim.x) * blockDim.x) {
+    const int row = int(idx / per_row), e = int(idx % per_row);
+    const long gi = l2.row_gidx[row];
+    const int sa = row / kSepDim, la = row % kSepDim;
+    const int cR = chunk_sys[sa], cL = (sa + 1 < n_chunks) ? chunk_sys[sa + 1] : -1;   // chunk sa: separator is its right border
+    if (e < S) {
+      const int col = row - (l2.hb - e);
+      double v = 0.0;
+      if (col >= 0) {
+        const int sb = col / kSepDim, lb = col % kSepDim;
+        v = hess_lookup(gi, l2.row_gidx[col], n_a, N_c, Aband, Bmat, Cmat);
+        if (col == row) rawdiag[row] = v;
+        if (sb == sa) {
+          if (cR >= 0) v -= gram_at(chunks[cR], kSepDim + la, kSepDim + lb);
+          if (cL >= 0) v -= gram_at(chunks[cL], la, lb);
+        } else if (sb == sa - 1) {
+          if (cR >= 0) v -= gram_at(chunks[cR], kSepDim + la, lb);
+        }
+      }
+      l2.L[size_t(row) * S + e] = v;
+    } else {
+      const int c = e - S;   // calibration column c, or rhs when c == N_c
+      double v = (c == l2.nbw - 1) ? grad[gi] : hess_lookup(gi, n_a + c, n_a, N_c, Aband, Bmat, Cmat);
+      if (cR >= 0) v -= gram_at(chunks[cR], kSepDim + la, 2 * kSepDim + c);
+      if (cL >= 0) v -= gram_at(chunks[cL], la, 2 * kSepDim + c);
+      l2.W[size_t(row) * l2.nbw + c] = v;
+    }
+  }
+}
+
+// Adds the LM damping to the level-2 diagonal (separate so a cross-rank sum can sit between build and damp).
+__global__ void level2_damp_kernel(BandSys l2, const double* __restrict__ dtil2) {
+  const int S = l2.hb + 1;
+  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < l2.n; row += gridDim.x * blockDim.x)
+    l2.L[size_t(row) * S + (S - 1)] += dtil2[l2.row_gidx[row]];
+}
+
+// Level-3 (calibration) system, augmented with the rhs as an extra ROW so that the Cholesky sweep forward-substitutes it:
+// Cw is [(N+1)][(N+1)] row-major; Cw[r][c] (r, c < N) = C - sum_chunks T1[cal, cal], Cw[N][c] = g_c - sum_chunks T1[rhs, cal].
+// The level-2 term and the damping are applied in reduced_solve_kernel. rawdiag_c = undamped diag of C.
+__global__ void __launch_bounds__(256) level3_build_kernel(const BandSys* __restrict__ chunks, int n_owned, long n_a, int N_c,
+                                                           const double* __restrict__ Cmat, const double* __restrict__ grad,
+                                                           double* __restrict__ Cw, double* __restrict__ rawdiag_c) {
+  const int ld = N_c + 1;
+  const long total = long(ld) * ld;
+  for (long idx = long(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += long(gridDim.x) * blockDim.x) {
+    const int r = int(idx / ld), c = int(idx % ld);
+    double v = 0.0;
+    if (c < N_c) {
+      v = r == N_c ? grad[n_a + c] : Cmat[size_t(r) * N_c + c];
+      if (c == r) rawdiag_c[r] = v;
+      for (int p = 0; p < n_owned; ++p) v -= gram_at(chunks[p], 2 * kSepDim + r, 2 * kSepDim + c);
+    }
+    Cw[idx] = v;
+  }
+}
+
+// Dense reduced solve (1 CTA): M = Cw[:N, :N] - T2[:N, :N] + diag(dtil2_c), rhs row Cw[N][:] - T2[N][:N]. Right-looking
+// Cholesky in global (L2-resident) memory with 32-column panels staged in shared memory; the rhs row rides along and
+// becomes z = L^-1 rhs; the backward solve L^T y = z prefetches the next factor row. y_c -> ytil[n_a + c].
+// l2 may have n == 0 (no separators). Requires N <= kRedThreads.
+constexpr int kRedThreads = 512;
+constexpr int kRedPanel = 32;
+__global__ void __launch_bounds__(kRedThreads) reduced_solve_kernel(BandSys l2, int N, long n_a, double* __restrict__ Cw,
+                                                                    const double* __restrict__ dtil2, double* __restrict__ ytil,
+                                                                    double* __restrict__ scal) {
+  double* Pn = dyn_smem<double>();    // [N + 1][kRedPanel + 1] panel
+  __shared__ int s_fail;
+  const int t = threadIdx.x;
+  const int ld = N + 1;
+  constexpr int PS = kRedPanel + 1;
+  if (t == 0) s_fail = 0;
+  for (long e = t; e < long(ld) * ld; e += kRedThreads) {
+    const int r = int(e / ld), c = int(e % ld);
+    if (c >= N) continue;
+    double v = Cw[e];
+    if (l2.n > 0) v -= gram_at(l2, r, c);
+    if (c == r) v += dtil2[n_a + r];
+    Cw[e] = v;
+  }
+  __syncthreads();
+  for (int p0 = 0; p0 < N; p0 += kRedPanel) {
+    const int pw = min(kRedPanel, N - p0);
+    const int nr = ld - p0;           // rows p0 .. N (includes the rhs row)
+    for (int e = t; e < nr * pw; e += kRedThreads) { const int r = e / pw, c = e % pw; Pn[r * PS + c] = Cw[size_t(p0 + r) * ld + p0 + c]; }
+    __syncthreads();
+    for (int c = 0; c < pw; ++c) {
+      if (t == 0) {
+        double d = Pn[c * PS + c];
+        if (!(d > 0.0) || !isfinite(d)) { s_fail = 1; d = 1.0; }
+        Pn[c * PS + c] = sqrt(d);
+      }
+      __syncthreads();
+      const double inv = 1.0 / Pn[c * PS + c];
+      for (int r = c + 1 + t; r < nr; r += kRedThreads) Pn[r * PS + c] *= inv;
+      __syncthreads();
+      const int nc2 = pw - c - 1;
+      for (int e = t; e < nc2 * nr; e += kRedThreads) {
+        const int c2 = c + 1 + e / nr, r = e % nr;
+        if (r >= c2) Pn[r * PS + c2] -= Pn[r * PS + c] * Pn[c2 * PS + c];
+      }
+      __syncthreads();
+    }
+    for (int e = t; e < nr * pw; e += kRedThreads) { const int r = e / pw, c = e % pw; Cw[size_t(p0 + r) * ld + p0 + c] = Pn[r * PS + c]; }
+    // trailing update: Cw(r, c2) -= sum_k Pn(r, k) Pn(c2, k) for r >= c2 >= p0 + pw (c2 < N)
+    const int ntr = nr - pw;
+    for (long e = t; e < long(ntr) * ntr; e += kRedThreads) {
+      const int rr = int(e / ntr), cc = int(e % ntr);
+      if (cc > rr || p0 + pw + cc >= N) continue;
+      const double* pr = Pn + (pw + rr) * PS;
+      const double* pc = Pn + (pw + cc) * PS;
+      double s = 0.0;
+      for (int k = 0; k < pw; ++k) s += pr[k] * pc[k];
+      Cw[size_t(p0 + pw + rr) * ld + p0 + pw + cc] -= s;
+    }
+    __syncthreads();
+  }
+  double* y = Pn;
+  if (t < N) y[t] = Cw[size_t(N) * ld + t];
+  __syncthreads();
+  double lj_next = (N > 0 && t <= N - 1) ? Cw[size_t(N - 1) * ld + t] : 0.0;
+  for (int j = N - 1; j >= 0; --j) {
+    const double lj = lj_next;
+    if (j > 0 && t <= j - 1) lj_next = Cw[size_t(j - 1) * ld + t];
+    if (t == j) y[j] = y[j] / lj;
+    __syncthreads();
+    if (t < j) y[t] -= lj * y[j];
+    __syncthreads();
+  }
+  if (t < N) ytil[n_a + t] = y[t];
+  if (t == 0 && s_fail) atomicAdd(&scal[kScSolveFail], 1.0);
+}
+
+// Back-substitution of one banded system: v = z - W[:, :nbw-1] * y[border], then L^T y = v (right-looking, 6 rows per step).
+// grid = systems, block = 256, dynamic shared memory: n doubles (v) + nbw doubles (border solution).
+constexpr int kBackThreads = 256;
+__global__ void __launch_bounds__(kBackThreads) band_backsolve_kernel(const BandSys* __restrict__ systems, double* __restrict__ ytil) {
+  const BandSys sy = systems[blockIdx.x];
+  const int n = sy.n, nbw = sy.nbw, S = sy.hb + 1, t = threadIdx.x;
+  double* v = dyn_smem<double>();
+  double* coef = v + n;
+  for (int c = t; c < nbw - 1; c += kBackThreads) { const int g = sy.col_gidx[c]; coef[c] = g >= 0 ? ytil[g] : 0.0; }
+  __syncthreads();
+  const int warp = t >> 5, lane = t & 31;
+  for (int i = warp; i < n; i += kBackThreads / 32) {
+    const double* wr = sy.W + size_t(i) * nbw;
+    double s = 0.0;
+    for (int c = lane; c < nbw - 1; c += 32) s += wr[c] * coef[c];
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+    if (lane == 0) v[i] = wr[nbw - 1] - s;
+  }
+  __syncthreads();
+  // Backward solve, 6 rows per step. The 6 factor rows of the NEXT step are prefetched into shared memory by the
+  // otherwise idle threads while thread 0 solves the 6x6 triangle of the current one.
+  __shared__ double Lb[2][6 * 60];
+  if (n >= 6) for (int e = t; e < 6 * S; e += kBackThreads) Lb[0][e] = sy.L[size_t(n - 6) * S + e];
+  __syncthreads();
+  int buf = 0;
+  for (int i0 = n - 6; i0 >= 0; i0 -= 6, buf ^= 1) {
+    const double* Lc = Lb[buf];
+    if (t == 0) {
+      double y6[6];
+      for (int k = 5; k >= 0; --k) {
+        double s = v[i0 + k];
+        for (int q = k + 1; q < 6; ++q) s -= Lc[q * S + (S - 1 - (q - k))] * y6[q];
+        y6[k] = s / Lc[k * S + (S - 1)];
+      }
+      for (int k = 0; k < 6; ++k) v[i0 + k] = y6[k];
+    } else if (t >= 64 && i0 >= 6) {
+      for (int e = t - 64; e < 6 * S; e += kBackThreads - 64) Lb[buf ^ 1][e] = sy.L[size_t(i0 - 6) * S + e];
+    }
+    __syncthreads();
+    // v(tc) -= sum_k L(i0+k, tc) y(i0+k) for the columns tc < i0 reached by these rows
+    for (int l = t; l < S - 1; l += kBackThreads) {
+      const int tc = i0 - 1 - l;
+      if (tc < 0) continue;
+      double s = 0.0;
+      for (int k = 0; k < 6; ++k) {
+        const int d = k + 1 + l;           // row - col
+        if (d <= S - 1) s += Lc[k * S + (S - 1 - d)] * v[i0 + k];
+      }
+      v[tc] -= s;
+    }
+    __syncthreads();
+  }
+  for (int i = t; i < n; i += kBackThreads) ytil[sy.row_gidx[i]] = v[i];
+}
+
+}  // namespace cb2

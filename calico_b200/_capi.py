@@ -58,7 +58,7 @@ class Options(C.Structure):
         self.num_threads = 1
         self.minimizer_progress_to_stdout = 0
         self.linear_solver = 0
-        self.use_cuda_graph = 1
+        self.use_cuda_graph = 0
         for k, v in kw.items():
             if not hasattr(self, k):
                 raise AttributeError(k)
@@ -105,6 +105,7 @@ class Stats(C.Structure):
         ("jacobian_kernel_ms", C.c_double), ("jacobian_bytes", C.c_double),
         ("normal_eq_ms", C.c_double), ("schur_ms", C.c_double), ("cost_eval_ms", C.c_double),
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+        ("lm_loop_ms", C.c_double), ("lm_iterations", C.c_int64),
     ]
 
 
@@ -150,7 +151,7 @@ class CApi:
             raise ImportError(
                 f"{lib_path} not found: the CUDA extension has not been built. Run "
                 f"`python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback).")
-        self.lib = C.CDLL(lib_path, mode=C.RTLD_GLOBAL)
+        self.lib = C.CDLL(lib_path)
         self.prefix = prefix
         self.options_cls = options_cls
         self._bind()
@@ -186,6 +187,17 @@ class CApi:
             "get_trajectory": ([vp, _dp], C.c_int),
             "get_residuals": ([vp, C.c_int, _dp, _up], C.c_int),
         }
+        if self.prefix == "cb2_":
+            sig.update({
+                "upload": ([vp], C.c_int),
+                "reset_parameters": ([vp], C.c_int),
+                "stats_reset": ([vp], C.c_int),
+                "stats_get": ([vp, C.c_void_p], C.c_int),
+                "set_sensor": ([vp, C.c_int, _dp, _dp, _dp, C.c_double], C.c_int),
+            })
+            self.lib.cb2_set_device.argtypes = [C.c_int]
+            self.lib.cb2_set_device.restype = C.c_int
+            self.lib.cb2_version.restype = C.c_char_p
         for name, (argtypes, restype) in sig.items():
             fn = self._f(name)
             fn.argtypes = argtypes
@@ -283,6 +295,27 @@ class CApi:
         ctrl = np.zeros((self.n_cp, 6))
         self._check(self._f("get_trajectory")(self.h, _d(ctrl)))
         return ctrl
+
+    def set_device(self, device: int):
+        if self.lib.cb2_set_device(int(device)) != OK:
+            raise CalicoError(INTERNAL, f"cannot select CUDA device {device}")
+
+    def version(self) -> str:
+        return self.lib.cb2_version().decode()
+
+    def upload(self):
+        self._check(self._f("upload")(self.h))
+
+    def reset_parameters(self):
+        self._check(self._f("reset_parameters")(self.h))
+
+    def stats_reset(self):
+        self._check(self._f("stats_reset")(self.h))
+
+    def stats(self) -> "Stats":
+        st = Stats()
+        self._check(self._f("stats_get")(self.h, C.addressof(st)))
+        return st
 
     def get_residuals(self, sid):
         m = 2 if self.kind[sid] == CAMERA else 3

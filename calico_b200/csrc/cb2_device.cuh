@@ -14,6 +14,8 @@
 namespace cb2 {
 
 constexpr int kTile = 128;          // observations per CTA in the residual/Jacobian sweep
+constexpr int kRecStride = kTile + 1;   // field stride of the compact records in shared memory: odd, so that both the
+                                        // per-thread writes ([field][lane]) and the per-warp expansion reads ([lane -> field][obs]) are bank-conflict free
 constexpr int kMaxCalib = 20;       // max calibration unknowns of one sensor: 12 intrinsics + 3 + 3 + 1
 constexpr int kCpCols = 6 * kK;     // 36 control-point columns per residual block
 

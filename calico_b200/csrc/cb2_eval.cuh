@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(kTile) eval_kernel(const SensorDesc* __restric
     const double knot0 = knots[seg + kK - 1], knot1 = knots[seg + kK];
     const double* M = basis + size_t(seg) * (kK * kK);
     const double* cp = ctrl + size_t(seg) * 6;
-    const Rec rc{rec + t, kTile};
+    const Rec rc{rec + t, kRecStride};
     if (KIND == kCamera) {
       const int p = sd.pt[o];
       ok = camera_block<MODE == kModeJacobian>(S, M, knot0, knot1, cp, stamp, sd.meas[2 * o], sd.meas[2 * o + 1],
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(kTile) eval_kernel(const SensorDesc* __restric
       if (lt >= tl.count) break;
       const long o = long(tl.start) + lt;
       const bool okb = s_ok[lt] != 0;
-      const Rec rc{rec + lt, kTile};
+      const Rec rc{rec + lt, kRecStride};
       const double rs = okb ? rc.get(rec_rs(KIND)) : 0.0;
       double* __restrict__ Jrow = sd.J + size_t(o) * rowlen;
       for (int idx = lane; idx < rowlen; idx += 32) {

@@ -100,6 +100,31 @@ struct HostSensor {
 
 struct ChunkPlan { int a, b; };   // interior control points [a, b)
 
+// CUDA-event phase timing on the library's stream; pairs are resolved after the next stream synchronisation.
+enum Phase { kPhJacobian = 0, kPhNormal = 1, kPhSchur = 2, kPhCost = 3, kPhLoop = 4, kPhCount = 5 };
+struct PhaseTimer {
+  struct Pair { cudaEvent_t a, b; int phase; };
+  std::vector<cudaEvent_t> pool;
+  std::vector<Pair> open_pairs;
+  cudaEvent_t cur_a[kPhCount] = {};
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+  void begin(int ph, cudaStream_t s) { cur_a[ph] = get(); cudaEventRecord(cur_a[ph], s); }
+  void end(int ph, cudaStream_t s) { cudaEvent_t b = get(); cudaEventRecord(b, s); open_pairs.push_back(Pair{cur_a[ph], b, ph}); }
+  void resolve(double* ms_by_phase) {   // call only after the stream has been synchronised
+    for (auto& pr : open_pairs) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, pr.a, pr.b);
+      ms_by_phase[pr.phase] += ms;
+      pool.push_back(pr.a); pool.push_back(pr.b);
+    }
+    open_pairs.clear();
+  }
+  ~PhaseTimer() { for (auto e : pool) cudaEventDestroy(e); for (auto& pr : open_pairs) { cudaEventDestroy(pr.a); cudaEventDestroy(pr.b); } }
+};
+
 }  // namespace cb2
 
 using namespace cb2;
@@ -148,12 +173,12 @@ struct cb2_problem {
   int max_tilepairs1 = 0, max_ksplit1 = 1;
   double* h_scal = nullptr;   // pinned
   cb2_stats stats{};
-  cudaEvent_t ev[2] = {nullptr, nullptr};
+  PhaseTimer timer;
+  double phase_ms[kPhCount] = {0, 0, 0, 0, 0};
   bool scaling_set = false;
 
   ~cb2_problem() {
     if (h_scal) cudaFreeHost(h_scal);
-    for (auto& e : ev) if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
   }
 
@@ -212,8 +237,6 @@ struct cb2_problem {
       return fail(CB2_INTERNAL, "No CUDA device available: calico_b200 has no CPU fallback.");
     if (device >= 0) CB2_CUDA(cudaSetDevice(device));
     CB2_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    CB2_CUDA(cudaEventCreate(&ev[0]));
-    CB2_CUDA(cudaEventCreate(&ev[1]));
     CB2_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_scal), sizeof(double) * kScCount));
     return CB2_OK;
   }
@@ -324,7 +347,7 @@ struct cb2_problem {
       for (int j = 0; j < kMaxIntrinsics; ++j) st.intr[j] = j < want ? s.intr[j] : 0.0;
       st.q = Q4{s.q[0], s.q[1], s.q[2], s.q[3]}; st.t = v3(s.t[0], s.t[1], s.t[2]);
       st.latency = s.latency; st.inv_sigma = 1.0 / s.sigma; st.loss_type = s.loss_type; st.loss_scale = s.loss_scale;
-      smem_eval[s.kind] = std::max(smem_eval[s.kind], size_t(rec_size(s.kind, want)) * kTile * sizeof(double));
+      smem_eval[s.kind] = std::max(smem_eval[s.kind], size_t(rec_size(s.kind, want)) * kRecStride * sizeof(double));
     }
     n_tot = n_a + N_c;
     if (N_c > kRedThreads) return fail(CB2_UNIMPLEMENTED, "More than 512 calibration unknowns are not supported.");
@@ -438,21 +461,22 @@ struct cb2_problem {
 
   void set_kernel_attributes() {
 #ifndef CB2_EMUL
-    const int big = 227 * 1024;
-    cudaFuncSetAttribute(eval_kernel<kCamera, kModeCost>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(eval_kernel<kCamera, kModeResiduals>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(eval_kernel<kCamera, kModeJacobian>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(eval_kernel<kGyroscope, kModeCost>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(eval_kernel<kGyroscope, kModeResiduals>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(eval_kernel<kGyroscope, kModeJacobian>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(eval_kernel<kAccelerometer, kModeCost>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(eval_kernel<kAccelerometer, kModeResiduals>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(eval_kernel<kAccelerometer, kModeJacobian>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(band_factor_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(band_factor_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(reduced_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(band_backsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaGetLastError();
+    // Opt in to > 48 KB of dynamic shared memory, per kernel, with the size actually used (static + dynamic <= 227 KB).
+    auto set = [&](auto kernel, size_t bytes) {
+      if (bytes > 48 * 1024) CB2_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)));
+    };
+    const size_t ev_max[3] = {size_t(rec_size(kCamera, 11)) * kRecStride * 8, size_t(rec_size(kGyroscope, 12)) * kRecStride * 8,
+                              size_t(rec_size(kAccelerometer, 12)) * kRecStride * 8};
+    set(eval_kernel<kCamera, kModeCost>, ev_max[0]); set(eval_kernel<kCamera, kModeResiduals>, ev_max[0]); set(eval_kernel<kCamera, kModeJacobian>, ev_max[0]);
+    set(eval_kernel<kGyroscope, kModeCost>, ev_max[1]); set(eval_kernel<kGyroscope, kModeResiduals>, ev_max[1]); set(eval_kernel<kGyroscope, kModeJacobian>, ev_max[1]);
+    set(eval_kernel<kAccelerometer, kModeCost>, ev_max[2]); set(eval_kernel<kAccelerometer, kModeResiduals>, ev_max[2]); set(eval_kernel<kAccelerometer, kModeJacobian>, ev_max[2]);
+    int max_n1 = 0;
+    for (const auto& sy : h_l1) max_n1 = std::max(max_n1, sy.n);
+    const int nbw1 = h_l1[0].nbw, nbw2 = h_l2.nbw;
+    set(band_factor_kernel<6>, (36 * 36 + 36 * size_t(nbw1)) * 8);
+    set(band_factor_kernel<10>, (60 * 60 + 60 * size_t(nbw2)) * 8);
+    set(reduced_solve_kernel, size_t(N_c + 1) * (kRedPanel + 1) * 8);
+    set(band_backsolve_kernel, size_t(std::max(max_n1 + nbw1, h_l2.n + nbw2)) * 8);
 #endif
   }
 
@@ -479,9 +503,10 @@ struct cb2_problem {
 
   // K1-K3 at x, then K4: normal equations, Hessian diagonal, gradient norms.
   void launch_jacobian_and_normal_equations() {
-    CB2_CUDA(cudaEventRecord(ev[0], stream));
+    timer.begin(kPhJacobian, stream);
     launch_eval<kModeJacobian>(cur, kScCost);
-    CB2_CUDA(cudaEventRecord(ev[1], stream));
+    timer.end(kPhJacobian, stream);
+    timer.begin(kPhNormal, stream);
     const int ns = int(sensors.size());
     CB2_K(accumulate_kernel, n_seg, kAccThreads, 0, stream, d_desc.p, ns, N_c, d_c2off.p, csz, d_segA.p, d_segG.p, d_segB.p, d_segC.p, d_segGc.p);
     const long total = n_a * 36 + n_a * N_c + n_a;
@@ -494,6 +519,7 @@ struct cb2_problem {
     }
     CB2_K(hess_diag_kernel, int(std::min<long>((n_tot + 255) / 256, 1024)), 256, 0, stream, n_a, N_c, d_Aband.p, d_Cmat.p, d_diag.p);
     CB2_K(gradient_norm_kernel, 1, kLmThreads, 0, stream, n_a, d_grad.p, d_desc.p, d_state[cur].p, ns, d_scal.p);
+    timer.end(kPhNormal, stream);
     ++stats.jacobian_sweeps;
   }
 
@@ -502,6 +528,7 @@ struct cb2_problem {
     const int P = int(chunks.size());
     const int ns = int(sensors.size());
     const int blocks = int(std::min<long>((n_tot + 255) / 256, 1024));
+    timer.begin(kPhSchur, stream);
     CB2_K(damping_kernel, blocks, 256, 0, stream, n_tot, d_diag.p, d_scaling.p, radius, opt.min_lm_diagonal, opt.max_lm_diagonal, d_dtil2.p);
     CB2_CUDA(cudaMemsetAsync(d_scal.p + kScSolveFail, 0, sizeof(double), stream));
     const int nbw1 = h_l1[0].nbw;
@@ -533,7 +560,10 @@ struct cb2_problem {
     CB2_K(band_backsolve_kernel, P, kBackThreads, size_t(max_n1 + nbw1) * sizeof(double), stream, d_l1.p, d_ytil.p);
     CB2_K(apply_step_kernel, 1, kLmThreads, 0, stream, n_a, d_ytil.p, d_grad.p, d_dtil2.p, d_cp_ref.p, d_ctrl[cur].p, d_ctrl[cur ^ 1].p, d_desc.p,
           d_state[cur].p, d_state[cur ^ 1].p, ns, N_c, d_scal.p);
+    timer.end(kPhSchur, stream);
+    timer.begin(kPhCost, stream);
     launch_eval<kModeCost>(cur ^ 1, kScCandCost);
+    timer.end(kPhCost, stream);
   }
 
   void sync_scalars() {
@@ -541,6 +571,9 @@ struct cb2_problem {
     CB2_CUDA(cudaStreamSynchronize(stream));
     CB2_CUDA(cudaGetLastError());
     stats.d2h_bytes += sizeof(double) * kScCount;
+    timer.resolve(phase_ms);
+    stats.jacobian_kernel_ms = phase_ms[kPhJacobian]; stats.normal_eq_ms = phase_ms[kPhNormal];
+    stats.schur_ms = phase_ms[kPhSchur]; stats.cost_eval_ms = phase_ms[kPhCost]; stats.lm_loop_ms = phase_ms[kPhLoop];
   }
 
   double jacobian_bytes_per_sweep() const {   // obs_read + 8 m w + 8 m per residual block
@@ -604,7 +637,7 @@ struct cb2_problem {
     int num_consecutive_invalid_steps = 0;
     bool atleast_one_successful_step = false;
     cb2_iteration it{};
-    float ms = 0;
+    timer.begin(kPhLoop, stream);
     const int blocks_tot = int(std::min<long>((n_tot + 255) / 256, 1024));
 
     auto evaluate_gradient_and_jacobian = [&](bool first) -> bool {
@@ -612,8 +645,6 @@ struct cb2_problem {
       launch_jacobian_and_normal_equations();
       if (first) CB2_K(jacobi_scaling_kernel, blocks_tot, 256, 0, stream, n_tot, d_diag.p, opt.jacobi_scaling, d_scaling.p);
       sync_scalars();
-      cudaEventElapsedTime(&ms, ev[0], ev[1]);
-      stats.jacobian_kernel_ms += ms;
       stats.jacobian_blocks += num_active_blocks();
       stats.jacobian_bytes += jacobian_bytes_per_sweep();
       S.jacobian_time += now_s() - t0;
@@ -719,6 +750,11 @@ struct cb2_problem {
     S.final_cost = S.initial_cost;
     for (const auto& e : L) S.final_cost = std::min(S.final_cost, e.cost);
     S.num_iterations = int(L.size());
+    stats.lm_iterations += int(L.size()) - 1;
+    timer.end(kPhLoop, stream);
+    CB2_CUDA(cudaStreamSynchronize(stream));
+    timer.resolve(phase_ms);
+    stats.lm_loop_ms = phase_ms[kPhLoop];
     S.total_time = now_s() - t_start;
     return CB2_OK;
   }
@@ -929,7 +965,7 @@ int cb2_evaluate_sensor(cb2_problem* p, int sid, double* residuals, double* jaco
     cpart.alloc(tiles.size()); ipart.alloc(tiles.size());
     const SensorState* st = p->d_state[p->cur].p + sid;
     const double* c = p->d_ctrl[p->cur].p;
-    const size_t smem = size_t(rec_size(s.kind, ni)) * kTile * sizeof(double);
+    const size_t smem = size_t(rec_size(s.kind, ni)) * kRecStride * sizeof(double);
     const int nt = int(tiles.size());
     cudaStream_t stream = p->stream;
     cb2_stats& stats = p->stats;
@@ -1017,7 +1053,7 @@ int cb2_reset_parameters(cb2_problem* p) {
   }
 }
 
-int cb2_stats_reset(cb2_problem* p) { p->stats = cb2_stats{}; return CB2_OK; }
+int cb2_stats_reset(cb2_problem* p) { p->stats = cb2_stats{}; for (auto& v : p->phase_ms) v = 0.0; return CB2_OK; }
 int cb2_stats_get(cb2_problem* p, cb2_stats* out) { *out = p->stats; return CB2_OK; }
 
 // Multi-GPU entry points are provided by cb2_comm.cu when built with NCCL support.

@@ -23,6 +23,21 @@ SEED = 20261017
 OPENCV5_TRUTH = np.array([785.0, 640.0, 400.0, -3.149e-1, 1.069e-1, 1.616e-4, 1.141e-4, -1.853e-2])
 KB_TRUTH = np.array([785.0, 640.0, 400.0, -3.149e-1, 1.069e-1, 1.616e-4, 1.141e-4])
 IMU_TRUTH = np.array([1.3, 0.01, -0.01, 0.01])
+# Intrinsics the reference's own model tests use (camera_models_test.cpp:107-108,128-130,153-154,174-175,195-196,216-217,237-238).
+CAMERA_TRUTH = {
+    1: OPENCV5_TRUTH,
+    2: np.array([785.0, 640.0, 400.0, -3.149e-1, 1.069e-1, 1.616e-4, 1.141e-4, -1.853e-2, 1.225e-1, -5.26e-2, 8.58e-3]),
+    3: KB_TRUTH,
+    4: np.array([785.0, 640.0, 400.0, 0.5, 0.5]),
+    5: np.array([785.0, 640.0, 400.0, 0.05]),
+    6: np.array([785.0, 640.0, 400.0, 0.5]),
+    7: np.array([785.0, 640.0, 400.0, 0.5, 0.5]),
+}
+IMU_MODEL_TRUTH = {
+    1: np.array([1.3]),
+    2: IMU_TRUTH,
+    3: np.array([1.3, 1.2, 0.9, 0.01, -0.02, 0.015, 0.03, -0.01, 0.02, 0.01, -0.01, 0.01]),
+}
 
 
 def aprilgrid_points(tag_rows=6, tag_cols=6, tag_size=0.088, tag_spacing=0.3):
@@ -52,6 +67,8 @@ class Config:
     imu_rate: float = 200.0
     knot_frequency: float = 10.0
     imu_is_rig: bool = False   # IMU frame = rig frame: IMU extrinsics/latency fixed, every camera block free
+    camera_models: tuple = ()  # per-camera model override (cycled); empty = camera_model for all
+    imu_models: tuple = ()     # per-IMU (gyro, accel) model override (cycled); empty = ScaleAndBias
 
 
 CONFIGS = {
@@ -64,6 +81,11 @@ CONFIGS = {
     # small shapes for tests / smoke
     "tiny": Config("tiny", 2, 1, 1, 40, 12),
     "tiny_kb": Config("tiny_kb", 2, 3, 0, 40, 12),
+    "small": Config("small", 2, 1, 1, 160, 10),
+    "small_huber": Config("small_huber", 2, 1, 1, 160, 10, huber=True, outlier_fraction=0.03),
+    "micro": Config("micro", 1, 1, 1, 24, 6),
+    # every camera and IMU intrinsics model once (Jacobian parity of the "next" models)
+    "tiny_models": Config("tiny_models", 7, 1, 3, 30, 10, camera_models=(1, 2, 3, 4, 5, 6, 7), imu_models=(1, 2, 3)),
 }
 
 
@@ -108,17 +130,19 @@ def build_truth(cfg: Config, seed: int = SEED) -> ProblemSpec:
     spec.bodies.append(RigidBodySpec(0, np.array([0.0, 0, 0, 1]), np.zeros(3), ids, pts, True, True))
     for i in range(cfg.n_cameras):
         q, t = _camera_extrinsics(i, cfg.n_cameras)
-        intr = (OPENCV5_TRUTH if cfg.camera_model == 1 else KB_TRUTH).copy()
+        model = cfg.camera_models[i % len(cfg.camera_models)] if cfg.camera_models else cfg.camera_model
+        intr = CAMERA_TRUTH[model].copy()
         if cfg.name == "C1":
             intr[3:] = 0.0   # "pinhole": true distortion = 0
-        spec.sensors.append(SensorSpec(CAMERA, cfg.camera_model, f"cam{i}", intr, q, t, latency=0.0 if i == 0 else 0.01, sigma=0.1))
+        spec.sensors.append(SensorSpec(CAMERA, model, f"cam{i}", intr, q, t, latency=0.0 if i == 0 else 0.01, sigma=0.1))
     for i in range(cfg.n_imus):
         qg = sp.angle_axis_to_quat_xyzw(np.deg2rad(2.0) * _unit(rng))[0]
         qa = sp.angle_axis_to_quat_xyzw(np.deg2rad(2.0) * _unit(rng))[0]
         if cfg.imu_is_rig:
             qg = qa = np.array([0.0, 0.0, 0.0, 1.0])
-        spec.sensors.append(SensorSpec(GYROSCOPE, 2, f"gyro{i}", IMU_TRUTH.copy(), qg, np.zeros(3), latency=0.02, sigma=1e-3))
-        spec.sensors.append(SensorSpec(ACCELEROMETER, 2, f"accel{i}", IMU_TRUTH.copy(), qa, 0.02 * rng.standard_normal(3) if i else np.zeros(3),
+        im = cfg.imu_models[i % len(cfg.imu_models)] if cfg.imu_models else 2
+        spec.sensors.append(SensorSpec(GYROSCOPE, im, f"gyro{i}", IMU_MODEL_TRUTH[im].copy(), qg, np.zeros(3), latency=0.02, sigma=1e-3))
+        spec.sensors.append(SensorSpec(ACCELEROMETER, im, f"accel{i}", IMU_MODEL_TRUTH[im].copy(), qa, 0.02 * rng.standard_normal(3) if i else np.zeros(3),
                                        latency=0.02, sigma=1e-2))
     return spec
 
@@ -213,7 +237,8 @@ def generate(cfg_name: str, api_factory: Callable, seed: int = SEED, noise: bool
     for si, s in enumerate(problem.sensors):
         if s.kind == CAMERA:
             s.intr = 1.01 * s.intr
-            s.intr[3:] = 0.0
+            if s.model in (1, 2, 3):
+                s.intr[3:] = 0.0
             s.en_intr = True
             if cfg.name == "C1":
                 s.en_extr = s.en_lat = False   # intrinsics-only
@@ -234,4 +259,83 @@ def generate(cfg_name: str, api_factory: Callable, seed: int = SEED, noise: bool
             if s.kind == ACCELEROMETER:
                 s.t = s.t + 0.01 * rng.standard_normal(3)
             s.latency = 0.0
+    return truth, problem
+
+
+# ---- the reference's own integration fixture -------------------------------------------------------------------------
+def default_synthetic_test():
+    """DefaultSyntheticTest (calico/test_utils.h:11-116): base pose Rz(pi)*Rx(pi) at z = 1 m; per axis 4 angular segments
+    (+-30 deg) then 4 linear segments (+-0.5 m), 10 cosine-eased samples per segment, dt = 0.075 s -> 240 poses; 6x6 planar
+    points with 0.3 m pitch. Returns (stamps, q_xyzw[n,4], t[n,3], points[36,3])."""
+    q0 = sp.quat_mul_xyzw(sp.angle_axis_to_quat_xyzw([0, 0, np.pi])[0], sp.angle_axis_to_quat_xyzw([np.pi, 0, 0])[0])
+    t0 = np.array([0.0, 0.0, 1.0])
+    ang = [0.0, np.deg2rad(30.0), 0.0, -np.deg2rad(30.0), 0.0]
+    pos = [0.0, 0.5, 0.0, -0.5, 0.0]
+    n_per, seg_dur = 10, 0.75
+    dt_interp = 1.0 / n_per
+    dt_actual = dt_interp * seg_dur
+    interp = [(np.sin(dt_interp * i * np.pi - np.pi / 2) + 1.0) / 2.0 for i in range(n_per)]
+    stamps, qs, ts = [], [], []
+    cur = 0.0
+    for axis in np.eye(3):
+        for i in range(1, len(ang)):
+            for it in interp:
+                theta = (ang[i] - ang[i - 1]) * it + ang[i - 1]
+                qs.append(sp.quat_mul_xyzw(q0, sp.angle_axis_to_quat_xyzw(theta * axis)[0]))
+                ts.append(t0.copy())
+                stamps.append(cur)
+                cur += dt_actual
+        for i in range(1, len(pos)):
+            for it in interp:
+                p = (pos[i] - pos[i - 1]) * it + pos[i - 1]
+                qs.append(q0.copy())
+                ts.append(axis * p + t0)
+                stamps.append(cur)
+                cur += dt_actual
+    pts = np.array([[i * 0.3 - 0.75, j * 0.3 - 0.75, 0.0] for i in range(6) for j in range(6)])
+    return np.array(stamps), np.array(qs), np.array(ts), pts
+
+
+def toy_stereo_imu_problem(api_factory: Callable, seed: int = 1):
+    """ToyStereoCameraAndImuCalibration (calico/test/batch_optimizer_test.cpp:32-213): two OpenCv5 cameras + gyroscope +
+    accelerometer (ScaleAndBias) on DefaultSyntheticTest, perfect data from the `*::Project` restatements, the test's initial
+    guess. The reference draws its perturbations from an unseeded Eigen Random(); here they are seeded. Returns (truth, problem)."""
+    rng = np.random.default_rng(seed)
+    stamps, q, t, pts = default_synthetic_test()
+    spl = sp.fit_trajectory(stamps, q, t, 10.0, 6)
+    truth = ProblemSpec(spline=spl)
+    truth.bodies.append(RigidBodySpec(0, np.array([0.0, 0, 0, 1]), np.zeros(3), np.arange(36, dtype=np.int32), pts, True, True))
+
+    def small_rot(deg):
+        return sp.angle_axis_to_quat_xyzw(np.deg2rad(deg) * _unit(rng))[0]
+    truth.sensors.append(SensorSpec(CAMERA, 1, "Left", OPENCV5_TRUTH.copy(), sigma=1.0))
+    truth.sensors.append(SensorSpec(CAMERA, 1, "Right", OPENCV5_TRUTH.copy(), small_rot(2.0), 0.05 * rng.uniform(-1, 1, 3), latency=0.01, sigma=1.0))
+    truth.sensors.append(SensorSpec(GYROSCOPE, 2, "Gyroscope", IMU_TRUTH.copy(), small_rot(2.0), np.zeros(3), latency=0.02, sigma=1.0))
+    truth.sensors.append(SensorSpec(ACCELEROMETER, 2, "Accelerometer", IMU_TRUTH.copy(), small_rot(2.0), np.zeros(3), latency=0.02, sigma=1.0))
+    problem = truth.clone()
+    body = truth.bodies[0]
+    for si, s in enumerate(truth.sensors):
+        ps = problem.sensors[si]
+        if s.kind == CAMERA:
+            proj, vis = project_sensor(api_factory, truth, si, stamps)
+            ti, fi = np.nonzero(vis)
+            ps.stamp = stamps[ti] + s.latency
+            ps.image_id = ti.astype(np.int32)
+            ps.feature_id = body.feature_ids[fi]
+            ps.model_id = np.zeros(ti.size, dtype=np.int32)
+            ps.meas = proj[ti, fi]
+        else:
+            ps.stamp = stamps + s.latency
+            ps.seq = np.arange(stamps.size, dtype=np.int32)
+            ps.meas = project_sensor(api_factory, truth, si, stamps)
+    init_intr = 1.01 * OPENCV5_TRUTH
+    init_intr[3:] = 0.0
+    left, right, gyro, accel = problem.sensors
+    left.intr, left.en_intr = init_intr.copy(), True
+    right.intr, right.en_intr, right.en_extr, right.en_lat = init_intr.copy(), True, True, True
+    right.t = right.t + 0.01 * rng.uniform(-1, 1, 3)
+    right.latency = 0.0
+    gyro.intr, gyro.en_intr, gyro.en_extr, gyro.en_lat, gyro.latency = 1.01 * IMU_TRUTH, True, True, True, 0.0
+    accel.intr, accel.en_intr, accel.en_extr, accel.en_lat, accel.latency = 1.01 * IMU_TRUTH, True, True, True, 0.0
+    accel.t = accel.t + 0.05 * rng.uniform(-1, 1, 3)
     return truth, problem

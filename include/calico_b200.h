@@ -58,7 +58,7 @@ typedef struct cb2_options {
   int32_t num_threads;                   /* host threads for packing; the solve runs on the GPU */
   int32_t minimizer_progress_to_stdout;  /* 1 in DefaultSolverOptions (batch_optimizer.cpp:13) */
   int32_t linear_solver;                 /* ignored: always block-banded Schur + dense reduced solve on device */
-  int32_t use_cuda_graph;                /* 1: replay the per-iteration kernel sequence from a CUDA graph */
+  int32_t use_cuda_graph;                /* reserved (0) */
 } cb2_options;
 
 /* One row of Ceres's minimizer progress table (the columns of demos/imu_camera_calibration.ipynb:350). */
@@ -88,8 +88,10 @@ typedef struct cb2_stats {
   int64_t jacobian_blocks;        /* residual blocks evaluated with Jacobians */
   double jacobian_kernel_ms;      /* CUDA-event time spent in K1-K3 */
   double jacobian_bytes;          /* algorithmic bytes moved by K1-K3 (SURVEY §8d definition) */
-  double normal_eq_ms, schur_ms, cost_eval_ms;
+  double normal_eq_ms, schur_ms, cost_eval_ms;   /* CUDA-event time in K4, K5-K7 (+ step update), K8 */
   int64_t h2d_bytes, d2h_bytes;
+  double lm_loop_ms;              /* CUDA-event time from the first to the last kernel of the LM loop(s) */
+  int64_t lm_iterations;          /* LM iterations (accepted + rejected) run since reset */
 } cb2_stats;
 
 void cb2_default_options(cb2_options* out);

@@ -1,0 +1,77 @@
+"""Kernel logic without a GPU: the SAME kernel sources compiled by g++ against tests/emul/cuda_emul.h (one OS thread per CUDA
+thread) and driven through the same C ABI, compared with the oracle on a micro problem. This exercises indexing and
+synchronisation of every kernel (sweep, accumulate/assemble, chunked band factor, Gram, level 2/3, back-substitution) — the
+GPU parity tests proper are in test_gpu_parity.py. The emulated library is a test artefact and is never loaded by the package."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from calico_b200 import _capi, synthetic
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "emul"))
+
+
+@pytest.fixture(scope="module")
+def emul_lib():
+    import build as emul_build
+    return emul_build.build()
+
+
+def test_analytic_jacobians_match_dual_numbers_on_host():
+    """cb2_functors.cuh compiled for the host against the oracle's dual numbers: all 7 camera models, 3 gyroscope and 3
+    accelerometer models, generic and small-angle regimes (tests/emul/check_functors.cpp)."""
+    import build as emul_build
+    exe = emul_build.build_functor_check()
+    out = subprocess.run([exe], capture_output=True, text=True)
+    worst = [ln for ln in out.stdout.splitlines() if ln.startswith("WORST")]
+    assert worst, out.stdout[-2000:]
+    # generic regime: 1e-11; the theta ~ 1e-9 cases are limited by cancellation in the ORACLE's dual-number path
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("kind") and "theta_scale 1:" in ln]
+    assert len(lines) == 13
+    for ln in lines:
+        assert float(ln.split()[-1]) < 1e-10, ln
+    assert float(worst[0].split()[1]) < 1e-5
+
+
+@pytest.mark.timeout(600)
+def test_emulated_sweep_matches_oracle(emul_lib, oracle):
+    truth, prob = synthetic.generate("micro", oracle.oracle_api, noise=True)
+    a, o = _capi.CApi(emul_lib), oracle.oracle_api()
+    ids_a, ids_o = prob.clone().push(a), prob.clone().push(o)
+    for sa, so in zip(ids_a, ids_o):
+        r1, J1, v1 = a.evaluate_sensor(sa)
+        r2, J2, v2 = o.evaluate_sensor(so)
+        assert (v1 == v2).all()
+        assert np.abs(r1 - r2).max() <= 1e-9 * max(1.0, np.abs(r2).max())
+        assert np.abs(J1 - J2).max() <= 1e-10 * np.abs(J2).max()
+    c1, _ = a.cost()
+    c2, _ = o.cost()
+    assert abs(c1 - c2) <= 1e-12 * c2
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("chunk", [None, "6"])
+def test_emulated_lm_iterations_match_oracle(chunk, emul_lib, oracle, monkeypatch):
+    """Three LM iterations through every kernel, single chunk and two chunks (+ separator level)."""
+    if chunk:
+        monkeypatch.setenv("CB2_CHUNK_CPS", chunk)
+    truth, prob = synthetic.generate("micro", oracle.oracle_api, noise=True)
+    a, o = _capi.CApi(emul_lib), oracle.oracle_api()
+    ids_a, ids_o = prob.clone().push(a), prob.clone().push(o)
+    sum_a, log_a = a.optimize(_capi.Options(minimizer_progress_to_stdout=0, max_num_iterations=3))
+    sum_o, log_o = o.optimize(oracle.OracleOptions(linear_solver=1, max_num_iterations=3))
+    assert len(log_a) == len(log_o) == 4
+    for x, y in zip(log_a, log_o):
+        assert abs(x.cost - y.cost) <= 1e-9 * abs(y.cost)
+        assert abs(x.step_norm - y.step_norm) <= 1e-7 * max(y.step_norm, 1e-12)
+        assert abs(x.gradient_max_norm - y.gradient_max_norm) <= 1e-7 * y.gradient_max_norm
+    pa, po = prob.clone(), prob.clone()
+    pa.pull(a, ids_a)
+    po.pull(o, ids_o)
+    np.testing.assert_allclose(pa.spline.ctrl, po.spline.ctrl, rtol=1e-8, atol=1e-9)
+    for s1, s2 in zip(pa.sensors, po.sensors):
+        np.testing.assert_allclose(s1.intr, s2.intr, rtol=1e-8, atol=1e-10)

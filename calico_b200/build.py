@@ -30,7 +30,7 @@ def needs_build() -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if force or needs_build():
-        cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+        cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("CB2_NVCC_EXTRA", "").split(), "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.check_call(cmd)

@@ -19,8 +19,11 @@ namespace cb2 {
 
 enum { kModeCost = 0, kModeResiduals = 1, kModeJacobian = 2 };
 
+#ifndef CB2_EVAL_MINBLOCKS
+#define CB2_EVAL_MINBLOCKS 3
+#endif
 template <int KIND, int MODE>
-__global__ void __launch_bounds__(kTile) eval_kernel(const SensorDesc* __restrict__ sensors, const SensorState* __restrict__ states,
+__global__ void __launch_bounds__(kTile, CB2_EVAL_MINBLOCKS) eval_kernel(const SensorDesc* __restrict__ sensors, const SensorState* __restrict__ states,
                                                      const EvalTile* __restrict__ tiles, const double* __restrict__ ctrl,
                                                      const double* __restrict__ knots, const double* __restrict__ basis,
                                                      const double* __restrict__ pw, double gx, double gy, double gz,
@@ -86,23 +89,49 @@ __global__ void __launch_bounds__(kTile) eval_kernel(const SensorDesc* __restric
     invalid_partial[blockIdx.x] = b;
   }
   if (MODE == kModeJacobian) {
+    // Phase 2. Lane l owns elements idx = l + 32 k of every m x jw row block; which two record fields each element multiplies
+    // does not depend on the observation, so the field offsets are computed once per thread and the per-observation loop is
+    // shared-memory loads, FMAs and one coalesced store per element.
+    constexpr int NQ = (KIND == kCamera) ? 1 : (KIND == kGyroscope ? 2 : 3);
+    constexpr int KMAX = (KIND == kCamera) ? 4 : 6;     // ceil(m * (36 + 19) / 32)
     const int warp = t >> 5, lane = t & 31;
     const int jw = sd.jw, ni = sd.ni;
     const int rowlen = m * jw;
+    int oa[KMAX][NQ], ob[KMAX][NQ];
+    bool live[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int idx = lane + 32 * k;
+      live[k] = idx < rowlen;
+      int fa[3], fb[3];
+      const int row = live[k] ? idx / jw : 0;
+      const int j = live[k] ? idx - row * jw : 0;
+      const int canon = j < kCpCols ? j : kCpCols + sd.jcanon[j - kCpCols];
+      jac_terms(KIND, ni, row, canon, fa, fb);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) { oa[k][q] = fa[q] * kRecStride; ob[k][q] = fb[q] * kRecStride; }
+    }
+    double* __restrict__ Jbase = sd.J;
+    double* __restrict__ rbase = sd.r;
+    const int rs_off = rec_rs(KIND) * kRecStride;
     for (int oo = 0; oo < 32; ++oo) {
       const int lt = warp * 32 + oo;
       if (lt >= tl.count) break;
-      const long o = long(tl.start) + lt;
+      const size_t o = size_t(tl.start) + lt;
       const bool okb = s_ok[lt] != 0;
-      const Rec rc{rec + lt, kRecStride};
-      const double rs = okb ? rc.get(rec_rs(KIND)) : 0.0;
-      double* __restrict__ Jrow = sd.J + size_t(o) * rowlen;
-      for (int idx = lane; idx < rowlen; idx += 32) {
-        const int row = idx / jw, j = idx - row * jw;
-        const int canon = j < kCpCols ? j : kCpCols + sd.jcanon[j - kCpCols];
-        Jrow[idx] = okb ? rs * jac_entry(KIND, ni, rc, row, canon) : 0.0;
+      const double* __restrict__ rb = rec + lt;
+      const double rs = rb[rs_off];
+      double* __restrict__ Jrow = Jbase + o * rowlen;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        if (live[k]) {
+          double v = 0.0;
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) v += rb[oa[k][q]] * rb[ob[k][q]];
+          Jrow[lane + 32 * k] = okb ? rs * v : 0.0;
+        }
       }
-      if (lane < m) sd.r[o * m + lane] = okb ? rs * rc.get(lane) : 0.0;
+      if (lane < m) rbase[o * m + lane] = okb ? rs * rb[lane * kRecStride] : 0.0;
     }
   }
 }

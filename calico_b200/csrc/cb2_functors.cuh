@@ -26,9 +26,11 @@ enum { kCamera = 0, kGyroscope = 1, kAccelerometer = 2 };
 enum { kLossNone = 0, kLossHuber = 1, kLossCauchy = 2 };
 
 // Field offsets of the compact record, per sensor kind. Ji (m x ni, row-major with stride ni) is last.
-struct CamRec { enum { r = 0, G0 = 2, Jq = 14, Jt = 20, Jl = 26, w0 = 28, rs = 34, Ji = 35 }; };
-struct GyrRec { enum { r = 0, G0 = 3, G1 = 12, Jq = 21, Jl = 30, w0 = 33, w1 = 39, rs = 45, Ji = 46 }; };
-struct AccRec { enum { r = 0, G0 = 3, G1 = 12, G2 = 21, Jq = 39, Jt = 48, Jl = 57, w0 = 60, w1 = 66, w2 = 72, rs = 78, Ji = 79 }; };
+// `one` / `zero` hold the constants 1.0 / 0.0 so that every Jacobian entry is a fixed-length sum of products of two record fields
+// (jac_terms below) and the expansion loop of the sweep kernel is branch-free.
+struct CamRec { enum { r = 0, G0 = 2, Jq = 14, Jt = 20, Jl = 26, w0 = 28, rs = 34, one = 35, zero = 36, Ji = 37 }; };
+struct GyrRec { enum { r = 0, G0 = 3, G1 = 12, Jq = 21, Jl = 30, w0 = 33, w1 = 39, rs = 45, one = 46, zero = 47, Ji = 48 }; };
+struct AccRec { enum { r = 0, G0 = 3, G1 = 12, G2 = 21, Jq = 39, Jt = 48, Jl = 57, w0 = 60, w1 = 66, w2 = 72, rs = 78, one = 79, zero = 80, Ji = 81 }; };
 CB2_HD int rec_size(int kind, int ni) { return kind == kCamera ? CamRec::Ji + 2 * ni : (kind == kGyroscope ? GyrRec::Ji + 3 * ni : AccRec::Ji + 3 * ni); }
 CB2_HD int rec_rs(int kind) { return kind == kCamera ? int(CamRec::rs) : (kind == kGyroscope ? int(GyrRec::rs) : int(AccRec::rs)); }
 CB2_HD int residual_dim(int kind) { return kind == kCamera ? 2 : 3; }
@@ -151,6 +153,7 @@ CB2_HD bool camera_block(const SensorState& S, const double* __restrict__ M, dou
       for (int j = 0; j < S.ni; ++j) out.put(CamRec::Ji + row * S.ni + j, -S.inv_sigma * di[row][j]);
     }
     for (int i = 0; i < kK; ++i) out.put(CamRec::w0 + i, w[0][i]);
+    out.put(CamRec::one, 1.0); out.put(CamRec::zero, 0.0);
   }
   return true;
 }
@@ -192,6 +195,7 @@ CB2_HD bool gyro_block(const SensorState& S, const double* __restrict__ M, doubl
       for (int j = 0; j < S.ni; ++j) out.put(GyrRec::Ji + row * S.ni + j, -S.inv_sigma * di[row][j]);
     }
     for (int i = 0; i < kK; ++i) { out.put(GyrRec::w0 + i, w[0][i]); out.put(GyrRec::w1 + i, w[1][i]); }
+    out.put(GyrRec::one, 1.0); out.put(GyrRec::zero, 0.0);
   }
   return true;
 }
@@ -254,32 +258,45 @@ CB2_HD bool accel_block(const SensorState& S, const V3& gravity, const double* _
       for (int j = 0; j < S.ni; ++j) out.put(AccRec::Ji + row * S.ni + j, -S.inv_sigma * di[row][j]);
     }
     for (int i = 0; i < kK; ++i) { out.put(AccRec::w0 + i, w[0][i]); out.put(AccRec::w1 + i, w[1][i]); out.put(AccRec::w2 + i, w[2][i]); }
+    out.put(AccRec::one, 1.0); out.put(AccRec::zero, 0.0);
   }
   return true;
 }
 
 // Canonical Jacobian column order of one residual block (include/calico_b200.h, cb2_evaluate_sensor):
 //   [control points 6k | intrinsics ni | extrinsic rotation 3 | extrinsic translation 3 | latency 1],  W = 6k + ni + 7.
-// Entry (row, col) of the un-robustified Jacobian from the compact record.
-CB2_HD double jac_entry(int kind, int ni, const Rec& rec, int row, int col) {
+// Entry (row, col) of the un-robustified Jacobian = sum_{q < kind_terms} rec[fa[q]] * rec[fb[q]]; unused terms point at `zero`.
+CB2_HD constexpr int kind_terms(int kind) { return kind == kCamera ? 1 : (kind == kGyroscope ? 2 : 3); }
+CB2_HD void jac_terms(int kind, int ni, int row, int col, int fa[3], int fb[3]) {
+  const int one = kind == kCamera ? int(CamRec::one) : (kind == kGyroscope ? int(GyrRec::one) : int(AccRec::one));
+  const int zero = one + 1;
+  for (int q = 0; q < 3; ++q) { fa[q] = zero; fb[q] = zero; }
   if (col < 6 * kK) {
     const int i = col / 6, d = col % 6;
-    if (kind == kCamera) return rec.get(CamRec::G0 + row * 6 + d) * rec.get(CamRec::w0 + i);
-    if (kind == kGyroscope) {
-      if (d >= 3) return 0.0;
-      return rec.get(GyrRec::G0 + row * 3 + d) * rec.get(GyrRec::w0 + i) + rec.get(GyrRec::G1 + row * 3 + d) * rec.get(GyrRec::w1 + i);
+    if (kind == kCamera) { fa[0] = CamRec::G0 + row * 6 + d; fb[0] = CamRec::w0 + i; }
+    else if (kind == kGyroscope) {
+      if (d < 3) { fa[0] = GyrRec::G0 + row * 3 + d; fb[0] = GyrRec::w0 + i; fa[1] = GyrRec::G1 + row * 3 + d; fb[1] = GyrRec::w1 + i; }
+    } else {
+      fa[0] = AccRec::G2 + row * 6 + d; fb[0] = AccRec::w2 + i;
+      if (d < 3) { fa[1] = AccRec::G0 + row * 3 + d; fb[1] = AccRec::w0 + i; fa[2] = AccRec::G1 + row * 3 + d; fb[2] = AccRec::w1 + i; }
     }
-    double v = rec.get(AccRec::G2 + row * 6 + d) * rec.get(AccRec::w2 + i);
-    if (d < 3) v += rec.get(AccRec::G0 + row * 3 + d) * rec.get(AccRec::w0 + i) + rec.get(AccRec::G1 + row * 3 + d) * rec.get(AccRec::w1 + i);
-    return v;
+    return;
   }
   col -= 6 * kK;
-  if (col < ni) return rec.get((kind == kCamera ? int(CamRec::Ji) : (kind == kGyroscope ? int(GyrRec::Ji) : int(AccRec::Ji))) + row * ni + col);
+  fb[0] = one;
+  if (col < ni) { fa[0] = (kind == kCamera ? int(CamRec::Ji) : (kind == kGyroscope ? int(GyrRec::Ji) : int(AccRec::Ji))) + row * ni + col; return; }
   col -= ni;
-  if (col < 3) return rec.get((kind == kCamera ? int(CamRec::Jq) : (kind == kGyroscope ? int(GyrRec::Jq) : int(AccRec::Jq))) + row * 3 + col);
+  if (col < 3) { fa[0] = (kind == kCamera ? int(CamRec::Jq) : (kind == kGyroscope ? int(GyrRec::Jq) : int(AccRec::Jq))) + row * 3 + col; return; }
   col -= 3;
-  if (col < 3) return kind == kGyroscope ? 0.0 : rec.get((kind == kCamera ? int(CamRec::Jt) : int(AccRec::Jt)) + row * 3 + col);
-  return rec.get((kind == kCamera ? int(CamRec::Jl) : (kind == kGyroscope ? int(GyrRec::Jl) : int(AccRec::Jl))) + row);
+  if (col < 3) { if (kind != kGyroscope) fa[0] = (kind == kCamera ? int(CamRec::Jt) : int(AccRec::Jt)) + row * 3 + col; return; }
+  fa[0] = (kind == kCamera ? int(CamRec::Jl) : (kind == kGyroscope ? int(GyrRec::Jl) : int(AccRec::Jl))) + row;
+}
+CB2_HD double jac_entry(int kind, int ni, const Rec& rec, int row, int col) {
+  int fa[3], fb[3];
+  jac_terms(kind, ni, row, col, fa, fb);
+  double v = 0.0;
+  for (int q = 0; q < kind_terms(kind); ++q) v += rec.get(fa[q]) * rec.get(fb[q]);
+  return v;
 }
 
 }  // namespace cb2

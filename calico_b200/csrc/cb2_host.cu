@@ -391,7 +391,7 @@ struct cb2_problem {
   // Chunk plan for the substructured Schur elimination (cb2_schur.cuh).
   // ------------------------------------------------------------------------------------------------------------
   int plan_schur() {
-    int target = 48;   // interior control points per chunk
+    int target = 110;   // interior control points per chunk (tuned on C4, profiles/)
     if (const char* e = std::getenv("CB2_CHUNK_CPS")) target = std::max(6, std::atoi(e));
     int P = std::max(1, (n_cp + 5) / (target + 5));
     while (P > 1 && (n_cp - 5 * (P - 1)) / P < 6) --P;
@@ -427,7 +427,7 @@ struct cb2_problem {
       for (int c = 0; c < N_c; ++c) colidx.push_back(int(n_a) + c);
       Loff[p] = Lsz; Woff[p] = Wsz; Toff[p] = Tsz;
       Lsz += size_t(sy.n) * 36; Wsz += size_t(sy.n) * nbw1; Tsz += size_t(sy.ksplit) * nbw1 * nbw1;
-      if (size_t(sy.n + nbw1) * sizeof(double) > 200 * 1024) return fail(CB2_INTERNAL, "Schur chunk too large for shared memory; lower CB2_CHUNK_CPS.");
+      if (backsolve_smem_bytes(sy.n, nbw1, 36) > 220 * 1024) return fail(CB2_INTERNAL, "Schur chunk too large for shared memory; lower CB2_CHUNK_CPS.");
     }
     const size_t row_off2 = rowidx.size();
     for (int p = 0; p + 1 < P; ++p) for (int j = 0; j < kSepDim; ++j) rowidx.push_back(6 * chunks[p].b + j);
@@ -476,7 +476,7 @@ struct cb2_problem {
     set(band_factor_kernel<6>, (36 * 36 + 36 * size_t(nbw1)) * 8);
     set(band_factor_kernel<10>, (60 * 60 + 60 * size_t(nbw2)) * 8);
     set(reduced_solve_kernel, size_t(N_c + 1) * (kRedPanel + 1) * 8);
-    set(band_backsolve_kernel, size_t(std::max(max_n1 + nbw1, h_l2.n + nbw2)) * 8);
+    set(band_backsolve_kernel, std::max(backsolve_smem_bytes(max_n1, nbw1, 36), backsolve_smem_bytes(h_l2.n, nbw2, 60)));
 #endif
   }
 
@@ -556,8 +556,8 @@ struct cb2_problem {
       CB2_K(reduced_solve_kernel, 1, kRedThreads, size_t(N_c + 1) * (kRedPanel + 1) * sizeof(double), stream, h_l2, N_c, n_a, d_Cw.p, d_dtil2.p,
             d_ytil.p, d_scal.p);
     }
-    if (h_l2.n > 0) CB2_K(band_backsolve_kernel, 1, kBackThreads, size_t(h_l2.n + h_l2.nbw) * sizeof(double), stream, d_l2.p, d_ytil.p);
-    CB2_K(band_backsolve_kernel, P, kBackThreads, size_t(max_n1 + nbw1) * sizeof(double), stream, d_l1.p, d_ytil.p);
+    if (h_l2.n > 0) CB2_K(band_backsolve_kernel, 1, kBackThreads, backsolve_smem_bytes(h_l2.n, h_l2.nbw, 60), stream, d_l2.p, d_ytil.p);
+    CB2_K(band_backsolve_kernel, P, kBackThreads, backsolve_smem_bytes(max_n1, nbw1, 36), stream, d_l1.p, d_ytil.p);
     CB2_K(apply_step_kernel, 1, kLmThreads, 0, stream, n_a, d_ytil.p, d_grad.p, d_dtil2.p, d_cp_ref.p, d_ctrl[cur].p, d_ctrl[cur ^ 1].p, d_desc.p,
           d_state[cur].p, d_state[cur ^ 1].p, ns, N_c, d_scal.p);
     timer.end(kPhSchur, stream);

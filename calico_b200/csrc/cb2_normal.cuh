@@ -8,8 +8,9 @@
 //
 // accumulate_kernel: one CTA per spline segment. All residual rows of a segment touch the same 36 control-point
 // columns, so the CTA accumulates one local (36 + n_calib + 1)^2 Gram matrix per sensor ([J | r]^T [J | r], r as an
-// extra column gives the gradient for free) in registers — 4x4 micro-tiles, lower triangle only — from J row tiles staged in
-// shared memory, and writes per-segment partials with plain stores (no atomics; summation order is fixed).
+// extra column gives the gradient for free) in registers — 6x6 micro-tiles, lower triangle only (55 threads) — from J row
+// tiles streamed into shared memory with cp.async (double-buffered, the next tile is in flight while the current one is
+// multiplied; 16-byte shared loads), and writes per-segment partials with plain stores (no atomics; fixed summation order).
 // assemble_*_kernel: sums the <= 6 overlapping segment partials per control-point entry into the banded storage and
 // reduces the calibration blocks over all segments.
 #pragma once
@@ -17,76 +18,147 @@
 
 namespace cb2 {
 
-constexpr int kAccThreads = 128;
+constexpr int kAccThreads = 64;
 constexpr int kAccRows = 32;   // J rows per shared-memory tile
-constexpr int kAccW = 60;      // local width: 36 cp | <= 20 calib | r at column 56 | 3 pad
+constexpr int kAccW = 60;      // local width: 36 cp | <= 20 calib | r at position 56 | 3 pad  (10 tiles of 6)
 constexpr int kAccRcol = 56;
-constexpr int kAccTiles = 120; // lower-triangular 4x4 tiles of a 15 x 15 tile grid
+constexpr int kAccTiles = 55;  // lower-triangular 6x6 tiles of a 10 x 10 tile grid
+
+// 8-byte asynchronous global -> shared copy (LDGSTS): the J tile of the NEXT step streams in while the current one is multiplied.
+CB2_D void cp_async8(double* dst, const double* src) {
+#if defined(CB2_EMUL)
+  *dst = *src;
+#else
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(dst));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(src));
+#endif
+}
+CB2_D void cp_async_commit() {
+#if !defined(CB2_EMUL)
+  asm volatile("cp.async.commit_group;\n" ::);
+#endif
+}
+template <int N>
+CB2_D void cp_async_wait() {
+#if !defined(CB2_EMUL)
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+#endif
+}
+
+struct AccCursor { int s, r0; };
 
 __global__ void __launch_bounds__(kAccThreads) accumulate_kernel(const SensorDesc* __restrict__ sensors, int n_sensors, int N_c,
                                                                  const int* __restrict__ c2off, int csz, double* __restrict__ segA,
                                                                  double* __restrict__ segG, double* __restrict__ segB,
                                                                  double* __restrict__ segC, double* __restrict__ segGc) {
-  __shared__ __align__(16) double tile[kAccRows * kAccW];
+  __shared__ __align__(16) double tile[2][kAccRows * kAccW];
   const int g = blockIdx.x, t = threadIdx.x;
   const bool has_tile = t < kAccTiles;
   int ti = 0, tj = 0;
   if (has_tile) { int rem = t; while (rem > ti) { rem -= ti + 1; ++ti; } tj = rem; }
-  double acc[4][4];
-  for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+  double acc[6][6];
+#pragma unroll
+  for (int a = 0; a < 6; ++a)
+#pragma unroll
+    for (int b = 0; b < 6; ++b) acc[a][b] = 0.0;
+
+  auto rows_of = [&](int s) { const SensorDesc& sd = sensors[s]; return (sd.seg_start[g + 1] - sd.seg_start[g]) * sd.m; };
+  auto skip_empty = [&](AccCursor c) { while (c.s < n_sensors && rows_of(c.s) == 0) ++c.s; return c; };
+  auto next_tile = [&](AccCursor c) {
+    c.r0 += kAccRows;
+    if (c.r0 >= rows_of(c.s)) { c.r0 = 0; ++c.s; c = skip_empty(c); }
+    return c;
+  };
+  // Thread t < 60 fills local column position t of every tile row: the J column that maps there, the residual, or zero.
+  auto issue_load = [&](AccCursor c, int buf) {
+    if (c.s < n_sensors && t < kAccW) {
+      const SensorDesc& sd = sensors[c.s];
+      const int m = sd.m, jw = sd.jw;
+      const int o0 = sd.seg_start[g];
+      const int rows = (sd.seg_start[g + 1] - o0) * m;
+      const int nr = min(kAccRows, rows - c.r0);
+      int src = -1;                       // J column feeding this position
+      if (t < kCpCols) src = t;
+      else if (t < kAccRcol) { for (int j = 0; j < sd.n_jcal; ++j) if (kCpCols + sd.junk[j] == t) src = kCpCols + j; }
+      double* dst = tile[buf] + t;
+      if (src >= 0) {
+        const double* base = sd.J + (size_t(o0) * m + c.r0) * jw + src;
+        for (int row = 0; row < nr; ++row) cp_async8(dst + row * kAccW, base + size_t(row) * jw);
+      } else if (t == kAccRcol) {
+        const double* base = sd.r + size_t(o0) * m + c.r0;
+        for (int row = 0; row < nr; ++row) cp_async8(dst + row * kAccW, base + row);
+      } else {
+        for (int row = 0; row < nr; ++row) dst[row * kAccW] = 0.0;
+      }
+    }
+    cp_async_commit();
+  };
+
+  AccCursor cu = skip_empty(AccCursor{0, 0});
+  int buf = 0;
+  issue_load(cu, buf);
   for (int s = 0; s < n_sensors; ++s) {
     const SensorDesc& sd = sensors[s];
-    const int m = sd.m, jw = sd.jw, nc = sd.n_calib;
-    const int o0 = sd.seg_start[g], o1 = sd.seg_start[g + 1];
-    const int rows = (o1 - o0) * m;
-    const double* __restrict__ Jbase = sd.J + size_t(o0) * m * jw;
-    const double* __restrict__ rbase = sd.r + size_t(o0) * m;
-    for (int r0 = 0; r0 < rows; r0 += kAccRows) {
-      const int nr = min(kAccRows, rows - r0);
-      __syncthreads();
-      for (int e = t; e < kAccRows * kAccW; e += kAccThreads) tile[e] = 0.0;
-      __syncthreads();
-      for (int e = t; e < nr * jw; e += kAccThreads) {
-        const int row = e / jw, j = e - row * jw;
-        const int pos = j < kCpCols ? j : kCpCols + sd.junk[j - kCpCols];
-        tile[row * kAccW + pos] = Jbase[size_t(r0) * jw + e];
-      }
-      for (int row = t; row < nr; row += kAccThreads) tile[row * kAccW + kAccRcol] = rbase[r0 + row];
+    const int nc = sd.n_calib;
+    while (cu.s == s) {
+      const int nr = min(kAccRows, rows_of(s) - cu.r0);
+      const AccCursor nx = next_tile(cu);
+      issue_load(nx, buf ^ 1);
+      cp_async_wait<1>();
       __syncthreads();
       if (has_tile) {
+        const double* tb = tile[buf];
         for (int row = 0; row < nr; ++row) {
-          const double* tr = tile + row * kAccW;
-          double a4[4], b4[4];
-          for (int a = 0; a < 4; ++a) { a4[a] = tr[4 * ti + a]; b4[a] = tr[4 * tj + a]; }
-          for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) acc[a][b] += a4[a] * b4[b];
+          const double2* pa = reinterpret_cast<const double2*>(tb + row * kAccW + 6 * ti);
+          const double2* pb = reinterpret_cast<const double2*>(tb + row * kAccW + 6 * tj);
+          const double2 a0 = pa[0], a1 = pa[1], a2 = pa[2], b0 = pb[0], b1 = pb[1], b2 = pb[2];
+          const double a6[6] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y};
+          const double b6[6] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y};
+#pragma unroll
+          for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int b = 0; b < 6; ++b) acc[a][b] += a6[a] * b6[b];
         }
       }
+      __syncthreads();
+      cu = nx;
+      buf ^= 1;
     }
-    // Flush every tile that involves this sensor's calibration columns, then reset it for the next sensor.
-    if (has_tile && (tj >= 9 || (ti >= 9 && ti < 14))) {
-      for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) {
-        const int I = 4 * ti + a, Jx = 4 * tj + b;
-        if (ti == 14) {                       // r row x calibration column -> calibration gradient
-          if (tj >= 9 && tj < 14 && a == 0) { const int lc = Jx - kCpCols; if (lc < nc) segGc[size_t(g) * N_c + sd.calib_off + lc] = acc[a][b]; }
-        } else if (tj < 9) {                  // calibration row x control-point column
-          const int lc = I - kCpCols;
-          if (lc < nc) segB[(size_t(g) * kCpCols + Jx) * N_c + sd.calib_off + lc] = acc[a][b];
-        } else {                              // calibration x calibration (lower)
-          const int li = I - kCpCols, lj = Jx - kCpCols;
-          if (li < nc && lj <= li) segC[size_t(g) * csz + c2off[s] + li * nc + lj] = acc[a][b];
+    // Flush every entry that involves this sensor's calibration columns, then reset it for the next sensor.
+    if (has_tile && ti >= 6) {
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = 0; b < 6; ++b) {
+          const int I = 6 * ti + a, Jx = 6 * tj + b;
+          if (I == kAccRcol) {                    // residual row
+            if (Jx < kCpCols) continue;          // control-point gradient: accumulated over all sensors
+            const int lc = Jx - kCpCols;
+            if (Jx < kAccRcol && lc < nc) segGc[size_t(g) * N_c + sd.calib_off + lc] = acc[a][b];
+          } else if (I < kAccRcol) {              // calibration row
+            const int li = I - kCpCols;
+            if (li < nc) {
+              if (Jx < kCpCols) segB[(size_t(g) * kCpCols + Jx) * N_c + sd.calib_off + li] = acc[a][b];
+              else if (Jx <= I) segC[size_t(g) * csz + c2off[s] + li * nc + (Jx - kCpCols)] = acc[a][b];
+            }
+          }
+          acc[a][b] = 0.0;
         }
-        if (!(ti == 14 && tj < 9)) acc[a][b] = 0.0;
-      }
     }
   }
-  if (has_tile && tj < 9) {
-    if (ti < 9) {
-      for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) {
-        const int I = 4 * ti + a, Jx = 4 * tj + b;
-        if (Jx <= I) segA[(size_t(g) * kCpCols + I) * kCpCols + Jx] = acc[a][b];
-      }
-    } else if (ti == 14) {
-      for (int b = 0; b < 4; ++b) segG[size_t(g) * kCpCols + 4 * tj + b] = acc[0][b];
+  cp_async_wait<0>();
+  if (has_tile) {
+    if (ti < 6) {
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = 0; b < 6; ++b) {
+          const int I = 6 * ti + a, Jx = 6 * tj + b;
+          if (Jx <= I) segA[(size_t(g) * kCpCols + I) * kCpCols + Jx] = acc[a][b];
+        }
+    } else if (ti == 9 && tj < 6) {
+#pragma unroll
+      for (int b = 0; b < 6; ++b) segG[size_t(g) * kCpCols + 6 * tj + b] = acc[kAccRcol - 54][b];
     }
   }
 }

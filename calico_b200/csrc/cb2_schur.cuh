@@ -75,10 +75,21 @@ __global__ void __launch_bounds__(256) gather_level1_kernel(const BandSys* __res
 
 // In-place banded Cholesky (right-looking, 6 columns per step) fused with the forward substitution of the border.
 // Shared memory: Wd[S][S] circular window of the band, Wr[S][nbw] ring of partially updated border rows.
-// Requires n % 6 == 0 and the block structure described in the header (entries beyond the block band are structurally zero).
+// Requires n % 6 == 0, nbw <= 2 * kFacThreads and the block structure described in the header (entries beyond the block band
+// are structurally zero). Per 6-column step, three block-wide phases:
+//   P1  thread 0 factors the 6x6 diagonal block (one rsqrt per column); meanwhile every thread has already issued the global
+//       loads of the 6 rows that enter the window at the end of the step (software prefetch into registers);
+//   P2  panel rows: 6-step triangular solve against the diagonal block, finished factor columns go to HBM;
+//       border rows j0..j0+5: same solve per border column, kept in registers and written to HBM;
+//   P3  trailing update of the band window and of the border ring (6 rows per batch for ILP); the prefetched rows are
+//       dropped into the slots of the retired rows.
 template <int NBLK>
 __global__ void __launch_bounds__(kFacThreads) band_factor_kernel(const BandSys* __restrict__ systems, double* __restrict__ scal) {
   constexpr int S = 6 * NBLK;
+  constexpr int NB1 = NBLK - 1;                       // trailing window, in 6x6 blocks
+  constexpr int NTB = NB1 * (NB1 + 1) / 2;            // lower-triangular 6x6 blocks of the trailing window
+  constexpr int PFB = (6 * S + kFacThreads - 1) / kFacThreads;
+  constexpr int PFW = 12;                             // 6 * nbw / kFacThreads <= 12 for nbw <= 512
   const BandSys sy = systems[blockIdx.x];
   const int n = sy.n, nbw = sy.nbw, t = threadIdx.x;
   double* Wd = dyn_smem<double>();
@@ -86,111 +97,159 @@ __global__ void __launch_bounds__(kFacThreads) band_factor_kernel(const BandSys*
   __shared__ double Ld[36];
   __shared__ double Linv[6];
   __shared__ int s_fail;
-  if (t == 0) s_fail = 0;
+  __shared__ unsigned char blk_i[NTB], blk_j[NTB];
+  if (t == 0) {
+    s_fail = 0;
+    int e = 0;
+    for (int bi = 0; bi < NB1; ++bi) for (int bj = 0; bj <= bi; ++bj) { blk_i[e] = (unsigned char)bi; blk_j[e] = (unsigned char)bj; ++e; }
+  }
+  double* __restrict__ Lg = sy.L;
+  double* __restrict__ Wg = sy.W;
   // Initial window: rows 0..min(S,n)-1.
   const int n0 = min(S, n);
   for (int e = t; e < n0 * S; e += kFacThreads) {
     const int i = e / S, d = e % S;
     const int j = i - (S - 1 - d);
-    if (j >= 0) Wd[i * S + j] = sy.L[size_t(i) * S + d];
+    if (j >= 0) Wd[i * S + j] = Lg[size_t(i) * S + d];
   }
-  for (int e = t; e < n0 * nbw; e += kFacThreads) Wr[e] = sy.W[e];
+  for (int e = t; e < n0 * nbw; e += kFacThreads) Wr[e] = Wg[e];
   __syncthreads();
   for (int j0 = 0; j0 < n; j0 += 6) {
-    const int jm = j0 % S;                       // window position of column/row j0 (6 consecutive, never wraps)
+    const int jm = j0 % S;                       // window slot of column/row j0 (6 consecutive slots, never wraps)
     const int r_end = min(j0 + S, n);            // rows j0+6 .. r_end-1 form the panel / trailing window
+    const int i0 = j0 + S;                       // rows i0 .. i0+5 enter the window at the end of this step
+    const bool incoming = i0 < n;
+    // P0: software prefetch of the incoming rows.
+    double pfb[PFB], pfw[PFW];
+    if (incoming) {
+#pragma unroll
+      for (int u = 0; u < PFB; ++u) { const int e = t + u * kFacThreads; if (e < 6 * S) pfb[u] = Lg[size_t(i0) * S + e]; }
+#pragma unroll
+      for (int u = 0; u < PFW; ++u) { const int e = t + u * kFacThreads; if (e < 6 * nbw) pfw[u] = Wg[size_t(i0) * nbw + e]; }
+    }
     // P1: factor the 6x6 diagonal block.
     if (t == 0) {
       double a[6][6];
-      for (int r = 0; r < 6; ++r) for (int c = 0; c <= r; ++c) a[r][c] = Wd[(jm + r) * S + jm + c];
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) a[r][c] = Wd[(jm + r) * S + jm + c];
       int fail = 0;
+#pragma unroll
       for (int c = 0; c < 6; ++c) {
         double d = a[c][c];
+#pragma unroll
         for (int k = 0; k < c; ++k) d -= a[c][k] * a[c][k];
         if (!(d > 0.0) || !isfinite(d)) { fail = 1; d = 1.0; }
-        d = sqrt(d);
-        a[c][c] = d;
-        const double inv = 1.0 / d;
+        const double inv = rsqrt(d);
+        a[c][c] = d * inv;
         Linv[c] = inv;
+#pragma unroll
         for (int r = c + 1; r < 6; ++r) {
-          double s = a[r][c];
-          for (int k = 0; k < c; ++k) s -= a[r][k] * a[c][k];
-          a[r][c] = s * inv;
+          double sacc = a[r][c];
+#pragma unroll
+          for (int k = 0; k < c; ++k) sacc -= a[r][k] * a[c][k];
+          a[r][c] = sacc * inv;
         }
       }
-      for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) Ld[r * 6 + c] = c <= r ? a[r][c] : 0.0;
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) Ld[r * 6 + c] = c <= r ? a[r][c] : 0.0;
       if (fail) s_fail = 1;
     }
     __syncthreads();
-    // P2a: panel rows r: L(r, j0+c) = (A(r, j0+c) - sum_{k<c} L(r, j0+k) Ld[c][k]) / Ld[c][c]
-    for (int r = j0 + 6 + t; r < r_end; r += kFacThreads) {
-      double* pr = Wd + (r % S) * S + jm;
-      double x[6];
-      for (int c = 0; c < 6; ++c) {
-        double s = pr[c];
-        for (int k = 0; k < c; ++k) s -= x[k] * Ld[c * 6 + k];
-        x[c] = s * Linv[c];
+    // P2a: panel rows r: L(r, j0+c) = (A(r, j0+c) - sum_{k<c} L(r, j0+k) Ld[c][k]) / Ld[c][c]; emit to HBM.
+    if (t < S - 6) {
+      const int r = j0 + 6 + t;
+      if (r < r_end) {
+        int rm = jm + 6 + t; if (rm >= S) rm -= S;
+        double* pr = Wd + rm * S + jm;
+        double x[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          double sacc = pr[c];
+#pragma unroll
+          for (int k = 0; k < c; ++k) sacc -= x[k] * Ld[c * 6 + k];
+          x[c] = sacc * Linv[c];
+        }
+#pragma unroll
+        for (int c = 0; c < 6; ++c) { pr[c] = x[c]; Lg[size_t(r) * S + (S - 1 - (r - j0 - c))] = x[c]; }
       }
-      for (int c = 0; c < 6; ++c) pr[c] = x[c];
+    } else if (t >= kFacThreads - 36) {
+      const int e = t - (kFacThreads - 36), r = e / 6, k = e % 6;   // diagonal block of the factor
+      if (k <= r) Lg[size_t(j0 + r) * S + (S - 1 - (r - k))] = Ld[e];
     }
-    // P2b: border rows j0..j0+5: forward-solve with the diagonal block, in place, and emit the finished rows.
-    for (int c = t; c < nbw; c += kFacThreads) {
-      double x[6];
-      for (int k = 0; k < 6; ++k) {
-        double s = Wr[(jm + k) * nbw + c];
-        for (int q = 0; q < k; ++q) s -= Ld[k * 6 + q] * x[q];
-        x[k] = s * Linv[k];
+    // P2b: border rows j0..j0+5: forward-solve with the diagonal block; results stay in registers for P3b.
+    double xb[2][6];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int c = t + u * kFacThreads;
+      if (c < nbw) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          double sacc = Wr[(jm + k) * nbw + c];
+#pragma unroll
+          for (int q = 0; q < k; ++q) sacc -= Ld[k * 6 + q] * xb[u][q];
+          xb[u][k] = sacc * Linv[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) Wg[size_t(j0 + k) * nbw + c] = xb[u][k];
       }
-      for (int k = 0; k < 6; ++k) { Wr[(jm + k) * nbw + c] = x[k]; sy.W[size_t(j0 + k) * nbw + c] = x[k]; }
     }
     __syncthreads();
-    // P3a: trailing update of the band window: A(r, c) -= sum_k L(r, j0+k) L(c, j0+k) for j0+6 <= c <= r < r_end.
-    {
-      const int nt = r_end - (j0 + 6);
-      for (int e = t; e < nt * nt; e += kFacThreads) {
-        const int rr = e / nt, cc = e % nt;
-        if (cc > rr) continue;
-        const int r = j0 + 6 + rr, c = j0 + 6 + cc;
-        const double* lr = Wd + (r % S) * S + jm;
-        const double* lc = Wd + (c % S) * S + jm;
-        double s = 0.0;
-        for (int k = 0; k < 6; ++k) s += lr[k] * lc[k];
-        Wd[(r % S) * S + (c % S)] -= s;
-      }
-      // P3b: border update: Wr(r, :) -= sum_k L(r, j0+k) w_k
-      for (int c = t; c < nbw; c += kFacThreads) {
-        double w6[6];
-        for (int k = 0; k < 6; ++k) w6[k] = Wr[(jm + k) * nbw + c];
-        for (int r = j0 + 6; r < r_end; ++r) {
-          const double* lr = Wd + (r % S) * S + jm;
-          double s = 0.0;
-          for (int k = 0; k < 6; ++k) s += lr[k] * w6[k];
-          Wr[(r % S) * nbw + c] -= s;
+    // P3a: trailing update of the band window, one entry per loop trip: A(r, c) -= sum_k L(r, j0+k) L(c, j0+k).
+    for (int e = t; e < NTB * 36; e += kFacThreads) {
+      const int blk = e / 36, w = e % 36;
+      const int a6 = w / 6, b6 = w % 6;
+      const int bi = blk_i[blk], bj = blk_j[blk];
+      const int rr = 6 * bi + a6, cc = 6 * bj + b6;
+      if (cc > rr || j0 + 6 + rr >= r_end) continue;
+      int rm = jm + 6 + rr; if (rm >= S) rm -= S;
+      int cm = jm + 6 + cc; if (cm >= S) cm -= S;
+      const double* lr = Wd + rm * S + jm;
+      const double* lc = Wd + cm * S + jm;
+      double sacc = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) sacc += lr[k] * lc[k];
+      Wd[rm * S + cm] -= sacc;
+    }
+    // P3b: border update, 6 rows per batch: Wr(r, :) -= sum_k L(r, j0+k) x_k.
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int c = t + u * kFacThreads;
+      if (c < nbw) {
+        for (int r = j0 + 6; r < r_end; r += 6) {
+          int rm = jm + (r - j0); if (rm >= S) rm -= S;
+          double acc[6];
+#pragma unroll
+          for (int v = 0; v < 6; ++v) acc[v] = Wr[(rm + v) * nbw + c];
+#pragma unroll
+          for (int v = 0; v < 6; ++v) {
+            const double* lr = Wd + (rm + v) * S + jm;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) acc[v] -= lr[k] * xb[u][k];
+          }
+#pragma unroll
+          for (int v = 0; v < 6; ++v) Wr[(rm + v) * nbw + c] = acc[v];
         }
       }
-      // P3c: emit the finished factor columns j0..j0+5 (diagonal block from Ld, panel from the window).
-      for (int e = t; e < (r_end - j0) * 6; e += kFacThreads) {
-        const int r = j0 + e / 6, k = e % 6;
-        const int col = j0 + k;
-        if (col > r) continue;
-        const double v = r < j0 + 6 ? Ld[(r - j0) * 6 + k] : Wd[(r % S) * S + jm + k];
-        sy.L[size_t(r) * S + (S - 1 - (r - col))] = v;
-      }
     }
-    __syncthreads();
-    // P4: rows j0+S .. j0+S+5 enter the window (they reuse the slots of the retired rows j0..j0+5).
-    {
-      const int i0 = j0 + S;
-      if (i0 < n) {
-        for (int e = t; e < 6 * S; e += kFacThreads) {
+    // P4: the prefetched rows take the slots of the retired rows j0..j0+5 (nobody reads those slots in P3).
+    if (incoming) {
+#pragma unroll
+      for (int u = 0; u < PFB; ++u) {
+        const int e = t + u * kFacThreads;
+        if (e < 6 * S) {
           const int i = i0 + e / S, d = e % S;
           const int j = i - (S - 1 - d);
-          Wd[(i % S) * S + (j % S)] = sy.L[size_t(i) * S + d];
+          Wd[(i % S) * S + (j % S)] = pfb[u];
         }
-        for (int e = t; e < 6 * nbw; e += kFacThreads) {
-          const int i = i0 + e / nbw, c = e % nbw;
-          Wr[(i % S) * nbw + c] = sy.W[size_t(i) * nbw + c];
-        }
+      }
+#pragma unroll
+      for (int u = 0; u < PFW; ++u) {
+        const int e = t + u * kFacThreads;
+        if (e < 6 * nbw) Wr[jm * nbw + e] = pfw[u];      // rows i0..i0+5 land in slots jm..jm+5, contiguous
       }
     }
     __syncthreads();
@@ -395,56 +454,75 @@ __global__ void __launch_bounds__(kRedThreads) reduced_solve_kernel(BandSys l2, 
 }
 
 // Back-substitution of one banded system: v = z - W[:, :nbw-1] * y[border], then L^T y = v (right-looking, 6 rows per step).
-// grid = systems, block = 256, dynamic shared memory: n doubles (v) + nbw doubles (border solution).
+// grid = systems, block = 256, dynamic shared memory: n doubles (v) + nbw doubles (border solution) + 2 * kBackRows * S
+// (factor rows, double-buffered: while one batch of kBackRows rows is being used, the next one is in flight in registers).
 constexpr int kBackThreads = 256;
+constexpr int kBackRows = 48;
+CB2_HD size_t backsolve_smem_bytes(int n, int nbw, int S) { return (size_t(n) + nbw + 2 * size_t(kBackRows) * S) * sizeof(double); }
 __global__ void __launch_bounds__(kBackThreads) band_backsolve_kernel(const BandSys* __restrict__ systems, double* __restrict__ ytil) {
   const BandSys sy = systems[blockIdx.x];
   const int n = sy.n, nbw = sy.nbw, S = sy.hb + 1, t = threadIdx.x;
   double* v = dyn_smem<double>();
   double* coef = v + n;
+  double* Lbuf = coef + nbw;
+  constexpr int PF = (kBackRows * 60 + kBackThreads - 1) / kBackThreads;   // S <= 60
+  const double* __restrict__ Lg = sy.L;
+  // First batch of factor rows goes straight to shared memory while the border product is computed.
+  int b_end = n, b_start = max(0, n - kBackRows);
+  for (int e = t; e < (b_end - b_start) * S; e += kBackThreads) Lbuf[e] = Lg[size_t(b_start) * S + e];
   for (int c = t; c < nbw - 1; c += kBackThreads) { const int g = sy.col_gidx[c]; coef[c] = g >= 0 ? ytil[g] : 0.0; }
   __syncthreads();
   const int warp = t >> 5, lane = t & 31;
   for (int i = warp; i < n; i += kBackThreads / 32) {
     const double* wr = sy.W + size_t(i) * nbw;
-    double s = 0.0;
-    for (int c = lane; c < nbw - 1; c += 32) s += wr[c] * coef[c];
-    for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
-    if (lane == 0) v[i] = wr[nbw - 1] - s;
+    double sacc = 0.0;
+    for (int c = lane; c < nbw - 1; c += 32) sacc += wr[c] * coef[c];
+    for (int off = 16; off > 0; off >>= 1) sacc += __shfl_down_sync(0xffffffffu, sacc, off);
+    if (lane == 0) v[i] = wr[nbw - 1] - sacc;
   }
   __syncthreads();
-  // Backward solve, 6 rows per step. The 6 factor rows of the NEXT step are prefetched into shared memory by the
-  // otherwise idle threads while thread 0 solves the 6x6 triangle of the current one.
-  __shared__ double Lb[2][6 * 60];
-  if (n >= 6) for (int e = t; e < 6 * S; e += kBackThreads) Lb[0][e] = sy.L[size_t(n - 6) * S + e];
-  __syncthreads();
   int buf = 0;
-  for (int i0 = n - 6; i0 >= 0; i0 -= 6, buf ^= 1) {
-    const double* Lc = Lb[buf];
-    if (t == 0) {
-      double y6[6];
-      for (int k = 5; k >= 0; --k) {
-        double s = v[i0 + k];
-        for (int q = k + 1; q < 6; ++q) s -= Lc[q * S + (S - 1 - (q - k))] * y6[q];
-        y6[k] = s / Lc[k * S + (S - 1)];
+  while (b_end > 0) {
+    const double* Lc = Lbuf + buf * kBackRows * S;
+    const int nb_end = b_start, nb_start = max(0, b_start - kBackRows);
+    double pf[PF];
+#pragma unroll
+    for (int u = 0; u < PF; ++u) { const int e = t + u * kBackThreads; if (e < (nb_end - nb_start) * S) pf[u] = Lg[size_t(nb_start) * S + e]; }
+    for (int i0 = b_end - 6; i0 >= b_start; i0 -= 6) {
+      const double* Lr = Lc + (i0 - b_start) * S;     // factor rows i0 .. i0+5
+      if (t == 0) {
+        double y6[6];
+#pragma unroll
+        for (int k = 5; k >= 0; --k) {
+          double sacc = v[i0 + k];
+#pragma unroll
+          for (int q = k + 1; q < 6; ++q) sacc -= Lr[q * S + (S - 1 - (q - k))] * y6[q];
+          y6[k] = sacc / Lr[k * S + (S - 1)];
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v[i0 + k] = y6[k];
       }
-      for (int k = 0; k < 6; ++k) v[i0 + k] = y6[k];
-    } else if (t >= 64 && i0 >= 6) {
-      for (int e = t - 64; e < 6 * S; e += kBackThreads - 64) Lb[buf ^ 1][e] = sy.L[size_t(i0 - 6) * S + e];
-    }
-    __syncthreads();
-    // v(tc) -= sum_k L(i0+k, tc) y(i0+k) for the columns tc < i0 reached by these rows
-    for (int l = t; l < S - 1; l += kBackThreads) {
-      const int tc = i0 - 1 - l;
-      if (tc < 0) continue;
-      double s = 0.0;
-      for (int k = 0; k < 6; ++k) {
-        const int d = k + 1 + l;           // row - col
-        if (d <= S - 1) s += Lc[k * S + (S - 1 - d)] * v[i0 + k];
+      __syncthreads();
+      // v(tc) -= sum_k L(i0+k, tc) y(i0+k) for the columns tc < i0 reached by these rows
+      if (t < S - 1) {
+        const int tc = i0 - 1 - t;
+        if (tc >= 0) {
+          double sacc = 0.0;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) {
+            const int d = k + 1 + t;           // row - col
+            if (d <= S - 1) sacc += Lr[k * S + (S - 1 - d)] * v[i0 + k];
+          }
+          v[tc] -= sacc;
+        }
       }
-      v[tc] -= s;
+      __syncthreads();
     }
+    double* Ln = Lbuf + (buf ^ 1) * kBackRows * S;
+#pragma unroll
+    for (int u = 0; u < PF; ++u) { const int e = t + u * kBackThreads; if (e < (nb_end - nb_start) * S) Ln[e] = pf[u]; }
     __syncthreads();
+    b_end = nb_end; b_start = nb_start; buf ^= 1;
   }
   for (int i = t; i < n; i += kBackThreads) ytil[sy.row_gidx[i]] = v[i];
 }

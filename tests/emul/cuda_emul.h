@@ -32,6 +32,8 @@ struct dim3 {
   dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
 
+struct alignas(16) double2 { double x, y; };
+
 namespace cb2emul {
 struct Tls { dim3 tIdx, bIdx, bDim, gDim; int linear_tid = 0; };
 inline Tls& tls() { static thread_local Tls t; return t; }

@@ -195,6 +195,12 @@ class CApi:
                 "stats_get": ([vp, C.c_void_p], C.c_int),
                 "set_sensor": ([vp, C.c_int, _dp, _dp, _dp, C.c_double], C.c_int),
             })
+            self.lib.cb2_comm_unique_id.argtypes = [_up]
+            self.lib.cb2_comm_unique_id.restype = C.c_int
+            self.lib.cb2_comm_init.argtypes = [vp, C.c_int, C.c_int, _up]
+            self.lib.cb2_comm_init.restype = C.c_int
+            self.lib.cb2_shard_plan.argtypes = [vp, C.c_int, C.c_int, _ip, _ip, _ip, _ip, _ip]
+            self.lib.cb2_shard_plan.restype = C.c_int
             self.lib.cb2_set_device.argtypes = [C.c_int]
             self.lib.cb2_set_device.restype = C.c_int
             self.lib.cb2_version.restype = C.c_char_p
@@ -299,6 +305,39 @@ class CApi:
     def set_device(self, device: int):
         if self.lib.cb2_set_device(int(device)) != OK:
             raise CalicoError(INTERNAL, f"cannot select CUDA device {device}")
+
+    def shard_plan(self, world: int, rank: int):
+        """(n_chunks, chunk_lo, chunk_hi, seg_lo, seg_hi) of rank `rank` of `world` (host-side plan, no GPU needed)."""
+        v = [C.c_int(0) for _ in range(5)]
+        self._check(self.lib.cb2_shard_plan(self.h, world, rank, *[C.byref(x) for x in v]))
+        return tuple(x.value for x in v)
+
+    def comm_init(self, world: int, rank: int, unique_id: bytes):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._check(self.lib.cb2_comm_init(self.h, world, rank, buf))
+
+    def comm_unique_id(self) -> bytes:
+        buf = (C.c_uint8 * 128)()
+        if self.lib.cb2_comm_unique_id(buf) != OK:
+            raise CalicoError(INTERNAL, "ncclGetUniqueId failed (is libnccl.so.2 loadable?)")
+        return bytes(buf)
+
+    def comm_init_torch(self, world: int, rank: int):
+        """NCCL communicator over the ranks of an initialised torch.distributed job: rank 0's unique id is broadcast."""
+        import torch
+        import torch.distributed as dist
+        t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(self.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, src=0)
+        self.comm_init(world, rank, bytes(t.cpu().numpy().tobytes()))
+
+    def comm_init_local(self, world: int, rank: int, group: str):
+        """Emulation build only (tests): ranks are host threads of this process."""
+        fn = self.lib.cb2_comm_init_local
+        fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
+        fn.restype = C.c_int
+        self._check(fn(self.h, world, rank, group.encode()))
 
     def version(self) -> str:
         return self.lib.cb2_version().decode()

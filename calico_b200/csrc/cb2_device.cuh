@@ -35,15 +35,20 @@ struct SensorDesc {
 
 struct EvalTile { int sensor, start, count; };
 
-// Scalars exchanged with the host once per LM iteration (device array of doubles).
+// Scalars exchanged with the host once per LM iteration (device array of doubles). With several ranks, slots [0, 3) and
+// [4, 11) are summed and slot 3 is max-reduced across ranks before the host reads them.
 enum Scal {
   kScCost = 0, kScInvalid = 1,            // cost at x (1/2 sum rho), number of residual blocks that failed to evaluate
-  kScCandCost = 2, kScCandInvalid = 3,    // same at the candidate point
-  kScGradMax = 4, kScGradNorm = 5,        // |x - Plus(x, -g)|_inf and _2  (trust_region_minimizer.cc, Ceres external)
+  kScGradSq = 2, kScGradMax = 3,          // |x - Plus(x, -g)|_2^2 and _inf  (trust_region_minimizer.cc, Ceres external)
+  kScCandCost = 4, kScCandInvalid = 5,    // same as slots 0, 1 at the candidate point
   kScSolveFail = 6,                       // > 0 when a Cholesky pivot was not positive / step not finite
   kScModelChange = 7,                     // model cost change of the computed step
   kScStepNorm2 = 8, kScXNorm2 = 9, kScCandXNorm2 = 10,
   kScCount = 16
 };
+
+// Ownership of a control point on this rank (time-range sharding): interiors of owned chunks are updated and
+// counted here; separators are replicated (updated everywhere, counted on rank 0 only); everything else belongs to a peer.
+enum { kCpPeer = 0, kCpOwned = 1, kCpShared = 2 };
 
 }  // namespace cb2

@@ -17,8 +17,16 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <memory>
 #include <unordered_map>
 #include <vector>
+#if defined(CB2_EMUL)
+#include <condition_variable>
+#include <map>
+#include <mutex>
+#else
+#include <dlfcn.h>
+#endif
 
 #include "../../include/calico_b200.h"
 #include "cb2_eval.cuh"
@@ -125,6 +133,96 @@ struct PhaseTimer {
   ~PhaseTimer() { for (auto e : pool) cudaEventDestroy(e); for (auto& pr : open_pairs) { cudaEventDestroy(pr.a); cudaEventDestroy(pr.b); } }
 };
 
+// ----------------------------------------------------------------------------------------------------------------
+// Cross-rank collectives (one process per GPU). The product uses NCCL, resolved at run time from the libnccl.so.2 the
+// process already has (torch's bundled copy) or the system one, so that single-GPU use has no NCCL dependency.
+// The SIMT-emulation test build replaces it by an in-process rendezvous between host threads.
+// ----------------------------------------------------------------------------------------------------------------
+struct Comm {
+  int world = 1, rank = 0;
+  virtual ~Comm() {}
+  virtual void allreduce_sum(double* buf, size_t n, cudaStream_t s) = 0;
+  virtual void allreduce_max(double* buf, size_t n, cudaStream_t s) = 0;
+};
+
+#if !defined(CB2_EMUL)
+struct NcclApi {
+  typedef struct { char internal[128]; } UniqueId;
+  typedef void* CommT;
+  int (*GetUniqueId)(UniqueId*) = nullptr;
+  int (*CommInitRank)(CommT*, int, UniqueId, int) = nullptr;
+  int (*CommDestroy)(CommT) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, CommT, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  void* handle = nullptr;
+  std::string error;
+  bool load() {
+    if (handle) return true;
+    const char* names[] = {std::getenv("CB2_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      if (!n) continue;
+      handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (handle) break;
+    }
+    if (!handle) { error = "cannot load libnccl.so.2 (set CB2_NCCL_LIB)"; return false; }
+    GetUniqueId = reinterpret_cast<decltype(GetUniqueId)>(dlsym(handle, "ncclGetUniqueId"));
+    CommInitRank = reinterpret_cast<decltype(CommInitRank)>(dlsym(handle, "ncclCommInitRank"));
+    CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(handle, "ncclCommDestroy"));
+    AllReduce = reinterpret_cast<decltype(AllReduce)>(dlsym(handle, "ncclAllReduce"));
+    GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(handle, "ncclGetErrorString"));
+    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce) { error = "libnccl is missing expected symbols"; return false; }
+    return true;
+  }
+};
+static NcclApi& nccl() { static NcclApi api; return api; }
+struct NcclComm : Comm {
+  NcclApi::CommT comm = nullptr;
+  ~NcclComm() override { if (comm) nccl().CommDestroy(comm); }
+  void check(int rc, const char* what) {
+    if (rc != 0) throw CudaFail{std::string("NCCL error in ") + what + ": " + (nccl().GetErrorString ? nccl().GetErrorString(rc) : "?")};
+  }
+  // ncclFloat64 = 8; ncclSum = 0, ncclMax = 2
+  void allreduce_sum(double* buf, size_t n, cudaStream_t s) override { check(nccl().AllReduce(buf, buf, n, 8, 0, comm, s), "allreduce(sum)"); }
+  void allreduce_max(double* buf, size_t n, cudaStream_t s) override { check(nccl().AllReduce(buf, buf, n, 8, 2, comm, s), "allreduce(max)"); }
+};
+#else
+// Test-only rendezvous: `world` host threads of one process, each driving its own handle, meet in every collective.
+struct LocalGroup {
+  std::mutex mu;
+  std::condition_variable cv;
+  int world = 0, arrived = 0, generation = 0;
+  std::vector<double*> bufs;
+  std::vector<double> result;
+};
+static std::mutex g_groups_mu;
+static std::map<std::string, LocalGroup*>& local_groups() { static std::map<std::string, LocalGroup*> m; return m; }
+struct LocalComm : Comm {
+  LocalGroup* grp = nullptr;
+  void reduce(double* buf, size_t n, bool is_max) {
+    std::unique_lock<std::mutex> lk(grp->mu);
+    const int gen = grp->generation;
+    if (grp->arrived == 0) grp->bufs.assign(world, nullptr);
+    grp->bufs[rank] = buf;
+    if (++grp->arrived == world) {
+      grp->result.assign(n, 0.0);
+      for (size_t i = 0; i < n; ++i) {
+        double v = grp->bufs[0][i];
+        for (int r = 1; r < world; ++r) v = is_max ? std::max(v, grp->bufs[r][i]) : v + grp->bufs[r][i];
+        grp->result[i] = v;
+      }
+      for (int r = 0; r < world; ++r) std::memcpy(grp->bufs[r], grp->result.data(), n * sizeof(double));
+      grp->arrived = 0;
+      ++grp->generation;
+      grp->cv.notify_all();
+    } else {
+      grp->cv.wait(lk, [&] { return grp->generation != gen; });
+    }
+  }
+  void allreduce_sum(double* buf, size_t n, cudaStream_t) override { reduce(buf, n, false); }
+  void allreduce_max(double* buf, size_t n, cudaStream_t) override { reduce(buf, n, true); }
+};
+#endif
+
 }  // namespace cb2
 
 using namespace cb2;
@@ -160,6 +258,15 @@ struct cb2_problem {
   DevBuf<int> d_c2off;
   DevBuf<CalibEntry> d_centries;
   DevBuf<double> d_segA, d_segG, d_segB, d_segC, d_segGc, d_Aband, d_Bmat, d_Cmat, d_grad, d_diag, d_scaling, d_dtil2, d_ytil;
+  // multi-GPU sharding: this rank owns the chunks [chunk_lo, chunk_hi) and the segments [g_lo, g_hi)
+  std::unique_ptr<Comm> comm;
+  int world = 1, rank = 0;
+  int chunk_lo = 0, chunk_hi = 0, g_lo = 0, g_hi = 0;
+  long total_blocks = 0, total_residuals = 0;    // over ALL ranks (summary counts)
+  DevBuf<unsigned char> d_cp_own;
+  DevBuf<int> d_shared_idx;
+  DevBuf<double> d_shared_buf, d_gradG, d_red;
+  int n_shared = 0;
   // Schur
   std::vector<ChunkPlan> chunks;
   std::vector<BandSys> h_l1;
@@ -167,7 +274,7 @@ struct cb2_problem {
   DevBuf<BandSys> d_l1;
   DevBuf<BandSys> d_l2;
   DevBuf<int> d_chunk_sys, d_rowidx, d_colidx;
-  DevBuf<double> d_L1, d_W1, d_T1, d_L2, d_W2, d_T2, d_Cw, d_rawdiag;
+  DevBuf<double> d_L1, d_W1, d_T1, d_T2, d_rawdiag;
   int cur = 0;   // which of the two parameter buffers holds x
   size_t smem_eval[3] = {0, 0, 0};
   int max_tilepairs1 = 0, max_ksplit1 = 1;
@@ -254,6 +361,8 @@ struct cb2_problem {
     n_seg = n_cp - (kK - 1);
     if (n_seg < 1) return fail(CB2_INVALID_ARGUMENT, "Trajectory has too few control points.");
     n_a = 6L * n_cp;
+    rc = plan_chunks();
+    if (rc != CB2_OK) return rc;
     // World points p_w = q_wm * p_m + t_wm.
     std::vector<double> pw;
     for (auto& b : bodies) {
@@ -271,6 +380,7 @@ struct cb2_problem {
     h_desc.assign(ns, SensorDesc{});
     h_state.assign(ns, SensorState{});
     std::vector<unsigned char> cp_ref(n_cp, 0);
+    total_blocks = total_residuals = 0;
     N_c = 0; csz = 0;
     std::vector<int> c2off(std::max(ns, 1), 0);
     std::vector<EvalTile> tiles;
@@ -292,10 +402,14 @@ struct cb2_problem {
           return fail(CB2_FAILED_PRECONDITION, "Attempted to create cost function from an observation for a rigidbody that does not exist in the world model.");   // camera.cpp:125-131
         const int sg = spline_index(s.stamp[o]);
         if (sg < 0 || sg >= n_seg) return fail(CB2_INVALID_ARGUMENT, "Observation stamp is outside the valid knots of the trajectory.");
+        for (int c = 0; c < kK; ++c) cp_ref[sg + c] = 1;          // referenced by some rank's residual block
+        ++total_blocks; total_residuals += m;
+        if (sg < g_lo || sg >= g_hi) continue;                     // another rank's time range
         seg_of[o] = sg;
         ++count[sg + 1];
         ++n_active;
       }
+      const bool ref_any = [&] { for (int o = 0; o < n; ++o) if (!(s.kind == kCamera && !s.outlier.empty() && s.outlier[o])) return true; return false; }();
       for (int g = 0; g < n_seg; ++g) count[g + 1] += count[g];
       std::vector<int> seg_start(count);
       s.perm.assign(n_active, 0);
@@ -312,14 +426,13 @@ struct cb2_problem {
         seg[i] = seg_of[o];
         for (int q = 0; q < m; ++q) meas[size_t(i) * m + q] = s.meas[size_t(o) * m + q];
         if (s.kind == kCamera) pt[i] = bodies[s.body_slot[o]].pw0 + s.feat_slot[o];
-        for (int c = 0; c < kK; ++c) cp_ref[seg_of[o] + c] = 1;
       }
       s.d_stamp.upload(stamp, h2d); s.d_meas.upload(meas, h2d); s.d_seg.upload(seg, h2d); s.d_pt.upload(pt, h2d);
       s.d_seg_start.upload(seg_start, h2d);
       // Unknown layout of this sensor (constant or unreferenced blocks drop out, as in Ceres's reduced program).
       SensorDesc& d = h_desc[si];
       d.kind = s.kind; d.model = s.model; d.ni = want; d.m = m; d.n_obs = n_active;
-      const bool ref = n_active > 0;
+      const bool ref = ref_any;   // referenced by a residual block on ANY rank: same unknown layout everywhere
       int u = 0;
       d.u_intr = (ref && s.en_intr) ? u : -1; if (d.u_intr >= 0) u += want;
       d.u_rot = (ref && s.en_extr) ? u : -1; if (d.u_rot >= 0) u += 3;
@@ -363,6 +476,14 @@ struct cb2_problem {
     d_ctrl0.upload(ctrl, h2d);
     d_knots.upload(knots, h2d); d_basis.upload(basis, h2d); d_pw.upload(pw, h2d);
     d_cp_ref.upload(cp_ref, h2d);
+    n_cp_referenced = 0;
+    for (auto v : cp_ref) n_cp_referenced += v;
+    {
+      std::vector<unsigned char> own(n_cp, kCpPeer);
+      for (int c = chunk_lo; c < chunk_hi; ++c) for (int i = chunks[c].a; i < chunks[c].b; ++i) own[i] = kCpOwned;
+      for (size_t c = 0; c + 1 < chunks.size(); ++c) for (int i = chunks[c].b; i < chunks[c].b + 5; ++i) own[i] = kCpShared;
+      d_cp_own.upload(own, h2d);
+    }
     d_scal.alloc(kScCount);
     cur = 0;
     // Normal-equation storage.
@@ -374,10 +495,13 @@ struct cb2_problem {
       for (int li = 0; li < d.n_calib; ++li) ce.push_back(CalibEntry{d.calib_off + li, d.calib_off + li, -1});
     }
     d_centries.upload(ce, h2d);
-    d_segA.alloc(size_t(n_seg) * 36 * 36); d_segG.alloc(size_t(n_seg) * 36);
-    d_segB.alloc(size_t(n_seg) * 36 * std::max(N_c, 1)); d_segC.alloc(size_t(n_seg) * std::max(csz, 1)); d_segGc.alloc(size_t(n_seg) * std::max(N_c, 1));
+    const size_t nsl = size_t(std::max(g_hi - g_lo, 1));
+    d_segA.alloc(nsl * 36 * 36); d_segG.alloc(nsl * 36);
+    d_segB.alloc(nsl * 36 * std::max(N_c, 1)); d_segC.alloc(nsl * std::max(csz, 1)); d_segGc.alloc(nsl * std::max(N_c, 1));
     d_Aband.alloc(size_t(n_a) * 36); d_Bmat.alloc(size_t(n_a) * std::max(N_c, 1)); d_Cmat.alloc(size_t(std::max(N_c, 1)) * std::max(N_c, 1));
     d_grad.alloc(n_tot); d_diag.alloc(n_tot); d_scaling.alloc(n_tot); d_dtil2.alloc(n_tot); d_ytil.alloc(n_tot);
+    d_Aband.zero(stream); d_Bmat.zero(stream); d_grad.zero(stream); d_ytil.zero(stream);
+    if (world > 1) d_gradG.alloc(n_tot);
     rc = plan_schur();
     if (rc != CB2_OK) return rc;
     set_kernel_attributes();
@@ -390,11 +514,14 @@ struct cb2_problem {
   // ------------------------------------------------------------------------------------------------------------
   // Chunk plan for the substructured Schur elimination (cb2_schur.cuh).
   // ------------------------------------------------------------------------------------------------------------
-  int plan_schur() {
+  // Global chunk plan (identical on every rank) and this rank's share of it: chunks [chunk_lo, chunk_hi), segments [g_lo, g_hi).
+  int plan_chunks() {
     int target = 110;   // interior control points per chunk (tuned on C4, profiles/)
     if (const char* e = std::getenv("CB2_CHUNK_CPS")) target = std::max(6, std::atoi(e));
     int P = std::max(1, (n_cp + 5) / (target + 5));
-    while (P > 1 && (n_cp - 5 * (P - 1)) / P < 6) --P;
+    P = (P + world - 1) / world * world;                       // same number of chunks on every rank
+    while (P > world && (n_cp - 5 * (P - 1)) / P < 6) P -= world;
+    if ((n_cp - 5 * (P - 1)) / P < 6 && P > 1) return fail(CB2_INVALID_ARGUMENT, "Trajectory too short to shard across this many GPUs.");
     const int interior = n_cp - 5 * (P - 1);
     chunks.clear();
     int a = 0;
@@ -403,61 +530,85 @@ struct cb2_problem {
       chunks.push_back(ChunkPlan{a, a + len});
       a += len + 5;
     }
+    const int per = P / world;
+    chunk_lo = rank * per; chunk_hi = chunk_lo + per;
+    // Segment g touches control points g..g+5. The separator after chunk c starts at control point chunks[c].b: segments
+    // below it belong to the left rank, segments from it on to the right rank.
+    g_lo = chunk_lo == 0 ? 0 : chunks[chunk_lo - 1].b;
+    g_hi = chunk_hi == P ? n_seg : chunks[chunk_hi - 1].b;
+    return CB2_OK;
+  }
+
+  // Device storage of the substructured Schur elimination (cb2_schur.cuh) for the owned chunks + the replicated separator level.
+  int plan_schur() {
+    const int P = int(chunks.size()), PL = chunk_hi - chunk_lo;
     const int nbw1 = 2 * kSepDim + N_c + 1, nbw2 = N_c + 1;
     const int n2 = kSepDim * (P - 1);
-    // index tables
     std::vector<int> rowidx, colidx;
-    std::vector<size_t> row_off(P + 1), col_off(P + 1);
+    std::vector<size_t> row_off(PL + 1), col_off(PL + 1);
     size_t Lsz = 0, Wsz = 0, Tsz = 0;
-    h_l1.assign(P, BandSys{});
+    h_l1.assign(PL, BandSys{});
     const int nt1 = (nbw1 + 63) / 64;
     max_tilepairs1 = nt1 * (nt1 + 1) / 2;
     max_ksplit1 = 1;
-    std::vector<size_t> Loff(P), Woff(P), Toff(P);
-    for (int p = 0; p < P; ++p) {
-      BandSys& sy = h_l1[p];
+    std::vector<size_t> Loff(PL), Woff(PL), Toff(PL);
+    for (int l = 0; l < PL; ++l) {
+      const int p = chunk_lo + l;
+      BandSys& sy = h_l1[l];
       sy.n = 6 * (chunks[p].b - chunks[p].a); sy.hb = 35; sy.nbw = nbw1;
-      sy.ksplit = std::max(1, std::min((sy.n + 63) / 64, (296 + P * max_tilepairs1 - 1) / (P * max_tilepairs1)));
+      sy.ksplit = std::max(1, std::min((sy.n + 63) / 64, (296 + PL * max_tilepairs1 - 1) / (PL * max_tilepairs1)));
       max_ksplit1 = std::max(max_ksplit1, sy.ksplit);
-      row_off[p] = rowidx.size();
+      row_off[l] = rowidx.size();
       for (int i = 0; i < sy.n; ++i) rowidx.push_back(6 * chunks[p].a + i);
-      col_off[p] = colidx.size();
+      col_off[l] = colidx.size();
       for (int j = 0; j < kSepDim; ++j) colidx.push_back(p > 0 ? 6 * (chunks[p].a - 5) + j : -1);
       for (int j = 0; j < kSepDim; ++j) colidx.push_back(p < P - 1 ? 6 * chunks[p].b + j : -1);
       for (int c = 0; c < N_c; ++c) colidx.push_back(int(n_a) + c);
-      Loff[p] = Lsz; Woff[p] = Wsz; Toff[p] = Tsz;
+      Loff[l] = Lsz; Woff[l] = Wsz; Toff[l] = Tsz;
       Lsz += size_t(sy.n) * 36; Wsz += size_t(sy.n) * nbw1; Tsz += size_t(sy.ksplit) * nbw1 * nbw1;
       if (backsolve_smem_bytes(sy.n, nbw1, 36) > 220 * 1024) return fail(CB2_INTERNAL, "Schur chunk too large for shared memory; lower CB2_CHUNK_CPS.");
+      if (nbw1 > 2 * kFacThreads) return fail(CB2_UNIMPLEMENTED, "Too many calibration unknowns for the band factor kernel.");
     }
     const size_t row_off2 = rowidx.size();
-    for (int p = 0; p + 1 < P; ++p) for (int j = 0; j < kSepDim; ++j) rowidx.push_back(6 * chunks[p].b + j);
+    std::vector<int> shared_idx;
+    for (int p = 0; p + 1 < P; ++p) for (int j = 0; j < kSepDim; ++j) { rowidx.push_back(6 * chunks[p].b + j); shared_idx.push_back(6 * chunks[p].b + j); }
+    for (int c = 0; c < N_c; ++c) shared_idx.push_back(int(n_a) + c);
+    n_shared = int(shared_idx.size());
     const size_t col_off2 = colidx.size();
     for (int c = 0; c < N_c; ++c) colidx.push_back(int(n_a) + c);
     d_rowidx.upload(rowidx); d_colidx.upload(colidx);
+    d_shared_idx.upload(shared_idx);
+    d_shared_buf.alloc(2 * size_t(std::max(n_shared, 1)));
     d_L1.alloc(Lsz); d_W1.alloc(Wsz); d_T1.alloc(Tsz);
-    for (int p = 0; p < P; ++p) {
-      BandSys& sy = h_l1[p];
-      sy.row_gidx = d_rowidx.p + row_off[p]; sy.col_gidx = d_colidx.p + col_off[p];
-      sy.L = d_L1.p + Loff[p]; sy.W = d_W1.p + Woff[p]; sy.T = d_T1.p + Toff[p];
+    for (int l = 0; l < PL; ++l) {
+      BandSys& sy = h_l1[l];
+      sy.row_gidx = d_rowidx.p + row_off[l]; sy.col_gidx = d_colidx.p + col_off[l];
+      sy.L = d_L1.p + Loff[l]; sy.W = d_W1.p + Woff[l]; sy.T = d_T1.p + Toff[l];
     }
     d_l1.upload(h_l1);
     h_l2 = BandSys{};
     h_l2.n = n2; h_l2.hb = 59; h_l2.nbw = nbw2;
     const int nt2 = (nbw2 + 63) / 64;
     h_l2.ksplit = std::max(1, std::min((n2 + 63) / 64, (148 + nt2 * (nt2 + 1) / 2 - 1) / (nt2 * (nt2 + 1) / 2)));
-    d_L2.alloc(size_t(std::max(n2, 1)) * 60); d_W2.alloc(size_t(std::max(n2, 1)) * nbw2); d_T2.alloc(size_t(h_l2.ksplit) * nbw2 * nbw2);
+    // The separator system and the calibration system live in ONE buffer: it is what the ranks sum (one allreduce per LM solve).
+    const size_t szL2 = size_t(n2) * 60, szW2 = size_t(n2) * nbw2, szCw = size_t(N_c + 1) * (N_c + 1);
+    d_red.alloc(szL2 + szW2 + szCw + 1);
+    d_T2.alloc(size_t(h_l2.ksplit) * nbw2 * nbw2);
     h_l2.row_gidx = d_rowidx.p + row_off2; h_l2.col_gidx = d_colidx.p + col_off2;
-    h_l2.L = d_L2.p; h_l2.W = d_W2.p; h_l2.T = d_T2.p;
+    h_l2.L = d_red.p; h_l2.W = d_red.p + szL2; h_l2.T = d_T2.p;
+    red_Cw = d_red.p + szL2 + szW2;
+    red_count = szL2 + szW2 + szCw;
     d_l2.upload(std::vector<BandSys>(1, h_l2));
-    std::vector<int> chunk_sys(P);
-    for (int p = 0; p < P; ++p) chunk_sys[p] = p;
+    std::vector<int> chunk_sys(P, -1);
+    for (int l = 0; l < PL; ++l) chunk_sys[chunk_lo + l] = l;
     d_chunk_sys.upload(chunk_sys);
-    d_Cw.alloc(size_t(N_c + 1) * (N_c + 1));
     d_rawdiag.alloc(size_t(std::max(n2, 1)) + std::max(N_c, 1));
     const size_t smem_f1 = (36 * 36 + 36 * size_t(nbw1)) * sizeof(double), smem_f2 = (60 * 60 + 60 * size_t(nbw2)) * sizeof(double);
     if (smem_f1 > 227 * 1024 || smem_f2 > 227 * 1024) return fail(CB2_UNIMPLEMENTED, "Too many calibration unknowns for the shared-memory Schur kernels.");
     return CB2_OK;
   }
+  double* red_Cw = nullptr;
+  size_t red_count = 0;
 
   void set_kernel_attributes() {
 #ifndef CB2_EMUL
@@ -508,24 +659,36 @@ struct cb2_problem {
     timer.end(kPhJacobian, stream);
     timer.begin(kPhNormal, stream);
     const int ns = int(sensors.size());
-    CB2_K(accumulate_kernel, n_seg, kAccThreads, 0, stream, d_desc.p, ns, N_c, d_c2off.p, csz, d_segA.p, d_segG.p, d_segB.p, d_segC.p, d_segGc.p);
+    const int nsl = g_hi - g_lo;
+    if (nsl > 0) CB2_K(accumulate_kernel, nsl, kAccThreads, 0, stream, d_desc.p, ns, N_c, g_lo, d_c2off.p, csz, d_segA.p, d_segG.p, d_segB.p, d_segC.p, d_segGc.p);
     const long total = n_a * 36 + n_a * N_c + n_a;
-    CB2_K(assemble_band_kernel, int(std::min<long>((total + 255) / 256, 148 * 16)), 256, 0, stream, n_cp, n_seg, N_c, d_segA.p, d_segG.p, d_segB.p,
+    CB2_K(assemble_band_kernel, int(std::min<long>((total + 255) / 256, 148 * 16)), 256, 0, stream, n_cp, g_lo, g_hi, N_c, d_segA.p, d_segG.p, d_segB.p,
           d_Aband.p, d_Bmat.p, d_grad.p);
     if (N_c > 0) {
       d_Cmat.zero(stream);
       const int ne = int(d_centries.n);
-      CB2_K(assemble_calib_kernel, (ne + 31) / 32, dim3(32, 8), 0, stream, n_seg, N_c, csz, ne, d_centries.p, d_segC.p, d_segGc.p, d_Cmat.p, d_grad.p + n_a);
+      CB2_K(assemble_calib_kernel, (ne + 31) / 32, dim3(32, 8), 0, stream, nsl, N_c, csz, ne, d_centries.p, d_segC.p, d_segGc.p, d_Cmat.p, d_grad.p + n_a);
     }
     CB2_K(hess_diag_kernel, int(std::min<long>((n_tot + 255) / 256, 1024)), 256, 0, stream, n_a, N_c, d_Aband.p, d_Cmat.p, d_diag.p);
-    CB2_K(gradient_norm_kernel, 1, kLmThreads, 0, stream, n_a, d_grad.p, d_desc.p, d_state[cur].p, ns, d_scal.p);
+    if (world > 1) {
+      // Separator rows and calibration receive contributions from several ranks: sum their gradient and Hessian diagonal
+      // (needed for the gradient norms, the Jacobi scaling and the LM damping); d_grad itself stays rank-local.
+      CB2_CUDA(cudaMemcpyAsync(d_gradG.p, d_grad.p, sizeof(double) * n_tot, cudaMemcpyDeviceToDevice, stream));
+      CB2_K(pack_shared_kernel, (n_shared + 255) / 256, 256, 0, stream, n_shared, d_shared_idx.p, d_gradG.p, d_diag.p, d_shared_buf.p);
+      comm->allreduce_sum(d_shared_buf.p, 2 * size_t(n_shared), stream);
+      CB2_K(unpack_shared_kernel, (n_shared + 255) / 256, 256, 0, stream, n_shared, d_shared_idx.p, d_shared_buf.p, d_gradG.p, d_diag.p);
+    }
+    CB2_K(gradient_norm_kernel, 1, kLmThreads, 0, stream, n_a, gradG(), d_cp_own.p, rank == 0 ? 1 : 0, d_desc.p, d_state[cur].p, ns, d_scal.p);
+    if (world > 1) { comm->allreduce_sum(d_scal.p + kScCost, 3, stream); comm->allreduce_max(d_scal.p + kScGradMax, 1, stream); }
     timer.end(kPhNormal, stream);
     ++stats.jacobian_sweeps;
   }
 
+  const double* gradG() const { return world > 1 ? d_gradG.p : d_grad.p; }   // gradient with cross-rank sums on the shared rows
+
   // One LM linear solve + candidate point + candidate cost. Everything is enqueued; the caller syncs once.
   void launch_step(double radius, const cb2_options& opt) {
-    const int P = int(chunks.size());
+    const int P = int(chunks.size()), PL = chunk_hi - chunk_lo;
     const int ns = int(sensors.size());
     const int blocks = int(std::min<long>((n_tot + 255) / 256, 1024));
     timer.begin(kPhSchur, stream);
@@ -534,35 +697,41 @@ struct cb2_problem {
     const int nbw1 = h_l1[0].nbw;
     int max_n1 = 0;
     for (const auto& sy : h_l1) max_n1 = std::max(max_n1, sy.n);
-    CB2_K(gather_level1_kernel, dim3(std::max(1, std::min(64, (max_n1 * (36 + nbw1) + 255) / 256)), P), 256, 0, stream, d_l1.p, n_a, N_c, d_Aband.p,
+    CB2_K(gather_level1_kernel, dim3(std::max(1, std::min(64, (max_n1 * (36 + nbw1) + 255) / 256)), PL), 256, 0, stream, d_l1.p, n_a, N_c, d_Aband.p,
           d_Bmat.p, d_Cmat.p, d_grad.p, d_dtil2.p);
     const size_t smem_f1 = (36 * 36 + 36 * size_t(nbw1)) * sizeof(double);
-    CB2_K((band_factor_kernel<6>), P, kFacThreads, smem_f1, stream, d_l1.p, d_scal.p);
-    CB2_K(border_gram_kernel, dim3(max_tilepairs1, P, max_ksplit1), dim3(16, 16), 0, stream, d_l1.p);
+    CB2_K((band_factor_kernel<6>), PL, kFacThreads, smem_f1, stream, d_l1.p, d_scal.p);
+    CB2_K(border_gram_kernel, dim3(max_tilepairs1, PL, max_ksplit1), dim3(16, 16), 0, stream, d_l1.p);
+    // Separator + calibration systems: rank-local direct terms minus the Schur terms of the owned chunks, summed across ranks.
     if (h_l2.n > 0) {
       const long tot2 = long(h_l2.n) * (60 + h_l2.nbw);
       CB2_K(level2_build_kernel, int(std::min<long>((tot2 + 255) / 256, 1024)), 256, 0, stream, h_l2, d_l1.p, d_chunk_sys.p, P, n_a, N_c, d_Aband.p,
             d_Bmat.p, d_Cmat.p, d_grad.p, d_rawdiag.p);
+    }
+    if (N_c > 0) {
+      const long tot3 = long(N_c + 1) * (N_c + 1);
+      CB2_K(level3_build_kernel, int(std::min<long>((tot3 + 255) / 256, 1024)), 256, 0, stream, d_l1.p, PL, n_a, N_c, d_Cmat.p, d_grad.p, red_Cw,
+            d_rawdiag.p + std::max(h_l2.n, 1));
+    }
+    if (world > 1 && red_count > 0) comm->allreduce_sum(d_red.p, red_count, stream);   // THE data-path collective of an LM iteration
+    if (h_l2.n > 0) {
       CB2_K(level2_damp_kernel, (h_l2.n + 255) / 256, 256, 0, stream, h_l2, d_dtil2.p);
       const size_t smem_f2 = (60 * 60 + 60 * size_t(h_l2.nbw)) * sizeof(double);
       CB2_K((band_factor_kernel<10>), 1, kFacThreads, smem_f2, stream, d_l2.p, d_scal.p);
       const int nt2 = (h_l2.nbw + 63) / 64;
       CB2_K(border_gram_kernel, dim3(nt2 * (nt2 + 1) / 2, 1, h_l2.ksplit), dim3(16, 16), 0, stream, d_l2.p);
     }
-    if (N_c > 0) {
-      const long tot3 = long(N_c + 1) * (N_c + 1);
-      CB2_K(level3_build_kernel, int(std::min<long>((tot3 + 255) / 256, 1024)), 256, 0, stream, d_l1.p, P, n_a, N_c, d_Cmat.p, d_grad.p, d_Cw.p,
-            d_rawdiag.p + std::max(h_l2.n, 1));
-      CB2_K(reduced_solve_kernel, 1, kRedThreads, size_t(N_c + 1) * (kRedPanel + 1) * sizeof(double), stream, h_l2, N_c, n_a, d_Cw.p, d_dtil2.p,
+    if (N_c > 0)
+      CB2_K(reduced_solve_kernel, 1, kRedThreads, size_t(N_c + 1) * (kRedPanel + 1) * sizeof(double), stream, h_l2, N_c, n_a, red_Cw, d_dtil2.p,
             d_ytil.p, d_scal.p);
-    }
     if (h_l2.n > 0) CB2_K(band_backsolve_kernel, 1, kBackThreads, backsolve_smem_bytes(h_l2.n, h_l2.nbw, 60), stream, d_l2.p, d_ytil.p);
-    CB2_K(band_backsolve_kernel, P, kBackThreads, backsolve_smem_bytes(max_n1, nbw1, 36), stream, d_l1.p, d_ytil.p);
-    CB2_K(apply_step_kernel, 1, kLmThreads, 0, stream, n_a, d_ytil.p, d_grad.p, d_dtil2.p, d_cp_ref.p, d_ctrl[cur].p, d_ctrl[cur ^ 1].p, d_desc.p,
-          d_state[cur].p, d_state[cur ^ 1].p, ns, N_c, d_scal.p);
+    CB2_K(band_backsolve_kernel, PL, kBackThreads, backsolve_smem_bytes(max_n1, nbw1, 36), stream, d_l1.p, d_ytil.p);
+    CB2_K(apply_step_kernel, 1, kLmThreads, 0, stream, n_a, d_ytil.p, gradG(), d_dtil2.p, d_cp_ref.p, d_cp_own.p, rank == 0 ? 1 : 0, d_ctrl[cur].p,
+          d_ctrl[cur ^ 1].p, d_desc.p, d_state[cur].p, d_state[cur ^ 1].p, ns, N_c, d_scal.p);
     timer.end(kPhSchur, stream);
     timer.begin(kPhCost, stream);
     launch_eval<kModeCost>(cur ^ 1, kScCandCost);
+    if (world > 1) comm->allreduce_sum(d_scal.p + kScCandCost, 7, stream);
     timer.end(kPhCost, stream);
   }
 
@@ -598,9 +767,8 @@ struct cb2_problem {
     nblocks += n_cp; nparams += 6 * n_cp; neff += 6 * n_cp;
     for (const auto& s : sensors) { nblocks += 4; nparams += int(s.intr.size()) + 8; neff += int(s.intr.size()) + 7; }
     S.num_parameter_blocks = nblocks; S.num_parameters = nparams; S.num_effective_parameters = neff;
-    int rb = 0, rr = 0, pbr = 0, pr = 0, per = 0;
+    int rb = int(total_blocks), rr = int(total_residuals), pbr = 0, pr = 0, per = 0;
     for (const auto& d : h_desc) {
-      rb += d.n_obs; rr += d.n_obs * d.m;
       if (d.u_intr >= 0) { ++pbr; pr += d.ni; per += d.ni; }
       if (d.u_rot >= 0) { pbr += 2; pr += 7; per += 6; }
       if (d.u_lat >= 0) { ++pbr; ++pr; ++per; }
@@ -617,16 +785,10 @@ struct cb2_problem {
     const double t_start = now_s();
     std::memset(&S, 0, sizeof(S));
     S.termination_type = CB2_FAILURE;
-    {
-      std::vector<unsigned char> ref;
-      d_cp_ref.download(ref);
-      n_cp_referenced = 0;
-      for (auto v : ref) n_cp_referenced += v;
-    }
     fill_summary_counts(S);
     auto msg = [&](const char* fmt, double a = 0, double b = 0) { std::snprintf(S.message, sizeof S.message, fmt, a, b); };
     L.clear();
-    if (num_active_blocks() == 0 || n_cp_referenced == 0) {
+    if (total_blocks == 0 || n_cp_referenced == 0) {
       S.termination_type = CB2_CONVERGENCE;
       msg("Function tolerance reached. No non-constant parameter blocks found.");
       S.total_time = now_s() - t_start;
@@ -652,7 +814,7 @@ struct cb2_problem {
       x_cost = h_scal[kScCost];
       it.cost = x_cost;
       it.gradient_max_norm = h_scal[kScGradMax];
-      it.gradient_norm = h_scal[kScGradNorm];
+      it.gradient_norm = std::sqrt(h_scal[kScGradSq]);
       return true;
     };
 
@@ -761,6 +923,14 @@ struct cb2_problem {
 
   // Device -> host write-back of the optimised parameters (the reference mutates the user's objects in place).
   void download_parameters() {
+    if (world > 1) {
+      // Every rank holds its own interiors + the separators; one sum of the masked vectors gives everybody the full trajectory.
+      double* tmp = d_ctrl[cur ^ 1].p;
+      CB2_K(mask_ctrl_kernel, int(std::min<long>((n_a + 255) / 256, 1024)), 256, 0, stream, n_a, d_cp_own.p, rank == 0 ? 1 : 0, d_ctrl[cur].p, tmp);
+      comm->allreduce_sum(tmp, size_t(n_a), stream);
+      CB2_CUDA(cudaMemcpyAsync(d_ctrl[cur].p, tmp, sizeof(double) * n_a, cudaMemcpyDeviceToDevice, stream));
+      CB2_CUDA(cudaStreamSynchronize(stream));
+    }
     d_ctrl[cur].download(ctrl, &stats.d2h_bytes);
     d_state[cur].download(h_state, &stats.d2h_bytes);
     for (size_t si = 0; si < sensors.size(); ++si) {
@@ -1002,6 +1172,7 @@ int cb2_cost(cb2_problem* p, double* cost, int* ok) {
   try {
     if (!p->uploaded) { const int rc = p->upload(); if (rc != CB2_OK) return rc; }
     p->launch_eval<kModeCost>(p->cur, kScCost);
+    if (p->world > 1) p->comm->allreduce_sum(p->d_scal.p + kScCost, 2, p->stream);
     p->sync_scalars();
     *cost = p->h_scal[kScCost];
     *ok = p->h_scal[kScInvalid] > 0 ? 0 : 1;
@@ -1056,12 +1227,76 @@ int cb2_reset_parameters(cb2_problem* p) {
 int cb2_stats_reset(cb2_problem* p) { p->stats = cb2_stats{}; for (auto& v : p->phase_ms) v = 0.0; return CB2_OK; }
 int cb2_stats_get(cb2_problem* p, cb2_stats* out) { *out = p->stats; return CB2_OK; }
 
-// Multi-GPU entry points are provided by cb2_comm.cu when built with NCCL support.
-int cb2_comm_unique_id(uint8_t* id128) { (void)id128; return CB2_UNIMPLEMENTED; }
-int cb2_comm_init(cb2_problem* p, int world_size, int rank, const uint8_t* id128) {
+// ---- multi-GPU: one process per GPU; call cb2_set_device first, then cb2_comm_init on every rank before cb2_upload/optimize ----
+int cb2_comm_unique_id(uint8_t* id128) {
+#if defined(CB2_EMUL)
   (void)id128;
-  if (world_size == 1 && rank == 0) return CB2_OK;
-  return p->fail(CB2_UNIMPLEMENTED, "Multi-GPU sharding is not built into this library yet.");
+  return CB2_UNIMPLEMENTED;
+#else
+  if (!nccl().load()) return CB2_INTERNAL;
+  NcclApi::UniqueId id;
+  if (nccl().GetUniqueId(&id) != 0) return CB2_INTERNAL;
+  std::memcpy(id128, &id, sizeof id);
+  return CB2_OK;
+#endif
+}
+int cb2_comm_init(cb2_problem* p, int world_size, int rank, const uint8_t* id128) {
+  if (world_size < 1 || rank < 0 || rank >= world_size) return p->fail(CB2_INVALID_ARGUMENT, "Invalid world size / rank.");
+  p->uploaded = false;
+  if (world_size == 1) { p->comm.reset(); p->world = 1; p->rank = 0; return CB2_OK; }
+#if defined(CB2_EMUL)
+  (void)id128;
+  return p->fail(CB2_UNIMPLEMENTED, "The emulation build has no NCCL; use cb2_comm_init_local.");
+#else
+  try {
+    if (!nccl().load()) return p->fail(CB2_INTERNAL, nccl().error);
+    const int rc0 = p->ensure_device();
+    if (rc0 != CB2_OK) return rc0;
+    std::unique_ptr<NcclComm> c(new NcclComm());
+    c->world = world_size; c->rank = rank;
+    NcclApi::UniqueId id;
+    std::memcpy(&id, id128, sizeof id);
+    c->check(nccl().CommInitRank(&c->comm, world_size, id, rank), "ncclCommInitRank");
+    p->comm = std::move(c);
+    p->world = world_size; p->rank = rank;
+    return CB2_OK;
+  } catch (const CudaFail& f) {
+    return p->fail(CB2_INTERNAL, f.msg);
+  }
+#endif
+}
+#if defined(CB2_EMUL)
+// Test hook of the emulation build: ranks are host threads of one process that meet in the group named `group`.
+int cb2_comm_init_local(cb2_problem* p, int world_size, int rank, const char* group) {
+  p->uploaded = false;
+  std::unique_ptr<LocalComm> c(new LocalComm());
+  c->world = world_size; c->rank = rank;
+  {
+    std::lock_guard<std::mutex> lk(g_groups_mu);
+    LocalGroup*& g = local_groups()[group];
+    if (!g) { g = new LocalGroup(); g->world = world_size; }
+    c->grp = g;
+  }
+  p->comm = std::move(c);
+  p->world = world_size; p->rank = rank;
+  return CB2_OK;
+}
+#endif
+// The shard this rank takes of a trajectory with n_cp control points (host-side plan only; no device needed):
+// chunks [chunk_lo, chunk_hi) of n_chunks, spline segments [seg_lo, seg_hi).
+int cb2_shard_plan(cb2_problem* p, int world_size, int rank, int* n_chunks, int* chunk_lo, int* chunk_hi, int* seg_lo, int* seg_hi) {
+  if (p->ctrl.empty()) return p->fail(CB2_FAILED_PRECONDITION, "Trajectory has not been set.");
+  if (world_size < 1 || rank < 0 || rank >= world_size) return p->fail(CB2_INVALID_ARGUMENT, "Invalid world size / rank.");
+  const int w0 = p->world, r0 = p->rank;
+  p->world = world_size; p->rank = rank;
+  p->n_cp = int(p->ctrl.size() / 6); p->n_seg = p->n_cp - (kK - 1);
+  const int rc = p->plan_chunks();
+  if (rc == CB2_OK) {
+    *n_chunks = int(p->chunks.size()); *chunk_lo = p->chunk_lo; *chunk_hi = p->chunk_hi; *seg_lo = p->g_lo; *seg_hi = p->g_hi;
+  }
+  p->world = w0; p->rank = r0;
+  p->uploaded = false;
+  return rc;
 }
 
 }  // extern "C"

@@ -48,14 +48,19 @@ CB2_D double block_max(double v, double* sh) {
   return sh[0];
 }
 
-// gradient_max_norm / gradient_norm = |x - Plus(x, -g)|_inf / _2 over the reduced parameter vector (ambient coordinates).
-__global__ void __launch_bounds__(kLmThreads) gradient_norm_kernel(long n_a, const double* __restrict__ grad, const SensorDesc* __restrict__ sensors,
+// gradient_max_norm / gradient_norm^2 = |x - Plus(x, -g)|_inf / _2^2 over the part of the reduced parameter vector this rank
+// counts (ambient coordinates): owned control points everywhere, shared control points and calibration where count_shared.
+__global__ void __launch_bounds__(kLmThreads) gradient_norm_kernel(long n_a, const double* __restrict__ grad, const unsigned char* __restrict__ cp_own,
+                                                                   int count_shared, const SensorDesc* __restrict__ sensors,
                                                                    const SensorState* __restrict__ states, int n_sensors, double* __restrict__ scal) {
   __shared__ double sh[kLmThreads];
   const int t = threadIdx.x;
   double mx = 0.0, sq = 0.0;
-  for (long i = t; i < n_a; i += kLmThreads) { const double g = grad[i]; mx = fmax(mx, fabs(g)); sq += g * g; }
-  for (int s = t; s < n_sensors; s += kLmThreads) {
+  for (long i = t; i < n_a; i += kLmThreads) {
+    const int own = cp_own[i / 6];
+    if (own == kCpOwned || (own == kCpShared && count_shared)) { const double g = grad[i]; mx = fmax(mx, fabs(g)); sq += g * g; }
+  }
+  if (count_shared) for (int s = t; s < n_sensors; s += kLmThreads) {
     const SensorDesc& sd = sensors[s];
     const double* gc = grad + n_a + sd.calib_off;
     for (int j = 0; j < sd.n_calib; ++j) {
@@ -71,15 +76,17 @@ __global__ void __launch_bounds__(kLmThreads) gradient_norm_kernel(long n_a, con
   }
   const double tot = block_sum(sq, sh);
   const double m = block_max(mx, sh);
-  if (t == 0) { scal[kScGradMax] = m; scal[kScGradNorm] = sqrt(tot); }
+  if (t == 0) { scal[kScGradMax] = m; scal[kScGradSq] = tot; }
 }
 
-// Candidate point x_cand = Plus(x, -ytil) (ctrl and every non-constant sensor block), with
+// Candidate point x_cand = Plus(x, -ytil) (owned + shared control points and every non-constant sensor block), with the part
+// this rank counts of
 //   step_norm^2 = |x - x_cand|^2, x_norm^2 = |x|^2, cand_x_norm^2 (ambient, reduced program only: cp_ref marks control
 //   points referenced by at least one residual block), the model cost change 1/2 ytil.(g + Dtil^2 ytil)
 //   (== -(J step)^T (r + J step / 2) for the exact solution of the damped system) and a finiteness check of the step.
 __global__ void __launch_bounds__(kLmThreads) apply_step_kernel(long n_a, const double* __restrict__ ytil, const double* __restrict__ grad,
                                                                 const double* __restrict__ dtil2, const unsigned char* __restrict__ cp_ref,
+                                                                const unsigned char* __restrict__ cp_own, int count_shared,
                                                                 const double* __restrict__ ctrl, double* __restrict__ ctrl_cand,
                                                                 const SensorDesc* __restrict__ sensors, const SensorState* __restrict__ states,
                                                                 SensorState* __restrict__ states_cand, int n_sensors, int N_c,
@@ -88,42 +95,48 @@ __global__ void __launch_bounds__(kLmThreads) apply_step_kernel(long n_a, const 
   const int t = threadIdx.x;
   double step2 = 0.0, x2 = 0.0, c2 = 0.0, model = 0.0, bad = 0.0;
   for (long i = t; i < n_a; i += kLmThreads) {
-    const double y = ytil[i], x = ctrl[i];
+    const int own = cp_own[i / 6];
+    const double x = ctrl[i];
+    if (own == kCpPeer) { ctrl_cand[i] = x; continue; }
+    const double y = ytil[i];
     const double xn = x - y;
     ctrl_cand[i] = xn;
     if (!isfinite(y)) bad = 1.0;
-    model += y * (grad[i] + dtil2[i] * y);
-    if (cp_ref[i / 6]) { step2 += (x - xn) * (x - xn); x2 += x * x; c2 += xn * xn; }
+    if (own == kCpOwned || count_shared) {
+      model += y * (grad[i] + dtil2[i] * y);
+      if (cp_ref[i / 6]) { step2 += (x - xn) * (x - xn); x2 += x * x; c2 += xn * xn; }
+    }
   }
   for (long j = t; j < N_c; j += kLmThreads) {
     const double y = ytil[n_a + j];
     if (!isfinite(y)) bad = 1.0;
-    model += y * (grad[n_a + j] + dtil2[n_a + j] * y);
+    if (count_shared) model += y * (grad[n_a + j] + dtil2[n_a + j] * y);
   }
+  const double cs = count_shared ? 1.0 : 0.0;
   for (int s = t; s < n_sensors; s += kLmThreads) {
     const SensorDesc& sd = sensors[s];
     SensorState S = states[s];
     const double* y = ytil + n_a + sd.calib_off;
     if (sd.u_intr >= 0) for (int j = 0; j < sd.ni; ++j) {
       const double x = S.intr[j], xn = x - y[sd.u_intr + j];
-      S.intr[j] = xn; step2 += (x - xn) * (x - xn); x2 += x * x; c2 += xn * xn;
+      S.intr[j] = xn; step2 += cs * (x - xn) * (x - xn); x2 += cs * x * x; c2 += cs * xn * xn;
     }
     if (sd.u_rot >= 0) {
       const Q4 q = S.q;
       const Q4 p = quat_plus(q, v3(-y[sd.u_rot], -y[sd.u_rot + 1], -y[sd.u_rot + 2]));
       S.q = p;
-      step2 += (q.x - p.x) * (q.x - p.x) + (q.y - p.y) * (q.y - p.y) + (q.z - p.z) * (q.z - p.z) + (q.w - p.w) * (q.w - p.w);
-      x2 += q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
-      c2 += p.x * p.x + p.y * p.y + p.z * p.z + p.w * p.w;
+      step2 += cs * ((q.x - p.x) * (q.x - p.x) + (q.y - p.y) * (q.y - p.y) + (q.z - p.z) * (q.z - p.z) + (q.w - p.w) * (q.w - p.w));
+      x2 += cs * (q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+      c2 += cs * (p.x * p.x + p.y * p.y + p.z * p.z + p.w * p.w);
     }
     if (sd.u_trans >= 0) {
       const V3 x = S.t;
       const V3 xn = v3(x.x - y[sd.u_trans], x.y - y[sd.u_trans + 1], x.z - y[sd.u_trans + 2]);
-      S.t = xn; step2 += dot(x - xn, x - xn); x2 += dot(x, x); c2 += dot(xn, xn);
+      S.t = xn; step2 += cs * dot(x - xn, x - xn); x2 += cs * dot(x, x); c2 += cs * dot(xn, xn);
     }
     if (sd.u_lat >= 0) {
       const double x = S.latency, xn = x - y[sd.u_lat];
-      S.latency = xn; step2 += (x - xn) * (x - xn); x2 += x * x; c2 += xn * xn;
+      S.latency = xn; step2 += cs * (x - xn) * (x - xn); x2 += cs * x * x; c2 += cs * xn * xn;
     }
     states_cand[s] = S;
   }
@@ -131,6 +144,25 @@ __global__ void __launch_bounds__(kLmThreads) apply_step_kernel(long n_a, const 
   if (t == 0) {
     scal[kScStepNorm2] = a; scal[kScXNorm2] = b; scal[kScCandXNorm2] = c; scal[kScModelChange] = 0.5 * d;
     if (e > 0.0) scal[kScSolveFail] += 1.0;
+  }
+}
+
+// Multi-rank glue: pack / unpack the entries of (gradient, Hessian diagonal) that several ranks contribute to — separator rows
+// and calibration — around one cross-rank sum. idx[i] = global unknown index of packed entry i.
+__global__ void __launch_bounds__(256) pack_shared_kernel(int n, const int* __restrict__ idx, const double* __restrict__ grad,
+                                                          const double* __restrict__ diag, double* __restrict__ buf) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { buf[i] = grad[idx[i]]; buf[n + i] = diag[idx[i]]; }
+}
+__global__ void __launch_bounds__(256) unpack_shared_kernel(int n, const int* __restrict__ idx, const double* __restrict__ buf,
+                                                            double* __restrict__ grad, double* __restrict__ diag) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { grad[idx[i]] = buf[i]; diag[idx[i]] = buf[n + i]; }
+}
+// Final control-point exchange: keep what this rank is responsible for, zero the rest, then sum across ranks.
+__global__ void __launch_bounds__(256) mask_ctrl_kernel(long n_a, const unsigned char* __restrict__ cp_own, int count_shared,
+                                                        const double* __restrict__ ctrl, double* __restrict__ out) {
+  for (long i = long(blockIdx.x) * blockDim.x + threadIdx.x; i < n_a; i += long(gridDim.x) * blockDim.x) {
+    const int own = cp_own[i / 6];
+    out[i] = (own == kCpOwned || (own == kCpShared && count_shared)) ? ctrl[i] : 0.0;
   }
 }
 

@@ -47,12 +47,12 @@ CB2_D void cp_async_wait() {
 
 struct AccCursor { int s, r0; };
 
-__global__ void __launch_bounds__(kAccThreads) accumulate_kernel(const SensorDesc* __restrict__ sensors, int n_sensors, int N_c,
+__global__ void __launch_bounds__(kAccThreads) accumulate_kernel(const SensorDesc* __restrict__ sensors, int n_sensors, int N_c, int g_lo,
                                                                  const int* __restrict__ c2off, int csz, double* __restrict__ segA,
                                                                  double* __restrict__ segG, double* __restrict__ segB,
                                                                  double* __restrict__ segC, double* __restrict__ segGc) {
   __shared__ __align__(16) double tile[2][kAccRows * kAccW];
-  const int g = blockIdx.x, t = threadIdx.x;
+  const int gl = blockIdx.x, g = g_lo + gl, t = threadIdx.x;   // gl: index into this rank's partial buffers, g: segment
   const bool has_tile = t < kAccTiles;
   int ti = 0, tj = 0;
   if (has_tile) { int rem = t; while (rem > ti) { rem -= ti + 1; ++ti; } tj = rem; }
@@ -134,12 +134,12 @@ __global__ void __launch_bounds__(kAccThreads) accumulate_kernel(const SensorDes
           if (I == kAccRcol) {                    // residual row
             if (Jx < kCpCols) continue;          // control-point gradient: accumulated over all sensors
             const int lc = Jx - kCpCols;
-            if (Jx < kAccRcol && lc < nc) segGc[size_t(g) * N_c + sd.calib_off + lc] = acc[a][b];
+            if (Jx < kAccRcol && lc < nc) segGc[size_t(gl) * N_c + sd.calib_off + lc] = acc[a][b];
           } else if (I < kAccRcol) {              // calibration row
             const int li = I - kCpCols;
             if (li < nc) {
-              if (Jx < kCpCols) segB[(size_t(g) * kCpCols + Jx) * N_c + sd.calib_off + li] = acc[a][b];
-              else if (Jx <= I) segC[size_t(g) * csz + c2off[s] + li * nc + (Jx - kCpCols)] = acc[a][b];
+              if (Jx < kCpCols) segB[(size_t(gl) * kCpCols + Jx) * N_c + sd.calib_off + li] = acc[a][b];
+              else if (Jx <= I) segC[size_t(gl) * csz + c2off[s] + li * nc + (Jx - kCpCols)] = acc[a][b];
             }
           }
           acc[a][b] = 0.0;
@@ -154,18 +154,18 @@ __global__ void __launch_bounds__(kAccThreads) accumulate_kernel(const SensorDes
 #pragma unroll
         for (int b = 0; b < 6; ++b) {
           const int I = 6 * ti + a, Jx = 6 * tj + b;
-          if (Jx <= I) segA[(size_t(g) * kCpCols + I) * kCpCols + Jx] = acc[a][b];
+          if (Jx <= I) segA[(size_t(gl) * kCpCols + I) * kCpCols + Jx] = acc[a][b];
         }
     } else if (ti == 9 && tj < 6) {
 #pragma unroll
-      for (int b = 0; b < 6; ++b) segG[size_t(g) * kCpCols + 6 * tj + b] = acc[kAccRcol - 54][b];
+      for (int b = 0; b < 6; ++b) segG[size_t(gl) * kCpCols + 6 * tj + b] = acc[kAccRcol - 54][b];
     }
   }
 }
 
 // Banded A (lower band, A(i,j) at Aband[i*36 + 35 - (i-j)]), dense border Bmat[6 n_cp][N_c] and the control-point part of
-// the gradient, from the per-segment partials. Control point c belongs to segments c-5..c.
-__global__ void __launch_bounds__(256) assemble_band_kernel(int n_cp, int n_seg, int N_c, const double* __restrict__ segA,
+// the gradient, from the per-segment partials of this rank's segments [g_lo, g_hi). Control point c belongs to segments c-5..c.
+__global__ void __launch_bounds__(256) assemble_band_kernel(int n_cp, int g_lo, int g_hi, int N_c, const double* __restrict__ segA,
                                                             const double* __restrict__ segG, const double* __restrict__ segB,
                                                             double* __restrict__ Aband, double* __restrict__ Bmat, double* __restrict__ grad) {
   const long n = 6L * n_cp;
@@ -178,24 +178,24 @@ __global__ void __launch_bounds__(256) assemble_band_kernel(int n_cp, int n_seg,
       double s = 0.0;
       if (j >= 0) {
         const int ci = i / 6, cj = j / 6;
-        const int g0 = max(ci - 5, 0), g1 = min(cj, n_seg - 1);
-        for (int g = g0; g <= g1; ++g) s += segA[(size_t(g) * kCpCols + (i - 6 * g)) * kCpCols + (j - 6 * g)];
+        const int g0 = max(ci - 5, g_lo), g1 = min(cj, g_hi - 1);
+        for (int g = g0; g <= g1; ++g) s += segA[(size_t(g - g_lo) * kCpCols + (i - 6 * g)) * kCpCols + (j - 6 * g)];
       }
       Aband[idx] = s;
     } else if (idx < nA + nB) {
       const long e = idx - nA;
       const int i = int(e / N_c), c = int(e % N_c);
       const int ci = i / 6;
-      const int g0 = max(ci - 5, 0), g1 = min(ci, n_seg - 1);
+      const int g0 = max(ci - 5, g_lo), g1 = min(ci, g_hi - 1);
       double s = 0.0;
-      for (int g = g0; g <= g1; ++g) s += segB[(size_t(g) * kCpCols + (i - 6 * g)) * N_c + c];
+      for (int g = g0; g <= g1; ++g) s += segB[(size_t(g - g_lo) * kCpCols + (i - 6 * g)) * N_c + c];
       Bmat[e] = s;
     } else {
       const int i = int(idx - nA - nB);
       const int ci = i / 6;
-      const int g0 = max(ci - 5, 0), g1 = min(ci, n_seg - 1);
+      const int g0 = max(ci - 5, g_lo), g1 = min(ci, g_hi - 1);
       double s = 0.0;
-      for (int g = g0; g <= g1; ++g) s += segG[size_t(g) * kCpCols + (i - 6 * g)];
+      for (int g = g0; g <= g1; ++g) s += segG[size_t(g - g_lo) * kCpCols + (i - 6 * g)];
       grad[i] = s;
     }
   }

@@ -150,6 +150,10 @@ int cb2_get_residuals(cb2_problem* p, int sensor_id, double* residuals, uint8_t*
 int cb2_comm_unique_id(uint8_t* id128);
 int cb2_comm_init(cb2_problem* p, int world_size, int rank, const uint8_t* id128);
 int cb2_set_device(int device);
+/* Host-side shard plan (no device needed): the chunks [chunk_lo, chunk_hi) of n_chunks and the spline segments
+ * [seg_lo, seg_hi) whose observations rank `rank` of `world_size` evaluates. Every rank is handed the whole problem and keeps
+ * its shard; in multi-GPU mode cb2_get_residuals / cb2_evaluate_sensor cover the local shard only. */
+int cb2_shard_plan(cb2_problem* p, int world_size, int rank, int* n_chunks, int* chunk_lo, int* chunk_hi, int* seg_lo, int* seg_hi);
 
 /* ---- bench accounting ---- */
 int cb2_stats_reset(cb2_problem* p);

@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -46,8 +47,11 @@ struct Block {
 inline Block& blk() { static Block b; return b; }
 inline unsigned char* dyn_smem_base() { return blk().dyn; }
 
+inline std::mutex& launch_mutex() { static std::mutex m; return m; }
+
 template <class F>
 void launch(dim3 grid, dim3 block, size_t smem, F&& f) {
+  std::lock_guard<std::mutex> launch_lock(launch_mutex());   // one emulated kernel at a time (several host threads = ranks)
   const int nt = int(block.x * block.y * block.z);
   const long nb = long(grid.x) * grid.y * grid.z;
   if (nt <= 0 || nb <= 0) return;

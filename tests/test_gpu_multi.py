@@ -1,0 +1,78 @@
+"""Multi-GPU parity (needs >= 2 GPUs; skipped on a single-GPU box): one process per GPU, NCCL, time-range sharding.
+Every rank must reproduce the oracle's LM trajectory and end with the full optimised trajectory."""
+import os
+
+import numpy as np
+import pytest
+
+from calico_b200 import _capi, synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def _worker(rank, world, port, lib, cfg, chunk, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    if chunk:
+        os.environ["CB2_CHUNK_CPS"] = chunk
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from oracle import oracle_py
+    truth, prob = synthetic.generate(cfg, oracle_py.oracle_api, noise=True)
+    a = _capi.CApi(lib)
+    a.set_device(rank)
+    pa = prob.clone()
+    ids = pa.push(a)
+    a.comm_init_torch(world, rank)
+    summ, log = a.optimize(_capi.Options(minimizer_progress_to_stdout=0))
+    pa.pull(a, ids)
+    out = {"rank": rank, "term": summ.termination_type, "costs": [it.cost for it in log], "ok": [it.step_is_successful for it in log],
+           "ctrl": pa.spline.ctrl.copy(), "intr": [s.intr.copy() for s in pa.sensors], "launches": a.stats().kernel_launches}
+    if rank == 0:
+        o = oracle_py.oracle_api()
+        po = prob.clone()
+        ido = po.push(o)
+        so, lo = o.optimize(oracle_py.OracleOptions(linear_solver=1, num_threads=os.cpu_count() or 1))
+        po.pull(o, ido)
+        out["oracle"] = {"term": so.termination_type, "costs": [it.cost for it in lo], "ok": [it.step_is_successful for it in lo],
+                         "ctrl": po.spline.ctrl.copy(), "intr": [s.intr.copy() for s in po.sensors]}
+    q.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs at least 2 GPUs")
+@pytest.mark.parametrize("world,cfg,chunk", [(2, "small", "9"), (2, "tiny", "6"), (4, "small", "7")])
+def test_multi_gpu_lm_matches_oracle(world, cfg, chunk, product_lib, oracle):
+    if _ngpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, product_lib, cfg, chunk, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    ref = next(o for o in outs if "oracle" in o)["oracle"]
+    for o in outs:
+        assert o["launches"] > 0
+        assert o["term"] == ref["term"]
+        assert o["ok"] == ref["ok"]
+        np.testing.assert_allclose(o["costs"], ref["costs"], rtol=1e-6)
+        np.testing.assert_allclose(o["ctrl"], ref["ctrl"], rtol=1e-6, atol=1e-6)
+        for a, b in zip(o["intr"], ref["intr"]):
+            np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-9)

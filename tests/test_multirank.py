@@ -1,0 +1,130 @@
+"""The N > 1 path without GPUs.
+
+1. world_size-2 `gloo` job: each rank asks the product library for its shard (cb2_shard_plan, host-side), evaluates ITS
+   observations with the oracle, and the ranks' costs / block counts are summed with torch.distributed — they must equal the
+   unsharded totals (every observation is owned by exactly one rank; separators are the only shared unknowns).
+2. The full multi-rank LM (rank-local sweeps, chunk elimination, the one cross-rank sum of the separator + calibration system,
+   scalar reductions, final trajectory exchange) in the SIMT-emulation build with ranks as host threads, against the oracle."""
+import os
+import sys
+import threading
+
+import numpy as np
+import pytest
+
+from calico_b200 import _capi, spline as sp, synthetic
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "emul"))
+
+
+def _gloo_worker(rank, world, port, lib, q):
+    import torch.distributed as dist
+    import torch
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle_py
+    truth, prob = synthetic.generate("tiny", oracle_py.oracle_api, noise=True)
+    a = _capi.CApi(lib)
+    prob.clone().push(a)
+    n_chunks, c_lo, c_hi, g_lo, g_hi = a.shard_plan(world, rank)
+    shard = prob.clone()
+    kept = 0
+    for s in shard.sensors:
+        seg = sp.spline_index(prob.spline.valid_knots, s.stamp)
+        m = (seg >= g_lo) & (seg < g_hi)
+        kept += int(m.sum())
+        for name in ("stamp", "meas", "image_id", "model_id", "feature_id", "seq"):
+            v = getattr(s, name)
+            if v is not None:
+                setattr(s, name, np.asarray(v)[m])
+    o = oracle_py.oracle_api()
+    shard.push(o)
+    cost, ok = o.cost()
+    t = torch.tensor([cost, float(kept), float(c_hi - c_lo)], dtype=torch.float64)
+    dist.all_reduce(t)
+    o2 = oracle_py.oracle_api()
+    prob.clone().push(o2)
+    full, _ = o2.cost()
+    if rank == 0:
+        q.put((t.tolist(), full, prob.counts()[0], n_chunks, (g_lo, g_hi)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_shards_partition_the_observations_gloo(product_lib, oracle, monkeypatch):
+    import torch.multiprocessing as mp
+    monkeypatch.setenv("CB2_CHUNK_CPS", "6")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, product_lib, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    (cost_sum, kept_sum, chunk_sum), full, nblocks, n_chunks, _ = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert kept_sum == nblocks
+    assert chunk_sum == n_chunks and n_chunks % 2 == 0
+    assert abs(cost_sum - full) <= 1e-12 * full
+
+
+def test_shard_plan_properties(product_lib, oracle):
+    """Chunks tile the control points with 5-point separators between them; segment ranges tile [0, n_seg)."""
+    truth, prob = synthetic.generate("small", oracle.oracle_api, noise=False)
+    a = _capi.CApi(product_lib)
+    prob.clone().push(a)
+    n_seg = prob.spline.ctrl.shape[0] - 5
+    for world in (1, 2, 3, 4):
+        hi_prev, c_prev = 0, 0
+        for rank in range(world):
+            n_chunks, c_lo, c_hi, g_lo, g_hi = a.shard_plan(world, rank)
+            assert n_chunks % world == 0 and c_hi - c_lo == n_chunks // world
+            assert c_lo == c_prev and g_lo == hi_prev and g_hi > g_lo
+            hi_prev, c_prev = g_hi, c_hi
+        assert hi_prev == n_seg and c_prev == n_chunks
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("world,cfg,iters", [(2, "tiny", 3), (3, "small", 2)])
+def test_emulated_multirank_lm_matches_oracle(world, cfg, iters, oracle, monkeypatch):
+    import build as emul_build
+    lib = emul_build.build()
+    monkeypatch.setenv("CB2_CHUNK_CPS", "6")
+    truth, prob = synthetic.generate(cfg, oracle.oracle_api, noise=True)
+    o = oracle.oracle_api()
+    po = prob.clone()
+    ids_o = po.push(o)
+    sum_o, log_o = o.optimize(oracle.OracleOptions(linear_solver=1, max_num_iterations=iters))
+    po.pull(o, ids_o)
+    results, errors = [None] * world, []
+
+    def run(rank):
+        try:
+            a = _capi.CApi(lib)
+            pa = prob.clone()
+            ids = pa.push(a)
+            a.comm_init_local(world, rank, f"grp{world}")
+            s, lg = a.optimize(_capi.Options(minimizer_progress_to_stdout=0, max_num_iterations=iters))
+            pa.pull(a, ids)
+            results[rank] = (s, lg, pa)
+        except Exception as e:   # noqa: BLE001
+            errors.append(e)
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for s, lg, pa in results:
+        assert s.num_residual_blocks == sum_o.num_residual_blocks
+        assert len(lg) == len(log_o)
+        for x, y in zip(lg, log_o):
+            assert abs(x.cost - y.cost) <= 1e-9 * y.cost
+            assert abs(x.gradient_max_norm - y.gradient_max_norm) <= 1e-7 * y.gradient_max_norm
+            assert abs(x.step_norm - y.step_norm) <= 1e-7 * max(y.step_norm, 1e-12)
+        np.testing.assert_allclose(pa.spline.ctrl, po.spline.ctrl, rtol=1e-8, atol=1e-9)    # full trajectory on every rank
+        for s1, s2 in zip(pa.sensors, po.sensors):
+            np.testing.assert_allclose(s1.intr, s2.intr, rtol=1e-8, atol=1e-9)

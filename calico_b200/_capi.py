@@ -199,6 +199,8 @@ class CApi:
             self.lib.cb2_comm_unique_id.restype = C.c_int
             self.lib.cb2_comm_init.argtypes = [vp, C.c_int, C.c_int, _up]
             self.lib.cb2_comm_init.restype = C.c_int
+            self.lib.cb2_comm_clone.argtypes = [vp, vp]
+            self.lib.cb2_comm_clone.restype = C.c_int
             self.lib.cb2_shard_plan.argtypes = [vp, C.c_int, C.c_int, _ip, _ip, _ip, _ip, _ip]
             self.lib.cb2_shard_plan.restype = C.c_int
             self.lib.cb2_set_device.argtypes = [C.c_int]
@@ -315,6 +317,9 @@ class CApi:
     def comm_init(self, world: int, rank: int, unique_id: bytes):
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         self._check(self.lib.cb2_comm_init(self.h, world, rank, buf))
+
+    def comm_clone(self, other: "CApi"):
+        self._check(self.lib.cb2_comm_clone(self.h, other.h))
 
     def comm_unique_id(self) -> bytes:
         buf = (C.c_uint8 * 128)()

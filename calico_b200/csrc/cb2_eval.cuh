@@ -65,10 +65,24 @@ __global__ void __launch_bounds__(kTile, CB2_EVAL_MINBLOCKS) eval_kernel(const S
       double rho0, rho1;
       loss_eval(S.loss_type, S.loss_scale, sq, &rho0, &rho1);
       cost = 0.5 * rho0;
-      if (MODE == kModeJacobian) rc.put(rec_rs(KIND), apply_loss ? sqrt(rho1) : 1.0);
+      if (MODE == kModeJacobian) {
+        // Loss corrector (rho'' <= 0 for Huber/Cauchy): residual and Jacobian rows are both scaled by sqrt(rho'). Folded
+        // into the derivative fields here so that the expansion phase is a pure sum of products.
+        const double rs = apply_loss ? sqrt(rho1) : 1.0;
+        if (rs != 1.0) {
+          constexpr int d0 = (KIND == kCamera) ? int(CamRec::G0) : (KIND == kGyroscope ? int(GyrRec::G0) : int(AccRec::G0));
+          constexpr int d1 = (KIND == kCamera) ? int(CamRec::w0) : (KIND == kGyroscope ? int(GyrRec::w0) : int(AccRec::w0));
+          constexpr int ji = (KIND == kCamera) ? int(CamRec::Ji) : (KIND == kGyroscope ? int(GyrRec::Ji) : int(AccRec::Ji));
+          for (int f = 0; f < m; ++f) rc.put(f, rs * rc.get(f));
+          for (int f = d0; f < d1; ++f) rc.put(f, rs * rc.get(f));
+          for (int f = ji; f < ji + m * S.ni; ++f) rc.put(f, rs * rc.get(f));
+        }
+      }
     } else {
       bad = 1;
+      if (MODE == kModeJacobian) { const int nf = rec_size(KIND, S.ni); for (int f = 0; f < nf; ++f) rc.put(f, 0.0); }   // rows of zeros
     }
+    if (MODE == kModeJacobian) for (int q = 0; q < m; ++q) sd.r[o * m + q] = rc.get(q);
     if (MODE == kModeResiduals) {
       for (int q = 0; q < m; ++q) sd.r[o * m + q] = ok ? rc.get(q) : 0.0;
       sd.valid[o] = ok ? 1 : 0;
@@ -89,49 +103,58 @@ __global__ void __launch_bounds__(kTile, CB2_EVAL_MINBLOCKS) eval_kernel(const S
     invalid_partial[blockIdx.x] = b;
   }
   if (MODE == kModeJacobian) {
-    // Phase 2. Lane l owns elements idx = l + 32 k of every m x jw row block; which two record fields each element multiplies
-    // does not depend on the observation, so the field offsets are computed once per thread and the per-observation loop is
-    // shared-memory loads, FMAs and one coalesced store per element.
+    // Phase 2. Every Jacobian entry is sum_q rec[fa_q] * rec[fb_q] with (fa, fb) depending only on the position inside the
+    // m x jw row block: a small table in shared memory. Each warp then streams the CONTIGUOUS region holding the row blocks
+    // of its 32 observations (32 * m * jw doubles, a multiple of 256 bytes from a 256-byte aligned start), so every warp store
+    // instruction writes one fully aligned 256-byte line: no partial sectors.
     constexpr int NQ = (KIND == kCamera) ? 1 : (KIND == kGyroscope ? 2 : 3);
-    constexpr int KMAX = (KIND == kCamera) ? 4 : 6;     // ceil(m * (36 + 19) / 32)
-    const int warp = t >> 5, lane = t & 31;
+    constexpr int kMaxRow = 3 * (kCpCols + kMaxCalib);
+    __shared__ __align__(16) int2 tab[NQ][kMaxRow];
     const int jw = sd.jw, ni = sd.ni;
     const int rowlen = m * jw;
-    int oa[KMAX][NQ], ob[KMAX][NQ];
-    bool live[KMAX];
-#pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      const int idx = lane + 32 * k;
-      live[k] = idx < rowlen;
-      int fa[3], fb[3];
-      const int row = live[k] ? idx / jw : 0;
-      const int j = live[k] ? idx - row * jw : 0;
+    for (int idx = t; idx < rowlen; idx += kTile) {
+      const int row = idx / jw, j = idx - row * jw;
       const int canon = j < kCpCols ? j : kCpCols + sd.jcanon[j - kCpCols];
+      int fa[3], fb[3];
       jac_terms(KIND, ni, row, canon, fa, fb);
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) { oa[k][q] = fa[q] * kRecStride; ob[k][q] = fb[q] * kRecStride; }
+      for (int q = 0; q < NQ; ++q) { int2 e; e.x = fa[q] * kRecStride; e.y = fb[q] * kRecStride; tab[q][idx] = e; }
     }
-    double* __restrict__ Jbase = sd.J;
-    double* __restrict__ rbase = sd.r;
-    const int rs_off = rec_rs(KIND) * kRecStride;
-    for (int oo = 0; oo < 32; ++oo) {
-      const int lt = warp * 32 + oo;
-      if (lt >= tl.count) break;
-      const size_t o = size_t(tl.start) + lt;
-      const bool okb = s_ok[lt] != 0;
-      const double* __restrict__ rb = rec + lt;
-      const double rs = rb[rs_off];
-      double* __restrict__ Jrow = Jbase + o * rowlen;
+    __syncthreads();
+    const int warp = t >> 5, lane = t & 31;
+    const int nobs = min(32, tl.count - warp * 32);
+    if (nobs > 0) {
+      const int total = nobs * rowlen;
+      double* __restrict__ Jw = sd.J + (size_t(tl.start) + warp * 32) * rowlen;
+      const double* __restrict__ rb = rec + warp * 32;
+      if ((rowlen & 1) == 0) {
+        // Even row blocks (camera, gyroscope): two consecutive entries per lane, one 16-byte store; 512 bytes per warp store.
+        int idx = 2 * lane, ol = 0;
+        while (idx >= rowlen) { idx -= rowlen; ++ol; }
+        for (int e = 2 * lane; e < total; e += 64) {
+          double v0 = 0.0, v1 = 0.0;
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k) {
-        if (live[k]) {
+          for (int q = 0; q < NQ; ++q) {
+            const int4 d = *reinterpret_cast<const int4*>(&tab[q][idx]);     // entries idx, idx + 1 (idx is even)
+            v0 += rb[d.x + ol] * rb[d.y + ol];
+            v1 += rb[d.z + ol] * rb[d.w + ol];
+          }
+          double2 v; v.x = v0; v.y = v1;
+          *reinterpret_cast<double2*>(Jw + e) = v;
+          idx += 64;
+          while (idx >= rowlen) { idx -= rowlen; ++ol; }
+        }
+      } else {
+        int idx = lane, ol = 0;
+        for (int e = lane; e < total; e += 32) {
           double v = 0.0;
 #pragma unroll
-          for (int q = 0; q < NQ; ++q) v += rb[oa[k][q]] * rb[ob[k][q]];
-          Jrow[lane + 32 * k] = okb ? rs * v : 0.0;
+          for (int q = 0; q < NQ; ++q) { const int2 d = tab[q][idx]; v += rb[d.x + ol] * rb[d.y + ol]; }
+          Jw[e] = v;
+          idx += 32;
+          if (idx >= rowlen) { idx -= rowlen; ++ol; }
         }
       }
-      if (lane < m) rbase[o * m + lane] = okb ? rs * rb[lane * kRecStride] : 0.0;
     }
   }
 }

@@ -110,18 +110,33 @@ struct SensorState {  // one sensor's parameters, as Ceres sees them
 };
 
 // ---- camera: r = (pixel - Project(intr, p_c)) / sigma,  p_c = R_rc^T (R_rw (p_w - t_wr) - t_rc) ----
-template <bool kJac>
-CB2_HD bool camera_block(const SensorState& S, const double* __restrict__ M, double knot0, double knot1, const double* __restrict__ cp,
-                         double stamp, double px, double py, const V3& p_w, const Rec& out) {
+// Everything that depends only on (sensor, stamp) — basis weights, spline pose and its time derivative, R_rw, J_l(phi), R_rc^T —
+// is shared by all corners of one image (25..144 residual blocks). It is computed once per image into a FRAME RECORD
+// (camera_frame) and each residual block only does the point-specific part (camera_block_from_frame).
+struct FrameRec { enum { w0 = 0, P1 = 6, R_rw = 12, Jl = 21, t_wr = 30, R_cr = 33, kSize = 44 }; };   // doubles, padded to 16 bytes
+
+CB2_HD void camera_frame(const SensorState& S, const double* __restrict__ M, double knot0, double knot1, const double* __restrict__ cp,
+                         double stamp, double* __restrict__ fr) {
   double w[2][kK];
   spline_weights<2>(M, knot0, knot1, stamp - S.latency, w);
-  double P0[6];
+  double P0[6], P1[6];
   spline_combine(w[0], cp, 0, 6, P0);
+  spline_combine(w[1], cp, 0, 6, P1);
   const V3 phi = v3(-P0[0], -P0[1], -P0[2]);
-  const V3 t_wr = v3(P0[3], P0[4], P0[5]);
   const SO3Coef c = so3_coef(phi);
   const M3 R_rw = so3_exp(phi, c);
+  const M3 Jl = so3_jacobian(phi, c);
   const M3 R_cr = quat_matrix(quat_inverse(S.q));   // R_rc^T
+  for (int i = 0; i < 6; ++i) { fr[FrameRec::w0 + i] = w[0][i]; fr[FrameRec::P1 + i] = P1[i]; }
+  for (int i = 0; i < 9; ++i) { fr[FrameRec::R_rw + i] = R_rw.m[i]; fr[FrameRec::Jl + i] = Jl.m[i]; fr[FrameRec::R_cr + i] = R_cr.m[i]; }
+  fr[FrameRec::t_wr] = P0[3]; fr[FrameRec::t_wr + 1] = P0[4]; fr[FrameRec::t_wr + 2] = P0[5];
+}
+
+template <bool kJac>
+CB2_HD bool camera_block_from_frame(const SensorState& S, const double* __restrict__ fr, double px, double py, const V3& p_w, const Rec& out) {
+  M3 R_rw, R_cr;
+  for (int i = 0; i < 9; ++i) { R_rw.m[i] = fr[FrameRec::R_rw + i]; R_cr.m[i] = fr[FrameRec::R_cr + i]; }
+  const V3 t_wr = v3(fr[FrameRec::t_wr], fr[FrameRec::t_wr + 1], fr[FrameRec::t_wr + 2]);
   const V3 a = R_rw * (p_w - t_wr);
   const V3 b = a - S.t;
   const V3 pc = R_cr * b;
@@ -131,9 +146,9 @@ CB2_HD bool camera_block(const SensorState& S, const double* __restrict__ M, dou
   if (!isfinite(r0) || !isfinite(r1)) return false;
   out.put(CamRec::r, r0); out.put(CamRec::r + 1, r1);
   if (kJac) {
-    double P1[6];
-    spline_combine(w[1], cp, 0, 6, P1);
-    const M3 AJ = skew(a) * so3_jacobian(phi, c);
+    M3 Jl;
+    for (int i = 0; i < 9; ++i) Jl.m[i] = fr[FrameRec::Jl + i];
+    const M3 AJ = skew(a) * Jl;
     for (int row = 0; row < 2; ++row) {
       const V3 D = v3(-S.inv_sigma * dp[row][0], -S.inv_sigma * dp[row][1], -S.inv_sigma * dp[row][2]);   // dr/dp_c
       // DR = D^T R_cr (row vector)
@@ -145,17 +160,26 @@ CB2_HD bool camera_block(const SensorState& S, const double* __restrict__ M, dou
         g[3 + j] = -(DR.x * R_rw.m[j] + DR.y * R_rw.m[3 + j] + DR.z * R_rw.m[6 + j]);
       }
       double jl = 0.0;
-      for (int j = 0; j < 6; ++j) { out.put(CamRec::G0 + row * 6 + j, g[j]); jl -= g[j] * P1[j]; }
+      for (int j = 0; j < 6; ++j) { out.put(CamRec::G0 + row * 6 + j, g[j]); jl -= g[j] * fr[FrameRec::P1 + j]; }
       out.put(CamRec::Jl + row, jl);
       out.put(CamRec::Jt + row * 3 + 0, -DR.x); out.put(CamRec::Jt + row * 3 + 1, -DR.y); out.put(CamRec::Jt + row * 3 + 2, -DR.z);
       const V3 jq = cross(DR, b);   // DR^T [b]x = (DR x b)^T
       out.put(CamRec::Jq + row * 3 + 0, 2.0 * jq.x); out.put(CamRec::Jq + row * 3 + 1, 2.0 * jq.y); out.put(CamRec::Jq + row * 3 + 2, 2.0 * jq.z);
       for (int j = 0; j < S.ni; ++j) out.put(CamRec::Ji + row * S.ni + j, -S.inv_sigma * di[row][j]);
     }
-    for (int i = 0; i < kK; ++i) out.put(CamRec::w0 + i, w[0][i]);
+    for (int i = 0; i < kK; ++i) out.put(CamRec::w0 + i, fr[FrameRec::w0 + i]);
     out.put(CamRec::one, 1.0); out.put(CamRec::zero, 0.0);
   }
   return true;
+}
+
+// One residual block evaluated on its own (frame record on the stack); the kernels share the record between the corners of an image.
+template <bool kJac>
+CB2_HD bool camera_block(const SensorState& S, const double* __restrict__ M, double knot0, double knot1, const double* __restrict__ cp,
+                         double stamp, double px, double py, const V3& p_w, const Rec& out) {
+  double fr[FrameRec::kSize];
+  camera_frame(S, M, knot0, knot1, cp, stamp, fr);
+  return camera_block_from_frame<kJac>(S, fr, px, py, p_w, out);
 }
 
 // ---- gyroscope: r = (meas - Project(intr, -R_rg^T J_l(phi) phid)) / sigma ----

@@ -79,6 +79,7 @@ struct HostBody {
   std::vector<int> feature_ids;
   std::vector<double> pts;
   std::unordered_map<int, int> slot;
+  std::vector<int> dense_slot;   // feature id -> slot for small non-negative ids (the common case), else empty
   int pw0 = 0;   // first index of this body's points in the world-point table
 };
 
@@ -240,7 +241,8 @@ struct cb2_problem {
   // ---- device state ----
   bool uploaded = false;
   int device = -1;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, stream_imu = nullptr;   // IMU sweeps overlap the camera sweep on a second stream
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int n_cp = 0, n_seg = 0, N_c = 0, csz = 0, n_tiles = 0;
   long n_a = 0, n_tot = 0;
   std::vector<SensorDesc> h_desc;
@@ -259,7 +261,7 @@ struct cb2_problem {
   DevBuf<CalibEntry> d_centries;
   DevBuf<double> d_segA, d_segG, d_segB, d_segC, d_segGc, d_Aband, d_Bmat, d_Cmat, d_grad, d_diag, d_scaling, d_dtil2, d_ytil;
   // multi-GPU sharding: this rank owns the chunks [chunk_lo, chunk_hi) and the segments [g_lo, g_hi)
-  std::unique_ptr<Comm> comm;
+  std::shared_ptr<Comm> comm;   // may be shared between handles of one process (cb2_comm_clone)
   int world = 1, rank = 0;
   int chunk_lo = 0, chunk_hi = 0, g_lo = 0, g_hi = 0;
   long total_blocks = 0, total_residuals = 0;    // over ALL ranks (summary counts)
@@ -274,7 +276,7 @@ struct cb2_problem {
   DevBuf<BandSys> d_l1;
   DevBuf<BandSys> d_l2;
   DevBuf<int> d_chunk_sys, d_rowidx, d_colidx;
-  DevBuf<double> d_L1, d_W1, d_T1, d_T2, d_rawdiag;
+  DevBuf<double> d_L1, d_W1, d_T1, d_T2, d_rawdiag, d_Dinv;
   int cur = 0;   // which of the two parameter buffers holds x
   size_t smem_eval[3] = {0, 0, 0};
   int max_tilepairs1 = 0, max_ksplit1 = 1;
@@ -286,6 +288,9 @@ struct cb2_problem {
 
   ~cb2_problem() {
     if (h_scal) cudaFreeHost(h_scal);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (stream_imu) cudaStreamDestroy(stream_imu);
     if (stream) cudaStreamDestroy(stream);
   }
 
@@ -344,6 +349,9 @@ struct cb2_problem {
       return fail(CB2_INTERNAL, "No CUDA device available: calico_b200 has no CPU fallback.");
     if (device >= 0) CB2_CUDA(cudaSetDevice(device));
     CB2_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CB2_CUDA(cudaStreamCreateWithFlags(&stream_imu, cudaStreamNonBlocking));
+    CB2_CUDA(cudaEventCreate(&ev_fork));
+    CB2_CUDA(cudaEventCreate(&ev_join));
     CB2_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_scal), sizeof(double) * kScCount));
     return CB2_OK;
   }
@@ -551,7 +559,8 @@ struct cb2_problem {
     const int nt1 = (nbw1 + 63) / 64;
     max_tilepairs1 = nt1 * (nt1 + 1) / 2;
     max_ksplit1 = 1;
-    std::vector<size_t> Loff(PL), Woff(PL), Toff(PL);
+    std::vector<size_t> Loff(PL), Woff(PL), Toff(PL), Doff(PL);
+    size_t Dsz = 0;
     for (int l = 0; l < PL; ++l) {
       const int p = chunk_lo + l;
       BandSys& sy = h_l1[l];
@@ -564,10 +573,10 @@ struct cb2_problem {
       for (int j = 0; j < kSepDim; ++j) colidx.push_back(p > 0 ? 6 * (chunks[p].a - 5) + j : -1);
       for (int j = 0; j < kSepDim; ++j) colidx.push_back(p < P - 1 ? 6 * chunks[p].b + j : -1);
       for (int c = 0; c < N_c; ++c) colidx.push_back(int(n_a) + c);
-      Loff[l] = Lsz; Woff[l] = Wsz; Toff[l] = Tsz;
+      Loff[l] = Lsz; Woff[l] = Wsz; Toff[l] = Tsz; Doff[l] = Dsz; Dsz += size_t(sy.n);
       Lsz += size_t(sy.n) * 36; Wsz += size_t(sy.n) * nbw1; Tsz += size_t(sy.ksplit) * nbw1 * nbw1;
       if (backsolve_smem_bytes(sy.n, nbw1, 36) > 220 * 1024) return fail(CB2_INTERNAL, "Schur chunk too large for shared memory; lower CB2_CHUNK_CPS.");
-      if (nbw1 > 2 * kFacThreads) return fail(CB2_UNIMPLEMENTED, "Too many calibration unknowns for the band factor kernel.");
+      if (nbw1 > 512) return fail(CB2_UNIMPLEMENTED, "Too many calibration unknowns for the band factor kernel.");   // PFW = 12 registers of border prefetch
     }
     const size_t row_off2 = rowidx.size();
     std::vector<int> shared_idx;
@@ -579,11 +588,11 @@ struct cb2_problem {
     d_rowidx.upload(rowidx); d_colidx.upload(colidx);
     d_shared_idx.upload(shared_idx);
     d_shared_buf.alloc(2 * size_t(std::max(n_shared, 1)));
-    d_L1.alloc(Lsz); d_W1.alloc(Wsz); d_T1.alloc(Tsz);
+    d_L1.alloc(Lsz); d_W1.alloc(Wsz); d_T1.alloc(Tsz); d_Dinv.alloc(Dsz + size_t(std::max(n2, 1)));
     for (int l = 0; l < PL; ++l) {
       BandSys& sy = h_l1[l];
       sy.row_gidx = d_rowidx.p + row_off[l]; sy.col_gidx = d_colidx.p + col_off[l];
-      sy.L = d_L1.p + Loff[l]; sy.W = d_W1.p + Woff[l]; sy.T = d_T1.p + Toff[l];
+      sy.L = d_L1.p + Loff[l]; sy.W = d_W1.p + Woff[l]; sy.T = d_T1.p + Toff[l]; sy.Dinv = d_Dinv.p + Doff[l];
     }
     d_l1.upload(h_l1);
     h_l2 = BandSys{};
@@ -595,7 +604,7 @@ struct cb2_problem {
     d_red.alloc(szL2 + szW2 + szCw + 1);
     d_T2.alloc(size_t(h_l2.ksplit) * nbw2 * nbw2);
     h_l2.row_gidx = d_rowidx.p + row_off2; h_l2.col_gidx = d_colidx.p + col_off2;
-    h_l2.L = d_red.p; h_l2.W = d_red.p + szL2; h_l2.T = d_T2.p;
+    h_l2.L = d_red.p; h_l2.W = d_red.p + szL2; h_l2.T = d_T2.p; h_l2.Dinv = d_Dinv.p + Dsz;
     red_Cw = d_red.p + szL2 + szW2;
     red_count = szL2 + szW2 + szCw;
     d_l2.upload(std::vector<BandSys>(1, h_l2));
@@ -603,7 +612,7 @@ struct cb2_problem {
     for (int l = 0; l < PL; ++l) chunk_sys[chunk_lo + l] = l;
     d_chunk_sys.upload(chunk_sys);
     d_rawdiag.alloc(size_t(std::max(n2, 1)) + std::max(N_c, 1));
-    const size_t smem_f1 = (36 * 36 + 36 * size_t(nbw1)) * sizeof(double), smem_f2 = (60 * 60 + 60 * size_t(nbw2)) * sizeof(double);
+    const size_t smem_f1 = factor_smem_bytes(36, nbw1), smem_f2 = factor_smem_bytes(60, nbw2);
     if (smem_f1 > 227 * 1024 || smem_f2 > 227 * 1024) return fail(CB2_UNIMPLEMENTED, "Too many calibration unknowns for the shared-memory Schur kernels.");
     return CB2_OK;
   }
@@ -624,8 +633,8 @@ struct cb2_problem {
     int max_n1 = 0;
     for (const auto& sy : h_l1) max_n1 = std::max(max_n1, sy.n);
     const int nbw1 = h_l1[0].nbw, nbw2 = h_l2.nbw;
-    set(band_factor_kernel<6>, (36 * 36 + 36 * size_t(nbw1)) * 8);
-    set(band_factor_kernel<10>, (60 * 60 + 60 * size_t(nbw2)) * 8);
+    set(band_factor_kernel<6>, factor_smem_bytes(36, nbw1));
+    set(band_factor_kernel<10>, factor_smem_bytes(60, nbw2));
     set(reduced_solve_kernel, size_t(N_c + 1) * (kRedPanel + 1) * 8);
     set(band_backsolve_kernel, std::max(backsolve_smem_bytes(max_n1, nbw1, 36), backsolve_smem_bytes(h_l2.n, nbw2, 60)));
 #endif
@@ -643,12 +652,16 @@ struct cb2_problem {
     const SensorState* st = d_state[which].p;
     const double* c = d_ctrl[which].p;
     const int nt[3] = {tile_off[1] - tile_off[0], tile_off[2] - tile_off[1], tile_off[3] - tile_off[2]};
+    const bool fork = (nt[1] || nt[2]) && nt[0];
+    cudaStream_t si = fork ? stream_imu : stream;
+    if (fork) { CB2_CUDA(cudaEventRecord(ev_fork, stream)); CB2_CUDA(cudaStreamWaitEvent(stream_imu, ev_fork, 0)); }
     if (nt[0]) CB2_K((eval_kernel<kCamera, MODE>), nt[0], kTile, smem_eval[0], stream, desc, st, d_tiles.p + tile_off[0], c, d_knots.p, d_basis.p, d_pw.p,
                      gravity[0], gravity[1], gravity[2], d_cost_partial.p + tile_off[0], d_invalid_partial.p + tile_off[0], 1);
-    if (nt[1]) CB2_K((eval_kernel<kGyroscope, MODE>), nt[1], kTile, smem_eval[1], stream, desc, st, d_tiles.p + tile_off[1], c, d_knots.p, d_basis.p, d_pw.p,
+    if (nt[1]) CB2_K((eval_kernel<kGyroscope, MODE>), nt[1], kTile, smem_eval[1], si, desc, st, d_tiles.p + tile_off[1], c, d_knots.p, d_basis.p, d_pw.p,
                      gravity[0], gravity[1], gravity[2], d_cost_partial.p + tile_off[1], d_invalid_partial.p + tile_off[1], 1);
-    if (nt[2]) CB2_K((eval_kernel<kAccelerometer, MODE>), nt[2], kTile, smem_eval[2], stream, desc, st, d_tiles.p + tile_off[2], c, d_knots.p, d_basis.p, d_pw.p,
+    if (nt[2]) CB2_K((eval_kernel<kAccelerometer, MODE>), nt[2], kTile, smem_eval[2], si, desc, st, d_tiles.p + tile_off[2], c, d_knots.p, d_basis.p, d_pw.p,
                      gravity[0], gravity[1], gravity[2], d_cost_partial.p + tile_off[2], d_invalid_partial.p + tile_off[2], 1);
+    if (fork) { CB2_CUDA(cudaEventRecord(ev_join, stream_imu)); CB2_CUDA(cudaStreamWaitEvent(stream, ev_join, 0)); }
     CB2_K(reduce_cost_kernel, 1, 256, 0, stream, d_cost_partial.p, d_invalid_partial.p, n_tiles, d_scal.p, slot);
   }
 
@@ -699,7 +712,7 @@ struct cb2_problem {
     for (const auto& sy : h_l1) max_n1 = std::max(max_n1, sy.n);
     CB2_K(gather_level1_kernel, dim3(std::max(1, std::min(64, (max_n1 * (36 + nbw1) + 255) / 256)), PL), 256, 0, stream, d_l1.p, n_a, N_c, d_Aband.p,
           d_Bmat.p, d_Cmat.p, d_grad.p, d_dtil2.p);
-    const size_t smem_f1 = (36 * 36 + 36 * size_t(nbw1)) * sizeof(double);
+    const size_t smem_f1 = factor_smem_bytes(36, nbw1);
     CB2_K((band_factor_kernel<6>), PL, kFacThreads, smem_f1, stream, d_l1.p, d_scal.p);
     CB2_K(border_gram_kernel, dim3(max_tilepairs1, PL, max_ksplit1), dim3(16, 16), 0, stream, d_l1.p);
     // Separator + calibration systems: rank-local direct terms minus the Schur terms of the owned chunks, summed across ranks.
@@ -716,15 +729,21 @@ struct cb2_problem {
     if (world > 1 && red_count > 0) comm->allreduce_sum(d_red.p, red_count, stream);   // THE data-path collective of an LM iteration
     if (h_l2.n > 0) {
       CB2_K(level2_damp_kernel, (h_l2.n + 255) / 256, 256, 0, stream, h_l2, d_dtil2.p);
-      const size_t smem_f2 = (60 * 60 + 60 * size_t(h_l2.nbw)) * sizeof(double);
+      const size_t smem_f2 = factor_smem_bytes(60, h_l2.nbw);
       CB2_K((band_factor_kernel<10>), 1, kFacThreads, smem_f2, stream, d_l2.p, d_scal.p);
       const int nt2 = (h_l2.nbw + 63) / 64;
       CB2_K(border_gram_kernel, dim3(nt2 * (nt2 + 1) / 2, 1, h_l2.ksplit), dim3(16, 16), 0, stream, d_l2.p);
     }
-    if (N_c > 0)
-      CB2_K(reduced_solve_kernel, 1, kRedThreads, size_t(N_c + 1) * (kRedPanel + 1) * sizeof(double), stream, h_l2, N_c, n_a, red_Cw, d_dtil2.p,
-            d_ytil.p, d_scal.p);
-    if (h_l2.n > 0) CB2_K(band_backsolve_kernel, 1, kBackThreads, backsolve_smem_bytes(h_l2.n, h_l2.nbw, 60), stream, d_l2.p, d_ytil.p);
+    if (N_c > 0) {
+      const long tot3 = long(N_c + 1) * (N_c + 1);
+      CB2_K(level3_finalize_kernel, int(std::min<long>((tot3 + 255) / 256, 1024)), 256, 0, stream, h_l2, N_c, n_a, red_Cw, d_dtil2.p);
+      CB2_K(reduced_solve_kernel, 1, kRedThreads, size_t(N_c + 1) * (kRedPanel + 1) * sizeof(double), stream, N_c, n_a, red_Cw, d_ytil.p, d_scal.p);
+    }
+    if (h_l2.n > 0) {
+      CB2_K(border_matvec_kernel, dim3(std::max(1, std::min(148, (h_l2.n + 7) / 8)), 1), 256, size_t(h_l2.nbw) * sizeof(double), stream, d_l2.p, d_ytil.p);
+      CB2_K(band_backsolve_kernel, 1, kBackThreads, backsolve_smem_bytes(h_l2.n, h_l2.nbw, 60), stream, d_l2.p, d_ytil.p);
+    }
+    CB2_K(border_matvec_kernel, dim3(std::max(1, std::min(32, (max_n1 + 7) / 8)), PL), 256, size_t(nbw1) * sizeof(double), stream, d_l1.p, d_ytil.p);
     CB2_K(band_backsolve_kernel, PL, kBackThreads, backsolve_smem_bytes(max_n1, nbw1, 36), stream, d_l1.p, d_ytil.p);
     CB2_K(apply_step_kernel, 1, kLmThreads, 0, stream, n_a, d_ytil.p, gradG(), d_dtil2.p, d_cp_ref.p, d_cp_own.p, rank == 0 ? 1 : 0, d_ctrl[cur].p,
           d_ctrl[cur ^ 1].p, d_desc.p, d_state[cur].p, d_state[cur ^ 1].p, ns, N_c, d_scal.p);
@@ -1029,7 +1048,12 @@ int cb2_add_rigid_body(cb2_problem* p, int id, const double* q, const double* t,
   b.pose_const = pose_const != 0; b.model_const = model_const != 0;
   b.feature_ids.assign(feature_ids, feature_ids + n_pts);
   b.pts.assign(pts, pts + size_t(n_pts) * 3);
-  for (int i = 0; i < n_pts; ++i) b.slot[feature_ids[i]] = i;
+  int max_id = -1, min_id = 0;
+  for (int i = 0; i < n_pts; ++i) { b.slot[feature_ids[i]] = i; max_id = std::max(max_id, feature_ids[i]); min_id = std::min(min_id, feature_ids[i]); }
+  if (min_id >= 0 && max_id < (1 << 22)) {
+    b.dense_slot.assign(size_t(max_id) + 1, -1);
+    for (int i = 0; i < n_pts; ++i) b.dense_slot[feature_ids[i]] = i;
+  }
   p->body_slot[id] = int(p->bodies.size());
   p->bodies.push_back(std::move(b));
   p->uploaded = false;
@@ -1057,19 +1081,28 @@ int cb2_add_camera_observations(cb2_problem* p, int sid, int n, const double* st
   (void)image_id;
   if (sid < 0 || sid >= int(p->sensors.size()) || p->sensors[sid].kind != kCamera) return p->fail(CB2_INVALID_ARGUMENT, "Not a camera sensor id.");
   HostSensor& s = p->sensors[sid];
+  const size_t base = s.stamp.size();
+  s.stamp.insert(s.stamp.end(), stamp, stamp + n);
+  s.meas.insert(s.meas.end(), pixel, pixel + size_t(n) * 2);
+  s.body_slot.resize(base + n); s.feat_slot.resize(base + n); s.outlier.resize(base + n);
+  int last_model = 0, last_bs = -2;   // consecutive observations almost always name the same rigid body
   for (int i = 0; i < n; ++i) {
-    int bs = -1, fs = -1;
-    auto it = p->body_slot.find(model_id[i]);
-    if (it != p->body_slot.end()) {
-      bs = it->second;
-      auto f = p->bodies[bs].slot.find(feature_id[i]);
-      if (f == p->bodies[bs].slot.end()) return p->fail(CB2_INVALID_ARGUMENT, "Feature id not in rigid body model definition.");
-      fs = f->second;
+    if (last_bs == -2 || model_id[i] != last_model) {
+      auto it = p->body_slot.find(model_id[i]);
+      last_bs = it != p->body_slot.end() ? it->second : -1;
+      last_model = model_id[i];
     }
-    s.stamp.push_back(stamp[i]);
-    s.body_slot.push_back(bs); s.feat_slot.push_back(fs);
-    s.meas.push_back(pixel[2 * i]); s.meas.push_back(pixel[2 * i + 1]);
-    s.outlier.push_back(outlier ? outlier[i] : 0);
+    const int bs = last_bs;
+    int fs = -1;
+    if (bs >= 0) {
+      const HostBody& b = p->bodies[bs];
+      const int fid = feature_id[i];
+      if (!b.dense_slot.empty()) fs = (fid >= 0 && size_t(fid) < b.dense_slot.size()) ? b.dense_slot[fid] : -1;
+      else { auto f = b.slot.find(fid); fs = f != b.slot.end() ? f->second : -1; }
+      if (fs < 0) return p->fail(CB2_INVALID_ARGUMENT, "Feature id not in rigid body model definition.");
+    }
+    s.body_slot[base + i] = bs; s.feat_slot[base + i] = fs;
+    s.outlier[base + i] = outlier ? outlier[i] : 0;
   }
   p->uploaded = false;
   return CB2_OK;
@@ -1257,7 +1290,7 @@ int cb2_comm_init(cb2_problem* p, int world_size, int rank, const uint8_t* id128
     NcclApi::UniqueId id;
     std::memcpy(&id, id128, sizeof id);
     c->check(nccl().CommInitRank(&c->comm, world_size, id, rank), "ncclCommInitRank");
-    p->comm = std::move(c);
+    p->comm = std::shared_ptr<Comm>(c.release());
     p->world = world_size; p->rank = rank;
     return CB2_OK;
   } catch (const CudaFail& f) {
@@ -1277,11 +1310,16 @@ int cb2_comm_init_local(cb2_problem* p, int world_size, int rank, const char* gr
     if (!g) { g = new LocalGroup(); g->world = world_size; }
     c->grp = g;
   }
-  p->comm = std::move(c);
+  p->comm = std::shared_ptr<Comm>(c.release());
   p->world = world_size; p->rank = rank;
   return CB2_OK;
 }
 #endif
+// Re-uses the communicator of another handle of this process (creating an NCCL communicator is a one-time, seconds-long setup).
+int cb2_comm_clone(cb2_problem* dst, cb2_problem* src) {
+  dst->comm = src->comm; dst->world = src->world; dst->rank = src->rank; dst->uploaded = false;
+  return CB2_OK;
+}
 // The shard this rank takes of a trajectory with n_cp control points (host-side plan only; no device needed):
 // chunks [chunk_lo, chunk_hi) of n_chunks, spline segments [seg_lo, seg_hi).
 int cb2_shard_plan(cb2_problem* p, int world_size, int rank, int* n_chunks, int* chunk_lo, int* chunk_hi, int* seg_lo, int* seg_hi) {

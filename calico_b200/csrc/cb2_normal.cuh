@@ -19,7 +19,13 @@
 namespace cb2 {
 
 constexpr int kAccThreads = 64;
-constexpr int kAccRows = 32;   // J rows per shared-memory tile
+#ifndef CB2_ACC_ROWS
+#define CB2_ACC_ROWS 24
+#endif
+#ifndef CB2_ACC_MINBLOCKS
+#define CB2_ACC_MINBLOCKS 8
+#endif
+constexpr int kAccRows = CB2_ACC_ROWS;   // J rows per shared-memory tile
 constexpr int kAccW = 60;      // local width: 36 cp | <= 20 calib | r at position 56 | 3 pad  (10 tiles of 6)
 constexpr int kAccRcol = 56;
 constexpr int kAccTiles = 55;  // lower-triangular 6x6 tiles of a 10 x 10 tile grid
@@ -47,7 +53,7 @@ CB2_D void cp_async_wait() {
 
 struct AccCursor { int s, r0; };
 
-__global__ void __launch_bounds__(kAccThreads) accumulate_kernel(const SensorDesc* __restrict__ sensors, int n_sensors, int N_c, int g_lo,
+__global__ void __launch_bounds__(kAccThreads, CB2_ACC_MINBLOCKS) accumulate_kernel(const SensorDesc* __restrict__ sensors, int n_sensors, int N_c, int g_lo,
                                                                  const int* __restrict__ c2off, int csz, double* __restrict__ segA,
                                                                  double* __restrict__ segG, double* __restrict__ segB,
                                                                  double* __restrict__ segC, double* __restrict__ segGc) {

@@ -27,12 +27,15 @@ struct BandSys {
   double* L;                // [n][hb+1]: A on entry, Cholesky factor on exit; (i, j) at L[i*(hb+1) + hb - (i-j)]
   double* W;                // [n][nbw]: border on entry, L^-1 border on exit
   double* T;                // [ksplit][nbw][nbw] partial Gram matrices W^T W
+  double* Dinv;             // [n] reciprocal diagonal of the factor (written by band_factor_kernel, used by the back-substitution)
 };
 
 constexpr int kSepDim = 30;   // (k-1) control points * 6
 constexpr int kFacThreads = 256;
 
 // H(gi, gj) from the assembled normal equations; gi, gj are global unknown indices.
+CB2_HD size_t factor_smem_bytes(int S, int nbw) { return (size_t(S) * S + size_t(S + 6) * nbw) * sizeof(double); }
+
 CB2_D double hess_lookup(long gi, long gj, long n_a, int N_c, const double* __restrict__ Aband, const double* __restrict__ Bmat,
                          const double* __restrict__ Cmat) {
   if (gi < gj) { const long tmp = gi; gi = gj; gj = tmp; }
@@ -74,15 +77,17 @@ __global__ void __launch_bounds__(256) gather_level1_kernel(const BandSys* __res
 }
 
 // In-place banded Cholesky (right-looking, 6 columns per step) fused with the forward substitution of the border.
-// Shared memory: Wd[S][S] circular window of the band, Wr[S][nbw] ring of partially updated border rows.
-// Requires n % 6 == 0, nbw <= 2 * kFacThreads and the block structure described in the header (entries beyond the block band
-// are structurally zero). Per 6-column step, three block-wide phases:
-//   P1  thread 0 factors the 6x6 diagonal block (one rsqrt per column); meanwhile every thread has already issued the global
-//       loads of the 6 rows that enter the window at the end of the step (software prefetch into registers);
-//   P2  panel rows: 6-step triangular solve against the diagonal block, finished factor columns go to HBM;
-//       border rows j0..j0+5: same solve per border column, kept in registers and written to HBM;
-//   P3  trailing update of the band window and of the border ring (6 rows per batch for ILP); the prefetched rows are
-//       dropped into the slots of the retired rows.
+// Shared memory: Wd[S][S] circular window of the band, Wr[S][nbw] ring of partially updated border rows, Xs[6][nbw].
+// Requires n % 6 == 0 and the block structure described in the header (entries beyond the block band are structurally
+// zero). One CTA of 8 warps per system. The 6x6 diagonal-block factorisation — the only inherently serial piece — is taken
+// off the critical path by a one-step lookahead: while warps 1..7 apply step s to the trailing window and the border, warp 0
+// updates the NEXT diagonal block first and factors it. Per step, two block-wide phases:
+//   P2  (needs the factored diagonal block of this step) warp 0: panel rows, 6-step triangular solve, finished factor columns
+//       to HBM; warps 1..7: border rows j0..j0+5, same solve per border column -> Xs and HBM;
+//   P3  warp 0: next diagonal block -= panel * panel^T, then its Cholesky (right-looking, one rsqrt per column);
+//       warps 1..7: rest of the trailing window; border ring update with the 6x6 factor block held in registers and reused over
+//       all border columns of a lane; every thread finally drops its software-prefetched incoming rows (global loads issued at
+//       the top of the step) into the slots of the retired rows.
 template <int NBLK>
 __global__ void __launch_bounds__(kFacThreads) band_factor_kernel(const BandSys* __restrict__ systems, double* __restrict__ scal) {
   constexpr int S = 6 * NBLK;
@@ -90,12 +95,15 @@ __global__ void __launch_bounds__(kFacThreads) band_factor_kernel(const BandSys*
   constexpr int NTB = NB1 * (NB1 + 1) / 2;            // lower-triangular 6x6 blocks of the trailing window
   constexpr int PFB = (6 * S + kFacThreads - 1) / kFacThreads;
   constexpr int PFW = 12;                             // 6 * nbw / kFacThreads <= 12 for nbw <= 512
+  constexpr int NW = kFacThreads - 32;                // worker threads (warps 1..7)
   const BandSys sy = systems[blockIdx.x];
   const int n = sy.n, nbw = sy.nbw, t = threadIdx.x;
+  const int warp = t >> 5, lane = t & 31;
   double* Wd = dyn_smem<double>();
   double* Wr = Wd + S * S;
-  __shared__ double Ld[36];
-  __shared__ double Linv[6];
+  double* Xs = Wr + S * nbw;          // [6][nbw] finished border rows of the current step
+  __shared__ __align__(16) double Ld[2][36];
+  __shared__ double Linv[2][6];
   __shared__ int s_fail;
   __shared__ unsigned char blk_i[NTB], blk_j[NTB];
   if (t == 0) {
@@ -105,6 +113,35 @@ __global__ void __launch_bounds__(kFacThreads) band_factor_kernel(const BandSys*
   }
   double* __restrict__ Lg = sy.L;
   double* __restrict__ Wg = sy.W;
+  // Factors the 6x6 diagonal block whose window slot is `slot` (global row jg); one thread.
+  auto factor_diag = [&](int slot, int jg, int buf) {
+    double a[6][6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = 0; c <= r; ++c) a[r][c] = Wd[(slot + r) * S + slot + c];
+    int fail = 0;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      double d = a[c][c];
+      if (!(d > 0.0) || !isfinite(d)) { fail = 1; d = 1.0; }
+      const double inv = rsqrt(d);
+      a[c][c] = d * inv;
+      Linv[buf][c] = inv;
+      sy.Dinv[jg + c] = inv;
+#pragma unroll
+      for (int r = c + 1; r < 6; ++r) a[r][c] *= inv;
+#pragma unroll
+      for (int r = c + 1; r < 6; ++r)
+#pragma unroll
+        for (int k = c + 1; k <= r; ++k) a[r][k] -= a[r][c] * a[k][c];
+    }
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) Ld[buf][r * 6 + c] = c <= r ? a[r][c] : 0.0;
+    if (fail) s_fail = 1;
+  };
   // Initial window: rows 0..min(S,n)-1.
   const int n0 = min(S, n);
   for (int e = t; e < n0 * S; e += kFacThreads) {
@@ -114,11 +151,16 @@ __global__ void __launch_bounds__(kFacThreads) band_factor_kernel(const BandSys*
   }
   for (int e = t; e < n0 * nbw; e += kFacThreads) Wr[e] = Wg[e];
   __syncthreads();
-  for (int j0 = 0; j0 < n; j0 += 6) {
+  if (t == 0 && n > 0) factor_diag(0, 0, 0);
+  __syncthreads();
+  int cur = 0;
+  for (int j0 = 0; j0 < n; j0 += 6, cur ^= 1) {
     const int jm = j0 % S;                       // window slot of column/row j0 (6 consecutive slots, never wraps)
     const int r_end = min(j0 + S, n);            // rows j0+6 .. r_end-1 form the panel / trailing window
     const int i0 = j0 + S;                       // rows i0 .. i0+5 enter the window at the end of this step
     const bool incoming = i0 < n;
+    const double* __restrict__ Ldc = Ld[cur];
+    const double* __restrict__ Lic = Linv[cur];
     // P0: software prefetch of the incoming rows.
     double pfb[PFB], pfw[PFW];
     if (incoming) {
@@ -127,109 +169,101 @@ __global__ void __launch_bounds__(kFacThreads) band_factor_kernel(const BandSys*
 #pragma unroll
       for (int u = 0; u < PFW; ++u) { const int e = t + u * kFacThreads; if (e < 6 * nbw) pfw[u] = Wg[size_t(i0) * nbw + e]; }
     }
-    // P1: factor the 6x6 diagonal block.
-    if (t == 0) {
-      double a[6][6];
+    // P2.
+    if (warp == 0) {
+      // panel rows r: L(r, j0+c) = (A(r, j0+c) - sum_{k<c} L(r, j0+k) Ld[c][k]) / Ld[c][c]; emit to HBM.
+      for (int rr = lane; rr < S - 6; rr += 32) {
+        const int r = j0 + 6 + rr;
+        if (r < r_end) {
+          int rm = jm + 6 + rr; if (rm >= S) rm -= S;
+          double* pr = Wd + rm * S + jm;
+          double x[6];
 #pragma unroll
-      for (int r = 0; r < 6; ++r)
+          for (int c = 0; c < 6; ++c) {
+            double sacc = pr[c];
 #pragma unroll
-        for (int c = 0; c <= r; ++c) a[r][c] = Wd[(jm + r) * S + jm + c];
-      int fail = 0;
+            for (int k = 0; k < c; ++k) sacc -= x[k] * Ldc[c * 6 + k];
+            x[c] = sacc * Lic[c];
+          }
 #pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        double d = a[c][c];
-#pragma unroll
-        for (int k = 0; k < c; ++k) d -= a[c][k] * a[c][k];
-        if (!(d > 0.0) || !isfinite(d)) { fail = 1; d = 1.0; }
-        const double inv = rsqrt(d);
-        a[c][c] = d * inv;
-        Linv[c] = inv;
-#pragma unroll
-        for (int r = c + 1; r < 6; ++r) {
-          double sacc = a[r][c];
-#pragma unroll
-          for (int k = 0; k < c; ++k) sacc -= a[r][k] * a[c][k];
-          a[r][c] = sacc * inv;
+          for (int c = 0; c < 6; ++c) { pr[c] = x[c]; Lg[size_t(r) * S + (S - 1 - (r - j0 - c))] = x[c]; }
         }
       }
-#pragma unroll
-      for (int r = 0; r < 6; ++r)
-#pragma unroll
-        for (int c = 0; c < 6; ++c) Ld[r * 6 + c] = c <= r ? a[r][c] : 0.0;
-      if (fail) s_fail = 1;
-    }
-    __syncthreads();
-    // P2a: panel rows r: L(r, j0+c) = (A(r, j0+c) - sum_{k<c} L(r, j0+k) Ld[c][k]) / Ld[c][c]; emit to HBM.
-    if (t < S - 6) {
-      const int r = j0 + 6 + t;
-      if (r < r_end) {
-        int rm = jm + 6 + t; if (rm >= S) rm -= S;
-        double* pr = Wd + rm * S + jm;
+      for (int e = lane; e < 36; e += 32) { const int r = e / 6, k = e % 6; if (k <= r) Lg[size_t(j0 + r) * S + (S - 1 - (r - k))] = Ldc[e]; }
+    } else {
+      // border rows j0..j0+5: forward-solve with the diagonal block -> Xs and HBM.
+      for (int c = t - 32; c < nbw; c += NW) {
         double x[6];
-#pragma unroll
-        for (int c = 0; c < 6; ++c) {
-          double sacc = pr[c];
-#pragma unroll
-          for (int k = 0; k < c; ++k) sacc -= x[k] * Ld[c * 6 + k];
-          x[c] = sacc * Linv[c];
-        }
-#pragma unroll
-        for (int c = 0; c < 6; ++c) { pr[c] = x[c]; Lg[size_t(r) * S + (S - 1 - (r - j0 - c))] = x[c]; }
-      }
-    } else if (t >= kFacThreads - 36) {
-      const int e = t - (kFacThreads - 36), r = e / 6, k = e % 6;   // diagonal block of the factor
-      if (k <= r) Lg[size_t(j0 + r) * S + (S - 1 - (r - k))] = Ld[e];
-    }
-    // P2b: border rows j0..j0+5: forward-solve with the diagonal block; results stay in registers for P3b.
-    double xb[2][6];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int c = t + u * kFacThreads;
-      if (c < nbw) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
           double sacc = Wr[(jm + k) * nbw + c];
 #pragma unroll
-          for (int q = 0; q < k; ++q) sacc -= Ld[k * 6 + q] * xb[u][q];
-          xb[u][k] = sacc * Linv[k];
+          for (int q = 0; q < k; ++q) sacc -= Ldc[k * 6 + q] * x[q];
+          x[k] = sacc * Lic[k];
         }
 #pragma unroll
-        for (int k = 0; k < 6; ++k) Wg[size_t(j0 + k) * nbw + c] = xb[u][k];
+        for (int k = 0; k < 6; ++k) { Xs[k * nbw + c] = x[k]; Wg[size_t(j0 + k) * nbw + c] = x[k]; }
       }
     }
     __syncthreads();
-    // P3a: trailing update of the band window, one entry per loop trip: A(r, c) -= sum_k L(r, j0+k) L(c, j0+k).
-    for (int e = t; e < NTB * 36; e += kFacThreads) {
-      const int blk = e / 36, w = e % 36;
-      const int a6 = w / 6, b6 = w % 6;
-      const int bi = blk_i[blk], bj = blk_j[blk];
-      const int rr = 6 * bi + a6, cc = 6 * bj + b6;
-      if (cc > rr || j0 + 6 + rr >= r_end) continue;
-      int rm = jm + 6 + rr; if (rm >= S) rm -= S;
-      int cm = jm + 6 + cc; if (cm >= S) cm -= S;
-      const double* lr = Wd + rm * S + jm;
-      const double* lc = Wd + cm * S + jm;
-      double sacc = 0.0;
+    // P3.
+    if (warp == 0) {
+      // lookahead: next diagonal block (rows/cols j0+6 .. j0+11) -= panel panel^T, then factor it for the next step.
+      if (j0 + 6 < n) {
+        int sm = jm + 6; if (sm >= S) sm -= S;
+        if (lane < 21) {
+          int a6 = 0, rem = lane; while (rem > a6) { rem -= a6 + 1; ++a6; }
+          const int b6 = rem;                       // entry (a6, b6), b6 <= a6
+          const double* lr = Wd + (sm + a6) * S + jm;
+          const double* lc = Wd + (sm + b6) * S + jm;
+          double sacc = 0.0;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) sacc += lr[k] * lc[k];
-      Wd[rm * S + cm] -= sacc;
-    }
-    // P3b: border update, 6 rows per batch: Wr(r, :) -= sum_k L(r, j0+k) x_k.
+          for (int k = 0; k < 6; ++k) sacc += lr[k] * lc[k];
+          Wd[(sm + a6) * S + sm + b6] -= sacc;
+        }
+        __syncwarp();
+        if (lane == 0) factor_diag(sm, j0 + 6, cur ^ 1);
+      }
+    } else {
+      const int wt = t - 32;
+      // trailing update of the band window except its first diagonal block: A(r, c) -= sum_k L(r, j0+k) L(c, j0+k).
+      for (int e = 36 + wt; e < NTB * 36; e += NW) {
+        const int blk = e / 36, w = e % 36;
+        const int a6 = w / 6, b6 = w % 6;
+        const int bi = blk_i[blk], bj = blk_j[blk];
+        const int rr = 6 * bi + a6, cc = 6 * bj + b6;
+        if (cc > rr || j0 + 6 + rr >= r_end) continue;
+        int rm = jm + 6 + rr; if (rm >= S) rm -= S;
+        int cm = jm + 6 + cc; if (cm >= S) cm -= S;
+        const double* lr = Wd + rm * S + jm;
+        const double* lc = Wd + cm * S + jm;
+        double sacc = 0.0;
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int c = t + u * kFacThreads;
-      if (c < nbw) {
-        for (int r = j0 + 6; r < r_end; r += 6) {
-          int rm = jm + (r - j0); if (rm >= S) rm -= S;
-          double acc[6];
+        for (int k = 0; k < 6; ++k) sacc += lr[k] * lc[k];
+        Wd[rm * S + cm] -= sacc;
+      }
+      // border ring update, one 6-row batch per warp trip: Wr(r, c) -= sum_k L(r, j0+k) x_k(c); the 6x6 factor block stays
+      // in registers and is reused for every border column of the lane.
+      const int nbatch = (r_end - (j0 + 6)) / 6;
+      for (int bq = warp - 1; bq < nbatch; bq += kFacThreads / 32 - 1) {
+        int rm = jm + 6 + 6 * bq; if (rm >= S) rm -= S;
+        double lb[6][6];
+#pragma unroll
+        for (int v = 0; v < 6; ++v) {
+          const double2* lr = reinterpret_cast<const double2*>(Wd + (rm + v) * S + jm);
+          const double2 l0 = lr[0], l1 = lr[1], l2 = lr[2];
+          lb[v][0] = l0.x; lb[v][1] = l0.y; lb[v][2] = l1.x; lb[v][3] = l1.y; lb[v][4] = l2.x; lb[v][5] = l2.y;
+        }
+        for (int c = lane; c < nbw; c += 32) {
+          double x[6], acc[6];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) x[k] = Xs[k * nbw + c];
 #pragma unroll
           for (int v = 0; v < 6; ++v) acc[v] = Wr[(rm + v) * nbw + c];
 #pragma unroll
-          for (int v = 0; v < 6; ++v) {
-            const double* lr = Wd + (rm + v) * S + jm;
+          for (int v = 0; v < 6; ++v)
 #pragma unroll
-            for (int k = 0; k < 6; ++k) acc[v] -= lr[k] * xb[u][k];
-          }
+            for (int k = 0; k < 6; ++k) acc[v] -= lb[v][k] * x[k];
 #pragma unroll
           for (int v = 0; v < 6; ++v) Wr[(rm + v) * nbw + c] = acc[v];
         }
@@ -377,22 +411,11 @@ __global__ void __launch_bounds__(256) level3_build_kernel(const BandSys* __rest
   }
 }
 
-// Dense reduced solve (1 CTA): M = Cw[:N, :N] - T2[:N, :N] + diag(dtil2_c), rhs row Cw[N][:] - T2[N][:N]. Right-looking
-// Cholesky in global (L2-resident) memory with 32-column panels staged in shared memory; the rhs row rides along and
-// becomes z = L^-1 rhs; the backward solve L^T y = z prefetches the next factor row. y_c -> ytil[n_a + c].
-// l2 may have n == 0 (no separators). Requires N <= kRedThreads.
-constexpr int kRedThreads = 512;
-constexpr int kRedPanel = 32;
-__global__ void __launch_bounds__(kRedThreads) reduced_solve_kernel(BandSys l2, int N, long n_a, double* __restrict__ Cw,
-                                                                    const double* __restrict__ dtil2, double* __restrict__ ytil,
-                                                                    double* __restrict__ scal) {
-  double* Pn = dyn_smem<double>();    // [N + 1][kRedPanel + 1] panel
-  __shared__ int s_fail;
-  const int t = threadIdx.x;
+// Grid-wide: Cw[:N, :N] -= T2[:N, :N] (separator-level Schur term), += diag(dtil2_c); rhs row Cw[N][:] -= T2[N][:N].
+__global__ void __launch_bounds__(256) level3_finalize_kernel(BandSys l2, int N, long n_a, double* __restrict__ Cw, const double* __restrict__ dtil2) {
   const int ld = N + 1;
-  constexpr int PS = kRedPanel + 1;
-  if (t == 0) s_fail = 0;
-  for (long e = t; e < long(ld) * ld; e += kRedThreads) {
+  const long total = long(ld) * ld;
+  for (long e = long(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += long(gridDim.x) * blockDim.x) {
     const int r = int(e / ld), c = int(e % ld);
     if (c >= N) continue;
     double v = Cw[e];
@@ -400,6 +423,22 @@ __global__ void __launch_bounds__(kRedThreads) reduced_solve_kernel(BandSys l2, 
     if (c == r) v += dtil2[n_a + r];
     Cw[e] = v;
   }
+}
+
+// Dense reduced solve (1 CTA) of the finalized system M = Cw[:N, :N], rhs row Cw[N][:]. Right-looking
+// Cholesky in global (L2-resident) memory with 32-column panels staged in shared memory; the rhs row rides along and
+// becomes z = L^-1 rhs; the backward solve L^T y = z prefetches the next factor row. y_c -> ytil[n_a + c].
+// l2 may have n == 0 (no separators). Requires N <= kRedThreads.
+constexpr int kRedThreads = 512;
+constexpr int kRedPanel = 32;
+__global__ void __launch_bounds__(kRedThreads) reduced_solve_kernel(int N, long n_a, double* __restrict__ Cw, double* __restrict__ ytil,
+                                                                    double* __restrict__ scal) {
+  double* Pn = dyn_smem<double>();    // [N + 1][kRedPanel + 1] panel
+  __shared__ int s_fail;
+  const int t = threadIdx.x;
+  const int ld = N + 1;
+  constexpr int PS = kRedPanel + 1;
+  if (t == 0) s_fail = 0;
   __syncthreads();
   for (int p0 = 0; p0 < N; p0 += kRedPanel) {
     const int pw = min(kRedPanel, N - p0);
@@ -453,33 +492,42 @@ __global__ void __launch_bounds__(kRedThreads) reduced_solve_kernel(BandSys l2, 
   if (t == 0 && s_fail) atomicAdd(&scal[kScSolveFail], 1.0);
 }
 
-// Back-substitution of one banded system: v = z - W[:, :nbw-1] * y[border], then L^T y = v (right-looking, 6 rows per step).
-// grid = systems, block = 256, dynamic shared memory: n doubles (v) + nbw doubles (border solution) + 2 * kBackRows * S
+// Right-hand sides of the back-substitution, all rows of all systems in parallel: ytil[row] <- z - W[row, :nbw-1] . y[border].
+// grid = (row blocks, systems), block = 256 (one warp per row, coalesced W reads).
+__global__ void __launch_bounds__(256) border_matvec_kernel(const BandSys* __restrict__ systems, double* __restrict__ ytil) {
+  const BandSys sy = systems[blockIdx.y];
+  const int nbw = sy.nbw, t = threadIdx.x;
+  double* coef = dyn_smem<double>();
+  for (int c = t; c < nbw - 1; c += 256) { const int g = sy.col_gidx[c]; coef[c] = g >= 0 ? ytil[g] : 0.0; }
+  __syncthreads();
+  const int warp = t >> 5, lane = t & 31;
+  for (int i = blockIdx.x * 8 + warp; i < sy.n; i += gridDim.x * 8) {
+    const double* wr = sy.W + size_t(i) * nbw;
+    double sacc = 0.0;
+    for (int c = lane; c < nbw - 1; c += 32) sacc += wr[c] * coef[c];
+    for (int off = 16; off > 0; off >>= 1) sacc += __shfl_down_sync(0xffffffffu, sacc, off);
+    if (lane == 0) ytil[sy.row_gidx[i]] = wr[nbw - 1] - sacc;
+  }
+}
+
+// Back-substitution of one banded system: v (from border_matvec_kernel, in ytil) -> L^T y = v (right-looking, 6 rows per step).
+// grid = systems, block = 256, dynamic shared memory: 2 n doubles (v, reciprocal diagonal) + 2 * kBackRows * S
 // (factor rows, double-buffered: while one batch of kBackRows rows is being used, the next one is in flight in registers).
 constexpr int kBackThreads = 256;
 constexpr int kBackRows = 48;
-CB2_HD size_t backsolve_smem_bytes(int n, int nbw, int S) { return (size_t(n) + nbw + 2 * size_t(kBackRows) * S) * sizeof(double); }
+CB2_HD size_t backsolve_smem_bytes(int n, int nbw, int S) { (void)nbw; return (2 * size_t(n) + 2 * size_t(kBackRows) * S) * sizeof(double); }
 __global__ void __launch_bounds__(kBackThreads) band_backsolve_kernel(const BandSys* __restrict__ systems, double* __restrict__ ytil) {
   const BandSys sy = systems[blockIdx.x];
-  const int n = sy.n, nbw = sy.nbw, S = sy.hb + 1, t = threadIdx.x;
+  const int n = sy.n, S = sy.hb + 1, t = threadIdx.x;
   double* v = dyn_smem<double>();
-  double* coef = v + n;
-  double* Lbuf = coef + nbw;
+  double* dinv = v + n;
+  double* Lbuf = dinv + n;
   constexpr int PF = (kBackRows * 60 + kBackThreads - 1) / kBackThreads;   // S <= 60
   const double* __restrict__ Lg = sy.L;
   // First batch of factor rows goes straight to shared memory while the border product is computed.
   int b_end = n, b_start = max(0, n - kBackRows);
   for (int e = t; e < (b_end - b_start) * S; e += kBackThreads) Lbuf[e] = Lg[size_t(b_start) * S + e];
-  for (int c = t; c < nbw - 1; c += kBackThreads) { const int g = sy.col_gidx[c]; coef[c] = g >= 0 ? ytil[g] : 0.0; }
-  __syncthreads();
-  const int warp = t >> 5, lane = t & 31;
-  for (int i = warp; i < n; i += kBackThreads / 32) {
-    const double* wr = sy.W + size_t(i) * nbw;
-    double sacc = 0.0;
-    for (int c = lane; c < nbw - 1; c += 32) sacc += wr[c] * coef[c];
-    for (int off = 16; off > 0; off >>= 1) sacc += __shfl_down_sync(0xffffffffu, sacc, off);
-    if (lane == 0) v[i] = wr[nbw - 1] - sacc;
-  }
+  for (int i = t; i < n; i += kBackThreads) { dinv[i] = sy.Dinv[i]; v[i] = ytil[sy.row_gidx[i]]; }
   __syncthreads();
   int buf = 0;
   while (b_end > 0) {
@@ -497,7 +545,7 @@ __global__ void __launch_bounds__(kBackThreads) band_backsolve_kernel(const Band
           double sacc = v[i0 + k];
 #pragma unroll
           for (int q = k + 1; q < 6; ++q) sacc -= Lr[q * S + (S - 1 - (q - k))] * y6[q];
-          y6[k] = sacc / Lr[k * S + (S - 1)];
+          y6[k] = sacc * dinv[i0 + k];
         }
 #pragma unroll
         for (int k = 0; k < 6; ++k) v[i0 + k] = y6[k];

@@ -150,6 +150,8 @@ int cb2_get_residuals(cb2_problem* p, int sensor_id, double* residuals, uint8_t*
 int cb2_comm_unique_id(uint8_t* id128);
 int cb2_comm_init(cb2_problem* p, int world_size, int rank, const uint8_t* id128);
 int cb2_set_device(int device);
+/* A second handle of the same process re-uses the first one's communicator (communicator creation is one-time setup). */
+int cb2_comm_clone(cb2_problem* dst, cb2_problem* src);
 /* Host-side shard plan (no device needed): the chunks [chunk_lo, chunk_hi) of n_chunks and the spline segments
  * [seg_lo, seg_hi) whose observations rank `rank` of `world_size` evaluates. Every rank is handed the whole problem and keeps
  * its shard; in multi-GPU mode cb2_get_residuals / cb2_evaluate_sensor cover the local shard only. */

@@ -1,0 +1,280 @@
+// calico_b200 — K5 level 1 by BLOCK CYCLIC REDUCTION: elimination of the spline control points of one chunk.
+//
+// A control point couples only to the k-1 = 5 control points on either side (camera_cost_functor.cpp:52-60), so in blocks of
+// 5 control points (30 unknowns) the control-point Hessian A of a chunk is BLOCK TRIDIAGONAL, with a dense border
+// [left separator 30 | right separator 30 | calibration N_c | rhs 1] (separators only with several chunks / GPUs).
+// Odd-even (cyclic) reduction eliminates every other block of the still-active blocks per level: all eliminations of a level are
+// independent, so the sequential depth is ceil(log2(n_blocks)) + 1 small dense steps (C4: 501 blocks -> 10 levels) instead of
+// the 2 505 dependent column-block steps of a left-to-right banded Cholesky. It is the same Cholesky elimination in a
+// nested-dissection ORDER (a symmetric permutation of an SPD matrix), i.e. the same LM step as Ceres's DENSE_SCHUR
+// (batch_optimizer.cpp:12; Ceres external) up to rounding.
+//
+// One kernel per level, one CTA per ACTIVE block i (stride = 2^level, active blocks are the multiples of stride):
+//   1. load the block's state  D_i (30x30), border_i (30 x nbw)  and subtract the pending Schur updates of the two blocks
+//      eliminated next to it on the previous level (scratch U, below); level 0 gathers from the assembled normal equations.
+//   2. survivor (even position): write the state back. Eliminated (odd position, or the last remaining block):
+//        D_i = L L^T (6x6-blocked Cholesky in shared memory),
+//        W = L^-1 [E_i | F_i | border_i]   (E_i, F_i: couplings to the active neighbours a = i - stride, b = i + stride;
+//                                            one thread per column, L broadcast from shared memory),
+//        U_i = [W_E W_F]^T W               (60 x (60 + nbw), FP64 tensor pipe: DMMA m8n8k4) -> scratch for the next level.
+//      L_i, W_E|W_F are kept for the back-substitution; the border part of W lands in the chunk's W[n][nbw] array, which the
+//      Gram / separator / calibration kernels of cb2_schur.cuh consume unchanged.
+// Back-substitution, one kernel per level in reverse: x_i = L^-T (v_i - W_E x_a - W_F x_b), v = z - W_border y from
+// border_matvec_kernel. One warp per block.
+#pragma once
+#include "cb2_normal.cuh"
+#include "cb2_schur.cuh"
+
+namespace cb2 {
+
+constexpr int kCrB = 30;            // block size: (k-1) control points x 6
+constexpr int kCrThreads = 256;
+constexpr int kCrLs = 31;           // row stride of the 30x30 diagonal block in shared memory
+
+CB2_HD int cr_row_stride(int nbw) { const int M = 2 * kCrB + nbw; return ((M + 7) / 8 * 8 - 4 + 15) / 16 * 16 + 4; }   // >= M rounded to 8, == 4 mod 16
+CB2_HD size_t cr_smem_bytes(int nbw) { return (size_t(32) * cr_row_stride(nbw) + size_t(kCrB) * kCrLs + 32) * sizeof(double); }
+CB2_HD size_t cr_u_size(int nbw) { return size_t(2 * kCrB) * (2 * kCrB + nbw); }
+CB2_HD int cr_levels(int nblk) { int l = 0; while (((nblk + (1 << l) - 1) >> l) > 1) ++l; return l + 1; }
+
+template <bool kFirst>
+__global__ void __launch_bounds__(kCrThreads) cr_level_kernel(const BandSys* __restrict__ systems, int level, long n_a, int N_c,
+                                                             const double* __restrict__ Aband, const double* __restrict__ Bmat,
+                                                             const double* __restrict__ Cmat, const double* __restrict__ grad,
+                                                             const double* __restrict__ dtil2, double* __restrict__ scal) {
+  const BandSys sy = systems[blockIdx.y];
+  const int stride = 1 << level;
+  const int j = blockIdx.x, i = j * stride;
+  if (i >= sy.nblk) return;
+  const int nact = (sy.nblk + stride - 1) >> level;
+  const bool elim = (j & 1) || nact == 1;
+  const bool has_a = (j & 1) != 0;                              // active left neighbour i - stride (odd positions always have one)
+  const bool has_b = (j & 1) && i + stride < sy.nblk;           // active right neighbour i + stride
+  const int nbw = sy.nbw, n = sy.n, t = threadIdx.x;
+  const int M = 2 * kCrB + nbw;                                 // columns of X = [E | F | border]
+  const int XS = cr_row_stride(nbw);
+  double* X = dyn_smem<double>();                               // [32][XS]; rows 30, 31 stay zero (k padding of the DMMA product)
+  double* Dm = X + 32 * XS;                                     // [30][31]
+  double* dinv = Dm + kCrB * kCrLs;                             // [30] reciprocal diagonal of L
+  __shared__ int s_fail;
+  const int r0 = i * kCrB;                                      // first chunk row of this block
+  const size_t usz = cr_u_size(nbw);
+  const int UW = M;                                             // row length of a scratch entry
+  // Scratch of the blocks eliminated on the previous level to the left / right of block i.
+  const double* UL = nullptr;
+  const double* UR = nullptr;
+  if (!kFirst) {
+    const int h = stride >> 1;
+    const double* Uprev = sy.crU + size_t((level - 1) & 1) * sy.cr_uslots * usz;
+    if (i - h >= 0) UL = Uprev + size_t((i - h) / stride) * usz;
+    if (i + h < sy.nblk) UR = Uprev + size_t((i + h) / stride) * usz;
+  }
+  if (t == 0) s_fail = 0;
+  // ---- 1. state of the block ----
+  for (int e = t; e < kCrB * kCrB; e += kCrThreads) {
+    const int r = e / kCrB, c = e % kCrB;
+    double v;
+    if (kFirst) {
+      if (r0 + r < n && r0 + c < n) {
+        const long gi = sy.row_gidx[r0 + r], gj = sy.row_gidx[r0 + c];
+        v = hess_lookup(gi, gj, n_a, N_c, Aband, Bmat, Cmat);
+        if (r == c) v += dtil2[gi];
+      } else v = r == c ? 1.0 : 0.0;                             // padding rows of a partial last block: identity
+    } else {
+      v = sy.crD[size_t(i) * (kCrB * kCrB) + e];
+      if (UL) v -= UL[size_t(kCrB + r) * UW + kCrB + c];
+      if (UR) v -= UR[size_t(r) * UW + c];
+    }
+    Dm[r * kCrLs + c] = v;
+  }
+  for (int e = t; e < kCrB * nbw; e += kCrThreads) {
+    const int r = e / nbw, c = e % nbw;
+    double v;
+    if (kFirst) {
+      v = 0.0;
+      if (r0 + r < n) {
+        const long gi = sy.row_gidx[r0 + r];
+        if (c == nbw - 1) v = grad[gi];
+        else { const long gj = sy.col_gidx[c]; if (gj >= 0) v = hess_lookup(gi, gj, n_a, N_c, Aband, Bmat, Cmat); }
+      }
+    } else {
+      v = sy.crBd[size_t(i) * kCrB * nbw + e];
+      if (UL) v -= UL[size_t(kCrB + r) * UW + 2 * kCrB + c];
+      if (UR) v -= UR[size_t(r) * UW + 2 * kCrB + c];
+    }
+    X[r * XS + 2 * kCrB + c] = v;
+  }
+  if (!elim) {
+    __syncthreads();
+    for (int e = t; e < kCrB * kCrB; e += kCrThreads) sy.crD[size_t(i) * (kCrB * kCrB) + e] = Dm[(e / kCrB) * kCrLs + e % kCrB];
+    for (int e = t; e < kCrB * nbw; e += kCrThreads) sy.crBd[size_t(i) * kCrB * nbw + e] = X[(e / nbw) * XS + 2 * kCrB + e % nbw];
+    return;
+  }
+  // couplings to the active neighbours: E = A(i, a) (rows of i, columns of a), F = A(i, b)
+  for (int e = t; e < kCrB * 2 * kCrB; e += kCrThreads) {
+    const int r = e / (2 * kCrB), c = e % (2 * kCrB);
+    double v = 0.0;
+    if (c < kCrB) {
+      if (has_a) {
+        if (kFirst) { if (r0 + r < n) v = hess_lookup(sy.row_gidx[r0 + r], sy.row_gidx[r0 - kCrB + c], n_a, N_c, Aband, Bmat, Cmat); }
+        else v = -UL[size_t(kCrB + r) * UW + c];
+      }
+    } else if (has_b) {
+      const int cb = c - kCrB;
+      if (kFirst) { if (r0 + r < n && r0 + kCrB + cb < n) v = hess_lookup(sy.row_gidx[r0 + r], sy.row_gidx[r0 + kCrB + cb], n_a, N_c, Aband, Bmat, Cmat); }
+      else v = -UR[size_t(kCrB + cb) * UW + r];
+    }
+    X[r * XS + c] = v;
+  }
+  for (int e = t; e < 2 * XS; e += kCrThreads) X[kCrB * XS + e] = 0.0;   // k-padding rows 30, 31
+  __syncthreads();
+  // ---- 2a. Cholesky of the diagonal block, 6 columns per step: thread 0 factors the 6x6 pivot block, then panel + trailing update ----
+  for (int c0 = 0; c0 < kCrB; c0 += 6) {
+    if (t == 0) {
+      double a[6][6];
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) a[r][c] = Dm[(c0 + r) * kCrLs + c0 + c];
+      int fail = 0;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        double d = a[c][c];
+        if (!(d > 0.0) || !isfinite(d)) { fail = 1; d = 1.0; }
+        const double inv = rsqrt(d);
+        a[c][c] = d * inv;
+        dinv[c0 + c] = inv;
+#pragma unroll
+        for (int r = c + 1; r < 6; ++r) a[r][c] *= inv;
+#pragma unroll
+        for (int r = c + 1; r < 6; ++r)
+#pragma unroll
+          for (int k = c + 1; k <= r; ++k) a[r][k] -= a[r][c] * a[k][c];
+      }
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) Dm[(c0 + r) * kCrLs + c0 + c] = a[r][c];
+      if (fail) s_fail = 1;
+    }
+    __syncthreads();
+    const int rem = kCrB - c0 - 6;                               // rows below the pivot block
+    if (t < rem) {                                               // panel row: forward-solve against the pivot block
+      double* pr = Dm + (c0 + 6 + t) * kCrLs + c0;
+      double x[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        double s = pr[c];
+#pragma unroll
+        for (int k = 0; k < c; ++k) s -= x[k] * Dm[(c0 + c) * kCrLs + c0 + k];
+        x[c] = s * dinv[c0 + c];
+      }
+#pragma unroll
+      for (int c = 0; c < 6; ++c) pr[c] = x[c];
+    }
+    __syncthreads();
+    for (int e = t; e < rem * rem; e += kCrThreads) {            // trailing update (lower triangle)
+      const int rr = e / rem, cc = e % rem;
+      if (cc > rr) continue;
+      const double* lr = Dm + (c0 + 6 + rr) * kCrLs + c0;
+      const double* lc = Dm + (c0 + 6 + cc) * kCrLs + c0;
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s += lr[k] * lc[k];
+      Dm[(c0 + 6 + rr) * kCrLs + c0 + 6 + cc] -= s;
+    }
+    __syncthreads();
+  }
+  // ---- 2b. W = L^-1 X, one thread per column (L is read as a shared-memory broadcast) ----
+  for (int c = t; c < M; c += kCrThreads) {
+    double w[kCrB];
+#pragma unroll
+    for (int r = 0; r < kCrB; ++r) {
+      double s = X[r * XS + c];
+#pragma unroll
+      for (int k = 0; k < r; ++k) s -= Dm[r * kCrLs + k] * w[k];
+      w[r] = s * dinv[r];
+    }
+#pragma unroll
+    for (int r = 0; r < kCrB; ++r) X[r * XS + c] = w[r];
+    if (c < 2 * kCrB) {
+#pragma unroll
+      for (int r = 0; r < kCrB; ++r) sy.crWef[(size_t(i) * kCrB + r) * (2 * kCrB) + c] = w[r];
+    } else {
+#pragma unroll
+      for (int r = 0; r < kCrB; ++r) if (r0 + r < n) sy.W[size_t(r0 + r) * nbw + (c - 2 * kCrB)] = w[r];
+    }
+  }
+  for (int e = t; e < kCrB * kCrB; e += kCrThreads) {
+    const int r = e / kCrB, c = e % kCrB;
+    sy.crL[size_t(i) * (kCrB * kCrB) + e] = c <= r ? Dm[r * kCrLs + c] : 0.0;
+  }
+  __syncthreads();
+  if (t == 0 && s_fail) atomicAdd(&scal[kScSolveFail], 1.0);
+  if (nact == 1) return;                                         // last block of the chunk: nothing left to update
+  // ---- 2c. U = [W_E W_F]^T W on the FP64 tensor pipe: 8x8 tiles, k = 32 (rows 30, 31 are zero) ----
+  {
+    double* U = sy.crU + size_t(level & 1) * sy.cr_uslots * usz + size_t(i / (2 * stride)) * usz;
+    const int warp = t >> 5, lane = t & 31, fr = lane & 3, fc = lane >> 2;
+    const int nqb = (M + 7) / 8;
+    for (int qb = warp; qb < nqb; qb += kCrThreads / 32) {
+      double bf[8];
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) bf[ks] = X[(4 * ks + fr) * XS + 8 * qb + fc];
+#pragma unroll
+      for (int pb = 0; pb < 8; ++pb) {
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) dmma_8x8x4(c0, c1, X[(4 * ks + fr) * XS + 8 * pb + fc], bf[ks]);
+        const int p = 8 * pb + fc, q = 8 * qb + 2 * fr;
+        if (p < 2 * kCrB) {
+          if (q < M) U[size_t(p) * UW + q] = c0;
+          if (q + 1 < M) U[size_t(p) * UW + q + 1] = c1;
+        }
+      }
+    }
+  }
+}
+
+// Back-substitution of one level: x_i = L^-T (v_i - W_E x_a - W_F x_b) for the blocks eliminated on `level`; one warp per block.
+// grid = (ceil(eliminated blocks / 8), chunks), block = 256.
+__global__ void __launch_bounds__(256) cr_back_kernel(const BandSys* __restrict__ systems, int level, double* __restrict__ ytil) {
+  const BandSys sy = systems[blockIdx.y];
+  const int stride = 1 << level;
+  const int nact = (sy.nblk + stride - 1) >> level;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * 8 + warp;                           // q-th eliminated block of this level
+  const int j = nact == 1 ? 0 : 2 * q + 1;
+  if (j >= nact || (nact == 1 && q > 0)) return;
+  const int i = j * stride, r0 = i * kCrB, n = sy.n;
+  const bool has_a = (j & 1) != 0, has_b = (j & 1) && i + stride < sy.nblk;
+  const int ra = (i - stride) * kCrB, rb = (i + stride) * kCrB;
+  // neighbour solutions: lane l holds x_a[l] and x_b[l]
+  double xa = 0.0, xb = 0.0;
+  if (lane < kCrB) {
+    if (has_a && ra + lane < n) xa = ytil[sy.row_gidx[ra + lane]];
+    if (has_b && rb + lane < n) xb = ytil[sy.row_gidx[rb + lane]];
+  }
+  double rhs = 0.0;
+  if (lane < kCrB && r0 + lane < n) rhs = ytil[sy.row_gidx[r0 + lane]];
+  const double* __restrict__ Wef = sy.crWef + size_t(i) * kCrB * (2 * kCrB);
+  if (has_a || has_b) {
+    double s = 0.0;
+    for (int c = 0; c < kCrB; ++c) {
+      const double va = __shfl_sync(0xffffffffu, xa, c), vb = __shfl_sync(0xffffffffu, xb, c);
+      if (lane < kCrB) s += Wef[lane * (2 * kCrB) + c] * va + Wef[lane * (2 * kCrB) + kCrB + c] * vb;
+    }
+    rhs -= s;
+  }
+  // L^T x = rhs, backwards; lane k owns component k.
+  const double* __restrict__ L = sy.crL + size_t(i) * (kCrB * kCrB);
+  double x = 0.0;
+  for (int c = kCrB - 1; c >= 0; --c) {
+    const double lcc = L[c * kCrB + c];
+    const double xc = __shfl_sync(0xffffffffu, rhs, c) / lcc;
+    if (lane == c) x = xc;
+    if (lane < c) rhs -= L[c * kCrB + lane] * xc;
+  }
+  if (lane < kCrB && r0 + lane < n) ytil[sy.row_gidx[r0 + lane]] = x;
+}
+
+}  // namespace cb2

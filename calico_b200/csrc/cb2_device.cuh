@@ -5,7 +5,8 @@
 //   state[2][n_sensors]        SensorState (intrinsics, extrinsics, latency, sigma, loss), current and candidate
 //   knots[n_cp+6], basis[n_seg*36]   knot vector and per-segment 6x6 basis matrices (bspline.hpp:192-244)
 //   pw[n_points*3]             world-frame model points R_wm p_m + t_wm (world model is constant: world_model.cpp:40-77)
-//   per sensor, observations SORTED BY SPLINE SEGMENT: stamp[n], meas[n*m], seg[n] (i32), pt[n] (i32, camera),
+//   frames[n_frames][44]       per camera image: pose-dependent quantities shared by its corners (FrameRec), rewritten by K0 every sweep
+//   per sensor, observations SORTED BY SPLINE SEGMENT (cameras: then by stamp): stamp[n], meas[n*m], seg[n] (i32) / frm[n] (i32, camera), pt[n] (i32, camera),
 //                              seg_start[n_seg+1] (CSR), r[n*m], J[n*m*jw]  (jw = 36 + enabled calibration columns)
 //   normal equations           see cb2_normal.cu / cb2_schur.cu
 #pragma once
@@ -30,6 +31,7 @@ struct SensorDesc {
   int u_intr, u_rot, u_trans, u_lat;   // calibration-local unknown offsets, -1 when the block is constant
   const double* stamp; const double* meas; const int* seg; const int* pt;
   const int* seg_start;
+  const int* frm;               // cameras: global image (frame) index of every observation, see camera_frame_kernel
   double* r; double* J; unsigned char* valid;
 };
 

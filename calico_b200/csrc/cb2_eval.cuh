@@ -22,11 +22,14 @@ enum { kModeCost = 0, kModeResiduals = 1, kModeJacobian = 2 };
 #ifndef CB2_EVAL_MINBLOCKS
 #define CB2_EVAL_MINBLOCKS 3
 #endif
+#ifndef CB2_EVAL_MINBLOCKS_CAM
+#define CB2_EVAL_MINBLOCKS_CAM 4      // 4 x (52 fields x 129 x 8 B + static) = 224 KB of the SM's 228 KB
+#endif
 template <int KIND, int MODE>
-__global__ void __launch_bounds__(kTile, CB2_EVAL_MINBLOCKS) eval_kernel(const SensorDesc* __restrict__ sensors, const SensorState* __restrict__ states,
+__global__ void __launch_bounds__(kTile, (KIND == kCamera ? CB2_EVAL_MINBLOCKS_CAM : CB2_EVAL_MINBLOCKS)) eval_kernel(const SensorDesc* __restrict__ sensors, const SensorState* __restrict__ states,
                                                      const EvalTile* __restrict__ tiles, const double* __restrict__ ctrl,
                                                      const double* __restrict__ knots, const double* __restrict__ basis,
-                                                     const double* __restrict__ pw, double gx, double gy, double gz,
+                                                     const double* __restrict__ pw, const double* __restrict__ frames, double gx, double gy, double gz,
                                                      double* __restrict__ cost_partial, int* __restrict__ invalid_partial, int apply_loss) {
   double* rec = dyn_smem<double>();
   __shared__ double s_red[kTile / 32];
@@ -43,21 +46,25 @@ __global__ void __launch_bounds__(kTile, CB2_EVAL_MINBLOCKS) eval_kernel(const S
   if (active) {
     const SensorState S = states[tl.sensor];
     const long o = long(tl.start) + t;
-    const double stamp = sd.stamp[o];
-    const int seg = sd.seg[o];
-    const double knot0 = knots[seg + kK - 1], knot1 = knots[seg + kK];
-    const double* M = basis + size_t(seg) * (kK * kK);
-    const double* cp = ctrl + size_t(seg) * 6;
     const Rec rc{rec + t, kRecStride};
     if (KIND == kCamera) {
+      // Everything that depends only on (camera, stamp) was computed once per image by camera_frame_kernel.
       const int p = sd.pt[o];
-      ok = camera_block<MODE == kModeJacobian>(S, M, knot0, knot1, cp, stamp, sd.meas[2 * o], sd.meas[2 * o + 1],
-                                               v3(pw[3 * p], pw[3 * p + 1], pw[3 * p + 2]), rc);
-    } else if (KIND == kGyroscope) {
-      ok = gyro_block<MODE == kModeJacobian>(S, M, knot0, knot1, cp, stamp, v3(sd.meas[3 * o], sd.meas[3 * o + 1], sd.meas[3 * o + 2]), rc);
+      const double2 px = reinterpret_cast<const double2*>(sd.meas)[o];
+      ok = camera_block_from_frame<MODE == kModeJacobian>(S, frames + size_t(sd.frm[o]) * FrameRec::kSize, px.x, px.y,
+                                                          v3(pw[3 * p], pw[3 * p + 1], pw[3 * p + 2]), rc);
     } else {
-      ok = accel_block<MODE == kModeJacobian>(S, v3(gx, gy, gz), M, knot0, knot1, cp, stamp,
-                                              v3(sd.meas[3 * o], sd.meas[3 * o + 1], sd.meas[3 * o + 2]), rc);
+      const double stamp = sd.stamp[o];
+      const int seg = sd.seg[o];
+      const double knot0 = knots[seg + kK - 1], knot1 = knots[seg + kK];
+      const double* M = basis + size_t(seg) * (kK * kK);
+      const double* cp = ctrl + size_t(seg) * 6;
+      if (KIND == kGyroscope) {
+        ok = gyro_block<MODE == kModeJacobian>(S, M, knot0, knot1, cp, stamp, v3(sd.meas[3 * o], sd.meas[3 * o + 1], sd.meas[3 * o + 2]), rc);
+      } else {
+        ok = accel_block<MODE == kModeJacobian>(S, v3(gx, gy, gz), M, knot0, knot1, cp, stamp,
+                                                v3(sd.meas[3 * o], sd.meas[3 * o + 1], sd.meas[3 * o + 2]), rc);
+      }
     }
     if (ok) {
       double sq = 0.0;
@@ -157,6 +164,22 @@ __global__ void __launch_bounds__(kTile, CB2_EVAL_MINBLOCKS) eval_kernel(const S
       }
     }
   }
+}
+
+// K0: one thread per camera image (sensor, stamp): basis weights, spline pose and velocity at stamp - latency, R_rw, J_l(phi),
+// R_rc^T -> frames[f][FrameRec::kSize]. The 25..144 residual blocks of the image read it back through L1 (warp-broadcast).
+__global__ void __launch_bounds__(128) camera_frame_kernel(int n_frames, const int* __restrict__ frame_sensor, const int* __restrict__ frame_seg,
+                                                           const double* __restrict__ frame_stamp, const SensorState* __restrict__ states,
+                                                           const double* __restrict__ ctrl, const double* __restrict__ knots,
+                                                           const double* __restrict__ basis, double* __restrict__ frames) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_frames) return;
+  const int seg = frame_seg[f];
+  double fr[FrameRec::kSize];
+  camera_frame(states[frame_sensor[f]], basis + size_t(seg) * (kK * kK), knots[seg + kK - 1], knots[seg + kK], ctrl + size_t(seg) * 6, frame_stamp[f], fr);
+  double* out = frames + size_t(f) * FrameRec::kSize;
+#pragma unroll
+  for (int i = 0; i < FrameRec::kSize; ++i) out[i] = fr[i];
 }
 
 // Sums the per-tile partials in a fixed order: scal[slot] = cost, scal[slot+1] = number of failed blocks.

@@ -28,11 +28,10 @@ enum { kLossNone = 0, kLossHuber = 1, kLossCauchy = 2 };
 // Field offsets of the compact record, per sensor kind. Ji (m x ni, row-major with stride ni) is last.
 // `one` / `zero` hold the constants 1.0 / 0.0 so that every Jacobian entry is a fixed-length sum of products of two record fields
 // (jac_terms below) and the expansion loop of the sweep kernel is branch-free.
-struct CamRec { enum { r = 0, G0 = 2, Jq = 14, Jt = 20, Jl = 26, w0 = 28, rs = 34, one = 35, zero = 36, Ji = 37 }; };
-struct GyrRec { enum { r = 0, G0 = 3, G1 = 12, Jq = 21, Jl = 30, w0 = 33, w1 = 39, rs = 45, one = 46, zero = 47, Ji = 48 }; };
-struct AccRec { enum { r = 0, G0 = 3, G1 = 12, G2 = 21, Jq = 39, Jt = 48, Jl = 57, w0 = 60, w1 = 66, w2 = 72, rs = 78, one = 79, zero = 80, Ji = 81 }; };
+struct CamRec { enum { r = 0, G0 = 2, Jq = 14, Jt = 20, Jl = 26, w0 = 28, one = 34, zero = 35, Ji = 36 }; };
+struct GyrRec { enum { r = 0, G0 = 3, G1 = 12, Jq = 21, Jl = 30, w0 = 33, w1 = 39, one = 45, zero = 46, Ji = 47 }; };
+struct AccRec { enum { r = 0, G0 = 3, G1 = 12, G2 = 21, Jq = 39, Jt = 48, Jl = 57, w0 = 60, w1 = 66, w2 = 72, one = 78, zero = 79, Ji = 80 }; };
 CB2_HD int rec_size(int kind, int ni) { return kind == kCamera ? CamRec::Ji + 2 * ni : (kind == kGyroscope ? GyrRec::Ji + 3 * ni : AccRec::Ji + 3 * ni); }
-CB2_HD int rec_rs(int kind) { return kind == kCamera ? int(CamRec::rs) : (kind == kGyroscope ? int(GyrRec::rs) : int(AccRec::rs)); }
 CB2_HD int residual_dim(int kind) { return kind == kCamera ? 2 : 3; }
 
 // A record sink: field f of this block lives at base[f * stride] (stride = tile width in shared memory, 1 on the host).

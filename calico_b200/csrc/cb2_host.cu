@@ -103,7 +103,7 @@ struct HostSensor {
   std::vector<int> perm;      // sorted position -> original observation index
   int n_active = 0;
   DevBuf<double> d_stamp, d_meas, d_r, d_J;
-  DevBuf<int> d_seg, d_pt, d_seg_start;
+  DevBuf<int> d_seg, d_pt, d_seg_start, d_frm;
   DevBuf<unsigned char> d_valid;
 };
 
@@ -252,6 +252,10 @@ struct cb2_problem {
   DevBuf<SensorState> d_state[2], d_state0;
   DevBuf<double> d_ctrl[2], d_ctrl0, d_knots, d_basis, d_pw;
   DevBuf<EvalTile> d_tiles;
+  // camera images (frames): one record per (camera, stamp), shared by the residual blocks of that image
+  int n_frames = 0;
+  DevBuf<int> d_frame_sensor, d_frame_seg;
+  DevBuf<double> d_frame_stamp, d_frames;
   DevBuf<double> d_cost_partial;
   DevBuf<int> d_invalid_partial;
   DevBuf<double> d_scal;
@@ -393,6 +397,8 @@ struct cb2_problem {
     std::vector<int> c2off(std::max(ns, 1), 0);
     std::vector<EvalTile> tiles;
     std::vector<std::vector<EvalTile>> tiles_by_kind(3);
+    std::vector<int> frame_sensor, frame_seg;
+    std::vector<double> frame_stamp;
     int64_t* h2d = &stats.h2d_bytes;
     for (int si = 0; si < ns; ++si) {
       HostSensor& s = sensors[si];
@@ -425,17 +431,30 @@ struct cb2_problem {
         std::vector<int> cursor(count.begin(), count.end() - 1);
         for (int o = 0; o < n; ++o) if (seg_of[o] >= 0) s.perm[cursor[seg_of[o]]++] = o;
       }
+      if (s.kind == kCamera) {
+        // The corners of one image (same stamp) must be adjacent: order each segment's observations by stamp (stable; usually a no-op).
+        auto by_stamp = [&](int a, int b) { return s.stamp[a] < s.stamp[b]; };
+        for (int g = 0; g < n_seg; ++g) {
+          int* b = s.perm.data() + seg_start[g];
+          int* e = s.perm.data() + seg_start[g + 1];
+          if (!std::is_sorted(b, e, by_stamp)) std::stable_sort(b, e, by_stamp);
+        }
+      }
       s.n_active = n_active;
       std::vector<double> stamp(n_active), meas(size_t(n_active) * m);
-      std::vector<int> seg(n_active), pt(s.kind == kCamera ? n_active : 0);
+      std::vector<int> seg(n_active), pt(s.kind == kCamera ? n_active : 0), frm(s.kind == kCamera ? n_active : 0);
       for (int i = 0; i < n_active; ++i) {
         const int o = s.perm[i];
         stamp[i] = s.stamp[o];
         seg[i] = seg_of[o];
         for (int q = 0; q < m; ++q) meas[size_t(i) * m + q] = s.meas[size_t(o) * m + q];
-        if (s.kind == kCamera) pt[i] = bodies[s.body_slot[o]].pw0 + s.feat_slot[o];
+        if (s.kind == kCamera) {
+          pt[i] = bodies[s.body_slot[o]].pw0 + s.feat_slot[o];
+          if (i == 0 || stamp[i] != stamp[i - 1]) { frame_sensor.push_back(si); frame_seg.push_back(seg[i]); frame_stamp.push_back(stamp[i]); }
+          frm[i] = int(frame_stamp.size()) - 1;
+        }
       }
-      s.d_stamp.upload(stamp, h2d); s.d_meas.upload(meas, h2d); s.d_seg.upload(seg, h2d); s.d_pt.upload(pt, h2d);
+      s.d_stamp.upload(stamp, h2d); s.d_meas.upload(meas, h2d); s.d_seg.upload(seg, h2d); s.d_pt.upload(pt, h2d); s.d_frm.upload(frm, h2d);
       s.d_seg_start.upload(seg_start, h2d);
       // Unknown layout of this sensor (constant or unreferenced blocks drop out, as in Ceres's reduced program).
       SensorDesc& d = h_desc[si];
@@ -459,7 +478,7 @@ struct cb2_problem {
       s.d_r.alloc(size_t(n_active) * m);
       s.d_J.alloc(size_t(n_active) * m * d.jw);
       s.d_valid.alloc(n_active);
-      d.stamp = s.d_stamp.p; d.meas = s.d_meas.p; d.seg = s.d_seg.p; d.pt = s.d_pt.p; d.seg_start = s.d_seg_start.p;
+      d.stamp = s.d_stamp.p; d.meas = s.d_meas.p; d.seg = s.d_seg.p; d.pt = s.d_pt.p; d.seg_start = s.d_seg_start.p; d.frm = s.d_frm.p;
       d.r = s.d_r.p; d.J = s.d_J.p; d.valid = s.d_valid.p;
       for (int o0 = 0; o0 < n_active; o0 += kTile) tiles_by_kind[s.kind].push_back(EvalTile{si, o0, std::min(kTile, n_active - o0)});
       // state
@@ -476,6 +495,9 @@ struct cb2_problem {
     for (int kd = 0; kd < 3; ++kd) { tiles.insert(tiles.end(), tiles_by_kind[kd].begin(), tiles_by_kind[kd].end()); tile_off[kd + 1] = int(tiles.size()); }
     n_tiles = int(tiles.size());
     d_tiles.upload(tiles, h2d);
+    n_frames = int(frame_stamp.size());
+    d_frame_sensor.upload(frame_sensor, h2d); d_frame_seg.upload(frame_seg, h2d); d_frame_stamp.upload(frame_stamp, h2d);
+    d_frames.alloc(size_t(std::max(n_frames, 1)) * FrameRec::kSize);
     d_cost_partial.alloc(std::max(n_tiles, 1)); d_invalid_partial.alloc(std::max(n_tiles, 1));
     d_desc.upload(h_desc, h2d);
     for (int b = 0; b < 2; ++b) d_state[b].upload(h_state, h2d);
@@ -630,6 +652,7 @@ struct cb2_problem {
     set(eval_kernel<kCamera, kModeCost>, ev_max[0]); set(eval_kernel<kCamera, kModeResiduals>, ev_max[0]); set(eval_kernel<kCamera, kModeJacobian>, ev_max[0]);
     set(eval_kernel<kGyroscope, kModeCost>, ev_max[1]); set(eval_kernel<kGyroscope, kModeResiduals>, ev_max[1]); set(eval_kernel<kGyroscope, kModeJacobian>, ev_max[1]);
     set(eval_kernel<kAccelerometer, kModeCost>, ev_max[2]); set(eval_kernel<kAccelerometer, kModeResiduals>, ev_max[2]); set(eval_kernel<kAccelerometer, kModeJacobian>, ev_max[2]);
+    set(accumulate_kernel<7>, kAccSmemBytes); set(accumulate_kernel<8>, kAccSmemBytes);
     int max_n1 = 0;
     for (const auto& sy : h_l1) max_n1 = std::max(max_n1, sy.n);
     const int nbw1 = h_l1[0].nbw, nbw2 = h_l2.nbw;
@@ -645,6 +668,13 @@ struct cb2_problem {
   // ------------------------------------------------------------------------------------------------------------
 #define CB2_K(...) do { CB2_LAUNCH(__VA_ARGS__); ++stats.kernel_launches; } while (0)
 
+  // K0: per-image records of every camera at parameter buffer `which`.
+  void launch_frames(int which) {
+    if (n_frames > 0)
+      CB2_K(camera_frame_kernel, (n_frames + 127) / 128, 128, 0, stream, n_frames, d_frame_sensor.p, d_frame_seg.p, d_frame_stamp.p, d_state[which].p,
+            d_ctrl[which].p, d_knots.p, d_basis.p, d_frames.p);
+  }
+
   // Residual sweep over every sensor at parameter buffer `which`; scalars land in d_scal[slot], d_scal[slot + 1].
   template <int MODE>
   void launch_eval(int which, int slot) {
@@ -655,12 +685,16 @@ struct cb2_problem {
     const bool fork = (nt[1] || nt[2]) && nt[0];
     cudaStream_t si = fork ? stream_imu : stream;
     if (fork) { CB2_CUDA(cudaEventRecord(ev_fork, stream)); CB2_CUDA(cudaStreamWaitEvent(stream_imu, ev_fork, 0)); }
-    if (nt[0]) CB2_K((eval_kernel<kCamera, MODE>), nt[0], kTile, smem_eval[0], stream, desc, st, d_tiles.p + tile_off[0], c, d_knots.p, d_basis.p, d_pw.p,
-                     gravity[0], gravity[1], gravity[2], d_cost_partial.p + tile_off[0], d_invalid_partial.p + tile_off[0], 1);
-    if (nt[1]) CB2_K((eval_kernel<kGyroscope, MODE>), nt[1], kTile, smem_eval[1], si, desc, st, d_tiles.p + tile_off[1], c, d_knots.p, d_basis.p, d_pw.p,
-                     gravity[0], gravity[1], gravity[2], d_cost_partial.p + tile_off[1], d_invalid_partial.p + tile_off[1], 1);
+    // The (long-latency, few-CTA) IMU kernels go first on the side stream; the camera sweep fills the rest of the machine.
     if (nt[2]) CB2_K((eval_kernel<kAccelerometer, MODE>), nt[2], kTile, smem_eval[2], si, desc, st, d_tiles.p + tile_off[2], c, d_knots.p, d_basis.p, d_pw.p,
-                     gravity[0], gravity[1], gravity[2], d_cost_partial.p + tile_off[2], d_invalid_partial.p + tile_off[2], 1);
+                     d_frames.p, gravity[0], gravity[1], gravity[2], d_cost_partial.p + tile_off[2], d_invalid_partial.p + tile_off[2], 1);
+    if (nt[1]) CB2_K((eval_kernel<kGyroscope, MODE>), nt[1], kTile, smem_eval[1], si, desc, st, d_tiles.p + tile_off[1], c, d_knots.p, d_basis.p, d_pw.p,
+                     d_frames.p, gravity[0], gravity[1], gravity[2], d_cost_partial.p + tile_off[1], d_invalid_partial.p + tile_off[1], 1);
+    if (nt[0]) {
+      launch_frames(which);
+      CB2_K((eval_kernel<kCamera, MODE>), nt[0], kTile, smem_eval[0], stream, desc, st, d_tiles.p + tile_off[0], c, d_knots.p, d_basis.p, d_pw.p,
+            d_frames.p, gravity[0], gravity[1], gravity[2], d_cost_partial.p + tile_off[0], d_invalid_partial.p + tile_off[0], 1);
+    }
     if (fork) { CB2_CUDA(cudaEventRecord(ev_join, stream_imu)); CB2_CUDA(cudaStreamWaitEvent(stream, ev_join, 0)); }
     CB2_K(reduce_cost_kernel, 1, 256, 0, stream, d_cost_partial.p, d_invalid_partial.p, n_tiles, d_scal.p, slot);
   }
@@ -673,7 +707,12 @@ struct cb2_problem {
     timer.begin(kPhNormal, stream);
     const int ns = int(sensors.size());
     const int nsl = g_hi - g_lo;
-    if (nsl > 0) CB2_K(accumulate_kernel, nsl, kAccThreads, 0, stream, d_desc.p, ns, N_c, g_lo, d_c2off.p, csz, d_segA.p, d_segG.p, d_segB.p, d_segC.p, d_segGc.p);
+    if (nsl > 0) {
+      int max_nc = 0;
+      for (const auto& d : h_desc) max_nc = std::max(max_nc, d.n_calib);
+      if (kAccCal0 + max_nc <= 56) CB2_K(accumulate_kernel<7>, nsl, kAccThreads, kAccSmemBytes, stream, d_desc.p, ns, N_c, g_lo, d_c2off.p, csz, d_segA.p, d_segG.p, d_segB.p, d_segC.p, d_segGc.p);
+      else CB2_K(accumulate_kernel<8>, nsl, kAccThreads, kAccSmemBytes, stream, d_desc.p, ns, N_c, g_lo, d_c2off.p, csz, d_segA.p, d_segG.p, d_segB.p, d_segC.p, d_segGc.p);
+    }
     const long total = n_a * 36 + n_a * N_c + n_a;
     CB2_K(assemble_band_kernel, int(std::min<long>((total + 255) / 256, 148 * 16)), 256, 0, stream, n_cp, g_lo, g_hi, N_c, d_segA.p, d_segG.p, d_segB.p,
           d_Aband.p, d_Bmat.p, d_grad.p);
@@ -1173,9 +1212,10 @@ int cb2_evaluate_sensor(cb2_problem* p, int sid, double* residuals, double* jaco
     cudaStream_t stream = p->stream;
     cb2_stats& stats = p->stats;
 #define CB2_EVAL(KIND, MODE)                                                                                                             \
-  CB2_K((eval_kernel<KIND, MODE>), nt, kTile, smem, stream, dd.p, st, dt.p, c, p->d_knots.p, p->d_basis.p, p->d_pw.p, p->gravity[0], \
-        p->gravity[1], p->gravity[2], cpart.p, ipart.p, 0)
+  CB2_K((eval_kernel<KIND, MODE>), nt, kTile, smem, stream, dd.p, st, dt.p, c, p->d_knots.p, p->d_basis.p, p->d_pw.p, p->d_frames.p, \
+        p->gravity[0], p->gravity[1], p->gravity[2], cpart.p, ipart.p, 0)
     // residuals + validity (un-robustified), then the Jacobian pass if requested
+    if (s.kind == kCamera) p->launch_frames(p->cur);
     if (s.kind == kCamera) CB2_EVAL(kCamera, kModeResiduals); else if (s.kind == kGyroscope) CB2_EVAL(kGyroscope, kModeResiduals); else CB2_EVAL(kAccelerometer, kModeResiduals);
     CB2_CUDA(cudaStreamSynchronize(stream));
     std::vector<double> hr; std::vector<unsigned char> hv;

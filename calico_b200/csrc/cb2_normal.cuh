@@ -6,11 +6,14 @@
 // residual touches k consecutive control points (camera_cost_functor.cpp:52-60); B = H[cp,calib] couples a segment to
 // the sensors observed in it; C = H[calib,calib] is block-diagonal per sensor (no residual involves two sensors).
 //
-// accumulate_kernel: one CTA per spline segment. All residual rows of a segment touch the same 36 control-point
-// columns, so the CTA accumulates one local (36 + n_calib + 1)^2 Gram matrix per sensor ([J | r]^T [J | r], r as an
-// extra column gives the gradient for free) in registers — 6x6 micro-tiles, lower triangle only (55 threads) — from J row
-// tiles streamed into shared memory with cp.async (double-buffered, the next tile is in flight while the current one is
-// multiplied; 16-byte shared loads), and writes per-segment partials with plain stores (no atomics; fixed summation order).
+// accumulate_kernel: one CTA per spline segment, one WARP per sensor (round-robin). All residual rows of a segment touch the
+// same 36 control-point columns, so each warp forms the local Gram matrix X^T X of X = [J_cp | r | 0 0 0 | J_calib | 0..]
+// (r as an extra column gives the gradient for free) on the FP64 TENSOR pipe: mma.sync.m8n8k4.f64 (SASS DMMA), 8x8
+// accumulator tiles in registers, lower block triangle only. For a Gram product the A and B fragments of a column block are
+// the same register (lane holds X[4 ks + lane % 4][8 b + lane / 4]), so a k-step of 4 rows costs NB shared loads for
+// NB (NB + 1) / 2 DMMAs. J row tiles stream global -> shared with cp.async (per-warp double buffer, row stride 68 doubles
+// == 4 mod 16: conflict-free fragment loads). The control-point block accumulates over all sensors of the warp and is
+// combined across warps in a fixed order at the end; the calibration blocks are flushed per sensor. No atomics.
 // assemble_*_kernel: sums the <= 6 overlapping segment partials per control-point entry into the banded storage and
 // reduces the calibration blocks over all segments.
 #pragma once
@@ -18,17 +21,16 @@
 
 namespace cb2 {
 
-constexpr int kAccThreads = 64;
-#ifndef CB2_ACC_ROWS
-#define CB2_ACC_ROWS 24
-#endif
+constexpr int kAccWarps = 4;
+constexpr int kAccThreads = 32 * kAccWarps;
+constexpr int kAccRows = 16;       // J rows per shared-memory tile (4 DMMA k-steps)
+constexpr int kAccStride = 68;     // doubles per tile row; 68 mod 16 == 4 -> the 16 lanes of a half warp hit 16 distinct 8-byte banks
+constexpr int kAccRcol = 36;       // local layout: cp 0..35 | r 36 | zeros 37..39 | calibration unknowns 40.. | zeros
+constexpr int kAccCal0 = 40;
+constexpr size_t kAccSmemBytes = size_t(kAccWarps) * 2 * (kAccRows * kAccStride + 4) * sizeof(double);
 #ifndef CB2_ACC_MINBLOCKS
-#define CB2_ACC_MINBLOCKS 8
+#define CB2_ACC_MINBLOCKS 3
 #endif
-constexpr int kAccRows = CB2_ACC_ROWS;   // J rows per shared-memory tile
-constexpr int kAccW = 60;      // local width: 36 cp | <= 20 calib | r at position 56 | 3 pad  (10 tiles of 6)
-constexpr int kAccRcol = 56;
-constexpr int kAccTiles = 55;  // lower-triangular 6x6 tiles of a 10 x 10 tile grid
 
 // 8-byte asynchronous global -> shared copy (LDGSTS): the J tile of the NEXT step streams in while the current one is multiplied.
 CB2_D void cp_async8(double* dst, const double* src) {
@@ -51,121 +53,137 @@ CB2_D void cp_async_wait() {
 #endif
 }
 
-struct AccCursor { int s, r0; };
+// D(8x8) += A(8x4) B(4x8) in FP64 on the tensor pipe. Lane l holds a = A[l / 4][l % 4], b = B[l % 4][l / 4],
+// c0, c1 = D[l / 4][2 (l % 4) + {0, 1}].
+CB2_D void dmma_8x8x4(double& c0, double& c1, double a, double b) {
+#if defined(CB2_EMUL)
+  ::cb2emul::dmma_8x8x4(c0, c1, a, b);
+#else
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+#endif
+}
 
-__global__ void __launch_bounds__(kAccThreads, CB2_ACC_MINBLOCKS) accumulate_kernel(const SensorDesc* __restrict__ sensors, int n_sensors, int N_c, int g_lo,
-                                                                 const int* __restrict__ c2off, int csz, double* __restrict__ segA,
-                                                                 double* __restrict__ segG, double* __restrict__ segB,
-                                                                 double* __restrict__ segC, double* __restrict__ segGc) {
-  __shared__ __align__(16) double tile[2][kAccRows * kAccW];
-  const int gl = blockIdx.x, g = g_lo + gl, t = threadIdx.x;   // gl: index into this rank's partial buffers, g: segment
-  const bool has_tile = t < kAccTiles;
-  int ti = 0, tj = 0;
-  if (has_tile) { int rem = t; while (rem > ti) { rem -= ti + 1; ++ti; } tj = rem; }
-  double acc[6][6];
+// NB = number of 8-column blocks of the local layout: 7 covers sensors with up to 16 calibration unknowns, 8 up to 20 (kMaxCalib).
+template <int NB>
+__global__ void __launch_bounds__(kAccThreads, (NB == 7 ? CB2_ACC_MINBLOCKS : 2)) accumulate_kernel(
+    const SensorDesc* __restrict__ sensors, int n_sensors, int N_c, int g_lo, const int* __restrict__ c2off, int csz, double* __restrict__ segA,
+    double* __restrict__ segG, double* __restrict__ segB, double* __restrict__ segC, double* __restrict__ segGc) {
+  // dynamic shared memory: per warp two tile buffers of kAccRows x kAccStride (+ 4 doubles: the last fragment reads past a row end)
+  typedef double TileBuf[2][kAccRows * kAccStride + 4];
+  TileBuf* tiles = dyn_smem<TileBuf>();
+  __shared__ int colpos[kAccWarps][kCpCols + kMaxCalib];
+  const int gl = blockIdx.x, g = g_lo + gl, t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int fr = lane & 3, fc = lane >> 2;   // fragment row (k) and column of this lane
+  double acc[NB][NB][2];                     // [bi][bj <= bi]: 8x8 tile of the local Gram matrix; the rest is dead code
 #pragma unroll
-  for (int a = 0; a < 6; ++a)
+  for (int bi = 0; bi < NB; ++bi)
 #pragma unroll
-    for (int b = 0; b < 6; ++b) acc[a][b] = 0.0;
+    for (int bj = 0; bj < NB; ++bj) { acc[bi][bj][0] = 0.0; acc[bi][bj][1] = 0.0; }
+  double* const tb0 = tiles[warp][0];
+  for (int i = lane; i < 2 * (kAccRows * kAccStride + 4); i += 32) tb0[i] = 0.0;   // padding columns stay zero for the whole kernel
+  __syncwarp();
 
-  auto rows_of = [&](int s) { const SensorDesc& sd = sensors[s]; return (sd.seg_start[g + 1] - sd.seg_start[g]) * sd.m; };
-  auto skip_empty = [&](AccCursor c) { while (c.s < n_sensors && rows_of(c.s) == 0) ++c.s; return c; };
-  auto next_tile = [&](AccCursor c) {
-    c.r0 += kAccRows;
-    if (c.r0 >= rows_of(c.s)) { c.r0 = 0; ++c.s; c = skip_empty(c); }
-    return c;
-  };
-  // Thread t < 60 fills local column position t of every tile row: the J column that maps there, the residual, or zero.
-  auto issue_load = [&](AccCursor c, int buf) {
-    if (c.s < n_sensors && t < kAccW) {
-      const SensorDesc& sd = sensors[c.s];
-      const int m = sd.m, jw = sd.jw;
-      const int o0 = sd.seg_start[g];
-      const int rows = (sd.seg_start[g + 1] - o0) * m;
-      const int nr = min(kAccRows, rows - c.r0);
-      int src = -1;                       // J column feeding this position
-      if (t < kCpCols) src = t;
-      else if (t < kAccRcol) { for (int j = 0; j < sd.n_jcal; ++j) if (kCpCols + sd.junk[j] == t) src = kCpCols + j; }
-      double* dst = tile[buf] + t;
-      if (src >= 0) {
-        const double* base = sd.J + (size_t(o0) * m + c.r0) * jw + src;
-        for (int row = 0; row < nr; ++row) cp_async8(dst + row * kAccW, base + size_t(row) * jw);
-      } else if (t == kAccRcol) {
-        const double* base = sd.r + size_t(o0) * m + c.r0;
-        for (int row = 0; row < nr; ++row) cp_async8(dst + row * kAccW, base + row);
-      } else {
-        for (int row = 0; row < nr; ++row) dst[row * kAccW] = 0.0;
-      }
-    }
-    cp_async_commit();
-  };
-
-  AccCursor cu = skip_empty(AccCursor{0, 0});
-  int buf = 0;
-  issue_load(cu, buf);
-  for (int s = 0; s < n_sensors; ++s) {
+  for (int s = warp; s < n_sensors; s += kAccWarps) {
     const SensorDesc& sd = sensors[s];
-    const int nc = sd.n_calib;
-    while (cu.s == s) {
-      const int nr = min(kAccRows, rows_of(s) - cu.r0);
-      const AccCursor nx = next_tile(cu);
-      issue_load(nx, buf ^ 1);
-      cp_async_wait<1>();
-      __syncthreads();
-      if (has_tile) {
-        const double* tb = tile[buf];
-        for (int row = 0; row < nr; ++row) {
-          const double2* pa = reinterpret_cast<const double2*>(tb + row * kAccW + 6 * ti);
-          const double2* pb = reinterpret_cast<const double2*>(tb + row * kAccW + 6 * tj);
-          const double2 a0 = pa[0], a1 = pa[1], a2 = pa[2], b0 = pb[0], b1 = pb[1], b2 = pb[2];
-          const double a6[6] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y};
-          const double b6[6] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y};
-#pragma unroll
-          for (int a = 0; a < 6; ++a)
-#pragma unroll
-            for (int b = 0; b < 6; ++b) acc[a][b] += a6[a] * b6[b];
+    const int m = sd.m, jw = sd.jw, nc = sd.n_calib;
+    const int o0 = sd.seg_start[g];
+    const int rows = (sd.seg_start[g + 1] - o0) * m;
+    if (rows == 0) continue;
+    // Local column of every stored J column. The previous sensor's calibration columns are cleared first.
+    for (int i = lane; i < 2 * (kAccRows * kAccStride + 4); i += 32) { const int c = i % (kAccRows * kAccStride + 4) % kAccStride; if (c >= kAccCal0) tb0[i] = 0.0; }
+    for (int c = lane; c < jw; c += 32) colpos[warp][c] = c < kCpCols ? c : kAccCal0 + sd.junk[c - kCpCols];
+    __syncwarp();
+    const double* __restrict__ Jg = sd.J + size_t(o0) * m * jw;
+    const double* __restrict__ rg = sd.r + size_t(o0) * m;
+    const int ntiles = (rows + kAccRows - 1) / kAccRows;
+    auto issue_load = [&](int tile, int buf) {
+      if (tile < ntiles) {
+        double* tb = tiles[warp][buf];
+        const int r0 = tile * kAccRows;
+        const int nr = min(kAccRows, rows - r0);
+        const double* src = Jg + size_t(r0) * jw;
+        const int total = nr * jw;
+        int row = 0, col = lane;            // jw >= 36 > 32: at most one wrap per step
+        for (int e = lane; e < total; e += 32) {
+          cp_async8(tb + row * kAccStride + colpos[warp][col], src + e);
+          col += 32;
+          if (col >= jw) { col -= jw; ++row; }
+        }
+        if (lane < kAccRows) {
+          if (lane < nr) cp_async8(tb + lane * kAccStride + kAccRcol, rg + r0 + lane);
+          else for (int c = 0; c < kAccStride; ++c) tb[lane * kAccStride + c] = 0.0;     // rows past the end of the segment
         }
       }
-      __syncthreads();
-      cu = nx;
-      buf ^= 1;
-    }
-    // Flush every entry that involves this sensor's calibration columns, then reset it for the next sensor.
-    if (has_tile && ti >= 6) {
+      cp_async_commit();
+    };
+    issue_load(0, 0);
+    for (int tile = 0; tile < ntiles; ++tile) {
+      const int buf = tile & 1;
+      issue_load(tile + 1, buf ^ 1);
+      cp_async_wait<1>();
+      __syncwarp();
+      const double* tb = tiles[warp][buf];
+      const int nr = min(kAccRows, rows - tile * kAccRows);
 #pragma unroll
-      for (int a = 0; a < 6; ++a)
+      for (int ks = 0; ks < kAccRows / 4; ++ks) {
+        if (4 * ks < nr) {
+          double f[NB];
 #pragma unroll
-        for (int b = 0; b < 6; ++b) {
-          const int I = 6 * ti + a, Jx = 6 * tj + b;
-          if (I == kAccRcol) {                    // residual row
-            if (Jx < kCpCols) continue;          // control-point gradient: accumulated over all sensors
-            const int lc = Jx - kCpCols;
-            if (Jx < kAccRcol && lc < nc) segGc[size_t(gl) * N_c + sd.calib_off + lc] = acc[a][b];
-          } else if (I < kAccRcol) {              // calibration row
-            const int li = I - kCpCols;
-            if (li < nc) {
-              if (Jx < kCpCols) segB[(size_t(gl) * kCpCols + Jx) * N_c + sd.calib_off + li] = acc[a][b];
-              else if (Jx <= I) segC[size_t(gl) * csz + c2off[s] + li * nc + (Jx - kCpCols)] = acc[a][b];
-            }
-          }
-          acc[a][b] = 0.0;
+          for (int b = 0; b < NB; ++b) f[b] = tb[(4 * ks + fr) * kAccStride + 8 * b + fc];
+#pragma unroll
+          for (int bi = 0; bi < NB; ++bi)
+#pragma unroll
+            for (int bj = 0; bj <= bi; ++bj) dmma_8x8x4(acc[bi][bj][0], acc[bi][bj][1], f[bi], f[bj]);
         }
+      }
+      __syncwarp();
+    }
+    cp_async_wait<0>();
+    // Flush every entry that involves this sensor's calibration unknowns (blocks 5..NB-1), then reset them for the next sensor.
+#pragma unroll
+    for (int bi = 5; bi < NB; ++bi) {
+      const int li = 8 * (bi - 5) + fc;       // calibration-local unknown of this lane's accumulator row
+#pragma unroll
+      for (int bj = 0; bj <= bi; ++bj) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int Jx = 8 * bj + 2 * fr + i;
+          const double v = acc[bi][bj][i];
+          if (li < nc) {
+            if (Jx < kCpCols) segB[(size_t(gl) * kCpCols + Jx) * N_c + sd.calib_off + li] = v;
+            else if (Jx == kAccRcol) segGc[size_t(gl) * N_c + sd.calib_off + li] = v;
+            else if (Jx >= kAccCal0 && Jx - kAccCal0 <= li) segC[size_t(gl) * csz + c2off[s] + li * nc + (Jx - kAccCal0)] = v;
+          }
+          acc[bi][bj][i] = 0.0;
+        }
+      }
     }
   }
-  cp_async_wait<0>();
-  if (has_tile) {
-    if (ti < 6) {
+  // Control-point block (+ gradient row 36): combine the warps in a fixed order through shared memory.
+  __syncwarp();
+  double* red = tiles[warp][0];             // 15 tiles x 64 doubles = 960 <= 2 * (16 * 68 + 4)
+  {
+    int tix = 0;
 #pragma unroll
-      for (int a = 0; a < 6; ++a)
+    for (int bi = 0; bi < 5; ++bi)
 #pragma unroll
-        for (int b = 0; b < 6; ++b) {
-          const int I = 6 * ti + a, Jx = 6 * tj + b;
-          if (Jx <= I) segA[(size_t(gl) * kCpCols + I) * kCpCols + Jx] = acc[a][b];
-        }
-    } else if (ti == 9 && tj < 6) {
-#pragma unroll
-      for (int b = 0; b < 6; ++b) segG[size_t(gl) * kCpCols + 6 * tj + b] = acc[kAccRcol - 54][b];
-    }
+      for (int bj = 0; bj <= bi; ++bj) {
+        red[tix * 64 + fc * 8 + 2 * fr] = acc[bi][bj][0];
+        red[tix * 64 + fc * 8 + 2 * fr + 1] = acc[bi][bj][1];
+        ++tix;
+      }
+  }
+  __syncthreads();
+  for (int e = t; e < 15 * 64; e += kAccThreads) {
+    const int tix = e >> 6, mrow = (e >> 3) & 7, ncol = e & 7;
+    int bi = 0, rem = tix;
+    while (rem > bi) { rem -= bi + 1; ++bi; }
+    const int I = 8 * bi + mrow, Jx = 8 * rem + ncol;
+    if (Jx > I || Jx >= kCpCols || I > kAccRcol) continue;
+    double v = 0.0;
+    for (int w = 0; w < kAccWarps; ++w) v += tiles[w][0][e];
+    if (I < kCpCols) segA[(size_t(gl) * kCpCols + I) * kCpCols + Jx] = v;
+    else segG[size_t(gl) * kCpCols + Jx] = v;
   }
 }
 

@@ -116,6 +116,33 @@ inline T warp_exchange(T v, int src_lane) {
 }
 }  // namespace cb2emul
 
+namespace cb2emul {
+// mma.sync.aligned.m8n8k4.row.col.f64: lane l holds a = A[l / 4][l % 4], b = B[l % 4][l / 4], c0, c1 = D[l / 4][2 (l % 4) + {0, 1}].
+inline void dmma_8x8x4(double& c0, double& c1, double a, double b) {
+  Block& B = blk();
+  const int tid = tls().linear_tid, w = tid / 32, lane = tid % 32;
+  double A[32], Bv[32];
+  uint64_t raw;
+  std::memcpy(&raw, &a, 8);
+  B.slots[size_t(w) * 32 + lane] = raw;
+  B.warp_bar[w]->arrive_and_wait();
+  for (int l = 0; l < 32; ++l) { raw = B.slots[size_t(w) * 32 + l]; std::memcpy(&A[l], &raw, 8); }
+  B.warp_bar[w]->arrive_and_wait();
+  std::memcpy(&raw, &b, 8);
+  B.slots[size_t(w) * 32 + lane] = raw;
+  B.warp_bar[w]->arrive_and_wait();
+  for (int l = 0; l < 32; ++l) { raw = B.slots[size_t(w) * 32 + l]; std::memcpy(&Bv[l], &raw, 8); }
+  B.warp_bar[w]->arrive_and_wait();
+  const int mrow = lane / 4;
+  for (int i = 0; i < 2; ++i) {
+    const int n = 2 * (lane % 4) + i;
+    double acc = i == 0 ? c0 : c1;
+    for (int k = 0; k < 4; ++k) acc = std::fma(A[mrow * 4 + k], Bv[n * 4 + k], acc);
+    (i == 0 ? c0 : c1) = acc;
+  }
+}
+}  // namespace cb2emul
+
 template <typename T> inline T __shfl_sync(unsigned, T v, int src, int width = 32) {
   const int lane = ::cb2emul::tls().linear_tid % 32;
   return ::cb2emul::warp_exchange(v, (lane / width) * width + (src % width));

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(kCrThreads) cr_level_kernel(const BandSys* __r
   const BandSys sy = systems[blockIdx.y];
   const int stride = 1 << level;
   const int j = blockIdx.x, i = j * stride;
-  if (i >= sy.nblk) return;
+  if (i >= sy.nblk || level >= cr_levels(sy.nblk)) return;   // chunks of unequal length: the shorter ones finish a level early
   const int nact = (sy.nblk + stride - 1) >> level;
   const bool elim = (j & 1) || nact == 1;
   const bool has_a = (j & 1) != 0;                              // active left neighbour i - stride (odd positions always have one)
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(kCrThreads) cr_level_kernel(const BandSys* __r
     for (int r = 0; r < kCrB; ++r) X[r * XS + c] = w[r];
     if (c < 2 * kCrB) {
 #pragma unroll
-      for (int r = 0; r < kCrB; ++r) sy.crWef[(size_t(i) * kCrB + r) * (2 * kCrB) + c] = w[r];
+      for (int r = 0; r < kCrB; ++r) sy.crWef[size_t(i) * kCrB * (2 * kCrB) + c * kCrB + r] = w[r];   // transposed: [60][30]
     } else {
 #pragma unroll
       for (int r = 0; r < kCrB; ++r) if (r0 + r < n) sy.W[size_t(r0 + r) * nbw + (c - 2 * kCrB)] = w[r];
@@ -235,46 +235,67 @@ __global__ void __launch_bounds__(kCrThreads) cr_level_kernel(const BandSys* __r
   }
 }
 
-// Back-substitution of one level: x_i = L^-T (v_i - W_E x_a - W_F x_b) for the blocks eliminated on `level`; one warp per block.
-// grid = (ceil(eliminated blocks / 8), chunks), block = 256.
-__global__ void __launch_bounds__(256) cr_back_kernel(const BandSys* __restrict__ systems, int level, double* __restrict__ ytil) {
+// Back-substitution of the levels level_hi .. level_lo (descending): x_i = L^-T (v_i - W_E x_a - W_F x_b) for the blocks eliminated
+// on each level; one warp per block. grid = (ceil(eliminated blocks / 8), chunks), block = 256. Several levels per launch only
+// when every one of them fits one CTA (<= 8 eliminated blocks): the levels are then separated by a block barrier.
+// Everything a block needs is fetched with independent, coalesced loads up front (factor rows and [W_E | W_F]^T in registers), so the
+// 30 dependent steps of the triangular solve cost one shuffle + one FMA each.
+__global__ void __launch_bounds__(256) cr_back_kernel(const BandSys* __restrict__ systems, int level_hi, int level_lo, double* ytil) {
   const BandSys sy = systems[blockIdx.y];
-  const int stride = 1 << level;
-  const int nact = (sy.nblk + stride - 1) >> level;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q = blockIdx.x * 8 + warp;                           // q-th eliminated block of this level
-  const int j = nact == 1 ? 0 : 2 * q + 1;
-  if (j >= nact || (nact == 1 && q > 0)) return;
-  const int i = j * stride, r0 = i * kCrB, n = sy.n;
-  const bool has_a = (j & 1) != 0, has_b = (j & 1) && i + stride < sy.nblk;
-  const int ra = (i - stride) * kCrB, rb = (i + stride) * kCrB;
-  // neighbour solutions: lane l holds x_a[l] and x_b[l]
-  double xa = 0.0, xb = 0.0;
-  if (lane < kCrB) {
-    if (has_a && ra + lane < n) xa = ytil[sy.row_gidx[ra + lane]];
-    if (has_b && rb + lane < n) xb = ytil[sy.row_gidx[rb + lane]];
-  }
-  double rhs = 0.0;
-  if (lane < kCrB && r0 + lane < n) rhs = ytil[sy.row_gidx[r0 + lane]];
-  const double* __restrict__ Wef = sy.crWef + size_t(i) * kCrB * (2 * kCrB);
-  if (has_a || has_b) {
-    double s = 0.0;
-    for (int c = 0; c < kCrB; ++c) {
-      const double va = __shfl_sync(0xffffffffu, xa, c), vb = __shfl_sync(0xffffffffu, xb, c);
-      if (lane < kCrB) s += Wef[lane * (2 * kCrB) + c] * va + Wef[lane * (2 * kCrB) + kCrB + c] * vb;
+  const int n = sy.n;
+  for (int level = level_hi; level >= level_lo; --level) {
+    if (level < cr_levels(sy.nblk)) {
+      const int stride = 1 << level;
+      const int nact = (sy.nblk + stride - 1) >> level;
+      const int q = blockIdx.x * 8 + warp;                           // q-th eliminated block of this level
+      const int j = nact == 1 ? 0 : 2 * q + 1;
+      if (j < nact && !(nact == 1 && q > 0)) {
+        const int i = j * stride, r0 = i * kCrB;
+        const bool has_a = (j & 1) != 0, has_b = (j & 1) && i + stride < sy.nblk;
+        const int ra = (i - stride) * kCrB, rb = (i + stride) * kCrB;
+        const int ll = lane < kCrB ? lane : kCrB - 1;
+        const double* __restrict__ L = sy.crL + size_t(i) * (kCrB * kCrB);
+        const double* __restrict__ WefT = sy.crWef + size_t(i) * kCrB * (2 * kCrB);   // [60][30]: column c of [W_E | W_F], contiguous over rows
+        double Lr[kCrB];
+#pragma unroll
+        for (int c = 0; c < kCrB; ++c) Lr[c] = L[c * kCrB + ll];      // lane l holds L[c][l] for every c (row c of L = column c of L^T)
+        // neighbour solutions: lane l holds x_a[l] and x_b[l]
+        double xa = 0.0, xb = 0.0, rhs = 0.0;
+        if (lane < kCrB) {
+          if (has_a && ra + lane < n) xa = ytil[sy.row_gidx[ra + lane]];
+          if (has_b && rb + lane < n) xb = ytil[sy.row_gidx[rb + lane]];
+          if (r0 + lane < n) rhs = ytil[sy.row_gidx[r0 + lane]];
+        }
+        if (has_a || has_b) {
+          double wa[kCrB], wb[kCrB];
+#pragma unroll
+          for (int c = 0; c < kCrB; ++c) { wa[c] = WefT[c * kCrB + ll]; wb[c] = WefT[(kCrB + c) * kCrB + ll]; }
+          double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+          for (int c = 0; c < kCrB; ++c) {
+            s0 += wa[c] * __shfl_sync(0xffffffffu, xa, c);
+            s1 += wb[c] * __shfl_sync(0xffffffffu, xb, c);
+          }
+          rhs -= s0 + s1;
+        }
+        // L^T x = rhs, backwards; lane k owns component k. Reciprocal diagonals are computed by all lanes at once.
+        double dsel = 1.0;
+#pragma unroll
+        for (int c = 0; c < kCrB; ++c) if (lane == c) dsel = Lr[c];
+        const double dinv = 1.0 / dsel;
+        double x = 0.0;
+#pragma unroll
+        for (int c = kCrB - 1; c >= 0; --c) {
+          const double xc = __shfl_sync(0xffffffffu, rhs * dinv, c);
+          if (lane == c) x = xc;
+          if (lane < c) rhs -= Lr[c] * xc;
+        }
+        if (lane < kCrB && r0 + lane < n) ytil[sy.row_gidx[r0 + lane]] = x;
+      }
     }
-    rhs -= s;
+    if (level > level_lo) { __threadfence_block(); __syncthreads(); }
   }
-  // L^T x = rhs, backwards; lane k owns component k.
-  const double* __restrict__ L = sy.crL + size_t(i) * (kCrB * kCrB);
-  double x = 0.0;
-  for (int c = kCrB - 1; c >= 0; --c) {
-    const double lcc = L[c * kCrB + c];
-    const double xc = __shfl_sync(0xffffffffu, rhs, c) / lcc;
-    if (lane == c) x = xc;
-    if (lane < c) rhs -= L[c * kCrB + lane] * xc;
-  }
-  if (lane < kCrB && r0 + lane < n) ytil[sy.row_gidx[r0 + lane]] = x;
 }
 
 }  // namespace cb2

@@ -33,6 +33,7 @@
 #include "cb2_lmkernels.cuh"
 #include "cb2_normal.cuh"
 #include "cb2_schur.cuh"
+#include "cb2_cr.cuh"
 
 namespace cb2 {
 
@@ -263,6 +264,7 @@ struct cb2_problem {
   // normal equations
   DevBuf<int> d_c2off;
   DevBuf<CalibEntry> d_centries;
+  DevBuf<double> d_cpartial;
   DevBuf<double> d_segA, d_segG, d_segB, d_segC, d_segGc, d_Aband, d_Bmat, d_Cmat, d_grad, d_diag, d_scaling, d_dtil2, d_ytil;
   // multi-GPU sharding: this rank owns the chunks [chunk_lo, chunk_hi) and the segments [g_lo, g_hi)
   std::shared_ptr<Comm> comm;   // may be shared between handles of one process (cb2_comm_clone)
@@ -281,9 +283,14 @@ struct cb2_problem {
   DevBuf<BandSys> d_l2;
   DevBuf<int> d_chunk_sys, d_rowidx, d_colidx;
   DevBuf<double> d_L1, d_W1, d_T1, d_T2, d_rawdiag, d_Dinv;
+  // level 1 by block cyclic reduction (cb2_cr.cuh): the default; CB2_SCHUR=band selects the chunked left-to-right band factor
+  bool use_cr = true;
+  int cr_nlevels = 0, cr_max_nblk = 0;
+  DevBuf<double> d_crD, d_crBd, d_crU, d_crWef, d_crL;
   int cur = 0;   // which of the two parameter buffers holds x
   size_t smem_eval[3] = {0, 0, 0};
   int max_tilepairs1 = 0, max_ksplit1 = 1;
+  bool gram_dmma1 = false;   // level-1 Gram product on the FP64 tensor pipe
   double* h_scal = nullptr;   // pinned
   cb2_stats stats{};
   PhaseTimer timer;
@@ -525,6 +532,7 @@ struct cb2_problem {
       for (int li = 0; li < d.n_calib; ++li) ce.push_back(CalibEntry{d.calib_off + li, d.calib_off + li, -1});
     }
     d_centries.upload(ce, h2d);
+    d_cpartial.alloc(std::max<size_t>(ce.size(), 1) * kCalibSlices);
     const size_t nsl = size_t(std::max(g_hi - g_lo, 1));
     d_segA.alloc(nsl * 36 * 36); d_segG.alloc(nsl * 36);
     d_segB.alloc(nsl * 36 * std::max(N_c, 1)); d_segC.alloc(nsl * std::max(csz, 1)); d_segGc.alloc(nsl * std::max(N_c, 1));
@@ -546,7 +554,10 @@ struct cb2_problem {
   // ------------------------------------------------------------------------------------------------------------
   // Global chunk plan (identical on every rank) and this rank's share of it: chunks [chunk_lo, chunk_hi), segments [g_lo, g_hi).
   int plan_chunks() {
-    int target = 110;   // interior control points per chunk (tuned on C4, profiles/)
+    int target = 110;   // interior control points per chunk of the band-factor path (tuned on C4, profiles/)
+    use_cr = true;
+    if (const char* e = std::getenv("CB2_SCHUR")) use_cr = std::string(e) != "band";
+    if (use_cr) target = 1 << 28;   // cyclic reduction parallelises inside a chunk: one chunk per rank
     if (const char* e = std::getenv("CB2_CHUNK_CPS")) target = std::max(6, std::atoi(e));
     int P = std::max(1, (n_cp + 5) / (target + 5));
     P = (P + world - 1) / world * world;                       // same number of chunks on every rank
@@ -572,7 +583,8 @@ struct cb2_problem {
   // Device storage of the substructured Schur elimination (cb2_schur.cuh) for the owned chunks + the replicated separator level.
   int plan_schur() {
     const int P = int(chunks.size()), PL = chunk_hi - chunk_lo;
-    const int nbw1 = 2 * kSepDim + N_c + 1, nbw2 = N_c + 1;
+    const int cal0 = P > 1 ? 2 * kSepDim : 0;   // a single chunk has no separator columns in its border
+    const int nbw1 = cal0 + N_c + 1, nbw2 = N_c + 1;
     const int n2 = kSepDim * (P - 1);
     std::vector<int> rowidx, colidx;
     std::vector<size_t> row_off(PL + 1), col_off(PL + 1);
@@ -580,24 +592,29 @@ struct cb2_problem {
     h_l1.assign(PL, BandSys{});
     const int nt1 = (nbw1 + 63) / 64;
     max_tilepairs1 = nt1 * (nt1 + 1) / 2;
+    gram_dmma1 = nbw1 <= kGramMaxNbw && !std::getenv("CB2_GRAM_SIMT");
     max_ksplit1 = 1;
     std::vector<size_t> Loff(PL), Woff(PL), Toff(PL), Doff(PL);
     size_t Dsz = 0;
     for (int l = 0; l < PL; ++l) {
       const int p = chunk_lo + l;
       BandSys& sy = h_l1[l];
-      sy.n = 6 * (chunks[p].b - chunks[p].a); sy.hb = 35; sy.nbw = nbw1;
+      sy.n = 6 * (chunks[p].b - chunks[p].a); sy.hb = 35; sy.nbw = nbw1; sy.cal0 = cal0;
+      sy.nblk = (sy.n + kCrB - 1) / kCrB;
       sy.ksplit = std::max(1, std::min((sy.n + 63) / 64, (296 + PL * max_tilepairs1 - 1) / (PL * max_tilepairs1)));
+      if (gram_dmma1) sy.ksplit = std::max(1, std::min((sy.n + 63) / 64, std::max(1, 148 / PL)));
       max_ksplit1 = std::max(max_ksplit1, sy.ksplit);
       row_off[l] = rowidx.size();
       for (int i = 0; i < sy.n; ++i) rowidx.push_back(6 * chunks[p].a + i);
       col_off[l] = colidx.size();
-      for (int j = 0; j < kSepDim; ++j) colidx.push_back(p > 0 ? 6 * (chunks[p].a - 5) + j : -1);
-      for (int j = 0; j < kSepDim; ++j) colidx.push_back(p < P - 1 ? 6 * chunks[p].b + j : -1);
+      if (cal0 > 0) {
+        for (int j = 0; j < kSepDim; ++j) colidx.push_back(p > 0 ? 6 * (chunks[p].a - 5) + j : -1);
+        for (int j = 0; j < kSepDim; ++j) colidx.push_back(p < P - 1 ? 6 * chunks[p].b + j : -1);
+      }
       for (int c = 0; c < N_c; ++c) colidx.push_back(int(n_a) + c);
       Loff[l] = Lsz; Woff[l] = Wsz; Toff[l] = Tsz; Doff[l] = Dsz; Dsz += size_t(sy.n);
       Lsz += size_t(sy.n) * 36; Wsz += size_t(sy.n) * nbw1; Tsz += size_t(sy.ksplit) * nbw1 * nbw1;
-      if (backsolve_smem_bytes(sy.n, nbw1, 36) > 220 * 1024) return fail(CB2_INTERNAL, "Schur chunk too large for shared memory; lower CB2_CHUNK_CPS.");
+      if (!use_cr && backsolve_smem_bytes(sy.n, nbw1, 36) > 220 * 1024) return fail(CB2_INTERNAL, "Schur chunk too large for shared memory; lower CB2_CHUNK_CPS.");
       if (nbw1 > 512) return fail(CB2_UNIMPLEMENTED, "Too many calibration unknowns for the band factor kernel.");   // PFW = 12 registers of border prefetch
     }
     const size_t row_off2 = rowidx.size();
@@ -610,11 +627,29 @@ struct cb2_problem {
     d_rowidx.upload(rowidx); d_colidx.upload(colidx);
     d_shared_idx.upload(shared_idx);
     d_shared_buf.alloc(2 * size_t(std::max(n_shared, 1)));
-    d_L1.alloc(Lsz); d_W1.alloc(Wsz); d_T1.alloc(Tsz); d_Dinv.alloc(Dsz + size_t(std::max(n2, 1)));
+    d_L1.alloc(use_cr ? 1 : Lsz); d_W1.alloc(Wsz); d_T1.alloc(Tsz); d_Dinv.alloc(Dsz + size_t(std::max(n2, 1)));
     for (int l = 0; l < PL; ++l) {
       BandSys& sy = h_l1[l];
       sy.row_gidx = d_rowidx.p + row_off[l]; sy.col_gidx = d_colidx.p + col_off[l];
-      sy.L = d_L1.p + Loff[l]; sy.W = d_W1.p + Woff[l]; sy.T = d_T1.p + Toff[l]; sy.Dinv = d_Dinv.p + Doff[l];
+      sy.L = use_cr ? nullptr : d_L1.p + Loff[l]; sy.W = d_W1.p + Woff[l]; sy.T = d_T1.p + Toff[l]; sy.Dinv = d_Dinv.p + Doff[l];
+    }
+    if (use_cr) {
+      // Cyclic-reduction storage of the owned chunks.
+      size_t blk_tot = 0, uslot_tot = 0;
+      cr_max_nblk = 0;
+      for (const auto& sy : h_l1) { blk_tot += size_t(sy.nblk); uslot_tot += size_t((sy.nblk + 1) / 2); cr_max_nblk = std::max(cr_max_nblk, sy.nblk); }
+      cr_nlevels = cr_levels(std::max(cr_max_nblk, 1));
+      const size_t usz = cr_u_size(nbw1);
+      d_crD.alloc(blk_tot * kCrB * kCrB); d_crL.alloc(blk_tot * kCrB * kCrB); d_crBd.alloc(blk_tot * kCrB * nbw1);
+      d_crWef.alloc(blk_tot * kCrB * 2 * kCrB); d_crU.alloc(2 * uslot_tot * usz);
+      size_t b0 = 0, u0 = 0;
+      for (auto& sy : h_l1) {
+        sy.cr_uslots = (sy.nblk + 1) / 2;
+        sy.crD = d_crD.p + b0 * kCrB * kCrB; sy.crL = d_crL.p + b0 * kCrB * kCrB; sy.crBd = d_crBd.p + b0 * kCrB * nbw1;
+        sy.crWef = d_crWef.p + b0 * kCrB * 2 * kCrB; sy.crU = d_crU.p + 2 * u0 * usz;
+        b0 += size_t(sy.nblk); u0 += size_t(sy.cr_uslots);
+      }
+      if (cr_smem_bytes(nbw1) > 227 * 1024) return fail(CB2_UNIMPLEMENTED, "Too many calibration unknowns for the shared-memory Schur kernels.");
     }
     d_l1.upload(h_l1);
     h_l2 = BandSys{};
@@ -635,7 +670,7 @@ struct cb2_problem {
     d_chunk_sys.upload(chunk_sys);
     d_rawdiag.alloc(size_t(std::max(n2, 1)) + std::max(N_c, 1));
     const size_t smem_f1 = factor_smem_bytes(36, nbw1), smem_f2 = factor_smem_bytes(60, nbw2);
-    if (smem_f1 > 227 * 1024 || smem_f2 > 227 * 1024) return fail(CB2_UNIMPLEMENTED, "Too many calibration unknowns for the shared-memory Schur kernels.");
+    if ((!use_cr && smem_f1 > 227 * 1024) || smem_f2 > 227 * 1024) return fail(CB2_UNIMPLEMENTED, "Too many calibration unknowns for the shared-memory Schur kernels.");
     return CB2_OK;
   }
   double* red_Cw = nullptr;
@@ -656,10 +691,13 @@ struct cb2_problem {
     int max_n1 = 0;
     for (const auto& sy : h_l1) max_n1 = std::max(max_n1, sy.n);
     const int nbw1 = h_l1[0].nbw, nbw2 = h_l2.nbw;
-    set(band_factor_kernel<6>, factor_smem_bytes(36, nbw1));
+    if (gram_dmma1) set(border_gram_dmma_kernel, gram_smem_bytes(nbw1));
+    if (use_cr) { set(cr_level_kernel<true>, cr_smem_bytes(nbw1)); set(cr_level_kernel<false>, cr_smem_bytes(nbw1)); }
+    else set(band_factor_kernel<6>, factor_smem_bytes(36, nbw1));
     set(band_factor_kernel<10>, factor_smem_bytes(60, nbw2));
     set(reduced_solve_kernel, size_t(N_c + 1) * (kRedPanel + 1) * 8);
-    set(band_backsolve_kernel, std::max(backsolve_smem_bytes(max_n1, nbw1, 36), backsolve_smem_bytes(h_l2.n, nbw2, 60)));
+    if (reduced_smem_bytes(N_c) <= 227 * 1024 - 256) set(reduced_solve_smem_kernel, reduced_smem_bytes(N_c));
+    set(band_backsolve_kernel, std::max(use_cr ? size_t(0) : backsolve_smem_bytes(max_n1, nbw1, 36), backsolve_smem_bytes(h_l2.n, nbw2, 60)));
 #endif
   }
 
@@ -719,7 +757,8 @@ struct cb2_problem {
     if (N_c > 0) {
       d_Cmat.zero(stream);
       const int ne = int(d_centries.n);
-      CB2_K(assemble_calib_kernel, (ne + 31) / 32, dim3(32, 8), 0, stream, nsl, N_c, csz, ne, d_centries.p, d_segC.p, d_segGc.p, d_Cmat.p, d_grad.p + n_a);
+      CB2_K(assemble_calib_kernel, dim3((ne + 31) / 32, kCalibSlices), dim3(32, 8), 0, stream, nsl, N_c, csz, ne, d_centries.p, d_segC.p, d_segGc.p, d_cpartial.p);
+      CB2_K(assemble_calib_final_kernel, (ne + 255) / 256, 256, 0, stream, N_c, ne, kCalibSlices, d_centries.p, d_cpartial.p, d_Cmat.p, d_grad.p + n_a);
     }
     CB2_K(hess_diag_kernel, int(std::min<long>((n_tot + 255) / 256, 1024)), 256, 0, stream, n_a, N_c, d_Aband.p, d_Cmat.p, d_diag.p);
     if (world > 1) {
@@ -749,11 +788,22 @@ struct cb2_problem {
     const int nbw1 = h_l1[0].nbw;
     int max_n1 = 0;
     for (const auto& sy : h_l1) max_n1 = std::max(max_n1, sy.n);
-    CB2_K(gather_level1_kernel, dim3(std::max(1, std::min(64, (max_n1 * (36 + nbw1) + 255) / 256)), PL), 256, 0, stream, d_l1.p, n_a, N_c, d_Aband.p,
-          d_Bmat.p, d_Cmat.p, d_grad.p, d_dtil2.p);
-    const size_t smem_f1 = factor_smem_bytes(36, nbw1);
-    CB2_K((band_factor_kernel<6>), PL, kFacThreads, smem_f1, stream, d_l1.p, d_scal.p);
-    CB2_K(border_gram_kernel, dim3(max_tilepairs1, PL, max_ksplit1), dim3(16, 16), 0, stream, d_l1.p);
+    if (use_cr) {
+      // Level 1 by block cyclic reduction: one small kernel per level, ceil(log2(blocks)) + 1 levels.
+      const size_t smem_cr = cr_smem_bytes(nbw1);
+      for (int lv = 0; lv < cr_nlevels; ++lv) {
+        const int nact = (cr_max_nblk + (1 << lv) - 1) >> lv;
+        if (lv == 0) CB2_K((cr_level_kernel<true>), dim3(nact, PL), kCrThreads, smem_cr, stream, d_l1.p, lv, n_a, N_c, d_Aband.p, d_Bmat.p, d_Cmat.p, d_grad.p, d_dtil2.p, d_scal.p);
+        else CB2_K((cr_level_kernel<false>), dim3(nact, PL), kCrThreads, smem_cr, stream, d_l1.p, lv, n_a, N_c, d_Aband.p, d_Bmat.p, d_Cmat.p, d_grad.p, d_dtil2.p, d_scal.p);
+      }
+    } else {
+      CB2_K(gather_level1_kernel, dim3(std::max(1, std::min(64, (max_n1 * (36 + nbw1) + 255) / 256)), PL), 256, 0, stream, d_l1.p, n_a, N_c, d_Aband.p,
+            d_Bmat.p, d_Cmat.p, d_grad.p, d_dtil2.p);
+      const size_t smem_f1 = factor_smem_bytes(36, nbw1);
+      CB2_K((band_factor_kernel<6>), PL, kFacThreads, smem_f1, stream, d_l1.p, d_scal.p);
+    }
+    if (gram_dmma1) CB2_K(border_gram_dmma_kernel, dim3(max_ksplit1, PL), 256, gram_smem_bytes(nbw1), stream, d_l1.p);
+    else CB2_K(border_gram_kernel, dim3(max_tilepairs1, PL, max_ksplit1), dim3(16, 16), 0, stream, d_l1.p);
     // Separator + calibration systems: rank-local direct terms minus the Schur terms of the owned chunks, summed across ranks.
     if (h_l2.n > 0) {
       const long tot2 = long(h_l2.n) * (60 + h_l2.nbw);
@@ -776,14 +826,27 @@ struct cb2_problem {
     if (N_c > 0) {
       const long tot3 = long(N_c + 1) * (N_c + 1);
       CB2_K(level3_finalize_kernel, int(std::min<long>((tot3 + 255) / 256, 1024)), 256, 0, stream, h_l2, N_c, n_a, red_Cw, d_dtil2.p);
-      CB2_K(reduced_solve_kernel, 1, kRedThreads, size_t(N_c + 1) * (kRedPanel + 1) * sizeof(double), stream, N_c, n_a, red_Cw, d_ytil.p, d_scal.p);
+      if (reduced_smem_bytes(N_c) <= 227 * 1024 - 256) CB2_K(reduced_solve_smem_kernel, 1, kRedThreads, reduced_smem_bytes(N_c), stream, N_c, n_a, red_Cw, d_ytil.p, d_scal.p);
+      else CB2_K(reduced_solve_kernel, 1, kRedThreads, size_t(N_c + 1) * (kRedPanel + 1) * sizeof(double), stream, N_c, n_a, red_Cw, d_ytil.p, d_scal.p);
     }
     if (h_l2.n > 0) {
       CB2_K(border_matvec_kernel, dim3(std::max(1, std::min(148, (h_l2.n + 7) / 8)), 1), 256, size_t(h_l2.nbw) * sizeof(double), stream, d_l2.p, d_ytil.p);
       CB2_K(band_backsolve_kernel, 1, kBackThreads, backsolve_smem_bytes(h_l2.n, h_l2.nbw, 60), stream, d_l2.p, d_ytil.p);
     }
-    CB2_K(border_matvec_kernel, dim3(std::max(1, std::min(32, (max_n1 + 7) / 8)), PL), 256, size_t(nbw1) * sizeof(double), stream, d_l1.p, d_ytil.p);
-    CB2_K(band_backsolve_kernel, PL, kBackThreads, backsolve_smem_bytes(max_n1, nbw1, 36), stream, d_l1.p, d_ytil.p);
+    CB2_K(border_matvec_kernel, dim3(std::max(1, std::min(std::max(32, 592 / std::max(PL, 1)), (max_n1 + 7) / 8)), PL), 256, size_t(nbw1) * sizeof(double), stream, d_l1.p, d_ytil.p);
+    if (use_cr) {
+      // Top levels with <= 8 eliminated blocks each share one launch (block barrier between levels); then one launch per level.
+      int lv = cr_nlevels - 1, lo = lv;
+      while (lo > 0 && std::max(1, ((cr_max_nblk + (1 << (lo - 1)) - 1) >> (lo - 1)) / 2) <= 8) --lo;
+      CB2_K(cr_back_kernel, dim3(1, PL), 256, 0, stream, d_l1.p, lv, lo, d_ytil.p);
+      for (lv = lo - 1; lv >= 0; --lv) {
+        const int nact = (cr_max_nblk + (1 << lv) - 1) >> lv;
+        const int nel = std::max(1, nact / 2);
+        CB2_K(cr_back_kernel, dim3((nel + 7) / 8, PL), 256, 0, stream, d_l1.p, lv, lv, d_ytil.p);
+      }
+    } else {
+      CB2_K(band_backsolve_kernel, PL, kBackThreads, backsolve_smem_bytes(max_n1, nbw1, 36), stream, d_l1.p, d_ytil.p);
+    }
     CB2_K(apply_step_kernel, 1, kLmThreads, 0, stream, n_a, d_ytil.p, gradG(), d_dtil2.p, d_cp_ref.p, d_cp_own.p, rank == 0 ? 1 : 0, d_ctrl[cur].p,
           d_ctrl[cur ^ 1].p, d_desc.p, d_state[cur].p, d_state[cur ^ 1].p, ns, N_c, d_scal.p);
     timer.end(kPhSchur, stream);

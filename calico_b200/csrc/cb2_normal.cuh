@@ -225,29 +225,40 @@ __global__ void __launch_bounds__(256) assemble_band_kernel(int n_cp, int g_lo, 
   }
 }
 
-// Calibration block C (dense N_c x N_c storage, symmetric fill) and calibration gradient: reduction over all segments.
-// blockDim = (32, 8): x = entry, y = segment slice; the 8 slices are combined in a fixed order.
+// Calibration block C (dense N_c x N_c storage, symmetric fill) and calibration gradient: reduction over all segments in two
+// deterministic stages. Stage 1: grid = (entries / 32, kCalibSlices), blockDim = (32, 8): x = entry, (blockIdx.y, y) = segment slice;
+// partial[slice][entry]. Stage 2: one thread per entry sums the slices in a fixed order and scatters.
 struct CalibEntry { int src; int dst_row, dst_col; };   // src: offset in a segment's segC (or segGc when dst_col < 0)
+constexpr int kCalibSlices = 16;
 __global__ void __launch_bounds__(256) assemble_calib_kernel(int n_seg, int N_c, int csz, int n_entries, const CalibEntry* __restrict__ entries,
                                                              const double* __restrict__ segC, const double* __restrict__ segGc,
-                                                             double* __restrict__ Cmat, double* __restrict__ grad_c) {
+                                                             double* __restrict__ partial) {
   __shared__ double part[8][33];
   const int e = blockIdx.x * 32 + threadIdx.x;
+  const int g0 = blockIdx.y * 8 + threadIdx.y, gs = 8 * gridDim.y;
   double s = 0.0;
-  CalibEntry ce; ce.src = 0; ce.dst_row = 0; ce.dst_col = 0;
   if (e < n_entries) {
-    ce = entries[e];
-    if (ce.dst_col >= 0) { for (int g = threadIdx.y; g < n_seg; g += 8) s += segC[size_t(g) * csz + ce.src]; }
-    else { for (int g = threadIdx.y; g < n_seg; g += 8) s += segGc[size_t(g) * N_c + ce.src]; }
+    const CalibEntry ce = entries[e];
+    if (ce.dst_col >= 0) { for (int g = g0; g < n_seg; g += gs) s += segC[size_t(g) * csz + ce.src]; }
+    else { for (int g = g0; g < n_seg; g += gs) s += segGc[size_t(g) * N_c + ce.src]; }
   }
   part[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && e < n_entries) {
     double tot = 0.0;
     for (int y = 0; y < 8; ++y) tot += part[y][threadIdx.x];
-    if (ce.dst_col >= 0) { Cmat[size_t(ce.dst_row) * N_c + ce.dst_col] = tot; Cmat[size_t(ce.dst_col) * N_c + ce.dst_row] = tot; }
-    else grad_c[ce.dst_row] = tot;
+    partial[size_t(blockIdx.y) * n_entries + e] = tot;
   }
+}
+__global__ void __launch_bounds__(256) assemble_calib_final_kernel(int N_c, int n_entries, int n_slices, const CalibEntry* __restrict__ entries,
+                                                                   const double* __restrict__ partial, double* __restrict__ Cmat, double* __restrict__ grad_c) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_entries) return;
+  const CalibEntry ce = entries[e];
+  double tot = 0.0;
+  for (int y = 0; y < n_slices; ++y) tot += partial[size_t(y) * n_entries + e];
+  if (ce.dst_col >= 0) { Cmat[size_t(ce.dst_row) * N_c + ce.dst_col] = tot; Cmat[size_t(ce.dst_col) * N_c + ce.dst_row] = tot; }
+  else grad_c[ce.dst_row] = tot;
 }
 
 }  // namespace cb2

@@ -28,6 +28,14 @@ struct BandSys {
   double* W;                // [n][nbw]: border on entry, L^-1 border on exit
   double* T;                // [ksplit][nbw][nbw] partial Gram matrices W^T W
   double* Dinv;             // [n] reciprocal diagonal of the factor (written by band_factor_kernel, used by the back-substitution)
+  int cal0;                 // first calibration column of the border: 60 with separator columns, 0 for a single chunk without separators
+  // block cyclic reduction (cb2_cr.cuh): state of the 30x30 blocks, nblk = ceil(n / 30)
+  int nblk, cr_uslots;
+  double* crD;              // [nblk][30*30] diagonal blocks of the still-active blocks
+  double* crBd;             // [nblk][30][nbw] their border rows
+  double* crU;              // [2][cr_uslots][60][60+nbw] Schur updates of the blocks eliminated on the previous / current level
+  double* crWef;            // [nblk][60][30] (L^-1 [E | F])^T of every eliminated block (back-substitution)
+  double* crL;              // [nblk][30*30] Cholesky factors of the diagonal blocks
 };
 
 constexpr int kSepDim = 30;   // (k-1) control points * 6
@@ -335,6 +343,74 @@ __global__ void __launch_bounds__(256) border_gram_kernel(const BandSys* __restr
   }
 }
 
+// The same Gram product on the FP64 tensor pipe (mma.sync.m8n8k4.f64, SASS DMMA) for borders of up to kGramMaxNbw columns:
+// grid = (ksplit, systems), one CTA per row split computes the whole lower block triangle (8x8 tiles, dealt round-robin to the 8
+// warps, accumulators in registers) while W streams through shared memory 32 rows at a time (row stride == 4 mod 16: conflict-free
+// fragment loads). A and B fragments of a Gram product are the same data: lane l holds W[4 ks + l % 4][8 b + l / 4].
+constexpr int kGramRows = 32;
+constexpr int kGramMaxTiles = 44;                      // per warp: 8 * 44 = 352 >= 26 * 27 / 2
+constexpr int kGramMaxNbw = 208;
+CB2_HD int gram_stride(int nbw) { const int w = (nbw + 7) / 8 * 8; return (w - 4 + 15) / 16 * 16 + 4; }
+CB2_HD size_t gram_smem_bytes(int nbw) { return size_t(kGramRows) * gram_stride(nbw) * sizeof(double); }
+CB2_D void gram_dmma(double& c0, double& c1, double a, double b) {
+#if defined(CB2_EMUL)
+  ::cb2emul::dmma_8x8x4(c0, c1, a, b);
+#else
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+#endif
+}
+__global__ void __launch_bounds__(256) border_gram_dmma_kernel(const BandSys* __restrict__ systems) {
+  const BandSys sy = systems[blockIdx.y];
+  if (int(blockIdx.x) >= sy.ksplit) return;
+  const int nbw = sy.nbw, nb = (nbw + 7) / 8, XS = gram_stride(nbw), ntile = nb * (nb + 1) / 2;
+  double* tile = dyn_smem<double>();
+  __shared__ unsigned char tbi[8 * kGramMaxTiles], tbj[8 * kGramMaxTiles];
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31, fr = lane & 3, fc = lane >> 2;
+  for (int e = t; e < ntile; e += 256) { int bi = 0, rem = e; while (rem > bi) { rem -= bi + 1; ++bi; } tbi[e] = (unsigned char)bi; tbj[e] = (unsigned char)rem; }
+  const int rows_per = ((sy.n + sy.ksplit - 1) / sy.ksplit + kGramRows - 1) / kGramRows * kGramRows;
+  const int r_begin = blockIdx.x * rows_per, r_end = min(sy.n, r_begin + rows_per);
+  double acc[kGramMaxTiles][2];
+#pragma unroll
+  for (int i = 0; i < kGramMaxTiles; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+  const double* __restrict__ Wg = sy.W;
+  const int wcols = nb * 8;
+  for (int r0 = r_begin; r0 < r_end; r0 += kGramRows) {
+    __syncthreads();
+    for (int e = t; e < kGramRows * wcols; e += 256) {
+      const int rr = e / wcols, cc = e - rr * wcols;
+      const int r = r0 + rr;
+      tile[rr * XS + cc] = (r < r_end && cc < nbw) ? Wg[size_t(r) * nbw + cc] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < kGramRows / 4; ++ks) {
+      const double* trow = tile + (4 * ks + fr) * XS + fc;
+#pragma unroll
+      for (int i = 0; i < kGramMaxTiles; ++i) {
+        const int e = warp + 8 * i;
+        if (e < ntile) gram_dmma(acc[i][0], acc[i][1], trow[8 * tbi[e]], trow[8 * tbj[e]]);
+      }
+    }
+  }
+  double* T = sy.T + size_t(blockIdx.x) * nbw * nbw;
+#pragma unroll
+  for (int i = 0; i < kGramMaxTiles; ++i) {
+    const int e = warp + 8 * i;
+    if (e < ntile) {
+      const int bi = tbi[e], bj = tbj[e];
+      const int a = 8 * bi + fc;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int b = 8 * bj + 2 * fr + q;
+        if (a < nbw && b < nbw) {
+          T[size_t(a) * nbw + b] = acc[i][q];
+          if (bi != bj) T[size_t(b) * nbw + a] = acc[i][q];
+        }
+      }
+    }
+  }
+}
+
 // Sum over the row splits of a system's Gram matrix.
 CB2_D double gram_at(const BandSys& sy, int a, int b) {
   double s = 0.0;
@@ -405,7 +481,7 @@ __global__ void __launch_bounds__(256) level3_build_kernel(const BandSys* __rest
     if (c < N_c) {
       v = r == N_c ? grad[n_a + c] : Cmat[size_t(r) * N_c + c];
       if (c == r) rawdiag_c[r] = v;
-      for (int p = 0; p < n_owned; ++p) v -= gram_at(chunks[p], 2 * kSepDim + r, 2 * kSepDim + c);
+      for (int p = 0; p < n_owned; ++p) { const int c0 = chunks[p].cal0; v -= gram_at(chunks[p], c0 + r, c0 + c); }
     }
     Cw[idx] = v;
   }
@@ -490,6 +566,143 @@ __global__ void __launch_bounds__(kRedThreads) reduced_solve_kernel(int N, long 
   }
   if (t < N) ytil[n_a + t] = y[t];
   if (t == 0 && s_fail) atomicAdd(&scal[kScSolveFail], 1.0);
+}
+
+// Same solve with the whole augmented matrix resident in shared memory (N <= ~165: (N+1) x ld doubles <= 227 KB): blocked
+// right-looking Cholesky, 8 columns per step: (1) thread 0 factors the 8x8 diagonal block in registers, (2) one thread per row
+// solves the panel against it and drops the result both in place and into a transposed panel buffer PT[k][row], (3) all threads
+// apply the rank-8 update to the trailing lower triangle in 4x4 register tiles (16-byte shared loads). The rhs row rides along.
+// The backward solve runs on one warp (32-column blocks, shuffle-broadcast inside a block).
+constexpr int kRsPanel = 8;
+CB2_HD int rs_ld(int N) { int ld = N + 1; while (ld % 16 != 2) ++ld; return ld; }       // even (16-byte rows), 2-way conflicts at worst down a column
+CB2_HD int rs_ldp(int N) { return (N + 1 + 3) / 4 * 4 + 4; }
+CB2_HD size_t reduced_smem_bytes(int N) { return (size_t(N + 1) * rs_ld(N) + size_t(kRsPanel) * rs_ldp(N) + N + 1) * sizeof(double); }
+__global__ void __launch_bounds__(kRedThreads) reduced_solve_smem_kernel(int N, long n_a, double* __restrict__ Cw, double* __restrict__ ytil,
+                                                                         double* __restrict__ scal) {
+  const int ld = rs_ld(N), ldp = rs_ldp(N), ldg = N + 1, t = threadIdx.x;
+  double* A = dyn_smem<double>();            // [N + 1][ld]
+  double* PT = A + size_t(N + 1) * ld;       // [8][ldp] transposed panel of the current step, indexed by row - (p0 + pw)
+  double* y = PT + kRsPanel * ldp;           // [N + 1]
+  __shared__ double Ld[kRsPanel * kRsPanel];
+  __shared__ double Linv[kRsPanel];
+  __shared__ int s_fail;
+  if (t == 0) s_fail = 0;
+  for (int e = t; e < ldg * ldg; e += kRedThreads) { const int r = e / ldg, c = e - r * ldg; A[r * ld + c] = Cw[e]; }
+  __syncthreads();
+  for (int p0 = 0; p0 < N; p0 += kRsPanel) {
+    const int pw = min(kRsPanel, N - p0);
+    if (t == 0) {
+      double a[kRsPanel][kRsPanel];
+#pragma unroll
+      for (int r = 0; r < kRsPanel; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) a[r][c] = (r < pw) ? A[(p0 + r) * ld + p0 + c] : (r == c ? 1.0 : 0.0);
+      int fail = 0;
+#pragma unroll
+      for (int c = 0; c < kRsPanel; ++c) {
+        double d = a[c][c];
+        if (!(d > 0.0) || !isfinite(d)) { fail = 1; d = 1.0; }
+        const double inv = rsqrt(d);
+        a[c][c] = d * inv;
+        Linv[c] = inv;
+#pragma unroll
+        for (int r = c + 1; r < kRsPanel; ++r) a[r][c] *= inv;
+#pragma unroll
+        for (int r = c + 1; r < kRsPanel; ++r)
+#pragma unroll
+          for (int k = c + 1; k <= r; ++k) a[r][k] -= a[r][c] * a[k][c];
+      }
+#pragma unroll
+      for (int r = 0; r < kRsPanel; ++r)
+#pragma unroll
+        for (int c = 0; c < kRsPanel; ++c) {
+          Ld[r * kRsPanel + c] = c <= r ? a[r][c] : 0.0;
+          if (c <= r && r < pw) A[(p0 + r) * ld + p0 + c] = a[r][c];
+        }
+      if (fail) s_fail = 1;
+    }
+    __syncthreads();
+    const int rbase = p0 + pw;               // first row below the diagonal block
+    const int nrem = ldg - rbase;            // rows rbase .. N (the last one is the rhs row)
+    for (int rr = t; rr < nrem; rr += kRedThreads) {
+      double* pr = A + (rbase + rr) * ld + p0;
+      double x[kRsPanel];
+#pragma unroll
+      for (int c = 0; c < kRsPanel; ++c) {
+        double sacc = c < pw ? pr[c] : 0.0;
+#pragma unroll
+        for (int k = 0; k < c; ++k) sacc -= x[k] * Ld[c * kRsPanel + k];
+        x[c] = sacc * Linv[c];
+      }
+#pragma unroll
+      for (int c = 0; c < kRsPanel; ++c) { if (c < pw) pr[c] = x[c]; PT[c * ldp + rr] = c < pw ? x[c] : 0.0; }
+    }
+    for (int rr = nrem + t; rr < (nrem + 3) / 4 * 4; rr += kRedThreads)      // zero the tile padding rows
+#pragma unroll
+      for (int c = 0; c < kRsPanel; ++c) PT[c * ldp + rr] = 0.0;
+    __syncthreads();
+    // trailing update: A(rbase + i, rbase + j) -= sum_k PT[k][i] PT[k][j] for i >= j, j < nrem - 1 (no rhs column)
+    const int TR = (nrem + 3) / 4, TC = (nrem - 1 + 3) / 4;
+    for (int e = t; e < TR * TC; e += kRedThreads) {
+      const int tr = e / TC, tc = e - tr * TC;
+      if (tc > tr) continue;
+      double acc[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+#pragma unroll
+      for (int k = 0; k < kRsPanel; ++k) {
+        const double2 r01 = *reinterpret_cast<const double2*>(PT + k * ldp + 4 * tr), r23 = *reinterpret_cast<const double2*>(PT + k * ldp + 4 * tr + 2);
+        const double2 c01 = *reinterpret_cast<const double2*>(PT + k * ldp + 4 * tc), c23 = *reinterpret_cast<const double2*>(PT + k * ldp + 4 * tc + 2);
+        const double rv[4] = {r01.x, r01.y, r23.x, r23.y}, cv[4] = {c01.x, c01.y, c23.x, c23.y};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] += rv[a] * cv[b];
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int i = 4 * tr + a;
+        if (i >= nrem) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int j = 4 * tc + b;
+          if (j <= i && j < nrem - 1) A[(rbase + i) * ld + rbase + j] -= acc[a][b];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // backward solve L^T y = z on warp 0; z = row N of A.
+  if (t < 32) {
+    const int lane = t;
+    for (int c = lane; c < N; c += 32) y[c] = A[N * ld + c];
+    __syncwarp();
+    for (int jb = (N - 1) / 32; jb >= 0; --jb) {
+      const int j = 32 * jb + lane;
+      const int jj = min(j, N - 1);
+      double rhs = j < N ? y[j] : 0.0;
+      const int k0 = 32 * (jb + 1);
+      double s0 = 0.0, s1 = 0.0;
+      int k = k0;
+      for (; k + 1 < N; k += 2) { s0 += A[k * ld + jj] * y[k]; s1 += A[(k + 1) * ld + jj] * y[k + 1]; }
+      if (k < N) s0 += A[k * ld + jj] * y[k];
+      rhs -= s0 + s1;
+      const double dinv = 1.0 / A[jj * ld + jj];
+      double x = 0.0;
+      const int cmax = min(31, N - 1 - 32 * jb);
+      for (int c = cmax; c >= 0; --c) {
+        const double xc = __shfl_sync(0xffffffffu, rhs * dinv, c);
+        if (lane == c) x = xc;
+        if (lane < c) rhs -= A[(32 * jb + c) * ld + jj] * xc;
+      }
+      if (j < N) y[j] = x;
+      __syncwarp();
+    }
+    for (int c = lane; c < N; c += 32) ytil[n_a + c] = y[c];
+    if (lane == 0 && s_fail) atomicAdd(&scal[kScSolveFail], 1.0);
+  }
 }
 
 // Right-hand sides of the back-substitution, all rows of all systems in parallel: ytil[row] <- z - W[row, :nbw-1] . y[border].

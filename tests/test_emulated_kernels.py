@@ -54,9 +54,11 @@ def test_emulated_sweep_matches_oracle(emul_lib, oracle):
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("chunk", [None, "6"])
-def test_emulated_lm_iterations_match_oracle(chunk, emul_lib, oracle, monkeypatch):
-    """Three LM iterations through every kernel, single chunk and two chunks (+ separator level)."""
+@pytest.mark.parametrize("schur,chunk", [("cr", None), ("cr", "6"), ("band", None), ("band", "6")])
+def test_emulated_lm_iterations_match_oracle(schur, chunk, emul_lib, oracle, monkeypatch):
+    """Three LM iterations through every kernel: level 1 by block cyclic reduction (default) and by the chunked band factor,
+    single chunk and two chunks (+ separator level)."""
+    monkeypatch.setenv("CB2_SCHUR", schur)
     if chunk:
         monkeypatch.setenv("CB2_CHUNK_CPS", chunk)
     truth, prob = synthetic.generate("micro", oracle.oracle_api, noise=True)

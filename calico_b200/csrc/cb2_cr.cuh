@@ -29,15 +29,34 @@ namespace cb2 {
 
 constexpr int kCrB = 30;            // block size: (k-1) control points x 6
 constexpr int kCrThreads = 256;
-constexpr int kCrLs = 31;           // row stride of the 30x30 diagonal block in shared memory
+constexpr int kCrLs = 31;           // row stride of the 30x30 diagonal block in shared memory (odd: column walks of the Cholesky are conflict-free)
+constexpr int kCrLc = 32;           // row stride of the finished factor's copy read by the triangular solve (16-byte broadcast loads)
 
 CB2_HD int cr_row_stride(int nbw) { const int M = 2 * kCrB + nbw; return ((M + 7) / 8 * 8 - 4 + 15) / 16 * 16 + 4; }   // >= M rounded to 8, == 4 mod 16
-CB2_HD size_t cr_smem_bytes(int nbw) { return (size_t(32) * cr_row_stride(nbw) + size_t(kCrB) * kCrLs + 32) * sizeof(double); }
+CB2_HD size_t cr_smem_bytes(int nbw) { return (size_t(32) * cr_row_stride(nbw) + size_t(kCrB) * (kCrLs + kCrLc) + 34 + (nbw + 1) / 2) * sizeof(double); }
 CB2_HD size_t cr_u_size(int nbw) { return size_t(2 * kCrB) * (2 * kCrB + nbw); }
 CB2_HD int cr_levels(int nblk) { int l = 0; while (((nblk + (1 << l) - 1) >> l) > 1) ++l; return l + 1; }
 
+#if defined(CB2_CR_CLOCKS) && !defined(CB2_EMUL)
+#define CB2_CLK(k) do { if (threadIdx.x == 0) clk_[k] = clock64(); } while (0)
+#else
+#define CB2_CLK(k) do { } while (0)
+#endif
+constexpr int kCrBatch = 8;
+// for e = t, t + T, ...: st(e, ld(e)), with kCrBatch loads in flight per thread.
+template <class LoadF, class StoreF>
+CB2_D void cr_batched(int total, int t, LoadF ld, StoreF st) {
+  for (int e0 = t; e0 < total; e0 += kCrBatch * kCrThreads) {
+    double v[kCrBatch];
+#pragma unroll
+    for (int u = 0; u < kCrBatch; ++u) v[u] = ld(min(e0 + u * kCrThreads, total - 1));   // clamped, never skipped: no branch between the loads
+#pragma unroll
+    for (int u = 0; u < kCrBatch; ++u) { const int e = e0 + u * kCrThreads; if (e < total) st(e, v[u]); }
+  }
+}
+
 template <bool kFirst>
-__global__ void __launch_bounds__(kCrThreads) cr_level_kernel(const BandSys* __restrict__ systems, int level, long n_a, int N_c,
+__global__ void __launch_bounds__(kCrThreads, (kFirst ? 2 : 1)) cr_level_kernel(const BandSys* __restrict__ systems, int level, long n_a, int N_c,
                                                              const double* __restrict__ Aband, const double* __restrict__ Bmat,
                                                              const double* __restrict__ Cmat, const double* __restrict__ grad,
                                                              const double* __restrict__ dtil2, double* __restrict__ scal) {
@@ -54,7 +73,8 @@ __global__ void __launch_bounds__(kCrThreads) cr_level_kernel(const BandSys* __r
   const int XS = cr_row_stride(nbw);
   double* X = dyn_smem<double>();                               // [32][XS]; rows 30, 31 stay zero (k padding of the DMMA product)
   double* Dm = X + 32 * XS;                                     // [30][31]
-  double* dinv = Dm + kCrB * kCrLs;                             // [30] reciprocal diagonal of L
+  double* Lc = Dm + kCrB * kCrLs + (kCrB * kCrLs & 1);          // [30][32] copy of the factor, 16-byte aligned rows
+  double* dinv = Lc + kCrB * kCrLc;                             // [30] reciprocal diagonal of L
   __shared__ int s_fail;
   const int r0 = i * kCrB;                                      // first chunk row of this block
   const size_t usz = cr_u_size(nbw);
@@ -68,40 +88,61 @@ __global__ void __launch_bounds__(kCrThreads) cr_level_kernel(const BandSys* __r
     if (i - h >= 0) UL = Uprev + size_t((i - h) / stride) * usz;
     if (i + h < sy.nblk) UR = Uprev + size_t((i + h) / stride) * usz;
   }
+  long long clk_[8];
+  (void)clk_;
+  CB2_CLK(0);
   if (t == 0) s_fail = 0;
-  // ---- 1. state of the block ----
-  for (int e = t; e < kCrB * kCrB; e += kCrThreads) {
-    const int r = e / kCrB, c = e % kCrB;
-    double v;
-    if (kFirst) {
-      if (r0 + r < n && r0 + c < n) {
-        const long gi = sy.row_gidx[r0 + r], gj = sy.row_gidx[r0 + c];
-        v = hess_lookup(gi, gj, n_a, N_c, Aband, Bmat, Cmat);
-        if (r == c) v += dtil2[gi];
-      } else v = r == c ? 1.0 : 0.0;                             // padding rows of a partial last block: identity
-    } else {
-      v = sy.crD[size_t(i) * (kCrB * kCrB) + e];
-      if (UL) v -= UL[size_t(kCrB + r) * UW + kCrB + c];
-      if (UR) v -= UR[size_t(r) * UW + c];
-    }
-    Dm[r * kCrLs + c] = v;
+  // Global loads are issued in batches of kCrBatch independent loads per thread before their first use: the level kernels are
+  // latency-bound (one CTA per block, ~17 k doubles from L2), so memory-level parallelism is what sets their duration.
+  const double* __restrict__ crD = sy.crD + size_t(i) * (kCrB * kCrB);
+  const double* __restrict__ crBd = sy.crBd + size_t(i) * kCrB * nbw;
+  const long g0 = kFirst ? long(sy.row_gidx[0]) : 0;             // level-1 chunk rows are consecutive unknowns: row -> g0 + row
+  int* colg = reinterpret_cast<int*>(dinv + 32);                 // [nbw] global unknown of every border column (level 0 only)
+  if (kFirst) {
+    for (int c = t; c < nbw - 1; c += kCrThreads) colg[c] = sy.col_gidx[c];
+    __syncthreads();
   }
-  for (int e = t; e < kCrB * nbw; e += kCrThreads) {
-    const int r = e / nbw, c = e % nbw;
-    double v;
+  // Every value below is ONE unconditional load from a clamped / substituted address followed by selects, so that the kCrBatch
+  // loads of a batch really are in flight together (no branches between them). Absent neighbours read the all-zero slot crZero.
+  const double* __restrict__ ULz = UL ? UL : sy.crZero;
+  const double* __restrict__ URz = UR ? UR : sy.crZero;
+  auto band_ptr = [&](long gi, long gj, bool& ok) -> const double* {   // &A(gi, gj) of the assembled band; ok = inside the block band
+    const long hi = gi > gj ? gi : gj, d = gi > gj ? gi - gj : gj - gi;
+    ok = d < kCpCols;
+    return Aband + hi * kCpCols + (kCpCols - 1 - (ok ? d : 0));
+  };
+  // ---- 1. state of the block ----
+  cr_batched(kCrB * kCrB, t, [&](int e) -> double {
+    const int r = e / kCrB, c = e - r * kCrB;
     if (kFirst) {
-      v = 0.0;
-      if (r0 + r < n) {
-        const long gi = sy.row_gidx[r0 + r];
-        if (c == nbw - 1) v = grad[gi];
-        else { const long gj = sy.col_gidx[c]; if (gj >= 0) v = hess_lookup(gi, gj, n_a, N_c, Aband, Bmat, Cmat); }
-      }
-    } else {
-      v = sy.crBd[size_t(i) * kCrB * nbw + e];
-      if (UL) v -= UL[size_t(kCrB + r) * UW + 2 * kCrB + c];
-      if (UR) v -= UR[size_t(r) * UW + 2 * kCrB + c];
+      const bool in = r0 + r < n && r0 + c < n;
+      const long gi = g0 + min(r0 + r, n - 1), gj = g0 + min(r0 + c, n - 1);
+      bool ok;
+      const double a = *band_ptr(gi, gj, ok), dd = dtil2[gi];
+      return in ? a + (r == c ? dd : 0.0) : (r == c ? 1.0 : 0.0);   // padding rows of a partial last block: identity
     }
-    X[r * XS + 2 * kCrB + c] = v;
+    return crD[e] - ULz[size_t(kCrB + r) * UW + kCrB + c] - URz[size_t(r) * UW + c];
+  }, [&](int e, double v) { const int r = e / kCrB; Dm[r * kCrLs + (e - r * kCrB)] = v; });
+  if (kFirst) {
+    // border = [separator columns (cal0 of them, only with several chunks) | calibration columns: rows of B | rhs: gradient]
+    const int cal0 = sy.cal0, ncal = nbw - 1 - cal0;
+    cr_batched(kCrB * ncal, t, [&](int e) -> double {
+      const int r = e / ncal, c = e - r * ncal;
+      const double v = Bmat[(g0 + min(r0 + r, n - 1)) * N_c + c];
+      return r0 + r < n ? v : 0.0;
+    }, [&](int e, double v) { const int r = e / ncal; X[r * XS + 2 * kCrB + cal0 + (e - r * ncal)] = v; });
+    if (t < kCrB) X[t * XS + 2 * kCrB + nbw - 1] = r0 + t < n ? grad[g0 + r0 + t] : 0.0;
+    if (cal0 > 0) cr_batched(kCrB * cal0, t, [&](int e) -> double {
+      const int r = e / cal0, c = e - r * cal0;
+      const long gi = g0 + min(r0 + r, n - 1), gj = colg[c];
+      bool ok;
+      const double v = *band_ptr(gi, gj < 0 ? gi : gj, ok);
+      return (r0 + r < n && ok && gj >= 0) ? v : 0.0;
+    }, [&](int e, double v) { const int r = e / cal0; X[r * XS + 2 * kCrB + (e - r * cal0)] = v; });
+  } else {
+    cr_batched(kCrB * nbw, t, [&](int e) -> double {
+      return crBd[e] - ULz[size_t(kCrB + e / nbw) * UW + 2 * kCrB + e % nbw] - URz[size_t(e / nbw) * UW + 2 * kCrB + e % nbw];
+    }, [&](int e, double v) { const int r = e / nbw; X[r * XS + 2 * kCrB + (e - r * nbw)] = v; });
   }
   if (!elim) {
     __syncthreads();
@@ -110,23 +151,23 @@ __global__ void __launch_bounds__(kCrThreads) cr_level_kernel(const BandSys* __r
     return;
   }
   // couplings to the active neighbours: E = A(i, a) (rows of i, columns of a), F = A(i, b)
-  for (int e = t; e < kCrB * 2 * kCrB; e += kCrThreads) {
-    const int r = e / (2 * kCrB), c = e % (2 * kCrB);
-    double v = 0.0;
-    if (c < kCrB) {
-      if (has_a) {
-        if (kFirst) { if (r0 + r < n) v = hess_lookup(sy.row_gidx[r0 + r], sy.row_gidx[r0 - kCrB + c], n_a, N_c, Aband, Bmat, Cmat); }
-        else v = -UL[size_t(kCrB + r) * UW + c];
-      }
-    } else if (has_b) {
-      const int cb = c - kCrB;
-      if (kFirst) { if (r0 + r < n && r0 + kCrB + cb < n) v = hess_lookup(sy.row_gidx[r0 + r], sy.row_gidx[r0 + kCrB + cb], n_a, N_c, Aband, Bmat, Cmat); }
-      else v = -UR[size_t(kCrB + cb) * UW + r];
+  cr_batched(kCrB * 2 * kCrB, t, [&](int e) -> double {
+    const int r = e / (2 * kCrB), c = e - r * (2 * kCrB);
+    const bool left = c < kCrB;
+    const int cb = left ? c : c - kCrB;
+    if (kFirst) {
+      const int col = left ? r0 - kCrB + cb : r0 + kCrB + cb;       // chunk row of the neighbour's unknown
+      const bool in = r0 + r < n && col >= 0 && col < n && (left ? has_a : has_b);
+      bool ok;
+      const double v = *band_ptr(g0 + min(r0 + r, n - 1), g0 + min(max(col, 0), n - 1), ok);
+      return (in && ok) ? v : 0.0;
     }
-    X[r * XS + c] = v;
-  }
+    const double v = left ? ULz[size_t(kCrB + r) * UW + cb] : URz[size_t(kCrB + cb) * UW + r];
+    return (left ? has_a : has_b) ? -v : 0.0;
+  }, [&](int e, double v) { const int r = e / (2 * kCrB); X[r * XS + (e - r * (2 * kCrB))] = v; });
   for (int e = t; e < 2 * XS; e += kCrThreads) X[kCrB * XS + e] = 0.0;   // k-padding rows 30, 31
   __syncthreads();
+  CB2_CLK(1);
   // ---- 2a. Cholesky of the diagonal block, 6 columns per step: thread 0 factors the 6x6 pivot block, then panel + trailing update ----
   for (int c0 = 0; c0 < kCrB; c0 += 6) {
     if (t == 0) {
@@ -184,15 +225,23 @@ __global__ void __launch_bounds__(kCrThreads) cr_level_kernel(const BandSys* __r
     }
     __syncthreads();
   }
+  for (int e = t; e < kCrB * kCrLc; e += kCrThreads) { const int r = e / kCrLc, c = e % kCrLc; Lc[e] = (c < r) ? Dm[r * kCrLs + c] : 0.0; }
+  __syncthreads();
+  CB2_CLK(2);
   // ---- 2b. W = L^-1 X, one thread per column (L is read as a shared-memory broadcast) ----
   for (int c = t; c < M; c += kCrThreads) {
     double w[kCrB];
 #pragma unroll
     for (int r = 0; r < kCrB; ++r) {
-      double s = X[r * XS + c];
+      // four interleaved partial sums shorten the dependent FMA chain; the factor row comes in 16-byte broadcast loads
+      double s0 = X[r * XS + c], s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-      for (int k = 0; k < r; ++k) s -= Dm[r * kCrLs + k] * w[k];
-      w[r] = s * dinv[r];
+      for (int k = 0; k + 1 < r; k += 2) {
+        const double2 l = *reinterpret_cast<const double2*>(Lc + r * kCrLc + k);
+        if ((k & 2) == 0) { s0 -= l.x * w[k]; s1 -= l.y * w[k + 1]; } else { s2 -= l.x * w[k]; s3 -= l.y * w[k + 1]; }
+      }
+      if (r & 1) s0 -= Lc[r * kCrLc + r - 1] * w[r - 1];
+      w[r] = ((s0 + s1) + (s2 + s3)) * dinv[r];
     }
 #pragma unroll
     for (int r = 0; r < kCrB; ++r) X[r * XS + c] = w[r];
@@ -209,6 +258,7 @@ __global__ void __launch_bounds__(kCrThreads) cr_level_kernel(const BandSys* __r
     sy.crL[size_t(i) * (kCrB * kCrB) + e] = c <= r ? Dm[r * kCrLs + c] : 0.0;
   }
   __syncthreads();
+  CB2_CLK(3);
   if (t == 0 && s_fail) atomicAdd(&scal[kScSolveFail], 1.0);
   if (nact == 1) return;                                         // last block of the chunk: nothing left to update
   // ---- 2c. U = [W_E W_F]^T W on the FP64 tensor pipe: 8x8 tiles, k = 32 (rows 30, 31 are zero) ----
@@ -216,23 +266,41 @@ __global__ void __launch_bounds__(kCrThreads) cr_level_kernel(const BandSys* __r
     double* U = sy.crU + size_t(level & 1) * sy.cr_uslots * usz + size_t(i / (2 * stride)) * usz;
     const int warp = t >> 5, lane = t & 31, fr = lane & 3, fc = lane >> 2;
     const int nqb = (M + 7) / 8;
-    for (int qb = warp; qb < nqb; qb += kCrThreads / 32) {
-      double bf[8];
+    // Warp w owns the 8 output rows p = 8 w .. 8 w + 7 (60 rows = 7.5 row blocks = the 8 warps): its A fragments (8 k-steps) stay in
+    // registers, the B fragments stream from shared memory, 4 column blocks (independent accumulators) at a time.
+    const int pb = warp;
+    double af[8];
 #pragma unroll
-      for (int ks = 0; ks < 8; ++ks) bf[ks] = X[(4 * ks + fr) * XS + 8 * qb + fc];
+    for (int ks = 0; ks < 8; ++ks) af[ks] = X[(4 * ks + fr) * XS + 8 * pb + fc];
+    const int p = 8 * pb + fc;
+    for (int qb0 = 0; qb0 < nqb; qb0 += 4) {
+      double acc[4][2];
 #pragma unroll
-      for (int pb = 0; pb < 8; ++pb) {
-        double c0 = 0.0, c1 = 0.0;
+      for (int u = 0; u < 4; ++u) { acc[u][0] = 0.0; acc[u][1] = 0.0; }
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) dmma_8x8x4(c0, c1, X[(4 * ks + fr) * XS + 8 * pb + fc], bf[ks]);
-        const int p = 8 * pb + fc, q = 8 * qb + 2 * fr;
-        if (p < 2 * kCrB) {
-          if (q < M) U[size_t(p) * UW + q] = c0;
-          if (q + 1 < M) U[size_t(p) * UW + q + 1] = c1;
+      for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int qb = min(qb0 + u, nqb - 1);
+          dmma_8x8x4(acc[u][0], acc[u][1], af[ks], X[(4 * ks + fr) * XS + 8 * qb + fc]);
+        }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int q = 8 * (qb0 + u) + 2 * fr;
+        if (qb0 + u < nqb && p < 2 * kCrB) {
+          if (q < M) U[size_t(p) * UW + q] = acc[u][0];
+          if (q + 1 < M) U[size_t(p) * UW + q + 1] = acc[u][1];
         }
       }
     }
   }
+#if defined(CB2_CR_CLOCKS) && !defined(CB2_EMUL)
+  __syncthreads();
+  CB2_CLK(4);
+  if (t == 0 && blockIdx.x == 1 && (level == 0 || level == 2))
+    printf("[cr clocks] level %d: load %lld chol %lld trisolve+store %lld dmma %lld total %lld\n", level, clk_[1] - clk_[0], clk_[2] - clk_[1], clk_[3] - clk_[2],
+           clk_[4] - clk_[3], clk_[4] - clk_[0]);
+#endif
 }
 
 // Back-substitution of the levels level_hi .. level_lo (descending): x_i = L^-T (v_i - W_E x_a - W_F x_b) for the blocks eliminated

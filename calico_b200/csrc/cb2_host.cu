@@ -20,9 +20,9 @@
 #include <memory>
 #include <unordered_map>
 #include <vector>
+#include <map>
 #if defined(CB2_EMUL)
 #include <condition_variable>
-#include <map>
 #include <mutex>
 #else
 #include <dlfcn.h>
@@ -133,6 +133,26 @@ struct PhaseTimer {
     open_pairs.clear();
   }
   ~PhaseTimer() { for (auto e : pool) cudaEventDestroy(e); for (auto& pr : open_pairs) { cudaEventDestroy(pr.a); cudaEventDestroy(pr.b); } }
+};
+
+// Developer aid (CB2_PROFILE=1): CUDA events around every kernel launch, warm and in pipeline order (what ncu's cold-cache,
+// serialised launch list cannot show); per-kernel totals are printed to stderr when the problem is destroyed.
+struct KernelProfiler {
+  struct Rec { const char* name; cudaEvent_t a, b; };
+  bool on = std::getenv("CB2_PROFILE") != nullptr;
+  std::vector<Rec> open;
+  std::map<std::string, std::pair<double, long>> tot;
+  void resolve() {
+    for (auto& r : open) { float ms = 0.f; cudaEventElapsedTime(&ms, r.a, r.b); auto& t = tot[r.name]; t.first += ms; ++t.second; cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    open.clear();
+  }
+  void report() {
+    if (!on || tot.empty()) return;
+    std::vector<std::pair<std::string, std::pair<double, long>>> v(tot.begin(), tot.end());
+    std::sort(v.begin(), v.end(), [](const auto& x, const auto& y) { return x.second.first > y.second.first; });
+    std::fprintf(stderr, "[cb2 profile] kernel, launches, total ms, avg us\n");
+    for (auto& e : v) std::fprintf(stderr, "[cb2 profile] %-44s %6ld %10.3f %9.2f\n", e.first.c_str(), e.second.second, e.second.first, 1e3 * e.second.first / e.second.second);
+  }
 };
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -294,10 +314,12 @@ struct cb2_problem {
   double* h_scal = nullptr;   // pinned
   cb2_stats stats{};
   PhaseTimer timer;
+  KernelProfiler kprof;
   double phase_ms[kPhCount] = {0, 0, 0, 0, 0};
   bool scaling_set = false;
 
   ~cb2_problem() {
+    kprof.report();
     if (h_scal) cudaFreeHost(h_scal);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
@@ -641,12 +663,13 @@ struct cb2_problem {
       cr_nlevels = cr_levels(std::max(cr_max_nblk, 1));
       const size_t usz = cr_u_size(nbw1);
       d_crD.alloc(blk_tot * kCrB * kCrB); d_crL.alloc(blk_tot * kCrB * kCrB); d_crBd.alloc(blk_tot * kCrB * nbw1);
-      d_crWef.alloc(blk_tot * kCrB * 2 * kCrB); d_crU.alloc(2 * uslot_tot * usz);
+      d_crWef.alloc(blk_tot * kCrB * 2 * kCrB); d_crU.alloc(2 * uslot_tot * usz + usz);
+      CB2_CUDA(cudaMemsetAsync(d_crU.p + 2 * uslot_tot * usz, 0, usz * sizeof(double), stream));
       size_t b0 = 0, u0 = 0;
       for (auto& sy : h_l1) {
         sy.cr_uslots = (sy.nblk + 1) / 2;
         sy.crD = d_crD.p + b0 * kCrB * kCrB; sy.crL = d_crL.p + b0 * kCrB * kCrB; sy.crBd = d_crBd.p + b0 * kCrB * nbw1;
-        sy.crWef = d_crWef.p + b0 * kCrB * 2 * kCrB; sy.crU = d_crU.p + 2 * u0 * usz;
+        sy.crWef = d_crWef.p + b0 * kCrB * 2 * kCrB; sy.crU = d_crU.p + 2 * u0 * usz; sy.crZero = d_crU.p + 2 * uslot_tot * usz;
         b0 += size_t(sy.nblk); u0 += size_t(sy.cr_uslots);
       }
       if (cr_smem_bytes(nbw1) > 227 * 1024) return fail(CB2_UNIMPLEMENTED, "Too many calibration unknowns for the shared-memory Schur kernels.");
@@ -704,7 +727,15 @@ struct cb2_problem {
   // ------------------------------------------------------------------------------------------------------------
   // Kernel launches.
   // ------------------------------------------------------------------------------------------------------------
+#ifdef CB2_EMUL
 #define CB2_K(...) do { CB2_LAUNCH(__VA_ARGS__); ++stats.kernel_launches; } while (0)
+#else
+#define CB2_K(kernel, grid, block, smem, strm, ...) do { \
+    if (kprof.on) { KernelProfiler::Rec pr_{#kernel, nullptr, nullptr}; cudaEventCreate(&pr_.a); cudaEventCreate(&pr_.b); cudaEventRecord(pr_.a, strm); \
+                    CB2_LAUNCH(kernel, grid, block, smem, strm, __VA_ARGS__); cudaEventRecord(pr_.b, strm); kprof.open.push_back(pr_); } \
+    else CB2_LAUNCH(kernel, grid, block, smem, strm, __VA_ARGS__); \
+    ++stats.kernel_launches; } while (0)
+#endif
 
   // K0: per-image records of every camera at parameter buffer `which`.
   void launch_frames(int which) {
@@ -862,6 +893,7 @@ struct cb2_problem {
     CB2_CUDA(cudaGetLastError());
     stats.d2h_bytes += sizeof(double) * kScCount;
     timer.resolve(phase_ms);
+    if (kprof.on) kprof.resolve();
     stats.jacobian_kernel_ms = phase_ms[kPhJacobian]; stats.normal_eq_ms = phase_ms[kPhNormal];
     stats.schur_ms = phase_ms[kPhSchur]; stats.cost_eval_ms = phase_ms[kPhCost]; stats.lm_loop_ms = phase_ms[kPhLoop];
   }
@@ -1274,6 +1306,7 @@ int cb2_evaluate_sensor(cb2_problem* p, int sid, double* residuals, double* jaco
     const int nt = int(tiles.size());
     cudaStream_t stream = p->stream;
     cb2_stats& stats = p->stats;
+    KernelProfiler& kprof = p->kprof;
 #define CB2_EVAL(KIND, MODE)                                                                                                             \
   CB2_K((eval_kernel<KIND, MODE>), nt, kTile, smem, stream, dd.p, st, dt.p, c, p->d_knots.p, p->d_basis.p, p->d_pw.p, p->d_frames.p, \
         p->gravity[0], p->gravity[1], p->gravity[2], cpart.p, ipart.p, 0)

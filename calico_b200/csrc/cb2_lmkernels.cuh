@@ -31,21 +31,28 @@ __global__ void __launch_bounds__(256) damping_kernel(long n, const double* __re
   }
 }
 
-CB2_D double block_sum(double v, double* sh) {   // all threads must call; returns the total to every thread
-  const int t = threadIdx.x;
+// Fixed-order block reductions of NV values at once (all kLmThreads threads must call): warp shuffles, then the first warp combines the
+// per-warp partials. sh must hold NV * 32 doubles. The result is valid in thread 0.
+template <int NV, bool kMax>
+CB2_D void block_reduce(double (&v)[NV], double* sh) {
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+    for (int q = 0; q < NV; ++q) { const double o = __shfl_down_sync(0xffffffffu, v[q], off); v[q] = kMax ? fmax(v[q], o) : v[q] + o; }
   __syncthreads();
-  sh[t] = v;
+  if (lane == 0)
+#pragma unroll
+    for (int q = 0; q < NV; ++q) sh[q * 32 + warp] = v[q];
   __syncthreads();
-  for (int s = kLmThreads / 2; s > 0; s >>= 1) { if (t < s) sh[t] += sh[t + s]; __syncthreads(); }
-  return sh[0];
-}
-CB2_D double block_max(double v, double* sh) {
-  const int t = threadIdx.x;
-  __syncthreads();
-  sh[t] = v;
-  __syncthreads();
-  for (int s = kLmThreads / 2; s > 0; s >>= 1) { if (t < s) sh[t] = fmax(sh[t], sh[t + s]); __syncthreads(); }
-  return sh[0];
+  if (warp == 0) {
+#pragma unroll
+    for (int q = 0; q < NV; ++q) v[q] = lane < kLmThreads / 32 ? sh[q * 32 + lane] : (kMax ? -1.0e308 : 0.0);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+      for (int q = 0; q < NV; ++q) { const double o = __shfl_down_sync(0xffffffffu, v[q], off); v[q] = kMax ? fmax(v[q], o) : v[q] + o; }
+  }
 }
 
 // gradient_max_norm / gradient_norm^2 = |x - Plus(x, -g)|_inf / _2^2 over the part of the reduced parameter vector this rank
@@ -53,7 +60,7 @@ CB2_D double block_max(double v, double* sh) {
 __global__ void __launch_bounds__(kLmThreads) gradient_norm_kernel(long n_a, const double* __restrict__ grad, const unsigned char* __restrict__ cp_own,
                                                                    int count_shared, const SensorDesc* __restrict__ sensors,
                                                                    const SensorState* __restrict__ states, int n_sensors, double* __restrict__ scal) {
-  __shared__ double sh[kLmThreads];
+  __shared__ double sh[32];
   const int t = threadIdx.x;
   double mx = 0.0, sq = 0.0;
   for (long i = t; i < n_a; i += kLmThreads) {
@@ -74,9 +81,10 @@ __global__ void __launch_bounds__(kLmThreads) gradient_norm_kernel(long n_a, con
       for (int k = 0; k < 4; ++k) { mx = fmax(mx, fabs(d[k])); sq += d[k] * d[k]; }
     }
   }
-  const double tot = block_sum(sq, sh);
-  const double m = block_max(mx, sh);
-  if (t == 0) { scal[kScGradMax] = m; scal[kScGradSq] = tot; }
+  double vs[1] = {sq}, vm[1] = {mx};
+  block_reduce<1, false>(vs, sh);
+  block_reduce<1, true>(vm, sh);
+  if (t == 0) { scal[kScGradMax] = vm[0]; scal[kScGradSq] = vs[0]; }
 }
 
 // Candidate point x_cand = Plus(x, -ytil) (owned + shared control points and every non-constant sensor block), with the part
@@ -91,7 +99,7 @@ __global__ void __launch_bounds__(kLmThreads) apply_step_kernel(long n_a, const 
                                                                 const SensorDesc* __restrict__ sensors, const SensorState* __restrict__ states,
                                                                 SensorState* __restrict__ states_cand, int n_sensors, int N_c,
                                                                 double* __restrict__ scal) {
-  __shared__ double sh[kLmThreads];
+  __shared__ double sh[5 * 32];
   const int t = threadIdx.x;
   double step2 = 0.0, x2 = 0.0, c2 = 0.0, model = 0.0, bad = 0.0;
   for (long i = t; i < n_a; i += kLmThreads) {
@@ -140,10 +148,11 @@ __global__ void __launch_bounds__(kLmThreads) apply_step_kernel(long n_a, const 
     }
     states_cand[s] = S;
   }
-  const double a = block_sum(step2, sh), b = block_sum(x2, sh), c = block_sum(c2, sh), d = block_sum(model, sh), e = block_sum(bad, sh);
+  double red[5] = {step2, x2, c2, model, bad};
+  block_reduce<5, false>(red, sh);
   if (t == 0) {
-    scal[kScStepNorm2] = a; scal[kScXNorm2] = b; scal[kScCandXNorm2] = c; scal[kScModelChange] = 0.5 * d;
-    if (e > 0.0) scal[kScSolveFail] += 1.0;
+    scal[kScStepNorm2] = red[0]; scal[kScXNorm2] = red[1]; scal[kScCandXNorm2] = red[2]; scal[kScModelChange] = 0.5 * red[3];
+    if (red[4] > 0.0) scal[kScSolveFail] += 1.0;
   }
 }
 

@@ -33,6 +33,7 @@ struct BandSys {
   int nblk, cr_uslots;
   double* crD;              // [nblk][30*30] diagonal blocks of the still-active blocks
   double* crBd;             // [nblk][30][nbw] their border rows
+  const double* crZero;     // one all-zero U slot: stands in for the update of a neighbour that does not exist
   double* crU;              // [2][cr_uslots][60][60+nbw] Schur updates of the blocks eliminated on the previous / current level
   double* crWef;            // [nblk][60][30] (L^-1 [E | F])^T of every eliminated block (back-substitution)
   double* crL;              // [nblk][30*30] Cholesky factors of the diagonal blocks
@@ -413,9 +414,18 @@ __global__ void __launch_bounds__(256) border_gram_dmma_kernel(const BandSys* __
 
 // Sum over the row splits of a system's Gram matrix.
 CB2_D double gram_at(const BandSys& sy, int a, int b) {
-  double s = 0.0;
   const size_t stride = size_t(sy.nbw) * sy.nbw;
-  for (int k = 0; k < sy.ksplit; ++k) s += sy.T[k * stride + size_t(a) * sy.nbw + b];
+  const double* __restrict__ T = sy.T + size_t(a) * sy.nbw + b;
+  double s = 0.0;
+  int k = 0;
+  for (; k + 8 <= sy.ksplit; k += 8) {   // 8 independent loads in flight, summed in the fixed order k = 0, 1, 2, ...
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = T[(k + u) * stride];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += v[u];
+  }
+  for (; k < sy.ksplit; ++k) s += T[k * stride];
   return s;
 }
 

@@ -14,9 +14,13 @@
 
 namespace cb2 {
 
-constexpr int kTile = 128;          // observations per CTA in the residual/Jacobian sweep
-constexpr int kRecStride = kTile + 1;   // field stride of the compact records in shared memory: odd, so that both the
-                                        // per-thread writes ([field][lane]) and the per-warp expansion reads ([lane -> field][obs]) are bank-conflict free
+// Observations per CTA in the residual/Jacobian sweep. Cameras: 128 (streaming, HBM-bound). IMU blocks are few (2 x 50 k at C4) and
+// FP64-latency-bound: one warp per CTA keeps their shared-memory footprint small enough to slip between the camera CTAs of the
+// concurrently running camera sweep instead of fencing whole SMs off.
+CB2_HD constexpr int eval_tile(int kind) { return kind == 0 ? 128 : 32; }
+// Field stride of the compact records in shared memory: odd, so that both the per-thread writes ([field][lane]) and the per-warp
+// expansion reads ([lane -> field][obs]) are bank-conflict free.
+CB2_HD constexpr int eval_rec_stride(int kind) { return eval_tile(kind) + 1; }
 constexpr int kMaxCalib = 20;       // max calibration unknowns of one sensor: 12 intrinsics + 3 + 3 + 1
 constexpr int kCpCols = 6 * kK;     // 36 control-point columns per residual block
 

@@ -26,11 +26,12 @@ enum { kModeCost = 0, kModeResiduals = 1, kModeJacobian = 2 };
 #define CB2_EVAL_MINBLOCKS_CAM 4      // 4 x (52 fields x 129 x 8 B + static) = 224 KB of the SM's 228 KB
 #endif
 template <int KIND, int MODE>
-__global__ void __launch_bounds__(kTile, (KIND == kCamera ? CB2_EVAL_MINBLOCKS_CAM : CB2_EVAL_MINBLOCKS)) eval_kernel(const SensorDesc* __restrict__ sensors, const SensorState* __restrict__ states,
+__global__ void __launch_bounds__(eval_tile(KIND), (KIND == kCamera ? CB2_EVAL_MINBLOCKS_CAM : CB2_EVAL_MINBLOCKS)) eval_kernel(const SensorDesc* __restrict__ sensors, const SensorState* __restrict__ states,
                                                      const EvalTile* __restrict__ tiles, const double* __restrict__ ctrl,
                                                      const double* __restrict__ knots, const double* __restrict__ basis,
                                                      const double* __restrict__ pw, const double* __restrict__ frames, double gx, double gy, double gz,
                                                      double* __restrict__ cost_partial, int* __restrict__ invalid_partial, int apply_loss) {
+  constexpr int kTile = eval_tile(KIND), kRecStride = eval_rec_stride(KIND);
   double* rec = dyn_smem<double>();
   __shared__ double s_red[kTile / 32];
   __shared__ int s_bad[kTile / 32];
@@ -111,22 +112,11 @@ __global__ void __launch_bounds__(kTile, (KIND == kCamera ? CB2_EVAL_MINBLOCKS_C
   }
   if (MODE == kModeJacobian) {
     // Phase 2. Every Jacobian entry is sum_q rec[fa_q] * rec[fb_q] with (fa, fb) depending only on the position inside the
-    // m x jw row block: a small table in shared memory. Each warp then streams the CONTIGUOUS region holding the row blocks
-    // of its 32 observations (32 * m * jw doubles, a multiple of 256 bytes from a 256-byte aligned start), so every warp store
-    // instruction writes one fully aligned 256-byte line: no partial sectors.
+    // m x jw row block. Each warp streams the CONTIGUOUS region holding the row blocks of its 32 observations, one observation
+    // (m * jw doubles) at a time; a lane always produces the same entries of a row block, so their field offsets live in registers.
     constexpr int NQ = (KIND == kCamera) ? 1 : (KIND == kGyroscope ? 2 : 3);
-    constexpr int kMaxRow = 3 * (kCpCols + kMaxCalib);
-    __shared__ __align__(16) int2 tab[NQ][kMaxRow];
     const int jw = sd.jw, ni = sd.ni;
     const int rowlen = m * jw;
-    for (int idx = t; idx < rowlen; idx += kTile) {
-      const int row = idx / jw, j = idx - row * jw;
-      const int canon = j < kCpCols ? j : kCpCols + sd.jcanon[j - kCpCols];
-      int fa[3], fb[3];
-      jac_terms(KIND, ni, row, canon, fa, fb);
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) { int2 e; e.x = fa[q] * kRecStride; e.y = fb[q] * kRecStride; tab[q][idx] = e; }
-    }
     __syncthreads();
     const int warp = t >> 5, lane = t & 31;
     const int nobs = min(32, tl.count - warp * 32);
@@ -135,31 +125,88 @@ __global__ void __launch_bounds__(kTile, (KIND == kCamera ? CB2_EVAL_MINBLOCKS_C
       double* __restrict__ Jw = sd.J + (size_t(tl.start) + warp * 32) * rowlen;
       const double* __restrict__ rb = rec + warp * 32;
       if ((rowlen & 1) == 0) {
-        // Even row blocks (camera, gyroscope): two consecutive entries per lane, one 16-byte store; 512 bytes per warp store.
-        int idx = 2 * lane, ol = 0;
-        while (idx >= rowlen) { idx -= rowlen; ++ol; }
-        for (int e = 2 * lane; e < total; e += 64) {
-          double v0 = 0.0, v1 = 0.0;
+        // Even row blocks (camera, gyroscope): lane l owns the fixed entry pairs l, l + 32, ... of the row block; the record fields
+        // of its entries are loop-invariant registers, so an observation costs the lane 4 NQ shared loads per pair and one 16-byte
+        // store; the warp writes each 8 * rowlen-byte row block as contiguous 512-byte pieces. kUnr observations in flight.
+        constexpr int P = (KIND == kCamera) ? 2 : 3;               // ceil(m (36 + max stored calibration columns) / 64)
+        constexpr int kUnr = 4;
+        const int npairs = rowlen >> 1;
+        int fa0[P][NQ], fb0[P][NQ], fa1[P][NQ], fb1[P][NQ];
 #pragma unroll
-          for (int q = 0; q < NQ; ++q) {
-            const int4 d = *reinterpret_cast<const int4*>(&tab[q][idx]);     // entries idx, idx + 1 (idx is even)
-            v0 += rb[d.x + ol] * rb[d.y + ol];
-            v1 += rb[d.z + ol] * rb[d.w + ol];
+        for (int pp = 0; pp < P; ++pp) {
+          const int pr = min(lane + 32 * pp, npairs - 1);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int idx = 2 * pr + h;
+            const int row = idx / jw, j = idx - row * jw;
+            const int canon = j < kCpCols ? j : kCpCols + sd.jcanon[j - kCpCols];
+            int fa[3], fb[3];
+            jac_terms(KIND, ni, row, canon, fa, fb);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+              if (h == 0) { fa0[pp][q] = fa[q] * kRecStride; fb0[pp][q] = fb[q] * kRecStride; }
+              else { fa1[pp][q] = fa[q] * kRecStride; fb1[pp][q] = fb[q] * kRecStride; }
+            }
           }
-          double2 v; v.x = v0; v.y = v1;
-          *reinterpret_cast<double2*>(Jw + e) = v;
-          idx += 64;
-          while (idx >= rowlen) { idx -= rowlen; ++ol; }
+        }
+        for (int o0 = 0; o0 < nobs; o0 += kUnr) {
+          double2 v[kUnr][P];
+#pragma unroll
+          for (int u = 0; u < kUnr; ++u) {
+            const double* __restrict__ ro = rb + min(o0 + u, nobs - 1);
+#pragma unroll
+            for (int pp = 0; pp < P; ++pp) {
+              double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+              for (int q = 0; q < NQ; ++q) { v0 += ro[fa0[pp][q]] * ro[fb0[pp][q]]; v1 += ro[fa1[pp][q]] * ro[fb1[pp][q]]; }
+              v[u][pp].x = v0; v[u][pp].y = v1;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kUnr; ++u)
+            if (o0 + u < nobs) {
+              double* __restrict__ Jo = Jw + size_t(o0 + u) * rowlen;
+#pragma unroll
+              for (int pp = 0; pp < P; ++pp)
+                if (lane + 32 * pp < npairs) *reinterpret_cast<double2*>(Jo + 2 * (lane + 32 * pp)) = v[u][pp];
+            }
         }
       } else {
-        int idx = lane, ol = 0;
-        for (int e = lane; e < total; e += 32) {
-          double v = 0.0;
+        // Odd row blocks (accelerometer with an odd column count): same scheme with single entries and 8-byte stores.
+        constexpr int P1 = (3 * (kCpCols + kMaxCalib) + 31) / 32;
+        constexpr int kUnr = 2;
+        int fa1[P1][NQ], fb1[P1][NQ];
 #pragma unroll
-          for (int q = 0; q < NQ; ++q) { const int2 d = tab[q][idx]; v += rb[d.x + ol] * rb[d.y + ol]; }
-          Jw[e] = v;
-          idx += 32;
-          if (idx >= rowlen) { idx -= rowlen; ++ol; }
+        for (int pp = 0; pp < P1; ++pp) {
+          const int idx = min(lane + 32 * pp, rowlen - 1);
+          const int row = idx / jw, j = idx - row * jw;
+          const int canon = j < kCpCols ? j : kCpCols + sd.jcanon[j - kCpCols];
+          int fa[3], fb[3];
+          jac_terms(KIND, ni, row, canon, fa, fb);
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) { fa1[pp][q] = fa[q] * kRecStride; fb1[pp][q] = fb[q] * kRecStride; }
+        }
+        for (int o0 = 0; o0 < nobs; o0 += kUnr) {
+          double v[kUnr][P1];
+#pragma unroll
+          for (int u = 0; u < kUnr; ++u) {
+            const double* __restrict__ ro = rb + min(o0 + u, nobs - 1);
+#pragma unroll
+            for (int pp = 0; pp < P1; ++pp) {
+              double acc = 0.0;
+#pragma unroll
+              for (int q = 0; q < NQ; ++q) acc += ro[fa1[pp][q]] * ro[fb1[pp][q]];
+              v[u][pp] = acc;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kUnr; ++u)
+            if (o0 + u < nobs) {
+              double* __restrict__ Jo = Jw + size_t(o0 + u) * rowlen;
+#pragma unroll
+              for (int pp = 0; pp < P1; ++pp)
+                if (lane + 32 * pp < rowlen) Jo[lane + 32 * pp] = v[u][pp];
+            }
         }
       }
     }

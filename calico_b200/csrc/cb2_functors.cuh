@@ -56,24 +56,27 @@ CB2_HD void loss_eval(int type, double a, double s, double* rho0, double* rho1) 
 
 // Basis weights w[d][c] = (U_d * M)[c] for derivative orders d < ND (bspline.hpp:40-72):
 // U_d[i] = i!/(i-d)! u^(i-d) dt^-d for i >= d, u = (t - knot0)/(knot1 - knot0). M is the 6x6 row-major basis matrix.
+// Falling factorial i (i-1) ... (i-d+1) = i! / (i-d)!, a compile-time constant once the loops below are unrolled.
+CB2_HD constexpr double falling_factorial(int i, int d) { double c = 1.0; for (int j = i - d; j < i; ++j) c *= double(j + 1); return c; }
 template <int ND>
 CB2_HD void spline_weights(const double* __restrict__ M, double knot0, double knot1, double t, double w[ND][kK]) {
   const double dt_inv = 1.0 / (knot1 - knot0);
   const double u = (t - knot0) * dt_inv;
   double pw[kK];
   pw[0] = 1.0;
+#pragma unroll
   for (int i = 1; i < kK; ++i) pw[i] = pw[i - 1] * u;
   double Mr[kK * kK];
+#pragma unroll
   for (int i = 0; i < kK * kK; ++i) Mr[i] = M[i];
   double scale = 1.0;
+#pragma unroll
   for (int d = 0; d < ND; ++d) {
+#pragma unroll
     for (int c = 0; c < kK; ++c) {
       double s = 0.0;
-      for (int i = d; i < kK; ++i) {
-        double coef = 1.0;
-        for (int j = i - d; j < i; ++j) coef *= double(j + 1);
-        s += coef * pw[i - d] * Mr[i * kK + c];
-      }
+#pragma unroll
+      for (int i = d; i < kK; ++i) s += (falling_factorial(i, d) * pw[i - d]) * Mr[i * kK + c];
       w[d][c] = s * scale;
     }
     scale *= dt_inv;
@@ -81,8 +84,11 @@ CB2_HD void spline_weights(const double* __restrict__ M, double knot0, double kn
 }
 // P[j] = sum_c w[c] * cp[c][j] for j in [j0, j1)
 CB2_HD void spline_combine(const double w[kK], const double* __restrict__ cp, int j0, int j1, double* P) {
-  for (int j = j0; j < j1; ++j) {
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    if (j < j0 || j >= j1) continue;
     double s = 0.0;
+#pragma unroll
     for (int c = 0; c < kK; ++c) s += w[c] * cp[c * 6 + j];
     P[j] = s;
   }
@@ -164,7 +170,8 @@ CB2_HD bool camera_block_from_frame(const SensorState& S, const double* __restri
       out.put(CamRec::Jt + row * 3 + 0, -DR.x); out.put(CamRec::Jt + row * 3 + 1, -DR.y); out.put(CamRec::Jt + row * 3 + 2, -DR.z);
       const V3 jq = cross(DR, b);   // DR^T [b]x = (DR x b)^T
       out.put(CamRec::Jq + row * 3 + 0, 2.0 * jq.x); out.put(CamRec::Jq + row * 3 + 1, 2.0 * jq.y); out.put(CamRec::Jq + row * 3 + 2, 2.0 * jq.z);
-      for (int j = 0; j < S.ni; ++j) out.put(CamRec::Ji + row * S.ni + j, -S.inv_sigma * di[row][j]);
+#pragma unroll
+      for (int j = 0; j < kMaxIntrinsics; ++j) if (j < S.ni) out.put(CamRec::Ji + row * S.ni + j, -S.inv_sigma * di[row][j]);   // constant indices: di stays in registers
     }
     for (int i = 0; i < kK; ++i) out.put(CamRec::w0 + i, fr[FrameRec::w0 + i]);
     out.put(CamRec::one, 1.0); out.put(CamRec::zero, 0.0);
@@ -215,7 +222,8 @@ CB2_HD bool gyro_block(const SensorState& S, const double* __restrict__ M, doubl
       double jl = 0.0;
       for (int j = 0; j < 3; ++j) jl -= G0.m[row * 3 + j] * P1[j] + G1.m[row * 3 + j] * P2[j];
       out.put(GyrRec::Jl + row, jl);
-      for (int j = 0; j < S.ni; ++j) out.put(GyrRec::Ji + row * S.ni + j, -S.inv_sigma * di[row][j]);
+#pragma unroll
+      for (int j = 0; j < kMaxIntrinsics; ++j) if (j < S.ni) out.put(GyrRec::Ji + row * S.ni + j, -S.inv_sigma * di[row][j]);   // constant indices: di stays in registers
     }
     for (int i = 0; i < kK; ++i) { out.put(GyrRec::w0 + i, w[0][i]); out.put(GyrRec::w1 + i, w[1][i]); }
     out.put(GyrRec::one, 1.0); out.put(GyrRec::zero, 0.0);
@@ -278,7 +286,8 @@ CB2_HD bool accel_block(const SensorState& S, const V3& gravity, const double* _
         jl -= G0.m[row * 3 + j] * P1[j] + G1.m[row * 3 + j] * P2[j] + G2r.m[row * 3 + j] * P3[j] + G2t.m[row * 3 + j] * P3[3 + j];
       }
       out.put(AccRec::Jl + row, jl);
-      for (int j = 0; j < S.ni; ++j) out.put(AccRec::Ji + row * S.ni + j, -S.inv_sigma * di[row][j]);
+#pragma unroll
+      for (int j = 0; j < kMaxIntrinsics; ++j) if (j < S.ni) out.put(AccRec::Ji + row * S.ni + j, -S.inv_sigma * di[row][j]);   // constant indices: di stays in registers
     }
     for (int i = 0; i < kK; ++i) { out.put(AccRec::w0 + i, w[0][i]); out.put(AccRec::w1 + i, w[1][i]); out.put(AccRec::w2 + i, w[2][i]); }
     out.put(AccRec::one, 1.0); out.put(AccRec::zero, 0.0);

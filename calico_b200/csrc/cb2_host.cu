@@ -382,7 +382,11 @@ struct cb2_problem {
       return fail(CB2_INTERNAL, "No CUDA device available: calico_b200 has no CPU fallback.");
     if (device >= 0) CB2_CUDA(cudaSetDevice(device));
     CB2_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    CB2_CUDA(cudaStreamCreateWithFlags(&stream_imu, cudaStreamNonBlocking));
+    {
+      int lo = 0, hi = 0;   // the IMU sweep runs at a higher priority so that its long-latency CTAs are placed as soon as a slot frees up
+      CB2_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CB2_CUDA(cudaStreamCreateWithPriority(&stream_imu, cudaStreamNonBlocking, hi));
+    }
     CB2_CUDA(cudaEventCreate(&ev_fork));
     CB2_CUDA(cudaEventCreate(&ev_join));
     CB2_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_scal), sizeof(double) * kScCount));
@@ -509,14 +513,14 @@ struct cb2_problem {
       s.d_valid.alloc(n_active);
       d.stamp = s.d_stamp.p; d.meas = s.d_meas.p; d.seg = s.d_seg.p; d.pt = s.d_pt.p; d.seg_start = s.d_seg_start.p; d.frm = s.d_frm.p;
       d.r = s.d_r.p; d.J = s.d_J.p; d.valid = s.d_valid.p;
-      for (int o0 = 0; o0 < n_active; o0 += kTile) tiles_by_kind[s.kind].push_back(EvalTile{si, o0, std::min(kTile, n_active - o0)});
+      for (int o0 = 0, T = eval_tile(s.kind); o0 < n_active; o0 += T) tiles_by_kind[s.kind].push_back(EvalTile{si, o0, std::min(T, n_active - o0)});
       // state
       SensorState& st = h_state[si];
       st.kind = s.kind; st.model = s.model; st.ni = want;
       for (int j = 0; j < kMaxIntrinsics; ++j) st.intr[j] = j < want ? s.intr[j] : 0.0;
       st.q = Q4{s.q[0], s.q[1], s.q[2], s.q[3]}; st.t = v3(s.t[0], s.t[1], s.t[2]);
       st.latency = s.latency; st.inv_sigma = 1.0 / s.sigma; st.loss_type = s.loss_type; st.loss_scale = s.loss_scale;
-      smem_eval[s.kind] = std::max(smem_eval[s.kind], size_t(rec_size(s.kind, want)) * kRecStride * sizeof(double));
+      smem_eval[s.kind] = std::max(smem_eval[s.kind], size_t(rec_size(s.kind, want)) * eval_rec_stride(s.kind) * sizeof(double));
     }
     n_tot = n_a + N_c;
     if (N_c > kRedThreads) return fail(CB2_UNIMPLEMENTED, "More than 512 calibration unknowns are not supported.");
@@ -705,8 +709,8 @@ struct cb2_problem {
     auto set = [&](auto kernel, size_t bytes) {
       if (bytes > 48 * 1024) CB2_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)));
     };
-    const size_t ev_max[3] = {size_t(rec_size(kCamera, 11)) * kRecStride * 8, size_t(rec_size(kGyroscope, 12)) * kRecStride * 8,
-                              size_t(rec_size(kAccelerometer, 12)) * kRecStride * 8};
+    const size_t ev_max[3] = {size_t(rec_size(kCamera, 11)) * eval_rec_stride(kCamera) * 8, size_t(rec_size(kGyroscope, 12)) * eval_rec_stride(kGyroscope) * 8,
+                              size_t(rec_size(kAccelerometer, 12)) * eval_rec_stride(kAccelerometer) * 8};
     set(eval_kernel<kCamera, kModeCost>, ev_max[0]); set(eval_kernel<kCamera, kModeResiduals>, ev_max[0]); set(eval_kernel<kCamera, kModeJacobian>, ev_max[0]);
     set(eval_kernel<kGyroscope, kModeCost>, ev_max[1]); set(eval_kernel<kGyroscope, kModeResiduals>, ev_max[1]); set(eval_kernel<kGyroscope, kModeJacobian>, ev_max[1]);
     set(eval_kernel<kAccelerometer, kModeCost>, ev_max[2]); set(eval_kernel<kAccelerometer, kModeResiduals>, ev_max[2]); set(eval_kernel<kAccelerometer, kModeJacobian>, ev_max[2]);
@@ -755,13 +759,13 @@ struct cb2_problem {
     cudaStream_t si = fork ? stream_imu : stream;
     if (fork) { CB2_CUDA(cudaEventRecord(ev_fork, stream)); CB2_CUDA(cudaStreamWaitEvent(stream_imu, ev_fork, 0)); }
     // The (long-latency, few-CTA) IMU kernels go first on the side stream; the camera sweep fills the rest of the machine.
-    if (nt[2]) CB2_K((eval_kernel<kAccelerometer, MODE>), nt[2], kTile, smem_eval[2], si, desc, st, d_tiles.p + tile_off[2], c, d_knots.p, d_basis.p, d_pw.p,
+    if (nt[2]) CB2_K((eval_kernel<kAccelerometer, MODE>), nt[2], eval_tile(kAccelerometer), smem_eval[2], si, desc, st, d_tiles.p + tile_off[2], c, d_knots.p, d_basis.p, d_pw.p,
                      d_frames.p, gravity[0], gravity[1], gravity[2], d_cost_partial.p + tile_off[2], d_invalid_partial.p + tile_off[2], 1);
-    if (nt[1]) CB2_K((eval_kernel<kGyroscope, MODE>), nt[1], kTile, smem_eval[1], si, desc, st, d_tiles.p + tile_off[1], c, d_knots.p, d_basis.p, d_pw.p,
+    if (nt[1]) CB2_K((eval_kernel<kGyroscope, MODE>), nt[1], eval_tile(kGyroscope), smem_eval[1], si, desc, st, d_tiles.p + tile_off[1], c, d_knots.p, d_basis.p, d_pw.p,
                      d_frames.p, gravity[0], gravity[1], gravity[2], d_cost_partial.p + tile_off[1], d_invalid_partial.p + tile_off[1], 1);
     if (nt[0]) {
       launch_frames(which);
-      CB2_K((eval_kernel<kCamera, MODE>), nt[0], kTile, smem_eval[0], stream, desc, st, d_tiles.p + tile_off[0], c, d_knots.p, d_basis.p, d_pw.p,
+      CB2_K((eval_kernel<kCamera, MODE>), nt[0], eval_tile(kCamera), smem_eval[0], stream, desc, st, d_tiles.p + tile_off[0], c, d_knots.p, d_basis.p, d_pw.p,
             d_frames.p, gravity[0], gravity[1], gravity[2], d_cost_partial.p + tile_off[0], d_invalid_partial.p + tile_off[0], 1);
     }
     if (fork) { CB2_CUDA(cudaEventRecord(ev_join, stream_imu)); CB2_CUDA(cudaStreamWaitEvent(stream, ev_join, 0)); }
@@ -1297,18 +1301,18 @@ int cb2_evaluate_sensor(cb2_problem* p, int sid, double* residuals, double* jaco
     d.J = J.p; d.r = r.p; d.valid = v.p;
     dd.upload(std::vector<SensorDesc>(1, d));
     std::vector<EvalTile> tiles;
-    for (int o0 = 0; o0 < na; o0 += kTile) tiles.push_back(EvalTile{0, o0, std::min(kTile, na - o0)});
+    for (int o0 = 0, T = eval_tile(s.kind); o0 < na; o0 += T) tiles.push_back(EvalTile{0, o0, std::min(T, na - o0)});
     dt.upload(tiles);
     cpart.alloc(tiles.size()); ipart.alloc(tiles.size());
     const SensorState* st = p->d_state[p->cur].p + sid;
     const double* c = p->d_ctrl[p->cur].p;
-    const size_t smem = size_t(rec_size(s.kind, ni)) * kRecStride * sizeof(double);
+    const size_t smem = size_t(rec_size(s.kind, ni)) * eval_rec_stride(s.kind) * sizeof(double);
     const int nt = int(tiles.size());
     cudaStream_t stream = p->stream;
     cb2_stats& stats = p->stats;
     KernelProfiler& kprof = p->kprof;
 #define CB2_EVAL(KIND, MODE)                                                                                                             \
-  CB2_K((eval_kernel<KIND, MODE>), nt, kTile, smem, stream, dd.p, st, dt.p, c, p->d_knots.p, p->d_basis.p, p->d_pw.p, p->d_frames.p, \
+  CB2_K((eval_kernel<KIND, MODE>), nt, eval_tile(KIND), smem, stream, dd.p, st, dt.p, c, p->d_knots.p, p->d_basis.p, p->d_pw.p, p->d_frames.p, \
         p->gravity[0], p->gravity[1], p->gravity[2], cpart.p, ipart.p, 0)
     // residuals + validity (un-robustified), then the Jacobian pass if requested
     if (s.kind == kCamera) p->launch_frames(p->cur);

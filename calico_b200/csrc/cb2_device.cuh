@@ -35,7 +35,8 @@ struct SensorDesc {
   int u_intr, u_rot, u_trans, u_lat;   // calibration-local unknown offsets, -1 when the block is constant
   const double* stamp; const double* meas; const int* seg; const int* pt;
   const int* seg_start;
-  const int* frm;               // cameras: global image (frame) index of every observation, see camera_frame_kernel
+  const int* frm;               // cameras: sensor-local image (frame) index of every observation, see camera_frame_kernel
+  int frame_base;               // global index of this sensor's first image
   double* r; double* J; unsigned char* valid;
 };
 

@@ -20,7 +20,7 @@ namespace cb2 {
 enum { kModeCost = 0, kModeResiduals = 1, kModeJacobian = 2 };
 
 #ifndef CB2_EVAL_MINBLOCKS
-#define CB2_EVAL_MINBLOCKS 3
+#define CB2_EVAL_MINBLOCKS 8         // one-warp IMU CTAs: 8 per SM = up to 255 registers per thread
 #endif
 #ifndef CB2_EVAL_MINBLOCKS_CAM
 #define CB2_EVAL_MINBLOCKS_CAM 4      // 4 x (52 fields x 129 x 8 B + static) = 224 KB of the SM's 228 KB
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(eval_tile(KIND), (KIND == kCamera ? CB2_EVAL_M
       // Everything that depends only on (camera, stamp) was computed once per image by camera_frame_kernel.
       const int p = sd.pt[o];
       const double2 px = reinterpret_cast<const double2*>(sd.meas)[o];
-      ok = camera_block_from_frame<MODE == kModeJacobian>(S, frames + size_t(sd.frm[o]) * FrameRec::kSize, px.x, px.y,
+      ok = camera_block_from_frame<MODE == kModeJacobian>(S, frames + size_t(sd.frame_base + sd.frm[o]) * FrameRec::kSize, px.x, px.y,
                                                           v3(pw[3 * p], pw[3 * p + 1], pw[3 * p + 2]), rc);
     } else {
       const double stamp = sd.stamp[o];
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(eval_tile(KIND), (KIND == kCamera ? CB2_EVAL_M
 
 // K0: one thread per camera image (sensor, stamp): basis weights, spline pose and velocity at stamp - latency, R_rw, J_l(phi),
 // R_rc^T -> frames[f][FrameRec::kSize]. The 25..144 residual blocks of the image read it back through L1 (warp-broadcast).
-__global__ void __launch_bounds__(128) camera_frame_kernel(int n_frames, const int* __restrict__ frame_sensor, const int* __restrict__ frame_seg,
+__global__ void __launch_bounds__(32) camera_frame_kernel(int n_frames, const int* __restrict__ frame_sensor, const int* __restrict__ frame_seg,
                                                            const double* __restrict__ frame_stamp, const SensorState* __restrict__ states,
                                                            const double* __restrict__ ctrl, const double* __restrict__ knots,
                                                            const double* __restrict__ basis, double* __restrict__ frames) {
@@ -229,21 +229,29 @@ __global__ void __launch_bounds__(128) camera_frame_kernel(int n_frames, const i
   for (int i = 0; i < FrameRec::kSize; ++i) out[i] = fr[i];
 }
 
-// Sums the per-tile partials in a fixed order: scal[slot] = cost, scal[slot+1] = number of failed blocks.
-__global__ void __launch_bounds__(256) reduce_cost_kernel(const double* __restrict__ cost_partial, const int* __restrict__ invalid_partial,
-                                                          int n, double* __restrict__ scal, int slot) {
-  __shared__ double sc[256];
-  __shared__ int sb[256];
-  const int t = threadIdx.x;
+// Sums the per-tile partials in a fixed order: scal[slot] = cost, scal[slot+1] = number of failed blocks. One CTA of 1024 threads,
+// 4 independent loads in flight per thread, shuffle reduction.
+__global__ void __launch_bounds__(1024) reduce_cost_kernel(const double* __restrict__ cost_partial, const int* __restrict__ invalid_partial,
+                                                           int n, double* __restrict__ scal, int slot) {
+  __shared__ double sc[32];
+  __shared__ int sb[32];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   double c = 0.0; int b = 0;
-  for (int i = t; i < n; i += 256) { c += cost_partial[i]; b += invalid_partial[i]; }
-  sc[t] = c; sb[t] = b;
-  __syncthreads();
-  for (int s = 128; s > 0; s >>= 1) {
-    if (t < s) { sc[t] += sc[t + s]; sb[t] += sb[t + s]; }
-    __syncthreads();
+  for (int i0 = t; i0 < n; i0 += 4 * 1024) {
+    double cv[4]; int bv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int i = i0 + u * 1024; const int ic = min(i, n - 1); cv[u] = cost_partial[ic]; bv[u] = invalid_partial[ic]; if (i >= n) { cv[u] = 0.0; bv[u] = 0; } }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { c += cv[u]; b += bv[u]; }
   }
-  if (t == 0) { scal[slot] = sc[0]; scal[slot + 1] = double(sb[0]); }
+  for (int off = 16; off > 0; off >>= 1) { c += __shfl_down_sync(0xffffffffu, c, off); b += __shfl_down_sync(0xffffffffu, b, off); }
+  if (lane == 0) { sc[warp] = c; sb[warp] = b; }
+  __syncthreads();
+  if (warp == 0) {
+    c = sc[lane]; b = sb[lane];
+    for (int off = 16; off > 0; off >>= 1) { c += __shfl_down_sync(0xffffffffu, c, off); b += __shfl_down_sync(0xffffffffu, b, off); }
+    if (lane == 0) { scal[slot] = c; scal[slot + 1] = double(b); }
+  }
 }
 
 }  // namespace cb2

@@ -21,6 +21,8 @@
 #include <unordered_map>
 #include <vector>
 #include <map>
+#include <atomic>
+#include <thread>
 #if defined(CB2_EMUL)
 #include <condition_variable>
 #include <mutex>
@@ -56,11 +58,26 @@ struct DevBuf {
   DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
   DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
   ~DevBuf() { release(); }
-  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  // Device memory comes from the device's default stream-ordered pool with the release threshold lifted (dev_pool_init): freed
+  // blocks stay cached in the process, so the second and later problems of a session (re-optimisation after outlier marking,
+  // camera.cpp:258-299, creates a new problem per Optimize call) do not pay cudaMalloc / cudaFree again. Allocation and release are
+  // ordered on the legacy default stream; the owner synchronises its own streams before releasing and the device after allocating.
+  void release() {
+#ifdef CB2_EMUL
+    if (p) cudaFree(p);
+#else
+    if (p) cudaFreeAsync(p, nullptr);
+#endif
+    p = nullptr; n = 0;
+  }
   void alloc(size_t count) {
     release();
     n = count;
+#ifdef CB2_EMUL
     if (count) CB2_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), std::max<size_t>(count, 1) * sizeof(T)));
+#else
+    if (count) CB2_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&p), std::max<size_t>(count, 1) * sizeof(T), nullptr));
+#endif
   }
   void zero(cudaStream_t s) { if (n) CB2_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
   void upload(const std::vector<T>& h, int64_t* counter = nullptr) {
@@ -111,7 +128,7 @@ struct HostSensor {
 struct ChunkPlan { int a, b; };   // interior control points [a, b)
 
 // CUDA-event phase timing on the library's stream; pairs are resolved after the next stream synchronisation.
-enum Phase { kPhJacobian = 0, kPhNormal = 1, kPhSchur = 2, kPhCost = 3, kPhLoop = 4, kPhCount = 5 };
+enum Phase { kPhJacobian = 0, kPhNormal = 1, kPhSchur = 2, kPhCost = 3, kPhLoop = 4, kPhCamera = 5, kPhCount = 6 };
 struct PhaseTimer {
   struct Pair { cudaEvent_t a, b; int phase; };
   std::vector<cudaEvent_t> pool;
@@ -264,6 +281,10 @@ struct cb2_problem {
   int device = -1;
   cudaStream_t stream = nullptr, stream_imu = nullptr;   // IMU sweeps overlap the camera sweep on a second stream
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool imu_side_stream = std::getenv("CB2_IMU_STREAM") != nullptr;
+  bool speculative_imu = std::getenv("CB2_SPECULATIVE_IMU") != nullptr;   // measured neutral on C4 (Jacobian-mode IMU blocks cost +53 us over cost mode): off by default
+  int imu_jac_point = -1;       // parameter buffer (0 / 1) whose IMU Jacobians, residuals and cost partials are current; -1 = none
+  bool last_sweep_imu = true;
   int n_cp = 0, n_seg = 0, N_c = 0, csz = 0, n_tiles = 0;
   long n_a = 0, n_tot = 0;
   std::vector<SensorDesc> h_desc;
@@ -315,10 +336,12 @@ struct cb2_problem {
   cb2_stats stats{};
   PhaseTimer timer;
   KernelProfiler kprof;
-  double phase_ms[kPhCount] = {0, 0, 0, 0, 0};
+  double phase_ms[kPhCount] = {0, 0, 0, 0, 0, 0};
   bool scaling_set = false;
 
   ~cb2_problem() {
+    if (stream) cudaStreamSynchronize(stream);       // device buffers are released (stream-ordered, default stream) after this body
+    if (stream_imu) cudaStreamSynchronize(stream_imu);
     kprof.report();
     if (h_scal) cudaFreeHost(h_scal);
     if (ev_fork) cudaEventDestroy(ev_fork);
@@ -381,6 +404,16 @@ struct cb2_problem {
     if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0)
       return fail(CB2_INTERNAL, "No CUDA device available: calico_b200 has no CPU fallback.");
     if (device >= 0) CB2_CUDA(cudaSetDevice(device));
+#ifndef CB2_EMUL
+    {
+      int dev = 0;
+      CB2_CUDA(cudaGetDevice(&dev));
+      cudaMemPool_t pool;
+      CB2_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+      unsigned long long keep = ~0ull;   // never trim: freed blocks are reused by the next problem of this process
+      CB2_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
+#endif
     CB2_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     {
       int lo = 0, hi = 0;   // the IMU sweep runs at a higher priority so that its long-latency CTAs are placed as soon as a slot frees up
@@ -395,6 +428,7 @@ struct cb2_problem {
 
   int upload_impl() {
     uploaded = false;
+    if (stream) CB2_CUDA(cudaStreamSynchronize(stream));
     if (knots.empty() || ctrl.empty()) return fail(CB2_FAILED_PRECONDITION, "Trajectory has not been set.");
     if (k != kK) return fail(CB2_UNIMPLEMENTED, "Only spline order 6 (calico::Trajectory::kSplineOrder, trajectory.h:28) is supported.");
     for (const auto& b : bodies)
@@ -433,12 +467,25 @@ struct cb2_problem {
     std::vector<int> frame_sensor, frame_seg;
     std::vector<double> frame_stamp;
     int64_t* h2d = &stats.h2d_bytes;
-    for (int si = 0; si < ns; ++si) {
+    // Phase A (one host thread per sensor): validation, segment lookup, counting sort by segment, SoA packing.
+    struct Packed {
+      int rc = CB2_OK; std::string err;
+      int want = 0, n_active = 0; long blocks = 0, residuals = 0; bool ref_any = false;
+      std::vector<int> seg_start, seg, pt, frm, frame_seg;
+      std::vector<double> stamp, meas, frame_stamp;
+      std::vector<unsigned char> cp_ref;
+    };
+    std::vector<Packed> packed(ns);
+    auto pack_sensor = [&](int si) {
       HostSensor& s = sensors[si];
+      Packed& P = packed[si];
+      auto bad = [&](int code, const char* msg) { P.rc = code; P.err = msg; };
       const int want = s.kind == kCamera ? camera_num_params(s.model) : imu_num_params(s.model);
-      if (want < 0) return fail(CB2_FAILED_PRECONDITION, "Cannot add sensor parameters. Model is not yet defined.");   // camera.cpp:95
-      if (int(s.intr.size()) != want) return fail(CB2_INVALID_ARGUMENT, "Invalid number of intrinsics parameters.");
+      P.want = want;
+      if (want < 0) return bad(CB2_FAILED_PRECONDITION, "Cannot add sensor parameters. Model is not yet defined.");   // camera.cpp:95
+      if (int(s.intr.size()) != want) return bad(CB2_INVALID_ARGUMENT, "Invalid number of intrinsics parameters.");
       const int m = s.m(), n = s.n_obs();
+      P.cp_ref.assign(n_cp, 0);
       // segment of each active observation; stable counting sort by segment
       std::vector<int> seg_of(n, -1);
       std::vector<int> count(n_seg + 1, 0);
@@ -446,19 +493,20 @@ struct cb2_problem {
       for (int o = 0; o < n; ++o) {
         if (s.kind == kCamera && !s.outlier.empty() && s.outlier[o]) continue;   // camera.cpp:121-124
         if (s.kind == kCamera && s.body_slot[o] < 0)
-          return fail(CB2_FAILED_PRECONDITION, "Attempted to create cost function from an observation for a rigidbody that does not exist in the world model.");   // camera.cpp:125-131
+          return bad(CB2_FAILED_PRECONDITION, "Attempted to create cost function from an observation for a rigidbody that does not exist in the world model.");   // camera.cpp:125-131
         const int sg = spline_index(s.stamp[o]);
-        if (sg < 0 || sg >= n_seg) return fail(CB2_INVALID_ARGUMENT, "Observation stamp is outside the valid knots of the trajectory.");
-        for (int c = 0; c < kK; ++c) cp_ref[sg + c] = 1;          // referenced by some rank's residual block
-        ++total_blocks; total_residuals += m;
+        if (sg < 0 || sg >= n_seg) return bad(CB2_INVALID_ARGUMENT, "Observation stamp is outside the valid knots of the trajectory.");
+        for (int c = 0; c < kK; ++c) P.cp_ref[sg + c] = 1;        // referenced by some rank's residual block
+        ++P.blocks; P.residuals += m;
+        P.ref_any = true;
         if (sg < g_lo || sg >= g_hi) continue;                     // another rank's time range
         seg_of[o] = sg;
         ++count[sg + 1];
         ++n_active;
       }
-      const bool ref_any = [&] { for (int o = 0; o < n; ++o) if (!(s.kind == kCamera && !s.outlier.empty() && s.outlier[o])) return true; return false; }();
       for (int g = 0; g < n_seg; ++g) count[g + 1] += count[g];
-      std::vector<int> seg_start(count);
+      P.seg_start = count;
+      const std::vector<int>& seg_start = P.seg_start;
       s.perm.assign(n_active, 0);
       {
         std::vector<int> cursor(count.begin(), count.end() - 1);
@@ -473,25 +521,52 @@ struct cb2_problem {
           if (!std::is_sorted(b, e, by_stamp)) std::stable_sort(b, e, by_stamp);
         }
       }
-      s.n_active = n_active;
-      std::vector<double> stamp(n_active), meas(size_t(n_active) * m);
-      std::vector<int> seg(n_active), pt(s.kind == kCamera ? n_active : 0), frm(s.kind == kCamera ? n_active : 0);
+      s.n_active = P.n_active = n_active;
+      P.stamp.resize(n_active); P.meas.resize(size_t(n_active) * m); P.seg.resize(n_active);
+      if (s.kind == kCamera) { P.pt.resize(n_active); P.frm.resize(n_active); }
       for (int i = 0; i < n_active; ++i) {
         const int o = s.perm[i];
-        stamp[i] = s.stamp[o];
-        seg[i] = seg_of[o];
-        for (int q = 0; q < m; ++q) meas[size_t(i) * m + q] = s.meas[size_t(o) * m + q];
+        P.stamp[i] = s.stamp[o];
+        P.seg[i] = seg_of[o];
+        for (int q = 0; q < m; ++q) P.meas[size_t(i) * m + q] = s.meas[size_t(o) * m + q];
         if (s.kind == kCamera) {
-          pt[i] = bodies[s.body_slot[o]].pw0 + s.feat_slot[o];
-          if (i == 0 || stamp[i] != stamp[i - 1]) { frame_sensor.push_back(si); frame_seg.push_back(seg[i]); frame_stamp.push_back(stamp[i]); }
-          frm[i] = int(frame_stamp.size()) - 1;
+          P.pt[i] = bodies[s.body_slot[o]].pw0 + s.feat_slot[o];
+          if (i == 0 || P.stamp[i] != P.stamp[i - 1]) { P.frame_seg.push_back(P.seg[i]); P.frame_stamp.push_back(P.stamp[i]); }
+          P.frm[i] = int(P.frame_stamp.size()) - 1;                // sensor-local image index; SensorDesc::frame_base makes it global
         }
       }
+    };
+#ifdef CB2_EMUL
+    for (int si = 0; si < ns; ++si) pack_sensor(si);
+#else
+    {
+      const int nth = std::max(1, std::min<int>(ns, int(std::thread::hardware_concurrency())));
+      std::atomic<int> next{0};
+      std::vector<std::thread> pool;
+      for (int th = 0; th < nth; ++th) pool.emplace_back([&] { for (int si = next++; si < ns; si = next++) pack_sensor(si); });
+      for (auto& th : pool) th.join();
+    }
+#endif
+    // Phase B (serial): unknown layout, device buffers, uploads.
+    for (int si = 0; si < ns; ++si) {
+      HostSensor& s = sensors[si];
+      Packed& P = packed[si];
+      if (P.rc != CB2_OK) return fail(P.rc, P.err);
+      const int want = P.want, m = s.m(), n_active = P.n_active;
+      const bool ref_any = P.ref_any;
+      total_blocks += P.blocks; total_residuals += P.residuals;
+      for (int c = 0; c < n_cp; ++c) cp_ref[c] |= P.cp_ref[c];
+      const int frame_base = int(frame_stamp.size());
+      frame_sensor.insert(frame_sensor.end(), P.frame_stamp.size(), si);
+      frame_seg.insert(frame_seg.end(), P.frame_seg.begin(), P.frame_seg.end());
+      frame_stamp.insert(frame_stamp.end(), P.frame_stamp.begin(), P.frame_stamp.end());
+      const std::vector<double>&stamp = P.stamp, &meas = P.meas;
+      const std::vector<int>&seg = P.seg, &pt = P.pt, &frm = P.frm, &seg_start = P.seg_start;
       s.d_stamp.upload(stamp, h2d); s.d_meas.upload(meas, h2d); s.d_seg.upload(seg, h2d); s.d_pt.upload(pt, h2d); s.d_frm.upload(frm, h2d);
       s.d_seg_start.upload(seg_start, h2d);
       // Unknown layout of this sensor (constant or unreferenced blocks drop out, as in Ceres's reduced program).
       SensorDesc& d = h_desc[si];
-      d.kind = s.kind; d.model = s.model; d.ni = want; d.m = m; d.n_obs = n_active;
+      d.kind = s.kind; d.model = s.model; d.ni = want; d.m = m; d.n_obs = n_active; d.frame_base = frame_base;
       const bool ref = ref_any;   // referenced by a residual block on ANY rank: same unknown layout everywhere
       int u = 0;
       d.u_intr = (ref && s.en_intr) ? u : -1; if (d.u_intr >= 0) u += want;
@@ -744,38 +819,56 @@ struct cb2_problem {
   // K0: per-image records of every camera at parameter buffer `which`.
   void launch_frames(int which) {
     if (n_frames > 0)
-      CB2_K(camera_frame_kernel, (n_frames + 127) / 128, 128, 0, stream, n_frames, d_frame_sensor.p, d_frame_seg.p, d_frame_stamp.p, d_state[which].p,
+      CB2_K(camera_frame_kernel, (n_frames + 31) / 32, 32, 0, stream, n_frames, d_frame_sensor.p, d_frame_seg.p, d_frame_stamp.p, d_state[which].p,
             d_ctrl[which].p, d_knots.p, d_basis.p, d_frames.p);
   }
 
   // Residual sweep over every sensor at parameter buffer `which`; scalars land in d_scal[slot], d_scal[slot + 1].
   template <int MODE>
-  void launch_eval(int which, int slot) {
-    const SensorDesc* desc = d_desc.p;
-    const SensorState* st = d_state[which].p;
-    const double* c = d_ctrl[which].p;
-    const int nt[3] = {tile_off[1] - tile_off[0], tile_off[2] - tile_off[1], tile_off[3] - tile_off[2]};
-    const bool fork = (nt[1] || nt[2]) && nt[0];
-    cudaStream_t si = fork ? stream_imu : stream;
-    if (fork) { CB2_CUDA(cudaEventRecord(ev_fork, stream)); CB2_CUDA(cudaStreamWaitEvent(stream_imu, ev_fork, 0)); }
-    // The (long-latency, few-CTA) IMU kernels go first on the side stream; the camera sweep fills the rest of the machine.
+  void launch_imu(cudaStream_t si, const SensorDesc* desc, const SensorState* st, const double* c, const int* nt) {
     if (nt[2]) CB2_K((eval_kernel<kAccelerometer, MODE>), nt[2], eval_tile(kAccelerometer), smem_eval[2], si, desc, st, d_tiles.p + tile_off[2], c, d_knots.p, d_basis.p, d_pw.p,
                      d_frames.p, gravity[0], gravity[1], gravity[2], d_cost_partial.p + tile_off[2], d_invalid_partial.p + tile_off[2], 1);
     if (nt[1]) CB2_K((eval_kernel<kGyroscope, MODE>), nt[1], eval_tile(kGyroscope), smem_eval[1], si, desc, st, d_tiles.p + tile_off[1], c, d_knots.p, d_basis.p, d_pw.p,
                      d_frames.p, gravity[0], gravity[1], gravity[2], d_cost_partial.p + tile_off[1], d_invalid_partial.p + tile_off[1], 1);
+  }
+  // imu: kImuSame = IMU sensors in MODE too; kImuJacobian = IMU sensors in Jacobian mode whatever MODE is (speculative Jacobians of
+  // the trial point, see launch_step); kImuSkip = their Jacobians, residuals and cost partials of this point already exist.
+  enum { kImuSame = 0, kImuJacobian = 1, kImuSkip = 2 };
+  template <int MODE>
+  void launch_eval(int which, int slot, int imu = kImuSame) {
+    const SensorDesc* desc = d_desc.p;
+    const SensorState* st = d_state[which].p;
+    const double* c = d_ctrl[which].p;
+    const int nt[3] = {tile_off[1] - tile_off[0], tile_off[2] - tile_off[1], tile_off[3] - tile_off[2]};
+    // One stream by default: the IMU kernels are FP64-latency-bound and, run beside the camera sweep, only fence SMs off from it
+    // (measured: no net overlap), while a serial order lets the camera kernel — the dominant, HBM-bound one — be timed alone.
+    // CB2_IMU_STREAM=1 moves them to a second (high-priority) stream.
+    const bool fork = imu_side_stream && (nt[1] || nt[2]) && nt[0];
+    cudaStream_t si = fork ? stream_imu : stream;
+    if (fork) { CB2_CUDA(cudaEventRecord(ev_fork, stream)); CB2_CUDA(cudaStreamWaitEvent(stream_imu, ev_fork, 0)); }
     if (nt[0]) {
       launch_frames(which);
+      if (MODE == kModeJacobian) timer.begin(kPhCamera, stream);
       CB2_K((eval_kernel<kCamera, MODE>), nt[0], eval_tile(kCamera), smem_eval[0], stream, desc, st, d_tiles.p + tile_off[0], c, d_knots.p, d_basis.p, d_pw.p,
             d_frames.p, gravity[0], gravity[1], gravity[2], d_cost_partial.p + tile_off[0], d_invalid_partial.p + tile_off[0], 1);
+      if (MODE == kModeJacobian) timer.end(kPhCamera, stream);
+    }
+    if (imu != kImuSkip) {
+      if (imu == kImuJacobian || MODE == kModeJacobian) launch_imu<kModeJacobian>(si, desc, st, c, nt);
+      else launch_imu<MODE>(si, desc, st, c, nt);
     }
     if (fork) { CB2_CUDA(cudaEventRecord(ev_join, stream_imu)); CB2_CUDA(cudaStreamWaitEvent(stream, ev_join, 0)); }
-    CB2_K(reduce_cost_kernel, 1, 256, 0, stream, d_cost_partial.p, d_invalid_partial.p, n_tiles, d_scal.p, slot);
+    CB2_K(reduce_cost_kernel, 1, 1024, 0, stream, d_cost_partial.p, d_invalid_partial.p, n_tiles, d_scal.p, slot);
   }
 
   // K1-K3 at x, then K4: normal equations, Hessian diagonal, gradient norms.
   void launch_jacobian_and_normal_equations() {
     timer.begin(kPhJacobian, stream);
-    launch_eval<kModeJacobian>(cur, kScCost);
+    // IMU Jacobians of this point were already produced by the trial-cost pass that led to its acceptance (launch_step).
+    const bool imu_reuse = imu_jac_point == cur;
+    launch_eval<kModeJacobian>(cur, kScCost, imu_reuse ? kImuSkip : kImuSame);
+    imu_jac_point = cur;
+    last_sweep_imu = !imu_reuse;
     timer.end(kPhJacobian, stream);
     timer.begin(kPhNormal, stream);
     const int ns = int(sensors.size());
@@ -886,7 +979,11 @@ struct cb2_problem {
           d_ctrl[cur ^ 1].p, d_desc.p, d_state[cur].p, d_state[cur ^ 1].p, ns, N_c, d_scal.p);
     timer.end(kPhSchur, stream);
     timer.begin(kPhCost, stream);
-    launch_eval<kModeCost>(cur ^ 1, kScCandCost);
+    // Trial point: cameras in cost-only mode; the (few, FP64-latency-bound) IMU blocks in Jacobian mode. Their Jacobians at x are not
+    // needed any more (the normal equations of x are already assembled and survive a rejected step), and if the step is accepted the
+    // Jacobians of the new x are then already there: the next sweep is the camera kernel alone.
+    launch_eval<kModeCost>(cur ^ 1, kScCandCost, speculative_imu ? kImuJacobian : kImuSame);
+    if (speculative_imu) { imu_jac_point = cur ^ 1; stats.jacobian_blocks += num_active_blocks(true); }
     if (world > 1) comm->allreduce_sum(d_scal.p + kScCandCost, 7, stream);
     timer.end(kPhCost, stream);
   }
@@ -899,19 +996,20 @@ struct cb2_problem {
     timer.resolve(phase_ms);
     if (kprof.on) kprof.resolve();
     stats.jacobian_kernel_ms = phase_ms[kPhJacobian]; stats.normal_eq_ms = phase_ms[kPhNormal];
-    stats.schur_ms = phase_ms[kPhSchur]; stats.cost_eval_ms = phase_ms[kPhCost]; stats.lm_loop_ms = phase_ms[kPhLoop];
+    stats.schur_ms = phase_ms[kPhSchur]; stats.cost_eval_ms = phase_ms[kPhCost]; stats.lm_loop_ms = phase_ms[kPhLoop]; stats.camera_kernel_ms = phase_ms[kPhCamera];
   }
 
-  double jacobian_bytes_per_sweep() const {   // obs_read + 8 m w + 8 m per residual block
+  double jacobian_bytes_per_sweep(int only_kind = -1) const {   // obs_read + 8 m w + 8 m per residual block
     double total = 0.0;
     for (size_t si = 0; si < sensors.size(); ++si) {
       const SensorDesc& d = h_desc[si];
+      if (only_kind >= 0 && d.kind != only_kind) continue;
       const double obs = d.kind == kCamera ? 32.0 : 40.0;
       total += double(d.n_obs) * (obs + 8.0 * d.m * d.jw + 8.0 * d.m);
     }
     return total;
   }
-  long num_active_blocks() const { long n = 0; for (const auto& d : h_desc) n += d.n_obs; return n; }
+  long num_active_blocks(bool imu_only = false) const { long n = 0; for (const auto& d : h_desc) if (!imu_only || d.kind != kCamera) n += d.n_obs; return n; }
 
   // ------------------------------------------------------------------------------------------------------------
   // Trust-region Levenberg-Marquardt loop: TrustRegionMinimizer::Minimize (Ceres external), same control flow as the
@@ -951,6 +1049,7 @@ struct cb2_problem {
       S.total_time = now_s() - t_start;
       return CB2_OK;
     }
+    imu_jac_point = -1;
     double radius = opt.initial_trust_region_radius, decrease_factor = 2.0;
     double x_cost = 0, x_norm = 0, candidate_cost = 0, model_cost_change = 0, reference_cost = 0;
     int num_consecutive_invalid_steps = 0;
@@ -964,8 +1063,9 @@ struct cb2_problem {
       launch_jacobian_and_normal_equations();
       if (first) CB2_K(jacobi_scaling_kernel, blocks_tot, 256, 0, stream, n_tot, d_diag.p, opt.jacobi_scaling, d_scaling.p);
       sync_scalars();
-      stats.jacobian_blocks += num_active_blocks();
-      stats.jacobian_bytes += jacobian_bytes_per_sweep();
+      stats.jacobian_blocks += last_sweep_imu ? num_active_blocks() : num_active_blocks() - num_active_blocks(true);
+      stats.jacobian_bytes += last_sweep_imu ? jacobian_bytes_per_sweep() : jacobian_bytes_per_sweep(kCamera);
+      stats.camera_kernel_bytes += jacobian_bytes_per_sweep(kCamera);
       S.jacobian_time += now_s() - t0;
       if (h_scal[kScInvalid] > 0) return false;
       x_cost = h_scal[kScCost];

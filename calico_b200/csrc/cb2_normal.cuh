@@ -90,24 +90,28 @@ __global__ void __launch_bounds__(kAccThreads, (NB == 7 ? CB2_ACC_MINBLOCKS : 2)
     const int rows = (sd.seg_start[g + 1] - o0) * m;
     if (rows == 0) continue;
     // Local column of every stored J column. The previous sensor's calibration columns are cleared first.
-    for (int i = lane; i < 2 * (kAccRows * kAccStride + 4); i += 32) { const int c = i % (kAccRows * kAccStride + 4) % kAccStride; if (c >= kAccCal0) tb0[i] = 0.0; }
+    if (lane < kAccStride - kAccCal0)
+#pragma unroll 4
+      for (int rr = 0; rr < 2 * kAccRows; ++rr) tb0[(rr / kAccRows) * (kAccRows * kAccStride + 4) + (rr % kAccRows) * kAccStride + kAccCal0 + lane] = 0.0;
     for (int c = lane; c < jw; c += 32) colpos[warp][c] = c < kCpCols ? c : kAccCal0 + sd.junk[c - kCpCols];
     __syncwarp();
     const double* __restrict__ Jg = sd.J + size_t(o0) * m * jw;
     const double* __restrict__ rg = sd.r + size_t(o0) * m;
     const int ntiles = (rows + kAccRows - 1) / kAccRows;
+    // Lane l always copies stored columns l and l + 32 (jw <= 56): their local positions are loop-invariant registers, a warp
+    // instruction reads 256 contiguous bytes of one J row.
+    const int cp0 = colpos[warp][min(lane, jw - 1)], cp1 = colpos[warp][min(lane + 32, jw - 1)];
+    const bool has1 = lane + 32 < jw;
     auto issue_load = [&](int tile, int buf) {
       if (tile < ntiles) {
         double* tb = tiles[warp][buf];
         const int r0 = tile * kAccRows;
         const int nr = min(kAccRows, rows - r0);
-        const double* src = Jg + size_t(r0) * jw;
-        const int total = nr * jw;
-        int row = 0, col = lane;            // jw >= 36 > 32: at most one wrap per step
-        for (int e = lane; e < total; e += 32) {
-          cp_async8(tb + row * kAccStride + colpos[warp][col], src + e);
-          col += 32;
-          if (col >= jw) { col -= jw; ++row; }
+        const double* src = Jg + size_t(r0) * jw + lane;
+#pragma unroll 4
+        for (int rr = 0; rr < nr; ++rr) {
+          cp_async8(tb + rr * kAccStride + cp0, src + rr * jw);
+          if (has1) cp_async8(tb + rr * kAccStride + cp1, src + rr * jw + 32);
         }
         if (lane < kAccRows) {
           if (lane < nr) cp_async8(tb + lane * kAccStride + kAccRcol, rg + r0 + lane);
@@ -174,13 +178,15 @@ __global__ void __launch_bounds__(kAccThreads, (NB == 7 ? CB2_ACC_MINBLOCKS : 2)
       }
   }
   __syncthreads();
+  // tix -> (bi, bj) of the lower block triangle without a search loop: tix = bi (bi + 1) / 2 + bj, bi < 5.
   for (int e = t; e < 15 * 64; e += kAccThreads) {
     const int tix = e >> 6, mrow = (e >> 3) & 7, ncol = e & 7;
-    int bi = 0, rem = tix;
-    while (rem > bi) { rem -= bi + 1; ++bi; }
+    const int bi = tix >= 10 ? 4 : (tix >= 6 ? 3 : (tix >= 3 ? 2 : (tix >= 1 ? 1 : 0)));
+    const int rem = tix - bi * (bi + 1) / 2;
     const int I = 8 * bi + mrow, Jx = 8 * rem + ncol;
     if (Jx > I || Jx >= kCpCols || I > kAccRcol) continue;
     double v = 0.0;
+#pragma unroll
     for (int w = 0; w < kAccWarps; ++w) v += tiles[w][0][e];
     if (I < kCpCols) segA[(size_t(gl) * kCpCols + I) * kCpCols + Jx] = v;
     else segG[size_t(gl) * kCpCols + Jx] = v;

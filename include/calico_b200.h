@@ -92,6 +92,8 @@ typedef struct cb2_stats {
   int64_t h2d_bytes, d2h_bytes;
   double lm_loop_ms;              /* CUDA-event time from the first to the last kernel of the LM loop(s) */
   int64_t lm_iterations;          /* LM iterations (accepted + rejected) run since reset */
+  double camera_kernel_ms;        /* CUDA-event time of the camera residual+Jacobian kernel alone (the dominant kernel of the sweep) */
+  double camera_kernel_bytes;     /* its algorithmic bytes (camera blocks only), same definition as jacobian_bytes */
 } cb2_stats;
 
 void cb2_default_options(cb2_options* out);

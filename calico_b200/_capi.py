@@ -368,3 +368,48 @@ class CApi:
         valid = np.zeros(self.n_obs[sid], dtype=np.uint8)
         self._check(self._f("get_residuals")(self.h, sid, _d(r), _u(valid)))
         return r, valid.astype(bool)
+
+
+# ---- trajectory spline fit (stateless entry points) ----
+def _fit_lib(lib_path):
+    if not os.path.exists(lib_path):
+        raise ImportError(f"{lib_path} not found: the CUDA extension has not been built (there is no CPU fallback).")
+    lib = C.CDLL(lib_path)
+    lib.cb2_fit_spline_size.argtypes = [C.c_int, _dp, C.c_int, C.c_double, _ip, _ip]
+    lib.cb2_fit_spline_size.restype = C.c_int
+    lib.cb2_fit_spline.argtypes = [C.c_int, _dp, _dp, C.c_int, C.c_double, C.c_int, _dp, C.c_int, _dp]
+    lib.cb2_fit_spline.restype = C.c_int
+    lib.cb2_fit_trajectory.argtypes = [C.c_int, _dp, _dp, _dp, C.c_int, C.c_double, C.c_int, _dp, C.c_int, _dp]
+    lib.cb2_fit_trajectory.restype = C.c_int
+    lib.cb2_fit_last_error.restype = C.c_char_p
+    return lib
+
+
+def _fit_check(lib, rc):
+    if rc != OK:
+        raise CalicoError(rc, (lib.cb2_fit_last_error() or b"").decode())
+
+
+def fit_spline(times, data6, spline_order=6, knot_frequency=10.0, lib_path: str = LIB_PATH):
+    """BSpline<6>::FitToData (bspline.hpp:20-38) on the device: returns (knots[n_knots], ctrl[n_cp, 6])."""
+    lib = _fit_lib(lib_path)
+    times, data6 = f64(times), f64(data6, (-1, 6))
+    if data6.shape[0] != times.size:
+        raise CalicoError(INVALID_ARGUMENT, "Data and time vectors are not the same size.")
+    nk, ncp = C.c_int(0), C.c_int(0)
+    _fit_check(lib, lib.cb2_fit_spline_size(times.size, _d(times), spline_order, knot_frequency, C.byref(nk), C.byref(ncp)))
+    knots, ctrl = np.zeros(nk.value), np.zeros((ncp.value, 6))
+    _fit_check(lib, lib.cb2_fit_spline(times.size, _d(times), _d(data6), spline_order, knot_frequency, nk.value, _d(knots), ncp.value, _d(ctrl)))
+    return knots, ctrl
+
+
+def fit_trajectory(stamps, q_xyzw, t_world_rig, knot_frequency=10.0, spline_order=6, lib_path: str = LIB_PATH):
+    """Trajectory::FitSpline (trajectory.cpp:14-49) on the device: returns (knots, ctrl[n_cp, 6] = [axis-angle ; translation])."""
+    lib = _fit_lib(lib_path)
+    stamps, q, t = f64(stamps), f64(q_xyzw, (-1, 4)), f64(t_world_rig, (-1, 3))
+    ts = np.sort(stamps)
+    nk, ncp = C.c_int(0), C.c_int(0)
+    _fit_check(lib, lib.cb2_fit_spline_size(ts.size, _d(ts), spline_order, knot_frequency, C.byref(nk), C.byref(ncp)))
+    knots, ctrl = np.zeros(nk.value), np.zeros((ncp.value, 6))
+    _fit_check(lib, lib.cb2_fit_trajectory(stamps.size, _d(stamps), _d(q), _d(t), spline_order, knot_frequency, nk.value, _d(knots), ncp.value, _d(ctrl)))
+    return knots, ctrl

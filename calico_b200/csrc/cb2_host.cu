@@ -36,6 +36,7 @@
 #include "cb2_normal.cuh"
 #include "cb2_schur.cuh"
 #include "cb2_cr.cuh"
+#include "cb2_fit.cuh"
 
 namespace cb2 {
 
@@ -1501,6 +1502,120 @@ int cb2_stats_reset(cb2_problem* p) { p->stats = cb2_stats{}; for (auto& v : p->
 int cb2_stats_get(cb2_problem* p, cb2_stats* out) { *out = p->stats; return CB2_OK; }
 
 // ---- multi-GPU: one process per GPU; call cb2_set_device first, then cb2_comm_init on every rank before cb2_upload/optimize ----
+// ---- trajectory spline fit: BSpline<6>::FitToData / FitSpline (bspline.hpp:20-38,247-297) and
+//      Trajectory::FitSpline (trajectory.cpp:14-49) ----
+static thread_local std::string g_fit_error;
+static int fit_fail(int code, const std::string& msg) { g_fit_error = msg; return code; }
+const char* cb2_fit_last_error(void) { return g_fit_error.c_str(); }
+
+int cb2_fit_spline_size(int n, const double* times, int spline_order, double knot_frequency, int* n_knots, int* n_cp) {
+  // CheckDataForSplineFit (bspline.hpp:299-327) + ComputeKnotVector (bspline.hpp:164-180)
+  if (n <= 0 || !times) return fit_fail(CB2_INVALID_ARGUMENT, "Attempted to fit data on empty time vector.");
+  for (int i = 1; i < n; ++i) if (times[i - 1] > times[i]) return fit_fail(CB2_INVALID_ARGUMENT, "Time vector is not monotonically increasing.");
+  if (spline_order < 2) return fit_fail(CB2_INVALID_ARGUMENT, "Spline order must be greater than 2. Got " + std::to_string(spline_order));
+  if (!(knot_frequency > 0)) return fit_fail(CB2_INVALID_ARGUMENT, "Knot frequency must be greater than 0.");
+  if (spline_order != kK) return fit_fail(CB2_UNIMPLEMENTED, "Only spline order 6 (calico::Trajectory::kSplineOrder, trajectory.h:28) is supported.");
+  const double duration = times[n - 1] - times[0];
+  const int num_valid = 1 + int(std::ceil(duration * knot_frequency));
+  if (num_valid < 2) return fit_fail(CB2_INVALID_ARGUMENT, "Time span too short for a spline segment.");
+  if (n_knots) *n_knots = num_valid + 2 * (spline_order - 1);
+  if (n_cp) *n_cp = num_valid + spline_order - 2;
+  return CB2_OK;
+}
+
+int cb2_fit_spline(int n, const double* times, const double* data6, int spline_order, double knot_frequency, int n_knots, double* knots_out,
+                   int n_cp, double* ctrl_out) {
+  int nk = 0, ncp = 0;
+  int rc = cb2_fit_spline_size(n, times, spline_order, knot_frequency, &nk, &ncp);
+  if (rc != CB2_OK) return rc;
+  if (!data6) return fit_fail(CB2_INVALID_ARGUMENT, "Attempted to fit on empty data.");
+  if (nk != n_knots || ncp != n_cp || !knots_out || !ctrl_out) return fit_fail(CB2_INVALID_ARGUMENT, "Output sizes do not match cb2_fit_spline_size.");
+  try {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return fit_fail(CB2_INTERNAL, "No CUDA device available: calico_b200 has no CPU fallback.");
+    const int deg = spline_order - 1, n_seg = nk - 2 * deg - 1;
+    std::vector<double> knots(nk);
+    const double dt = 1.0 / knot_frequency;
+    for (int i = -deg; i < nk - deg; ++i) knots[i + deg] = times[0] + dt * i;
+    std::vector<double> basis(size_t(n_seg) * 36);
+    for (int sg = 0; sg < n_seg; ++sg) cb2_problem::basis_matrix(knots, sg + deg, &basis[size_t(sg) * 36]);
+    // Segment of every sample (FitSpline's lookup, bspline.hpp:255-267; times are sorted): CSR over segments.
+    const double* vk = knots.data() + deg;
+    const int nv = n_seg + 1;
+    std::vector<int> seg_start(n_seg + 1, 0);
+    for (int j = 0; j < n; ++j) {
+      const double t = times[j];
+      int sg;
+      if (t == vk[nv - 1]) sg = n_seg - 1;
+      else if (t < vk[nv - 1]) sg = int(std::upper_bound(vk, vk + nv, t) - vk) - 1;
+      else return fit_fail(CB2_INVALID_ARGUMENT, "Sample time is past the last valid knot.");
+      ++seg_start[sg + 1];
+    }
+    for (int g = 0; g < n_seg; ++g) seg_start[g + 1] += seg_start[g];
+    cudaStream_t st;
+    CB2_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    {
+      DevBuf<double> d_t, d_d, d_kn, d_bs, d_sg, d_sr, d_A, d_B, d_L, d_c;
+      DevBuf<int> d_ss, d_fail;
+      d_t.upload(std::vector<double>(times, times + n)); d_d.upload(std::vector<double>(data6, data6 + size_t(n) * 6));
+      d_kn.upload(knots); d_bs.upload(basis); d_ss.upload(seg_start);
+      d_sg.alloc(size_t(n_seg) * kFitGram); d_sr.alloc(size_t(n_seg) * 36);
+      d_A.alloc(size_t(ncp) * 6); d_B.alloc(size_t(ncp) * 6); d_L.alloc(size_t(ncp) * 6); d_c.alloc(size_t(ncp) * 6); d_fail.alloc(1);
+      CB2_CUDA(cudaDeviceSynchronize());
+      CB2_LAUNCH(fit_accumulate_kernel, (n_seg + 3) / 4, 128, 0, st, n_seg, d_ss.p, d_t.p, d_d.p, d_kn.p, d_bs.p, d_sg.p, d_sr.p);
+      CB2_LAUNCH(fit_assemble_kernel, std::min((ncp * 12 + 255) / 256, 1024), 256, 0, st, ncp, n_seg, d_sg.p, d_sr.p, d_A.p, d_B.p);
+      CB2_LAUNCH(fit_solve_kernel, 1, 32, 0, st, ncp, d_A.p, d_B.p, 1e-14, d_L.p, d_c.p, d_fail.p);
+      CB2_CUDA(cudaStreamSynchronize(st));
+      CB2_CUDA(cudaGetLastError());
+      std::vector<double> c; std::vector<int> f;
+      d_c.download(c); d_fail.download(f);
+      if (f[0]) { cudaStreamDestroy(st); return fit_fail(CB2_INTERNAL, "Spline fit: normal equations are not positive definite."); }
+      std::memcpy(ctrl_out, c.data(), sizeof(double) * c.size());
+      std::memcpy(knots_out, knots.data(), sizeof(double) * knots.size());
+    }
+    cudaStreamDestroy(st);
+    return CB2_OK;
+  } catch (const CudaFail& f) {
+    return fit_fail(CB2_INTERNAL, f.msg);
+  }
+}
+
+int cb2_fit_trajectory(int n, const double* stamps, const double* q_xyzw, const double* t3, int spline_order, double knot_frequency, int n_knots,
+                       double* knots_out, int n_cp, double* ctrl_out) {
+  if (n <= 0 || !stamps || !q_xyzw || !t3) return fit_fail(CB2_INVALID_ARGUMENT, "Attempted to fit data on empty time vector.");
+  // trajectory.cpp:19-24: timestamps sorted; :29-37: Eigen::AngleAxisd(rotation) -> axis * angle; :38 UnwrapPhaseLogMap (:81-93).
+  std::vector<int> order(n);
+  for (int i = 0; i < n; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return stamps[a] < stamps[b]; });
+  std::vector<double> ts(n), data(size_t(n) * 6);
+  for (int i = 0; i < n; ++i) {
+    const int o = order[i];
+    ts[i] = stamps[o];
+    const double x = q_xyzw[4 * o], y = q_xyzw[4 * o + 1], z = q_xyzw[4 * o + 2], w = q_xyzw[4 * o + 3];
+    // Eigen::AngleAxis = Quaternion: angle = 2 atan2(|vec|, |w|), axis = vec / |vec| (negated when w < 0); identity -> axis (1,0,0), angle 0.
+    const double nrm = std::sqrt(x * x + y * y + z * z);
+    double ax = 1.0, ay = 0.0, az = 0.0, angle = 0.0;
+    if (nrm > 0.0) {
+      angle = 2.0 * std::atan2(nrm, std::fabs(w));
+      const double sgn = w < 0.0 ? -1.0 : 1.0;
+      ax = sgn * x / nrm; ay = sgn * y / nrm; az = sgn * z / nrm;
+    }
+    double* d = &data[size_t(i) * 6];
+    d[0] = ax * angle; d[1] = ay * angle; d[2] = az * angle;
+    d[3] = t3[3 * o]; d[4] = t3[3 * o + 1]; d[5] = t3[3 * o + 2];
+  }
+  for (int i = 1; i < n; ++i) {   // UnwrapPhaseLogMap, trajectory.cpp:81-93
+    double* p = &data[size_t(i) * 6];
+    const double* q = &data[size_t(i - 1) * 6];
+    const double theta = std::sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+    if (theta == 0.0) continue;
+    const double k = std::round((p[0] * q[0] + p[1] * q[1] + p[2] * q[2] - theta * theta) / (2.0 * M_PI * theta));
+    const double sc = 1.0 + 2.0 * M_PI * k / theta;
+    p[0] *= sc; p[1] *= sc; p[2] *= sc;
+  }
+  return cb2_fit_spline(n, ts.data(), data.data(), spline_order, knot_frequency, n_knots, knots_out, n_cp, ctrl_out);
+}
+
 int cb2_comm_unique_id(uint8_t* id128) {
 #if defined(CB2_EMUL)
   (void)id128;

@@ -2,9 +2,9 @@
 
 This is the step immediately before the hot path (SURVEY §8f rank 1): the reference's `BSpline<N>::FitToData`
 (calico/bspline.hpp:20-38,247-297) and `Trajectory::FitSpline` (calico/trajectory.cpp:14-49). It produces the knot
-vector and control points handed to `cb2_set_trajectory`. The fit solves the same normal equations X'X c = X'd as the
-reference, but through the banded Cholesky its own TODO asks for (bspline.hpp:287-289) instead of a dense
-column-pivoted QR of an N_cp x N_cp matrix.
+vector and control points handed to `cb2_set_trajectory`. The fit itself runs on the device (cb2_fit_spline, csrc/cb2_fit.cuh): the
+same normal equations X'X c = X'd as the reference, solved by the banded Cholesky its own TODO asks for (bspline.hpp:287-289)
+instead of a dense column-pivoted QR of an N_cp x N_cp matrix. This module keeps the bookkeeping (knots, basis, evaluation).
 """
 from __future__ import annotations
 
@@ -112,37 +112,15 @@ class Spline:
         return np.einsum("nj,njd->nd", W, self.ctrl[idx])
 
 
-def fit_spline(times, data, spline_order=6, knot_frequency=10.0) -> Spline:
-    """BSpline::FitToData + FitSpline (bspline.hpp:20-38, 247-297): least squares for the control points."""
-    from scipy.linalg import solveh_banded
-
-    times = np.asarray(times, dtype=np.float64)
+def fit_spline(times, data, spline_order=6, knot_frequency=10.0, lib_path=None) -> Spline:
+    """BSpline::FitToData + FitSpline (bspline.hpp:20-38, 247-297) on the device through the C ABI (cb2_fit_spline): banded
+    normal equations, banded Cholesky. There is no host fallback: without the CUDA library this raises."""
+    from . import _capi
     data = np.asarray(data, dtype=np.float64)
-    if times.size == 0:
-        raise ValueError("Attempted to fit data on empty time vector.")
-    if data.shape[0] != times.size:
-        raise ValueError("Data and time vectors are not the same size.")
-    if spline_order < 2:
-        raise ValueError(f"Spline order must be greater than 2. Got {spline_order}")
-    if knot_frequency <= 0:
-        raise ValueError("Knot frequency must be greater than 0.")
-    k = spline_order
-    knots, valid = compute_knot_vector(times[0], times[-1], knot_frequency, k)
-    n_cp = knots.size - k
-    sp = Spline(k, knots, np.zeros((n_cp, data.shape[1] if data.shape[1] == 6 else 6)))
-    W, seg = sp.weights(times, 0)
-    # Banded normal equations: X'X has half-bandwidth k-1 in control-point units.
-    ab = np.zeros((k, n_cp))          # upper form for solveh_banded: ab[k-1 + i - j, j] = A[i, j], i <= j
-    rhs = np.zeros((n_cp, data.shape[1]))
-    for a in range(k):
-        np.add.at(rhs, seg + a, W[:, a:a + 1] * data)
-        for b in range(a, k):
-            np.add.at(ab[k - 1 - (b - a)], seg + b, W[:, a] * W[:, b])
-    # Control points with no supporting data make X'X singular (the reference's pivoted QR returns a minimum-norm-ish
-    # answer there); regularise just enough to stay factorable.
-    ab[k - 1] += 1e-14 * max(1.0, ab[k - 1].max())
-    ctrl = solveh_banded(ab, rhs, lower=False)
-    return Spline(k, knots, ctrl)
+    if data.ndim != 2 or data.shape[1] != 6:
+        raise ValueError("fit_spline expects [n, 6] pose vectors [axis-angle ; translation]")
+    knots, ctrl = _capi.fit_spline(times, data, spline_order, knot_frequency, **({"lib_path": lib_path} if lib_path else {}))
+    return Spline(spline_order, knots, ctrl)
 
 
 # ---- SO(3) helpers used by Trajectory::FitSpline (trajectory.cpp:14-49,81-93) ----
@@ -170,13 +148,12 @@ def unwrap_phase_log_map(phi):
     return phi
 
 
-def fit_trajectory(stamps, q_xyzw, t_world_rig, knot_frequency=10.0, spline_order=6) -> Spline:
-    """Trajectory::FitSpline, trajectory.cpp:14-49: poses → [axis-angle ; translation] 6-vectors → spline fit."""
-    order = np.argsort(stamps)
-    stamps = np.asarray(stamps, dtype=np.float64)[order]
-    phi = unwrap_phase_log_map(quat_xyzw_to_angle_axis(np.asarray(q_xyzw)[order]))
-    data = np.concatenate([phi, np.asarray(t_world_rig, dtype=np.float64)[order]], axis=1)
-    return fit_spline(stamps, data, spline_order, knot_frequency)
+def fit_trajectory(stamps, q_xyzw, t_world_rig, knot_frequency=10.0, spline_order=6, lib_path=None) -> Spline:
+    """Trajectory::FitSpline, trajectory.cpp:14-49, through the C ABI (cb2_fit_trajectory): poses -> [axis-angle ; translation]
+    6-vectors (sorted, phase-unwrapped on the host side of the library) -> device spline fit."""
+    from . import _capi
+    knots, ctrl = _capi.fit_trajectory(stamps, q_xyzw, t_world_rig, knot_frequency, spline_order, **({"lib_path": lib_path} if lib_path else {}))
+    return Spline(spline_order, knots, ctrl)
 
 
 def angle_axis_to_quat_xyzw(aa):

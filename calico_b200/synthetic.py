@@ -89,7 +89,7 @@ CONFIGS = {
 }
 
 
-def truth_trajectory(cfg: Config, rng: np.random.Generator) -> sp.Spline:
+def truth_trajectory(cfg: Config, rng: np.random.Generator, fit=None) -> sp.Spline:
     """Camera-facing-chart base pose (test_utils.h:16-20: Rz(pi)*Rx(pi), 1 m stand-off) + smooth excitation: sum of 3
     sinusoids per axis (+-20 deg, +-0.3 m, periods 3-11 s), sampled at frame times and fitted like Trajectory::FitSpline."""
     t = np.arange(cfg.n_frames) / cfg.frame_rate
@@ -106,7 +106,7 @@ def truth_trajectory(cfg: Config, rng: np.random.Generator) -> sp.Spline:
     q = sp.quat_mul_xyzw(q0[None, :], sp.angle_axis_to_quat_xyzw(rot))
     chart_center = np.array([0.343, 0.343, 0.0])  # look at the middle of the 6x6 AprilGrid
     pos = pos + np.array([0.0, 0.0, 1.0]) + chart_center
-    return sp.fit_trajectory(t, q, pos, cfg.knot_frequency, 6)
+    return (fit or sp.fit_trajectory)(t, q, pos, cfg.knot_frequency, 6)
 
 
 def _camera_extrinsics(i: int, n: int):
@@ -122,9 +122,9 @@ def _camera_extrinsics(i: int, n: int):
     return q, 0.05 * np.array([np.cos(ang), np.sin(ang), 0.0])
 
 
-def build_truth(cfg: Config, seed: int = SEED) -> ProblemSpec:
+def build_truth(cfg: Config, seed: int = SEED, fit=None) -> ProblemSpec:
     rng = np.random.default_rng(seed)
-    spl = truth_trajectory(cfg, rng)
+    spl = truth_trajectory(cfg, rng, fit)
     ids, pts = aprilgrid_points()
     spec = ProblemSpec(spline=spl)
     spec.bodies.append(RigidBodySpec(0, np.array([0.0, 0, 0, 1]), np.zeros(3), ids, pts, True, True))
@@ -188,7 +188,9 @@ def project_sensor(api_factory: Callable, truth: ProblemSpec, s_idx: int, times:
 def generate(cfg_name: str, api_factory: Callable, seed: int = SEED, noise: bool = True, chunk_frames: int = 512):
     """Returns (truth, problem): `truth` holds the ground-truth state, `problem` the measurements + initial guess."""
     cfg = CONFIGS[cfg_name] if isinstance(cfg_name, str) else cfg_name
-    truth = build_truth(cfg, seed)
+    # The trajectory fit runs where the projections run: cb2_fit_trajectory on the device for a C-ABI handle factory, the CPU oracle's
+    # restatement when the factory is the oracle's (it carries a `fit_trajectory` attribute; tests only).
+    truth = build_truth(cfg, seed, getattr(api_factory, "fit_trajectory", None))
     rng = np.random.default_rng(seed + 1)
     frame_t = np.arange(cfg.n_frames) / cfg.frame_rate
     t_end = frame_t[-1]
@@ -302,7 +304,7 @@ def toy_stereo_imu_problem(api_factory: Callable, seed: int = 1):
     guess. The reference draws its perturbations from an unseeded Eigen Random(); here they are seeded. Returns (truth, problem)."""
     rng = np.random.default_rng(seed)
     stamps, q, t, pts = default_synthetic_test()
-    spl = sp.fit_trajectory(stamps, q, t, 10.0, 6)
+    spl = (getattr(api_factory, "fit_trajectory", None) or sp.fit_trajectory)(stamps, q, t, 10.0, 6)
     truth = ProblemSpec(spline=spl)
     truth.bodies.append(RigidBodySpec(0, np.array([0.0, 0, 0, 1]), np.zeros(3), np.arange(36, dtype=np.int32), pts, True, True))
 

@@ -159,6 +159,22 @@ int cb2_comm_clone(cb2_problem* dst, cb2_problem* src);
  * its shard; in multi-GPU mode cb2_get_residuals / cb2_evaluate_sensor cover the local shard only. */
 int cb2_shard_plan(cb2_problem* p, int world_size, int rank, int* n_chunks, int* chunk_lo, int* chunk_hi, int* seg_lo, int* seg_hi);
 
+/* ---- trajectory spline fit, the step before the hot path (no problem handle; errors through cb2_fit_last_error) ----
+ * BSpline<6, double>::FitToData (bspline.hpp:20-38): validation of CheckDataForSplineFit (bspline.hpp:299-327), knot vector of
+ * ComputeKnotVector (bspline.hpp:164-180), basis matrices (bspline.hpp:192-244) and the least-squares fit of FitSpline
+ * (bspline.hpp:247-297) — solved on the device as the banded SPD system the reference's TODO (bspline.hpp:287-289) describes.
+ * cb2_fit_spline_size returns the sizes the caller must allocate: n_knots = n_valid + 2 (order - 1), n_cp = n_knots - order. */
+int cb2_fit_spline_size(int n, const double* times, int spline_order, double knot_frequency, int* n_knots, int* n_cp);
+/* times[n] ascending, data6[n][6]; knots_out[n_knots], ctrl_out[n_cp][6]. */
+int cb2_fit_spline(int n, const double* times, const double* data6, int spline_order, double knot_frequency, int n_knots, double* knots_out,
+                   int n_cp, double* ctrl_out);
+/* Trajectory::FitSpline (trajectory.cpp:14-49): poses (stamp, q_xyzw world<-rig, t_world_rig) in any order -> sorted by stamp,
+ * rotation -> axis * angle (Eigen::AngleAxisd), UnwrapPhaseLogMap (trajectory.cpp:81-93), then cb2_fit_spline on [phi ; t].
+ * Sizes from cb2_fit_spline_size on the sorted stamps (only first and last matter). */
+int cb2_fit_trajectory(int n, const double* stamps, const double* q_xyzw, const double* t3, int spline_order, double knot_frequency, int n_knots,
+                       double* knots_out, int n_cp, double* ctrl_out);
+const char* cb2_fit_last_error(void);
+
 /* ---- bench accounting ---- */
 int cb2_stats_reset(cb2_problem* p);
 int cb2_stats_get(cb2_problem* p, cb2_stats* out);

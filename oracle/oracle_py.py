@@ -43,6 +43,17 @@ def oracle_api() -> _capi.CApi:
     return _capi.CApi(LIB, "orc_", OracleOptions)
 
 
+def _oracle_fit_trajectory(stamps, q_xyzw, t_world_rig, knot_frequency=10.0, spline_order=6):
+    """Trajectory::FitSpline restated on the CPU (oracle/spline_fit.py) for workloads generated without a GPU (tests only)."""
+    from calico_b200 import spline as sp
+    from oracle import spline_fit
+    knots, _, _, ctrl = spline_fit.fit_trajectory(stamps, q_xyzw, t_world_rig, knot_frequency, spline_order)
+    return sp.Spline(spline_order, knots, ctrl)
+
+
+oracle_api.fit_trajectory = _oracle_fit_trajectory
+
+
 _lib = None
 
 

@@ -52,7 +52,7 @@ def _worker(rank, world, port, lib, cfg, chunk, q):
 
 
 @pytest.mark.skipif(_ngpus() < 2, reason="needs at least 2 GPUs")
-@pytest.mark.parametrize("world,cfg,chunk", [(2, "small", "9"), (2, "tiny", "6"), (4, "small", "7")])
+@pytest.mark.parametrize("world,cfg,chunk", [(2, "small", None), (2, "small", "9"), (2, "tiny", "6"), (4, "small", "7")])
 def test_multi_gpu_lm_matches_oracle(world, cfg, chunk, product_lib, oracle):
     if _ngpus() < world:
         pytest.skip(f"needs {world} GPUs")

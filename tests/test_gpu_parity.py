@@ -112,7 +112,10 @@ def test_perfect_data_gives_zero_cost(oracle, product_lib):
     t2.clone().push(o)
     c2, _ = a2.cost()
     co, _ = o.cost()
-    assert abs(c2 - co) <= 1e-9 * co + 1e-18
+    # co ~ 1e-10 comes from residuals ~ 1e-7 px formed as differences of ~1e3 px quantities: two correct FP64 evaluations that round
+    # differently (FMA contraction, summation order) agree to ~1e-12 px per residual, i.e. ~1e-6 relative on this cost.
+    print(f"latency-in-place cost: cuda {c2:.6e} oracle {co:.6e} rel {abs(c2 - co) / co:.2e}")
+    assert abs(c2 - co) <= 1e-5 * co + 1e-18
 
 
 def test_reference_integration_test_on_the_cuda_path(oracle, product_lib):

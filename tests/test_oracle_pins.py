@@ -72,7 +72,9 @@ def test_spline_interpolation_precision(oracle):
     0..3 within 1e-6 / 1e-5 / 1e-4 / 1e-2 of the analytic values, evaluated by the oracle's BSpline::Evaluate restatement."""
     t, data = _bspline_fixture()
     data6 = np.concatenate([data, np.zeros_like(data)], axis=1)
-    spl = sp.fit_spline(t, data6, 6, 5.0)
+    from oracle import spline_fit as ofit
+    knots, _, _, ctrl = ofit.fit_spline(t, data6, 6, 5.0)     # the oracle's restatement of BSpline::FitSpline (dense normal equations)
+    spl = sp.Spline(6, knots, ctrl)
     api = oracle.oracle_api()
     api.set_trajectory(6, spl.knots, spl.ctrl)
     ti = (t[-1] - t[0]) / 201 * np.arange(201)
@@ -90,7 +92,9 @@ def test_spline_invalid_arguments(oracle):
     """bspline_test.cpp:34-50: derivative -1 or >= order, or a time outside the valid knots -> kInvalidArgument (3)."""
     from calico_b200 import _capi
     t, data = _bspline_fixture()
-    spl = sp.fit_spline(t, np.concatenate([data, data], axis=1), 6, 5.0)
+    from oracle import spline_fit as ofit
+    knots, _, _, ctrl = ofit.fit_spline(t, np.concatenate([data, data], axis=1), 6, 5.0)
+    spl = sp.Spline(6, knots, ctrl)
     api = oracle.oracle_api()
     api.set_trajectory(6, spl.knots, spl.ctrl)
     for bad in (-1, 6):
@@ -171,7 +175,7 @@ def test_trust_region_radius_schedule_matches_stored_ceres_log(oracle):
 def test_gyro_and_accel_kinematics_against_finite_differences(oracle):
     """gyroscope_test.cpp:106-157 / accelerometer_test.cpp:106-177: the analytic angular velocity and specific force of the
     functors agree with finite differences of the spline pose. Identity intrinsics (scale 1), identity extrinsics."""
-    truth = synthetic.build_truth(synthetic.CONFIGS["tiny"])
+    truth = synthetic.build_truth(synthetic.CONFIGS["tiny"], fit=oracle.oracle_api.fit_trajectory)
     spl = truth.spline
     api = oracle.oracle_api()
     api.set_trajectory(6, spl.knots, spl.ctrl)

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) fit_assemble_kernel(int n_cp, int n_seg, 
 // Lane l < 6 fetches band entry d = l and right-hand side c = l of the NEXT row while the current one is factored.
 __global__ void __launch_bounds__(32) fit_solve_kernel(int n_cp, const double* __restrict__ Aband, const double* __restrict__ Bfit, double rel_eps,
                                                        double* __restrict__ Lband, double* __restrict__ ctrl, int* __restrict__ fail) {
-  __shared__ double ring[kK][kK];       // ring[i % 6][d] = L(i, i - d) of the last 6 rows
+  __shared__ double ring[kK][kK + 1];   // ring[i % 6][d] = L(i, i - d) of the last 6 rows; [kK] = 1 / L(i, i)
   const int lane = threadIdx.x, l6 = min(lane, 5);
   // Regularisation scale: control points without supporting samples make X^T X singular (the reference's pivoted QR then returns
   // a basic solution); a relative 1e-14 on the diagonal keeps the factorisation defined and does not move supported control points.
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(32) fit_solve_kernel(int n_cp, const double* _
     const double a_cur = a_next, b_cur = b_next;
     if (i + 1 < n_cp) { a_next = Aband[size_t(i + 1) * 6 + l6]; b_next = Bfit[size_t(i + 1) * 6 + l6]; }
     // Row i of L (every lane computes the same values; lane 0 publishes them) and this lane's right-hand side.
-    double Li[kK];
+    double Li[kK], Linv = 1.0;
 #pragma unroll
     for (int d = kK - 1; d >= 0; --d) {
       const int j = i - d;
@@ -112,8 +112,8 @@ __global__ void __launch_bounds__(32) fit_solve_kernel(int n_cp, const double* _
         for (int m = 1; m <= kK - 1; ++m) {          // common predecessors j - m: L(i, j-m) = Li[d + m], L(j, j-m) = row j of the ring
           if (d + m <= kK - 1 && j - m >= 0) s -= Li[d + m] * (d == 0 ? Li[m] : ring[j % kK][m]);
         }
-        if (d > 0) s /= ring[j % kK][0];
-        else { if (!(s > 0.0) || !isfinite(s)) { bad = 1; s = 1.0; } s = sqrt(s); }
+        if (d > 0) s *= ring[j % kK][kK];
+        else { if (!(s > 0.0) || !isfinite(s)) { bad = 1; s = 1.0; } Linv = rsqrt(s); s *= Linv; }
       } else s = 0.0;
       Li[d] = s;
     }
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(32) fit_solve_kernel(int n_cp, const double* _
       double y = b_cur;
 #pragma unroll
       for (int d = 1; d <= kK - 1; ++d) y -= Li[d] * yh[d - 1];   // Li[d] = 0 for rows before the first
-      y /= Li[0];
+      y *= Linv;
 #pragma unroll
       for (int d = kK - 2; d > 0; --d) yh[d] = yh[d - 1];
       yh[0] = y;
@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(32) fit_solve_kernel(int n_cp, const double* _
     if (lane == 0) {
 #pragma unroll
       for (int d = 0; d < kK; ++d) { ring[i % kK][d] = Li[d]; Lband[size_t(i) * kK + d] = Li[d]; }
+      ring[i % kK][kK] = Linv;
     }
     __syncwarp();
   }

@@ -71,18 +71,22 @@ struct DevBuf {
 #endif
     p = nullptr; n = 0;
   }
-  void alloc(size_t count) {
+  // Pool blocks come back with the previous owner's contents: every allocation that is not immediately overwritten by an upload is
+  // cleared (per-segment partials of (segment, sensor) pairs without observations, padding rows, ... are never written by a kernel).
+  void alloc(size_t count, bool clear = true) {
     release();
     n = count;
 #ifdef CB2_EMUL
     if (count) CB2_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), std::max<size_t>(count, 1) * sizeof(T)));
+    if (count && clear) CB2_CUDA(cudaMemsetAsync(p, 0, count * sizeof(T), nullptr));
 #else
     if (count) CB2_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&p), std::max<size_t>(count, 1) * sizeof(T), nullptr));
+    if (count && clear) CB2_CUDA(cudaMemsetAsync(p, 0, count * sizeof(T), nullptr));
 #endif
   }
   void zero(cudaStream_t s) { if (n) CB2_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
   void upload(const std::vector<T>& h, int64_t* counter = nullptr) {
-    alloc(h.size());
+    alloc(h.size(), false);
     if (!h.empty()) { CB2_CUDA(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice)); if (counter) *counter += int64_t(h.size() * sizeof(T)); }
   }
   void download(std::vector<T>& h, int64_t* counter = nullptr) const {
@@ -1117,6 +1121,9 @@ struct cb2_problem {
       sync_scalars();
       S.linear_solver_time += now_s() - t_ls;
       const bool solved = !(h_scal[kScSolveFail] > 0);
+      if (std::getenv("CB2_DEBUG"))
+        std::fprintf(stderr, "[cb2 debug] iter %d radius %.3e solve_fail %.0f model_change %.6e step2 %.3e cand_cost %.6e cand_invalid %.0f\n", next_iter, radius,
+                     h_scal[kScSolveFail], h_scal[kScModelChange], h_scal[kScStepNorm2], h_scal[kScCandCost], h_scal[kScCandInvalid]);
       it.step_is_valid = 0;
       if (solved) {
         model_cost_change = h_scal[kScModelChange];

@@ -153,7 +153,7 @@ def main():
                   f"({r['sample_blocks']} residual blocks), {r['n']} LM iterations in {r['seconds']:.2f} s; iterations/s scaled linearly by the frame "
                   f"ratio to the full workload (favours the CPU: its dense reduced solve grows cubically)")
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": 1e3 / r["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "ms_per_step": 1e3 / r["value"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"{args.config}: {workload}", "cpu_sample": sample},
                 "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

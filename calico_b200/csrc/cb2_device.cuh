@@ -37,6 +37,8 @@ struct SensorDesc {
   const int* seg_start;
   const int* frm;               // cameras: sensor-local image (frame) index of every observation, see camera_frame_kernel
   int frame_base;               // global index of this sensor's first image
+  const int* frame_obs;         // cameras: [n_images + 1] first observation of every image (CSR over the sorted observations)
+  const int* seg_frame;         // cameras: [n_seg + 1] first sensor-local image of every spline segment
   double* r; double* J; unsigned char* valid;
 };
 

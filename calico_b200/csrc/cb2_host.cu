@@ -126,7 +126,7 @@ struct HostSensor {
   std::vector<int> perm;      // sorted position -> original observation index
   int n_active = 0;
   DevBuf<double> d_stamp, d_meas, d_r, d_J;
-  DevBuf<int> d_seg, d_pt, d_seg_start, d_frm;
+  DevBuf<int> d_seg, d_pt, d_seg_start, d_frm, d_frame_obs, d_seg_frame;
   DevBuf<unsigned char> d_valid;
 };
 
@@ -337,6 +337,7 @@ struct cb2_problem {
   size_t smem_eval[3] = {0, 0, 0};
   int max_tilepairs1 = 0, max_ksplit1 = 1;
   bool gram_dmma1 = false;   // level-1 Gram product on the FP64 tensor pipe
+  bool acc_structured = std::getenv("CB2_ACC_STRUCTURED") != nullptr;   // image-wise Kronecker accumulation of camera rows (cb2_normal.cuh): opt-in
   double* h_scal = nullptr;   // pinned
   cb2_stats stats{};
   PhaseTimer timer;
@@ -476,7 +477,7 @@ struct cb2_problem {
     struct Packed {
       int rc = CB2_OK; std::string err;
       int want = 0, n_active = 0; long blocks = 0, residuals = 0; bool ref_any = false;
-      std::vector<int> seg_start, seg, pt, frm, frame_seg;
+      std::vector<int> seg_start, seg, pt, frm, frame_seg, frame_obs, seg_frame;
       std::vector<double> stamp, meas, frame_stamp;
       std::vector<unsigned char> cp_ref;
     };
@@ -536,9 +537,15 @@ struct cb2_problem {
         for (int q = 0; q < m; ++q) P.meas[size_t(i) * m + q] = s.meas[size_t(o) * m + q];
         if (s.kind == kCamera) {
           P.pt[i] = bodies[s.body_slot[o]].pw0 + s.feat_slot[o];
-          if (i == 0 || P.stamp[i] != P.stamp[i - 1]) { P.frame_seg.push_back(P.seg[i]); P.frame_stamp.push_back(P.stamp[i]); }
+          if (i == 0 || P.stamp[i] != P.stamp[i - 1]) { P.frame_seg.push_back(P.seg[i]); P.frame_stamp.push_back(P.stamp[i]); P.frame_obs.push_back(i); }
           P.frm[i] = int(P.frame_stamp.size()) - 1;                // sensor-local image index; SensorDesc::frame_base makes it global
         }
+      }
+      if (s.kind == kCamera) {                                     // image CSR for the structured accumulation (cb2_normal.cuh)
+        P.frame_obs.push_back(n_active);
+        P.seg_frame.assign(n_seg + 1, 0);
+        for (int sg : P.frame_seg) ++P.seg_frame[sg + 1];
+        for (int g = 0; g < n_seg; ++g) P.seg_frame[g + 1] += P.seg_frame[g];
       }
     };
 #ifdef CB2_EMUL
@@ -569,6 +576,7 @@ struct cb2_problem {
       const std::vector<int>&seg = P.seg, &pt = P.pt, &frm = P.frm, &seg_start = P.seg_start;
       s.d_stamp.upload(stamp, h2d); s.d_meas.upload(meas, h2d); s.d_seg.upload(seg, h2d); s.d_pt.upload(pt, h2d); s.d_frm.upload(frm, h2d);
       s.d_seg_start.upload(seg_start, h2d);
+      if (s.kind == kCamera) { s.d_frame_obs.upload(P.frame_obs, h2d); s.d_seg_frame.upload(P.seg_frame, h2d); }
       // Unknown layout of this sensor (constant or unreferenced blocks drop out, as in Ceres's reduced program).
       SensorDesc& d = h_desc[si];
       d.kind = s.kind; d.model = s.model; d.ni = want; d.m = m; d.n_obs = n_active; d.frame_base = frame_base;
@@ -593,6 +601,7 @@ struct cb2_problem {
       s.d_valid.alloc(n_active);
       d.stamp = s.d_stamp.p; d.meas = s.d_meas.p; d.seg = s.d_seg.p; d.pt = s.d_pt.p; d.seg_start = s.d_seg_start.p; d.frm = s.d_frm.p;
       d.r = s.d_r.p; d.J = s.d_J.p; d.valid = s.d_valid.p;
+      d.frame_obs = s.kind == kCamera ? s.d_frame_obs.p : nullptr; d.seg_frame = s.kind == kCamera ? s.d_seg_frame.p : nullptr;
       for (int o0 = 0, T = eval_tile(s.kind); o0 < n_active; o0 += T) tiles_by_kind[s.kind].push_back(EvalTile{si, o0, std::min(T, n_active - o0)});
       // state
       SensorState& st = h_state[si];
@@ -794,7 +803,7 @@ struct cb2_problem {
     set(eval_kernel<kCamera, kModeCost>, ev_max[0]); set(eval_kernel<kCamera, kModeResiduals>, ev_max[0]); set(eval_kernel<kCamera, kModeJacobian>, ev_max[0]);
     set(eval_kernel<kGyroscope, kModeCost>, ev_max[1]); set(eval_kernel<kGyroscope, kModeResiduals>, ev_max[1]); set(eval_kernel<kGyroscope, kModeJacobian>, ev_max[1]);
     set(eval_kernel<kAccelerometer, kModeCost>, ev_max[2]); set(eval_kernel<kAccelerometer, kModeResiduals>, ev_max[2]); set(eval_kernel<kAccelerometer, kModeJacobian>, ev_max[2]);
-    set(accumulate_kernel<7>, kAccSmemBytes); set(accumulate_kernel<8>, kAccSmemBytes);
+    set(accumulate_kernel<7>, acc_smem_bytes(true)); set(accumulate_kernel<8>, acc_smem_bytes(true));
     int max_n1 = 0;
     for (const auto& sy : h_l1) max_n1 = std::max(max_n1, sy.n);
     const int nbw1 = h_l1[0].nbw, nbw2 = h_l2.nbw;
@@ -881,8 +890,8 @@ struct cb2_problem {
     if (nsl > 0) {
       int max_nc = 0;
       for (const auto& d : h_desc) max_nc = std::max(max_nc, d.n_calib);
-      if (kAccCal0 + max_nc <= 56) CB2_K(accumulate_kernel<7>, nsl, kAccThreads, kAccSmemBytes, stream, d_desc.p, ns, N_c, g_lo, d_c2off.p, csz, d_segA.p, d_segG.p, d_segB.p, d_segC.p, d_segGc.p);
-      else CB2_K(accumulate_kernel<8>, nsl, kAccThreads, kAccSmemBytes, stream, d_desc.p, ns, N_c, g_lo, d_c2off.p, csz, d_segA.p, d_segG.p, d_segB.p, d_segC.p, d_segGc.p);
+      if (kAccCal0 + max_nc <= 56) CB2_K(accumulate_kernel<7>, nsl, kAccThreads, acc_smem_bytes(acc_structured), stream, d_desc.p, ns, N_c, g_lo, d_c2off.p, csz, d_segA.p, d_segG.p, d_segB.p, d_segC.p, d_segGc.p, d_frames.p, acc_structured ? 1 : 0);
+      else CB2_K(accumulate_kernel<8>, nsl, kAccThreads, acc_smem_bytes(acc_structured), stream, d_desc.p, ns, N_c, g_lo, d_c2off.p, csz, d_segA.p, d_segG.p, d_segB.p, d_segC.p, d_segGc.p, d_frames.p, acc_structured ? 1 : 0);
     }
     const long total = n_a * 36 + n_a * N_c + n_a;
     CB2_K(assemble_band_kernel, int(std::min<long>((total + 255) / 256, 148 * 16)), 256, 0, stream, n_cp, g_lo, g_hi, N_c, d_segA.p, d_segG.p, d_segB.p,

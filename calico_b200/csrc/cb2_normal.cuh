@@ -14,6 +14,13 @@
 // NB (NB + 1) / 2 DMMAs. J row tiles stream global -> shared with cp.async (per-warp double buffer, row stride 68 doubles
 // == 4 mod 16: conflict-free fragment loads). The control-point block accumulates over all sensors of the warp and is
 // combined across warps in a fixed order at the end; the calibration blocks are flushed per sensor. No atomics.
+// Camera rows have more structure: all rows of one image share the basis weights w, and their control-point part is the Kronecker
+// product g (x) w (g = d r / d pose, 6 numbers per row). Per image the kernel therefore multiplies only the COMPACT rows
+// [g^ | r | calibration] (24 columns = 6 DMMA tiles instead of 28; g^ = g w_istar is read straight from the J columns of the control point
+// with the largest weight) and expands once per image:  H[cp_a, cp_b] += (w_a w_b / w_istar^2) G^[.,.],  H[cp_a, r|calib] += (w_a / w_istar) ...
+// This cuts the tensor work of K4 by ~4.7x, but measured on C4 it does not pay yet (378 us vs 361 us for the plain product): DRAM still
+// fetches every sector of the J rows, the tile pipeline is one tile deep per warp, and the two warps that also own an IMU sensor become
+// the critical path. It is therefore OPT-IN (CB2_ACC_STRUCTURED=1) until images are balanced across warps; parity-tested either way.
 // assemble_*_kernel: sums the <= 6 overlapping segment partials per control-point entry into the banded storage and
 // reduces the calibration blocks over all segments.
 #pragma once
@@ -27,7 +34,13 @@ constexpr int kAccRows = 16;       // J rows per shared-memory tile (4 DMMA k-st
 constexpr int kAccStride = 68;     // doubles per tile row; 68 mod 16 == 4 -> the 16 lanes of a half warp hit 16 distinct 8-byte banks
 constexpr int kAccRcol = 36;       // local layout: cp 0..35 | r 36 | zeros 37..39 | calibration unknowns 40.. | zeros
 constexpr int kAccCal0 = 40;
-constexpr size_t kAccSmemBytes = size_t(kAccWarps) * 2 * (kAccRows * kAccStride + 4) * sizeof(double);
+constexpr int kAccMaxSensors = 64;
+constexpr int kAccMaxSlots = 16;   // camera images of one spline segment handled by the structured path (more: plain product for that segment)
+constexpr int kAccSlot = 144;      // per image: G^gg 6x6 | sum r g^ (6) | sum c g^ (6 x 16) | w_a / w_istar (6)
+constexpr int kAccSlotGr = 36, kAccSlotGc = 42, kAccSlotRho = 138;
+CB2_HD constexpr size_t acc_smem_bytes(bool structured) {
+  return (size_t(kAccWarps) * 2 * (kAccRows * kAccStride + 4) + (structured ? size_t(kAccMaxSlots) * kAccSlot : 0)) * sizeof(double);
+}
 #ifndef CB2_ACC_MINBLOCKS
 #define CB2_ACC_MINBLOCKS 3
 #endif
@@ -67,7 +80,8 @@ CB2_D void dmma_8x8x4(double& c0, double& c1, double a, double b) {
 template <int NB>
 __global__ void __launch_bounds__(kAccThreads, (NB == 7 ? CB2_ACC_MINBLOCKS : 2)) accumulate_kernel(
     const SensorDesc* __restrict__ sensors, int n_sensors, int N_c, int g_lo, const int* __restrict__ c2off, int csz, double* __restrict__ segA,
-    double* __restrict__ segG, double* __restrict__ segB, double* __restrict__ segC, double* __restrict__ segGc) {
+    double* __restrict__ segG, double* __restrict__ segB, double* __restrict__ segC, double* __restrict__ segGc, const double* __restrict__ frames,
+    int structured) {
   // dynamic shared memory: per warp two tile buffers of kAccRows x kAccStride (+ 4 doubles: the last fragment reads past a row end)
   typedef double TileBuf[2][kAccRows * kAccStride + 4];
   TileBuf* tiles = dyn_smem<TileBuf>();
@@ -81,7 +95,31 @@ __global__ void __launch_bounds__(kAccThreads, (NB == 7 ? CB2_ACC_MINBLOCKS : 2)
     for (int bj = 0; bj < NB; ++bj) { acc[bi][bj][0] = 0.0; acc[bi][bj][1] = 0.0; }
   double* const tb0 = tiles[warp][0];
   for (int i = lane; i < 2 * (kAccRows * kAccStride + 4); i += 32) tb0[i] = 0.0;   // padding columns stay zero for the whole kernel
+  bool dirty = false;
   __syncwarp();
+  // Per-image slots of the structured camera accumulation (shared memory behind the tile buffers) and their per-sensor offsets.
+  double* const slots = reinterpret_cast<double*>(tiles + kAccWarps);
+  __shared__ int s_slot_begin[kAccMaxSensors + 1];
+  __shared__ int s_use_struct;
+  if (warp == 0) {   // lane-parallel: one sensor per lane and round, exclusive prefix sum by shuffles (no serial chain of dependent loads)
+    const bool ok = structured && n_sensors <= kAccMaxSensors;
+    int base = 0;
+    for (int s0 = 0; ok && s0 < n_sensors; s0 += 32) {
+      const int s = s0 + lane;
+      int cnt = 0;
+      if (s < n_sensors) {
+        const SensorDesc& sd = sensors[s];
+        if (sd.kind == kCamera && sd.seg_frame != nullptr && sd.n_calib <= 16) cnt = sd.seg_frame[g + 1] - sd.seg_frame[g];
+      }
+      int incl = cnt;
+      for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += o; }
+      if (s < n_sensors) s_slot_begin[s] = base + incl - cnt;
+      base += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) { s_slot_begin[n_sensors <= kAccMaxSensors ? n_sensors : 0] = base; s_use_struct = (ok && base <= kAccMaxSlots) ? 1 : 0; }
+  }
+  __syncthreads();
+  const bool use_struct = s_use_struct != 0;
 
   for (int s = warp; s < n_sensors; s += kAccWarps) {
     const SensorDesc& sd = sensors[s];
@@ -89,6 +127,126 @@ __global__ void __launch_bounds__(kAccThreads, (NB == 7 ? CB2_ACC_MINBLOCKS : 2)
     const int o0 = sd.seg_start[g];
     const int rows = (sd.seg_start[g + 1] - o0) * m;
     if (rows == 0) continue;
+    if (use_struct && sd.kind == kCamera && nc <= 16) {
+      // ---- camera rows, image by image (see the header comment): compact Gram of [g^ | r | calibration]; the Kronecker expansion of its
+      //      g^ rows is deferred to the end of the kernel (per-image slots in shared memory), the [r | calibration] square is summed here ----
+      constexpr int CS = 28, CR = 16;                         // compact tile: 16 rows x 24 columns, row stride 28 (== 12 mod 16: conflict-free fragments)
+      static_assert(CR * CS <= kAccRows * kAccStride + 4, "compact tile does not fit a tile buffer");
+      double* const cb[2] = {tiles[warp][0], tiles[warp][1]};
+      dirty = true;
+      for (int i = lane; i < CR * CS; i += 32) { cb[0][i] = 0.0; cb[1][i] = 0.0; }
+      __syncwarp();
+      // lane -> the one compact column it copies: 0..5 g^ (J columns 6 istar + lane), 6 r, 8 + junk[j] calibration column j
+      const int njc = jw - kCpCols;
+      const int my_cal = lane - 8;
+      const int dst_col = lane < 6 ? lane : (lane == 6 ? 6 : ((my_cal >= 0 && my_cal < njc) ? 8 + sd.junk[my_cal] : -1));
+      const int f_begin = sd.seg_frame[g], f_end = sd.seg_frame[g + 1];
+      // Per-image metadata is fetched once, up front (lane k: image f_begin + k), so that no dependent global load sits in the tile pipeline.
+      const int nfr = f_end - f_begin;
+      int my_obs0 = 0, my_rows = 0, my_istar = 0;
+      if (lane < nfr) {
+        my_obs0 = sd.frame_obs[f_begin + lane];
+        my_rows = (sd.frame_obs[f_begin + lane + 1] - my_obs0) * 2;
+        const double* w = frames + size_t(sd.frame_base + f_begin + lane) * FrameRec::kSize + FrameRec::w0;
+        double bv = fabs(w[0]);
+#pragma unroll
+        for (int a = 1; a < kK; ++a) { const double v = fabs(w[a]); if (v > bv) { bv = v; my_istar = a; } }
+      }
+      auto item_rows = [&](int f) { return __shfl_sync(0xffffffffu, my_rows, (f - f_begin) & 31); };
+      auto item_obs0 = [&](int f) { return __shfl_sync(0xffffffffu, my_obs0, (f - f_begin) & 31); };
+      auto frame_istar = [&](int f) { return __shfl_sync(0xffffffffu, my_istar, (f - f_begin) & 31); };
+      // flattened (image, pass) pipeline: the tile of the next item streams in while the current one is multiplied
+      auto issue = [&](int f, int pass, int buf) {
+        if (f < f_end) {
+          const int nrows = item_rows(f), r0 = pass * CR, nr = min(CR, nrows - r0), istar = frame_istar(f);
+          const size_t row0 = size_t(item_obs0(f)) * 2 + r0;                       // first J row of this tile
+          double* tb = cb[buf];
+          if (dst_col >= 0) {
+            const double* src = lane == 6 ? sd.r + row0 : sd.J + row0 * jw + (lane < 6 ? 6 * istar + lane : kCpCols + my_cal);
+            const int sstride = lane == 6 ? 1 : jw;
+#pragma unroll 4
+            for (int rr = 0; rr < nr; ++rr) cp_async8(tb + rr * CS + dst_col, src + size_t(rr) * sstride);
+          }
+          if (lane < 24) for (int rr = nr; rr < min(CR, (nr + 3) & ~3); ++rr) tb[rr * CS + lane] = 0.0;   // complete the last k-step with zero rows
+        }
+        cp_async_commit();
+      };
+      int cf = f_begin, cp = 0;                               // current item
+      issue(cf, cp, 0);
+      int buf = 0;
+      double cg[6][2], cgS[6][2];                             // compact Gram of the current image / summed over the sensor's images
+#pragma unroll
+      for (int q = 0; q < 6; ++q) { cgS[q][0] = 0.0; cgS[q][1] = 0.0; }
+      while (cf < f_end) {
+        const int nrows = item_rows(cf), npass = (nrows + CR - 1) / CR;
+        int nf = cf, np = cp + 1;
+        if (np >= npass) { nf = cf + 1; np = 0; }
+        issue(nf, np, buf ^ 1);
+        cp_async_wait<1>();
+        __syncwarp();
+        if (cp == 0) {
+#pragma unroll
+          for (int q = 0; q < 6; ++q) { cg[q][0] = 0.0; cg[q][1] = 0.0; }
+        }
+        const double* tb = cb[buf];
+        const int nr = min(CR, nrows - cp * CR);
+#pragma unroll
+        for (int ks = 0; ks < CR / 4; ++ks) {
+          if (4 * ks < nr) {
+            const double* row = tb + (4 * ks + fr) * CS + fc;
+            const double f0 = row[0], f1 = row[8], f2 = row[16];
+            dmma_8x8x4(cg[0][0], cg[0][1], f0, f0);
+            dmma_8x8x4(cg[1][0], cg[1][1], f1, f0);
+            dmma_8x8x4(cg[2][0], cg[2][1], f1, f1);
+            dmma_8x8x4(cg[3][0], cg[3][1], f2, f0);
+            dmma_8x8x4(cg[4][0], cg[4][1], f2, f1);
+            dmma_8x8x4(cg[5][0], cg[5][1], f2, f2);
+          }
+        }
+        __syncwarp();
+        if (cp == npass - 1) {
+          // image complete: its g^ rows go to the image's slot (expanded at the end of the kernel), the rest into the sensor sums
+          double* slot = slots + size_t(s_slot_begin[s] + (cf - f_begin)) * kAccSlot;
+          const double* w = frames + size_t(sd.frame_base + cf) * FrameRec::kSize + FrameRec::w0;
+          const int istar = frame_istar(cf);
+          if (lane < kK) slot[kAccSlotRho + lane] = w[lane] / w[istar];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int Jc = 2 * fr + i;                       // compact column of this accumulator entry (tiles (0,0), (1,0), (2,0))
+            if (Jc < 6) {
+              if (fc < 6) slot[fc * 6 + Jc] = cg[0][i];                           // G^gg[fc][Jc]
+              else if (fc == 6) slot[kAccSlotGr + Jc] = cg[0][i];                 // sum r g^
+              slot[kAccSlotGc + Jc * 16 + fc] = cg[1][i];                         // sum c_fc g^_Jc
+              slot[kAccSlotGc + Jc * 16 + 8 + fc] = cg[3][i];
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 6; ++q) { cgS[q][0] += cg[q][0]; cgS[q][1] += cg[q][1]; }
+        }
+        cf = nf; cp = np; buf ^= 1;
+      }
+      cp_async_wait<0>();
+      __syncwarp();
+      // [r | calibration] x [r | calibration] of this sensor: calibration gradient and calibration block
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int Jc = 2 * fr + i;
+        if (Jc == 6) {                                        // column r of tiles (1,0), (2,0)
+          if (fc < nc) segGc[size_t(gl) * N_c + sd.calib_off + fc] = cgS[1][i];
+          if (8 + fc < nc) segGc[size_t(gl) * N_c + sd.calib_off + 8 + fc] = cgS[3][i];
+        }
+        // tiles (1,1): (li, lj) = (fc, Jc); (2,1): (8 + fc, Jc); (2,2): (8 + fc, 8 + Jc)
+        if (fc < nc && Jc <= fc) segC[size_t(gl) * csz + c2off[s] + fc * nc + Jc] = cgS[2][i];
+        if (8 + fc < nc && Jc < nc) segC[size_t(gl) * csz + c2off[s] + (8 + fc) * nc + Jc] = cgS[4][i];
+        if (8 + fc < nc && Jc <= fc) segC[size_t(gl) * csz + c2off[s] + (8 + fc) * nc + 8 + Jc] = cgS[5][i];
+      }
+      continue;
+    } else {
+    if (dirty) {   // a camera pass used these buffers with its own layout: restore the all-zero padding the generic path relies on
+      for (int i = lane; i < 2 * (kAccRows * kAccStride + 4); i += 32) tb0[i] = 0.0;
+      dirty = false;
+      __syncwarp();
+    }
     // Local column of every stored J column. The previous sensor's calibration columns are cleared first.
     if (lane < kAccStride - kAccCal0)
 #pragma unroll 4
@@ -143,6 +301,7 @@ __global__ void __launch_bounds__(kAccThreads, (NB == 7 ? CB2_ACC_MINBLOCKS : 2)
       __syncwarp();
     }
     cp_async_wait<0>();
+    }
     // Flush every entry that involves this sensor's calibration unknowns (blocks 5..NB-1), then reset them for the next sensor.
 #pragma unroll
     for (int bi = 5; bi < NB; ++bi) {
@@ -188,8 +347,32 @@ __global__ void __launch_bounds__(kAccThreads, (NB == 7 ? CB2_ACC_MINBLOCKS : 2)
     double v = 0.0;
 #pragma unroll
     for (int w = 0; w < kAccWarps; ++w) v += tiles[w][0][e];
+    if (use_struct) {   // Kronecker expansion of the camera images: (w_a w_b / w_istar^2) G^gg[p][q], (w_b / w_istar) sum r g^_q
+      const int nslots = s_slot_begin[n_sensors];
+      const int a6 = I / 6, p6 = I - 6 * a6, b6 = Jx / 6, q6 = Jx - 6 * b6;
+      for (int k = 0; k < nslots; ++k) {
+        const double* slot = slots + size_t(k) * kAccSlot;
+        if (I < kCpCols) v += slot[kAccSlotRho + a6] * slot[kAccSlotRho + b6] * slot[p6 * 6 + q6];
+        else v += slot[kAccSlotRho + b6] * slot[kAccSlotGr + q6];
+      }
+    }
     if (I < kCpCols) segA[(size_t(gl) * kCpCols + I) * kCpCols + Jx] = v;
     else segG[size_t(gl) * kCpCols + Jx] = v;
+  }
+  if (use_struct) {     // control points x calibration of every structured camera: (w_a / w_istar) sum c g^_p over its images
+    for (int s = 0; s < n_sensors; ++s) {
+      const int k0 = s_slot_begin[s], k1 = s_slot_begin[s + 1];
+      if (k1 == k0) continue;
+      const SensorDesc& sd = sensors[s];
+      const int nc = sd.n_calib;
+      for (int e = t; e < kCpCols * 16; e += kAccThreads) {
+        const int Jx = e >> 4, li = e & 15, a6 = Jx / 6, p6 = Jx - 6 * a6;
+        if (li >= nc) continue;
+        double v = 0.0;
+        for (int k = k0; k < k1; ++k) { const double* slot = slots + size_t(k) * kAccSlot; v += slot[kAccSlotRho + a6] * slot[kAccSlotGc + p6 * 16 + li]; }
+        segB[(size_t(gl) * kCpCols + Jx) * N_c + sd.calib_off + li] = v;
+      }
+    }
   }
 }
 

@@ -32,7 +32,8 @@ def main():
     rep, kre = sys.argv[1], sys.argv[2]
     idx = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 25
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre, "--launch-skip", str(idx), "--launch-count", "1",
+    filt = [] if kre == "-" else ["--kernel-name", "regex:" + kre]     # "-" = no name filter (reports holding a single kernel)
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", *filt, "--launch-skip", str(idx), "--launch-count", "1",
                           "--print-kernel-base", "mangled"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     h = [i for i, r in enumerate(rows) if "Source" in r and "# Samples" in r][0]

@@ -53,6 +53,7 @@ enum Scal {
   kScSolveFail = 6,                       // > 0 when a Cholesky pivot was not positive / step not finite
   kScModelChange = 7,                     // model cost change of the computed step
   kScStepNorm2 = 8, kScXNorm2 = 9, kScCandXNorm2 = 10,
+  kScRadius = 11, kScLmLo = 12, kScLmHi = 13,   // host -> device: trust-region radius, min / max LM diagonal of the coming solve
   kScCount = 16
 };
 

@@ -339,6 +339,10 @@ struct cb2_problem {
   bool gram_dmma1 = false;   // level-1 Gram product on the FP64 tensor pipe
   bool acc_structured = std::getenv("CB2_ACC_STRUCTURED") != nullptr;   // image-wise Kronecker accumulation of camera rows (cb2_normal.cuh): opt-in
   double* h_scal = nullptr;   // pinned
+  double* h_param = nullptr;  // pinned: {radius, min_lm_diagonal, max_lm_diagonal} of the coming solve
+  bool use_graphs = std::getenv("CB2_NO_GRAPHS") == nullptr;
+  cudaGraphExec_t g_solve[2] = {nullptr, nullptr};   // solve phase as a CUDA graph, one per parameter buffer (cur = 0 / 1)
+  int64_t g_solve_kernels = 0;
   cb2_stats stats{};
   PhaseTimer timer;
   KernelProfiler kprof;
@@ -349,11 +353,19 @@ struct cb2_problem {
     if (stream) cudaStreamSynchronize(stream);       // device buffers are released (stream-ordered, default stream) after this body
     if (stream_imu) cudaStreamSynchronize(stream_imu);
     kprof.report();
+    drop_graphs();
     if (h_scal) cudaFreeHost(h_scal);
+    if (h_param) cudaFreeHost(h_param);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
     if (stream_imu) cudaStreamDestroy(stream_imu);
     if (stream) cudaStreamDestroy(stream);
+  }
+
+  void drop_graphs() {
+#ifndef CB2_EMUL
+    for (auto& g : g_solve) { if (g) cudaGraphExecDestroy(g); g = nullptr; }
+#endif
   }
 
   int fail(int code, const std::string& msg) { error = msg; return code; }
@@ -429,12 +441,14 @@ struct cb2_problem {
     CB2_CUDA(cudaEventCreate(&ev_fork));
     CB2_CUDA(cudaEventCreate(&ev_join));
     CB2_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_scal), sizeof(double) * kScCount));
+    CB2_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_param), sizeof(double) * 4));
     return CB2_OK;
   }
 
   int upload_impl() {
     uploaded = false;
     if (stream) CB2_CUDA(cudaStreamSynchronize(stream));
+    drop_graphs();   // every device pointer baked into a captured solve phase is about to change
     if (knots.empty() || ctrl.empty()) return fail(CB2_FAILED_PRECONDITION, "Trajectory has not been set.");
     if (k != kK) return fail(CB2_UNIMPLEMENTED, "Only spline order 6 (calico::Trajectory::kSplineOrder, trajectory.h:28) is supported.");
     for (const auto& b : bodies)
@@ -803,7 +817,8 @@ struct cb2_problem {
     set(eval_kernel<kCamera, kModeCost>, ev_max[0]); set(eval_kernel<kCamera, kModeResiduals>, ev_max[0]); set(eval_kernel<kCamera, kModeJacobian>, ev_max[0]);
     set(eval_kernel<kGyroscope, kModeCost>, ev_max[1]); set(eval_kernel<kGyroscope, kModeResiduals>, ev_max[1]); set(eval_kernel<kGyroscope, kModeJacobian>, ev_max[1]);
     set(eval_kernel<kAccelerometer, kModeCost>, ev_max[2]); set(eval_kernel<kAccelerometer, kModeResiduals>, ev_max[2]); set(eval_kernel<kAccelerometer, kModeJacobian>, ev_max[2]);
-    set(accumulate_kernel<7>, acc_smem_bytes(true)); set(accumulate_kernel<8>, acc_smem_bytes(true));
+    set((accumulate_kernel<7, false>), acc_smem_bytes(false)); set((accumulate_kernel<8, false>), acc_smem_bytes(false));
+    set((accumulate_kernel<7, true>), acc_smem_bytes(true)); set((accumulate_kernel<8, true>), acc_smem_bytes(true));
     int max_n1 = 0;
     for (const auto& sy : h_l1) max_n1 = std::max(max_n1, sy.n);
     const int nbw1 = h_l1[0].nbw, nbw2 = h_l2.nbw;
@@ -890,8 +905,12 @@ struct cb2_problem {
     if (nsl > 0) {
       int max_nc = 0;
       for (const auto& d : h_desc) max_nc = std::max(max_nc, d.n_calib);
-      if (kAccCal0 + max_nc <= 56) CB2_K(accumulate_kernel<7>, nsl, kAccThreads, acc_smem_bytes(acc_structured), stream, d_desc.p, ns, N_c, g_lo, d_c2off.p, csz, d_segA.p, d_segG.p, d_segB.p, d_segC.p, d_segGc.p, d_frames.p, acc_structured ? 1 : 0);
-      else CB2_K(accumulate_kernel<8>, nsl, kAccThreads, acc_smem_bytes(acc_structured), stream, d_desc.p, ns, N_c, g_lo, d_c2off.p, csz, d_segA.p, d_segG.p, d_segB.p, d_segC.p, d_segGc.p, d_frames.p, acc_structured ? 1 : 0);
+#define CB2_ACC(NBV, STV) CB2_K((accumulate_kernel<NBV, STV>), nsl, kAccThreads, acc_smem_bytes(STV), stream, d_desc.p, ns, N_c, g_lo, d_c2off.p, csz, d_segA.p, \
+                                d_segG.p, d_segB.p, d_segC.p, d_segGc.p, d_frames.p)
+      const bool nb7 = kAccCal0 + max_nc <= 56;
+      if (acc_structured) { if (nb7) CB2_ACC(7, true); else CB2_ACC(8, true); }
+      else { if (nb7) CB2_ACC(7, false); else CB2_ACC(8, false); }
+#undef CB2_ACC
     }
     const long total = n_a * 36 + n_a * N_c + n_a;
     CB2_K(assemble_band_kernel, int(std::min<long>((total + 255) / 256, 148 * 16)), 256, 0, stream, n_cp, g_lo, g_hi, N_c, d_segA.p, d_segG.p, d_segB.p,
@@ -925,7 +944,23 @@ struct cb2_problem {
     const int ns = int(sensors.size());
     const int blocks = int(std::min<long>((n_tot + 255) / 256, 1024));
     timer.begin(kPhSchur, stream);
-    CB2_K(damping_kernel, blocks, 256, 0, stream, n_tot, d_diag.p, d_scaling.p, radius, opt.min_lm_diagonal, opt.max_lm_diagonal, d_dtil2.p);
+    h_param[0] = radius; h_param[1] = opt.min_lm_diagonal; h_param[2] = opt.max_lm_diagonal;
+    CB2_CUDA(cudaMemcpyAsync(d_scal.p + kScRadius, h_param, 3 * sizeof(double), cudaMemcpyHostToDevice, stream));
+    stats.h2d_bytes += 3 * sizeof(double);
+#ifndef CB2_EMUL
+    // The solve phase is ~25 small latency-bound kernels: replayed as ONE CUDA graph per parameter buffer (captured on first use).
+    const bool graph = use_graphs && world == 1 && !kprof.on;
+    if (graph && g_solve[cur]) {
+      CB2_CUDA(cudaGraphLaunch(g_solve[cur], stream));
+      stats.kernel_launches += g_solve_kernels;
+      timer.end(kPhSchur, stream);
+      launch_trial();
+      return;
+    }
+    const int64_t launches_before = stats.kernel_launches;
+    if (graph) CB2_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+#endif
+    CB2_K(damping_kernel, blocks, 256, 0, stream, n_tot, d_diag.p, d_scaling.p, d_scal.p, d_dtil2.p);
     CB2_CUDA(cudaMemsetAsync(d_scal.p + kScSolveFail, 0, sizeof(double), stream));
     const int nbw1 = h_l1[0].nbw;
     int max_n1 = 0;
@@ -991,7 +1026,21 @@ struct cb2_problem {
     }
     CB2_K(apply_step_kernel, 1, kLmThreads, 0, stream, n_a, d_ytil.p, gradG(), d_dtil2.p, d_cp_ref.p, d_cp_own.p, rank == 0 ? 1 : 0, d_ctrl[cur].p,
           d_ctrl[cur ^ 1].p, d_desc.p, d_state[cur].p, d_state[cur ^ 1].p, ns, N_c, d_scal.p);
+#ifndef CB2_EMUL
+    if (graph) {
+      cudaGraph_t g = nullptr;
+      CB2_CUDA(cudaStreamEndCapture(stream, &g));
+      CB2_CUDA(cudaGraphInstantiate(&g_solve[cur], g, 0));
+      CB2_CUDA(cudaGraphDestroy(g));
+      g_solve_kernels = stats.kernel_launches - launches_before;
+      CB2_CUDA(cudaGraphLaunch(g_solve[cur], stream));
+    }
+#endif
     timer.end(kPhSchur, stream);
+    launch_trial();
+  }
+
+  void launch_trial() {
     timer.begin(kPhCost, stream);
     // Trial point: cameras in cost-only mode; the (few, FP64-latency-bound) IMU blocks in Jacobian mode. Their Jacobians at x are not
     // needed any more (the normal equations of x are already assembled and survive a rejected step), and if the step is accepted the

@@ -24,7 +24,10 @@ __global__ void __launch_bounds__(256) jacobi_scaling_kernel(long n, const doubl
 // LM damping in unscaled coordinates. Ceres solves (S H S + D^2) y = S g with D^2 = clamp(diag(S H S), lo, hi) / radius and
 // applies delta = -S y. With ytil = S y this is (H + Dtil^2) ytil = g, Dtil^2_j = clamp(s_j^2 H_jj, lo, hi) / (radius s_j^2).
 __global__ void __launch_bounds__(256) damping_kernel(long n, const double* __restrict__ diag, const double* __restrict__ scaling,
-                                                      double radius, double lo, double hi, double* __restrict__ dtil2) {
+                                                      const double* __restrict__ scal, double* __restrict__ dtil2) {
+  // radius and the clamp bounds come from the scalar block (written by the host right before the launch), not from kernel arguments,
+  // so that the whole solve phase can be replayed as one CUDA graph with a different trust-region radius every iteration.
+  const double radius = scal[kScRadius], lo = scal[kScLmLo], hi = scal[kScLmHi];
   for (long j = long(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += long(gridDim.x) * blockDim.x) {
     const double s2 = scaling[j] * scaling[j];
     dtil2[j] = fmin(fmax(diag[j] * s2, lo), hi) / (radius * s2);

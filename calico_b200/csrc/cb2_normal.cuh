@@ -77,11 +77,11 @@ CB2_D void dmma_8x8x4(double& c0, double& c1, double a, double b) {
 }
 
 // NB = number of 8-column blocks of the local layout: 7 covers sensors with up to 16 calibration unknowns, 8 up to 20 (kMaxCalib).
-template <int NB>
+// kStruct = false compiles the structured camera path out entirely (the default build of the hot kernel carries none of its cost).
+template <int NB, bool kStruct>
 __global__ void __launch_bounds__(kAccThreads, (NB == 7 ? CB2_ACC_MINBLOCKS : 2)) accumulate_kernel(
     const SensorDesc* __restrict__ sensors, int n_sensors, int N_c, int g_lo, const int* __restrict__ c2off, int csz, double* __restrict__ segA,
-    double* __restrict__ segG, double* __restrict__ segB, double* __restrict__ segC, double* __restrict__ segGc, const double* __restrict__ frames,
-    int structured) {
+    double* __restrict__ segG, double* __restrict__ segB, double* __restrict__ segC, double* __restrict__ segGc, const double* __restrict__ frames) {
   // dynamic shared memory: per warp two tile buffers of kAccRows x kAccStride (+ 4 doubles: the last fragment reads past a row end)
   typedef double TileBuf[2][kAccRows * kAccStride + 4];
   TileBuf* tiles = dyn_smem<TileBuf>();
@@ -101,8 +101,8 @@ __global__ void __launch_bounds__(kAccThreads, (NB == 7 ? CB2_ACC_MINBLOCKS : 2)
   double* const slots = reinterpret_cast<double*>(tiles + kAccWarps);
   __shared__ int s_slot_begin[kAccMaxSensors + 1];
   __shared__ int s_use_struct;
-  if (warp == 0) {   // lane-parallel: one sensor per lane and round, exclusive prefix sum by shuffles (no serial chain of dependent loads)
-    const bool ok = structured && n_sensors <= kAccMaxSensors;
+  if (kStruct && warp == 0) {   // lane-parallel: one sensor per lane and round, exclusive prefix sum by shuffles (no serial chain of dependent loads)
+    const bool ok = n_sensors <= kAccMaxSensors;
     int base = 0;
     for (int s0 = 0; ok && s0 < n_sensors; s0 += 32) {
       const int s = s0 + lane;
@@ -118,8 +118,8 @@ __global__ void __launch_bounds__(kAccThreads, (NB == 7 ? CB2_ACC_MINBLOCKS : 2)
     }
     if (lane == 0) { s_slot_begin[n_sensors <= kAccMaxSensors ? n_sensors : 0] = base; s_use_struct = (ok && base <= kAccMaxSlots) ? 1 : 0; }
   }
-  __syncthreads();
-  const bool use_struct = s_use_struct != 0;
+  if (kStruct) __syncthreads();
+  const bool use_struct = kStruct && s_use_struct != 0;
 
   for (int s = warp; s < n_sensors; s += kAccWarps) {
     const SensorDesc& sd = sensors[s];
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kAccThreads, (NB == 7 ? CB2_ACC_MINBLOCKS : 2)
     const int o0 = sd.seg_start[g];
     const int rows = (sd.seg_start[g + 1] - o0) * m;
     if (rows == 0) continue;
-    if (use_struct && sd.kind == kCamera && nc <= 16) {
+    if (kStruct && use_struct && sd.kind == kCamera && nc <= 16) {
       // ---- camera rows, image by image (see the header comment): compact Gram of [g^ | r | calibration]; the Kronecker expansion of its
       //      g^ rows is deferred to the end of the kernel (per-image slots in shared memory), the [r | calibration] square is summed here ----
       constexpr int CS = 28, CR = 16;                         // compact tile: 16 rows x 24 columns, row stride 28 (== 12 mod 16: conflict-free fragments)
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(kAccThreads, (NB == 7 ? CB2_ACC_MINBLOCKS : 2)
     double v = 0.0;
 #pragma unroll
     for (int w = 0; w < kAccWarps; ++w) v += tiles[w][0][e];
-    if (use_struct) {   // Kronecker expansion of the camera images: (w_a w_b / w_istar^2) G^gg[p][q], (w_b / w_istar) sum r g^_q
+    if (kStruct && use_struct) {   // Kronecker expansion of the camera images: (w_a w_b / w_istar^2) G^gg[p][q], (w_b / w_istar) sum r g^_q
       const int nslots = s_slot_begin[n_sensors];
       const int a6 = I / 6, p6 = I - 6 * a6, b6 = Jx / 6, q6 = Jx - 6 * b6;
       for (int k = 0; k < nslots; ++k) {
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(kAccThreads, (NB == 7 ? CB2_ACC_MINBLOCKS : 2)
     if (I < kCpCols) segA[(size_t(gl) * kCpCols + I) * kCpCols + Jx] = v;
     else segG[size_t(gl) * kCpCols + Jx] = v;
   }
-  if (use_struct) {     // control points x calibration of every structured camera: (w_a / w_istar) sum c g^_p over its images
+  if (kStruct && use_struct) {     // control points x calibration of every structured camera: (w_a / w_istar) sum c g^_p over its images
     for (int s = 0; s < n_sensors; ++s) {
       const int k0 = s_slot_begin[s], k1 = s_slot_begin[s + 1];
       if (k1 == k0) continue;

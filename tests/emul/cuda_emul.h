@@ -208,6 +208,7 @@ enum { cudaSuccess = 0, cudaErrorEmul = 1 };
 typedef struct cb2emul_stream* cudaStream_t;
 struct cb2emul_event { std::chrono::steady_clock::time_point t; };
 typedef cb2emul_event* cudaEvent_t;
+typedef void* cudaGraphExec_t;
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
 enum { cudaStreamNonBlocking = 1, cudaEventDefault = 0 };
 inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }

@@ -341,8 +341,8 @@ struct cb2_problem {
   double* h_scal = nullptr;   // pinned
   double* h_param = nullptr;  // pinned: {radius, min_lm_diagonal, max_lm_diagonal} of the coming solve
   bool use_graphs = std::getenv("CB2_NO_GRAPHS") == nullptr;
-  cudaGraphExec_t g_solve[2] = {nullptr, nullptr};   // solve phase as a CUDA graph, one per parameter buffer (cur = 0 / 1)
-  int64_t g_solve_kernels = 0;
+  struct GraphSlot { cudaGraphExec_t exec = nullptr; int64_t kernels = 0; };
+  GraphSlot g_solve[2], g_trial[2], g_normal[2];   // LM phases as CUDA graphs, one per parameter buffer (cur = 0 / 1)
   cb2_stats stats{};
   PhaseTimer timer;
   KernelProfiler kprof;
@@ -364,7 +364,29 @@ struct cb2_problem {
 
   void drop_graphs() {
 #ifndef CB2_EMUL
-    for (auto& g : g_solve) { if (g) cudaGraphExecDestroy(g); g = nullptr; }
+    for (auto* set : {g_solve, g_trial, g_normal}) for (int i = 0; i < 2; ++i) { if (set[i].exec) cudaGraphExecDestroy(set[i].exec); set[i] = GraphSlot{}; }
+#endif
+  }
+  // Runs `body` (kernel launches and memsets on `stream` only) as a CUDA graph: captured and instantiated on first use, replayed afterwards.
+  // Only single-GPU (no NCCL inside) and not while the per-kernel profiler is on.
+  template <class F>
+  void graphed(GraphSlot& slot, F&& body) {
+#ifndef CB2_EMUL
+    const bool graph = use_graphs && world == 1 && !kprof.on;
+    if (graph && slot.exec) { CB2_CUDA(cudaGraphLaunch(slot.exec, stream)); stats.kernel_launches += slot.kernels; return; }
+    const int64_t before = stats.kernel_launches;
+    if (graph) CB2_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    body();
+    if (graph) {
+      cudaGraph_t g = nullptr;
+      CB2_CUDA(cudaStreamEndCapture(stream, &g));
+      CB2_CUDA(cudaGraphInstantiate(&slot.exec, g, 0));
+      CB2_CUDA(cudaGraphDestroy(g));
+      slot.kernels = stats.kernel_launches - before;
+      CB2_CUDA(cudaGraphLaunch(slot.exec, stream));
+    }
+#else
+    body();
 #endif
   }
 
@@ -900,6 +922,7 @@ struct cb2_problem {
     last_sweep_imu = !imu_reuse;
     timer.end(kPhJacobian, stream);
     timer.begin(kPhNormal, stream);
+    graphed(g_normal[cur], [&] {
     const int ns = int(sensors.size());
     const int nsl = g_hi - g_lo;
     if (nsl > 0) {
@@ -932,6 +955,7 @@ struct cb2_problem {
     }
     CB2_K(gradient_norm_kernel, 1, kLmThreads, 0, stream, n_a, gradG(), d_cp_own.p, rank == 0 ? 1 : 0, d_desc.p, d_state[cur].p, ns, d_scal.p);
     if (world > 1) { comm->allreduce_sum(d_scal.p + kScCost, 3, stream); comm->allreduce_max(d_scal.p + kScGradMax, 1, stream); }
+    });
     timer.end(kPhNormal, stream);
     ++stats.jacobian_sweeps;
   }
@@ -947,19 +971,8 @@ struct cb2_problem {
     h_param[0] = radius; h_param[1] = opt.min_lm_diagonal; h_param[2] = opt.max_lm_diagonal;
     CB2_CUDA(cudaMemcpyAsync(d_scal.p + kScRadius, h_param, 3 * sizeof(double), cudaMemcpyHostToDevice, stream));
     stats.h2d_bytes += 3 * sizeof(double);
-#ifndef CB2_EMUL
-    // The solve phase is ~25 small latency-bound kernels: replayed as ONE CUDA graph per parameter buffer (captured on first use).
-    const bool graph = use_graphs && world == 1 && !kprof.on;
-    if (graph && g_solve[cur]) {
-      CB2_CUDA(cudaGraphLaunch(g_solve[cur], stream));
-      stats.kernel_launches += g_solve_kernels;
-      timer.end(kPhSchur, stream);
-      launch_trial();
-      return;
-    }
-    const int64_t launches_before = stats.kernel_launches;
-    if (graph) CB2_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-#endif
+    // The solve phase is ~25 small latency-bound kernels: replayed as ONE CUDA graph per parameter buffer.
+    graphed(g_solve[cur], [&] {
     CB2_K(damping_kernel, blocks, 256, 0, stream, n_tot, d_diag.p, d_scaling.p, d_scal.p, d_dtil2.p);
     CB2_CUDA(cudaMemsetAsync(d_scal.p + kScSolveFail, 0, sizeof(double), stream));
     const int nbw1 = h_l1[0].nbw;
@@ -1026,16 +1039,7 @@ struct cb2_problem {
     }
     CB2_K(apply_step_kernel, 1, kLmThreads, 0, stream, n_a, d_ytil.p, gradG(), d_dtil2.p, d_cp_ref.p, d_cp_own.p, rank == 0 ? 1 : 0, d_ctrl[cur].p,
           d_ctrl[cur ^ 1].p, d_desc.p, d_state[cur].p, d_state[cur ^ 1].p, ns, N_c, d_scal.p);
-#ifndef CB2_EMUL
-    if (graph) {
-      cudaGraph_t g = nullptr;
-      CB2_CUDA(cudaStreamEndCapture(stream, &g));
-      CB2_CUDA(cudaGraphInstantiate(&g_solve[cur], g, 0));
-      CB2_CUDA(cudaGraphDestroy(g));
-      g_solve_kernels = stats.kernel_launches - launches_before;
-      CB2_CUDA(cudaGraphLaunch(g_solve[cur], stream));
-    }
-#endif
+    });
     timer.end(kPhSchur, stream);
     launch_trial();
   }
@@ -1045,7 +1049,7 @@ struct cb2_problem {
     // Trial point: cameras in cost-only mode; the (few, FP64-latency-bound) IMU blocks in Jacobian mode. Their Jacobians at x are not
     // needed any more (the normal equations of x are already assembled and survive a rejected step), and if the step is accepted the
     // Jacobians of the new x are then already there: the next sweep is the camera kernel alone.
-    launch_eval<kModeCost>(cur ^ 1, kScCandCost, speculative_imu ? kImuJacobian : kImuSame);
+    graphed(g_trial[cur], [&] { launch_eval<kModeCost>(cur ^ 1, kScCandCost, speculative_imu ? kImuJacobian : kImuSame); });
     if (speculative_imu) { imu_jac_point = cur ^ 1; stats.jacobian_blocks += num_active_blocks(true); }
     if (world > 1) comm->allreduce_sum(d_scal.p + kScCandCost, 7, stream);
     timer.end(kPhCost, stream);

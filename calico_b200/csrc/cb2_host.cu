@@ -289,6 +289,12 @@ struct cb2_problem {
   bool imu_side_stream = std::getenv("CB2_IMU_STREAM") != nullptr;
   bool speculative_imu = std::getenv("CB2_SPECULATIVE_IMU") != nullptr;   // measured neutral on C4 (Jacobian-mode IMU blocks cost +53 us over cost mode): off by default
   int imu_jac_point = -1;       // parameter buffer (0 / 1) whose IMU Jacobians, residuals and cost partials are current; -1 = none
+  // Speculative sweep: when the previous step was accepted the next one very likely is too, so its trial point is evaluated with the
+  // full residual + Jacobian sweep instead of the cost-only pass; on acceptance the sweep of the new x is then already done (saves the
+  // cost pass, K0 and a reduction per accepted iteration), on rejection the extra Jacobian write is the price (CB2_NO_SPECULATIVE_SWEEP=1: off).
+  bool speculative_sweep = std::getenv("CB2_NO_SPECULATIVE_SWEEP") == nullptr;
+  int jac_point = -1;           // parameter buffer whose complete sweep (all sensors: J, r, cost partials) is current; -1 = none
+  bool trial_was_sweep = false, sweep_skipped = false, speculate_next = true;
   bool last_sweep_imu = true;
   int n_cp = 0, n_seg = 0, N_c = 0, csz = 0, n_tiles = 0;
   long n_a = 0, n_tot = 0;
@@ -914,13 +920,21 @@ struct cb2_problem {
 
   // K1-K3 at x, then K4: normal equations, Hessian diagonal, gradient norms.
   void launch_jacobian_and_normal_equations() {
-    timer.begin(kPhJacobian, stream);
-    // IMU Jacobians of this point were already produced by the trial-cost pass that led to its acceptance (launch_step).
-    const bool imu_reuse = imu_jac_point == cur;
-    launch_eval<kModeJacobian>(cur, kScCost, imu_reuse ? kImuSkip : kImuSame);
-    imu_jac_point = cur;
-    last_sweep_imu = !imu_reuse;
-    timer.end(kPhJacobian, stream);
+    sweep_skipped = jac_point == cur;          // the trial pass that led to this point's acceptance was a full sweep (launch_trial)
+    if (!sweep_skipped) {
+      timer.begin(kPhJacobian, stream);
+      // IMU Jacobians of this point may already have been produced by the trial-cost pass (speculative_imu).
+      const bool imu_reuse = imu_jac_point == cur;
+      launch_eval<kModeJacobian>(cur, kScCost, imu_reuse ? kImuSkip : kImuSame);
+      imu_jac_point = cur;
+      jac_point = cur;
+      last_sweep_imu = !imu_reuse;
+      timer.end(kPhJacobian, stream);
+      ++stats.jacobian_sweeps;
+      stats.jacobian_blocks += last_sweep_imu ? num_active_blocks() : num_active_blocks() - num_active_blocks(true);
+      stats.jacobian_bytes += last_sweep_imu ? jacobian_bytes_per_sweep() : jacobian_bytes_per_sweep(kCamera);
+      stats.camera_kernel_bytes += jacobian_bytes_per_sweep(kCamera);
+    }
     timer.begin(kPhNormal, stream);
     graphed(g_normal[cur], [&] {
     const int ns = int(sensors.size());
@@ -957,7 +971,6 @@ struct cb2_problem {
     if (world > 1) { comm->allreduce_sum(d_scal.p + kScCost, 3, stream); comm->allreduce_max(d_scal.p + kScGradMax, 1, stream); }
     });
     timer.end(kPhNormal, stream);
-    ++stats.jacobian_sweeps;
   }
 
   const double* gradG() const { return world > 1 ? d_gradG.p : d_grad.p; }   // gradient with cross-rank sums on the shared rows
@@ -1045,6 +1058,22 @@ struct cb2_problem {
   }
 
   void launch_trial() {
+    // The candidate buffer has just been overwritten by apply_step: whatever sweep it held belongs to an older (rejected) candidate.
+    if (jac_point == (cur ^ 1)) jac_point = -1;
+    if (imu_jac_point == (cur ^ 1)) imu_jac_point = -1;
+    trial_was_sweep = speculative_sweep && speculate_next;
+    if (trial_was_sweep) {
+      timer.begin(kPhJacobian, stream);
+      launch_eval<kModeJacobian>(cur ^ 1, kScCandCost, kImuSame);
+      jac_point = cur ^ 1; imu_jac_point = cur ^ 1;
+      if (world > 1) comm->allreduce_sum(d_scal.p + kScCandCost, 7, stream);
+      timer.end(kPhJacobian, stream);
+      ++stats.jacobian_sweeps;
+      stats.jacobian_blocks += num_active_blocks();
+      stats.jacobian_bytes += jacobian_bytes_per_sweep();
+      stats.camera_kernel_bytes += jacobian_bytes_per_sweep(kCamera);
+      return;
+    }
     timer.begin(kPhCost, stream);
     // Trial point: cameras in cost-only mode; the (few, FP64-latency-bound) IMU blocks in Jacobian mode. Their Jacobians at x are not
     // needed any more (the normal equations of x are already assembled and survive a rejected step), and if the step is accepted the
@@ -1116,7 +1145,7 @@ struct cb2_problem {
       S.total_time = now_s() - t_start;
       return CB2_OK;
     }
-    imu_jac_point = -1;
+    imu_jac_point = -1; jac_point = -1; speculate_next = true;
     double radius = opt.initial_trust_region_radius, decrease_factor = 2.0;
     double x_cost = 0, x_norm = 0, candidate_cost = 0, model_cost_change = 0, reference_cost = 0;
     int num_consecutive_invalid_steps = 0;
@@ -1130,12 +1159,13 @@ struct cb2_problem {
       launch_jacobian_and_normal_equations();
       if (first) CB2_K(jacobi_scaling_kernel, blocks_tot, 256, 0, stream, n_tot, d_diag.p, opt.jacobi_scaling, d_scaling.p);
       sync_scalars();
-      stats.jacobian_blocks += last_sweep_imu ? num_active_blocks() : num_active_blocks() - num_active_blocks(true);
-      stats.jacobian_bytes += last_sweep_imu ? jacobian_bytes_per_sweep() : jacobian_bytes_per_sweep(kCamera);
-      stats.camera_kernel_bytes += jacobian_bytes_per_sweep(kCamera);
       S.jacobian_time += now_s() - t0;
-      if (h_scal[kScInvalid] > 0) return false;
-      x_cost = h_scal[kScCost];
+      if (!sweep_skipped) {
+        if (h_scal[kScInvalid] > 0) return false;
+        x_cost = h_scal[kScCost];
+      } else {
+        x_cost = candidate_cost;   // the accepted trial point was evaluated by a full sweep: its cost is the candidate cost just read
+      }
       it.cost = x_cost;
       it.gradient_max_norm = h_scal[kScGradMax];
       it.gradient_norm = std::sqrt(h_scal[kScGradSq]);
@@ -1200,6 +1230,7 @@ struct cb2_problem {
           break;
         }
         radius *= 0.5;
+        speculate_next = false;
         it.cost = x_cost; it.cost_change = 0.0; it.step_norm = 0.0; it.relative_decrease = 0.0;
         continue;
       }
@@ -1223,6 +1254,7 @@ struct cb2_problem {
         cur ^= 1;   // x = candidate_x
         if (!evaluate_gradient_and_jacobian(false)) { S.termination_type = CB2_FAILURE; msg("Residual and Jacobian evaluation failed."); break; }
         it.step_is_successful = 1;
+        speculate_next = true;
         radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * it.relative_decrease - 1.0, 3));
         radius = std::min(opt.max_trust_region_radius, radius);
         decrease_factor = 2.0;
@@ -1231,6 +1263,7 @@ struct cb2_problem {
         ++S.num_successful_steps;
       } else {
         it.step_is_successful = 0;
+        speculate_next = false;
         it.cost = candidate_cost;
         radius = radius / decrease_factor; decrease_factor *= 2.0;
         ++S.num_unsuccessful_steps;

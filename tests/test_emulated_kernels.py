@@ -80,3 +80,18 @@ def test_emulated_lm_iterations_match_oracle(schur, chunk, emul_lib, oracle, mon
     np.testing.assert_allclose(pa.spline.ctrl, po.spline.ctrl, rtol=1e-8, atol=1e-9)
     for s1, s2 in zip(pa.sensors, po.sensors):
         np.testing.assert_allclose(s1.intr, s2.intr, rtol=1e-8, atol=1e-10)
+
+
+@pytest.mark.timeout(900)
+def test_emulated_lm_with_rejected_steps_matches_oracle(emul_lib, oracle):
+    """The reference's toy stereo + IMU problem starts with three rejected steps (as in the stored Ceres log): exercises the
+    reject -> accept transitions of the speculative trial sweep (the candidate buffer is reused by every new candidate)."""
+    truth, prob = synthetic.toy_stereo_imu_problem(oracle.oracle_api, seed=3)
+    a, o = _capi.CApi(emul_lib), oracle.oracle_api()
+    prob.clone().push(a)
+    prob.clone().push(o)
+    sum_a, log_a = a.optimize(_capi.Options(minimizer_progress_to_stdout=0, max_num_iterations=5))
+    sum_o, log_o = o.optimize(oracle.OracleOptions(linear_solver=1, max_num_iterations=5))
+    assert [x.step_is_successful for x in log_a] == [x.step_is_successful for x in log_o] == [1, 0, 0, 0, 1, 0]
+    for x, y in zip(log_a, log_o):
+        assert abs(x.cost - y.cost) <= 1e-9 * abs(y.cost)

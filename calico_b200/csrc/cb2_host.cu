@@ -325,7 +325,7 @@ struct cb2_problem {
   long total_blocks = 0, total_residuals = 0;    // over ALL ranks (summary counts)
   DevBuf<unsigned char> d_cp_own;
   DevBuf<int> d_shared_idx;
-  DevBuf<double> d_shared_buf, d_gradG, d_red;
+  DevBuf<double> d_shared_buf, d_gradG, d_red, d_normbuf;
   int n_shared = 0;
   // Schur
   std::vector<ChunkPlan> chunks;
@@ -696,7 +696,7 @@ struct cb2_problem {
     d_Aband.alloc(size_t(n_a) * 36); d_Bmat.alloc(size_t(n_a) * std::max(N_c, 1)); d_Cmat.alloc(size_t(std::max(N_c, 1)) * std::max(N_c, 1));
     d_grad.alloc(n_tot); d_diag.alloc(n_tot); d_scaling.alloc(n_tot); d_dtil2.alloc(n_tot); d_ytil.alloc(n_tot);
     d_Aband.zero(stream); d_Bmat.zero(stream); d_grad.zero(stream); d_ytil.zero(stream);
-    if (world > 1) d_gradG.alloc(n_tot);
+    if (world > 1) { d_gradG.alloc(n_tot); d_normbuf.alloc(size_t(3 + world)); }
     rc = plan_schur();
     if (rc != CB2_OK) return rc;
     set_kernel_attributes();
@@ -968,7 +968,11 @@ struct cb2_problem {
       CB2_K(unpack_shared_kernel, (n_shared + 255) / 256, 256, 0, stream, n_shared, d_shared_idx.p, d_shared_buf.p, d_gradG.p, d_diag.p);
     }
     CB2_K(gradient_norm_kernel, 1, kLmThreads, 0, stream, n_a, gradG(), d_cp_own.p, rank == 0 ? 1 : 0, d_desc.p, d_state[cur].p, ns, d_scal.p);
-    if (world > 1) { comm->allreduce_sum(d_scal.p + kScCost, 3, stream); comm->allreduce_max(d_scal.p + kScGradMax, 1, stream); }
+    if (world > 1) {   // cost / invalid / |g|^2 (sums) and |g|_inf (max, as per-rank slots) in ONE collective
+      CB2_K(pack_norm_scalars_kernel, 1, 64, 0, stream, d_scal.p, world, rank, d_normbuf.p);
+      comm->allreduce_sum(d_normbuf.p, size_t(3 + world), stream);
+      CB2_K(unpack_norm_scalars_kernel, 1, 32, 0, stream, d_normbuf.p, world, d_scal.p);
+    }
     });
     timer.end(kPhNormal, stream);
   }

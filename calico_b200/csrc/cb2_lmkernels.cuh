@@ -169,6 +169,21 @@ __global__ void __launch_bounds__(256) unpack_shared_kernel(int n, const int* __
                                                             double* __restrict__ grad, double* __restrict__ diag) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { grad[idx[i]] = buf[i]; diag[idx[i]] = buf[n + i]; }
 }
+// One SUM allreduce instead of a sum and a max: buf = [cost, invalid, gradient_norm^2 | one slot per rank holding that rank's local
+// gradient max norm, zero elsewhere]; after the sum every rank takes the maximum of the rank slots.
+__global__ void pack_norm_scalars_kernel(const double* __restrict__ scal, int world, int rank, double* __restrict__ buf) {
+  const int t = threadIdx.x;
+  if (t < 3) buf[t] = scal[kScCost + t];
+  for (int r = t; r < world; r += blockDim.x) buf[3 + r] = r == rank ? scal[kScGradMax] : 0.0;
+}
+__global__ void unpack_norm_scalars_kernel(const double* __restrict__ buf, int world, double* __restrict__ scal) {
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < 3; ++q) scal[kScCost + q] = buf[q];
+    double m = 0.0;
+    for (int r = 0; r < world; ++r) m = fmax(m, buf[3 + r]);
+    scal[kScGradMax] = m;
+  }
+}
 // Final control-point exchange: keep what this rank is responsible for, zero the rest, then sum across ranks.
 __global__ void __launch_bounds__(256) mask_ctrl_kernel(long n_a, const unsigned char* __restrict__ cp_own, int count_shared,
                                                         const double* __restrict__ ctrl, double* __restrict__ out) {

@@ -1,5 +1,5 @@
 """The C++ host mirror (include/calico_b200.hpp) exercised by the reference's own integration test transcribed to it
-(tests/cpp/batch_optimizer_test.cpp <- calico/test/batch_optimizer_test.cpp:32-213): compiled with g++ and linked against the CUDA
+(tests/cpp/mirror_integration_test.cpp <- calico/test/batch_optimizer_test.cpp:32-213): compiled with g++ and linked against the CUDA
 library (GPU) or against the SIMT-emulation build of the same kernel sources (CPU, reduced fixture, a few iterations)."""
 import os
 import subprocess

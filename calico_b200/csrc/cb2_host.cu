@@ -295,6 +295,7 @@ struct cb2_problem {
   bool speculative_sweep = std::getenv("CB2_NO_SPECULATIVE_SWEEP") == nullptr;
   int jac_point = -1;           // parameter buffer whose complete sweep (all sensors: J, r, cost partials) is current; -1 = none
   bool trial_was_sweep = false, sweep_skipped = false, speculate_next = true;
+  bool defer_normal_sync = std::getenv("CB2_NO_DEFERRED_SYNC") == nullptr;
   bool last_sweep_imu = true;
   int n_cp = 0, n_seg = 0, N_c = 0, csz = 0, n_tiles = 0;
   long n_a = 0, n_tot = 0;
@@ -1176,6 +1177,13 @@ struct cb2_problem {
       return true;
     };
 
+    bool pending_grad = false;
+    auto resolve_pending_gradient = [&]() {
+      if (!pending_grad) return;
+      pending_grad = false;
+      L.back().gradient_max_norm = h_scal[kScGradMax];
+      L.back().gradient_norm = std::sqrt(h_scal[kScGradSq]);
+    };
     double t_iter = now_s();
     it.iteration = 0; it.trust_region_radius = radius;
     if (!evaluate_gradient_and_jacobian(true)) {
@@ -1198,8 +1206,9 @@ struct cb2_problem {
       if (opt.minimizer_progress_to_stdout)
         std::printf("% 4d % 8e   % 3.2e   % 3.2e  % 3.2e  % 3.2e % 3.2e     % 4d   % 3.2e   % 3.2e\n", it.iteration, it.cost, it.cost_change,
                     it.gradient_max_norm, it.step_norm, it.relative_decrease, it.trust_region_radius, 1, it.iteration_time, now_s() - t_start);
+      if (pending_grad && (it.iteration >= opt.max_num_iterations || radius <= opt.min_trust_region_radius)) { sync_scalars(); resolve_pending_gradient(); }
       if (it.iteration >= opt.max_num_iterations) { S.termination_type = CB2_NO_CONVERGENCE; msg("Maximum number of iterations reached. Number of iterations: %.0f.", it.iteration); break; }
-      if (it.step_is_successful && it.gradient_max_norm <= opt.gradient_tolerance) {
+      if (!pending_grad && it.step_is_successful && it.gradient_max_norm <= opt.gradient_tolerance) {
         S.termination_type = CB2_CONVERGENCE; msg("Gradient tolerance reached. Gradient max norm: %e <= %e", it.gradient_max_norm, opt.gradient_tolerance); break;
       }
       if (radius <= opt.min_trust_region_radius) {
@@ -1216,6 +1225,18 @@ struct cb2_problem {
       launch_step(radius, opt);
       sync_scalars();
       S.linear_solver_time += now_s() - t_ls;
+      if (pending_grad) {
+        // The normal equations of the point accepted in the previous iteration were enqueued without a host round trip; their gradient
+        // norms arrive with this one. If they meet the gradient tolerance the solve just done is simply discarded: same termination
+        // iteration, message and log as with an immediate check.
+        resolve_pending_gradient();
+        it.gradient_max_norm = L.back().gradient_max_norm; it.gradient_norm = L.back().gradient_norm;
+        if (L.back().step_is_successful && L.back().gradient_max_norm <= opt.gradient_tolerance) {
+          S.termination_type = CB2_CONVERGENCE;
+          msg("Gradient tolerance reached. Gradient max norm: %e <= %e", L.back().gradient_max_norm, opt.gradient_tolerance);
+          break;
+        }
+      }
       const bool solved = !(h_scal[kScSolveFail] > 0);
       if (std::getenv("CB2_DEBUG"))
         std::fprintf(stderr, "[cb2 debug] iter %d radius %.3e solve_fail %.0f model_change %.6e step2 %.3e cand_cost %.6e cand_invalid %.0f\n", next_iter, radius,
@@ -1256,7 +1277,14 @@ struct cb2_problem {
       if (it.relative_decrease > opt.min_relative_decrease) {
         x_norm = std::sqrt(h_scal[kScCandXNorm2]);
         cur ^= 1;   // x = candidate_x
-        if (!evaluate_gradient_and_jacobian(false)) { S.termination_type = CB2_FAILURE; msg("Residual and Jacobian evaluation failed."); break; }
+        if (defer_normal_sync && jac_point == cur && !opt.minimizer_progress_to_stdout) {
+          // The trial pass was a full sweep of this point: only the normal equations remain, and nothing the host must decide before the
+          // next solve depends on them except the gradient-tolerance test, which is applied one round trip later (see above).
+          launch_jacobian_and_normal_equations();
+          x_cost = candidate_cost;
+          it.cost = x_cost;
+          pending_grad = true;
+        } else if (!evaluate_gradient_and_jacobian(false)) { S.termination_type = CB2_FAILURE; msg("Residual and Jacobian evaluation failed."); break; }
         it.step_is_successful = 1;
         speculate_next = true;
         radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * it.relative_decrease - 1.0, 3));

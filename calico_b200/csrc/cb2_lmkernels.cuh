@@ -66,9 +66,13 @@ __global__ void __launch_bounds__(kLmThreads) gradient_norm_kernel(long n_a, con
   __shared__ double sh[32];
   const int t = threadIdx.x;
   double mx = 0.0, sq = 0.0;
-  for (long i = t; i < n_a; i += kLmThreads) {
-    const int own = cp_own[i / 6];
-    if (own == kCpOwned || (own == kCpShared && count_shared)) { const double g = grad[i]; mx = fmax(mx, fabs(g)); sq += g * g; }
+  for (long i0 = t; i0 < n_a; i0 += 4L * kLmThreads) {      // 4 independent loads in flight per thread (single CTA: latency-bound)
+    double g[4]; int own[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const long i = min(i0 + long(u) * kLmThreads, n_a - 1); g[u] = grad[i]; own[u] = cp_own[i / 6]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i0 + long(u) * kLmThreads < n_a && (own[u] == kCpOwned || (own[u] == kCpShared && count_shared))) { mx = fmax(mx, fabs(g[u])); sq += g[u] * g[u]; }
   }
   if (count_shared) for (int s = t; s < n_sensors; s += kLmThreads) {
     const SensorDesc& sd = sensors[s];
@@ -105,17 +109,27 @@ __global__ void __launch_bounds__(kLmThreads) apply_step_kernel(long n_a, const 
   __shared__ double sh[5 * 32];
   const int t = threadIdx.x;
   double step2 = 0.0, x2 = 0.0, c2 = 0.0, model = 0.0, bad = 0.0;
-  for (long i = t; i < n_a; i += kLmThreads) {
-    const int own = cp_own[i / 6];
-    const double x = ctrl[i];
-    if (own == kCpPeer) { ctrl_cand[i] = x; continue; }
-    const double y = ytil[i];
-    const double xn = x - y;
-    ctrl_cand[i] = xn;
-    if (!isfinite(y)) bad = 1.0;
-    if (own == kCpOwned || count_shared) {
-      model += y * (grad[i] + dtil2[i] * y);
-      if (cp_ref[i / 6]) { step2 += (x - xn) * (x - xn); x2 += x * x; c2 += xn * xn; }
+  for (long i0 = t; i0 < n_a; i0 += 4L * kLmThreads) {      // 4 elements per thread per round, all loads issued before their first use
+    double xv[4], yv[4], gv[4], dv[4]; int own[4], ref[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long i = min(i0 + long(u) * kLmThreads, n_a - 1);
+      xv[u] = ctrl[i]; yv[u] = ytil[i]; gv[u] = grad[i]; dv[u] = dtil2[i]; own[u] = cp_own[i / 6]; ref[u] = cp_ref[i / 6];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long i = i0 + long(u) * kLmThreads;
+      if (i >= n_a) continue;
+      const double x = xv[u];
+      if (own[u] == kCpPeer) { ctrl_cand[i] = x; continue; }
+      const double y = yv[u];
+      const double xn = x - y;
+      ctrl_cand[i] = xn;
+      if (!isfinite(y)) bad = 1.0;
+      if (own[u] == kCpOwned || count_shared) {
+        model += y * (gv[u] + dv[u] * y);
+        if (ref[u]) { step2 += (x - xn) * (x - xn); x2 += x * x; c2 += xn * xn; }
+      }
     }
   }
   for (long j = t; j < N_c; j += kLmThreads) {

@@ -287,6 +287,8 @@ struct cb2_problem {
   cudaStream_t stream = nullptr, stream_imu = nullptr;   // IMU sweeps overlap the camera sweep on a second stream
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool imu_side_stream = std::getenv("CB2_IMU_STREAM") != nullptr;
+  bool imu_pair_streams = std::getenv("CB2_NO_IMU_PAIR") == nullptr;
+  bool capturing = false;       // inside graphed(): stay on one stream
   bool speculative_imu = std::getenv("CB2_SPECULATIVE_IMU") != nullptr;   // measured neutral on C4 (Jacobian-mode IMU blocks cost +53 us over cost mode): off by default
   int imu_jac_point = -1;       // parameter buffer (0 / 1) whose IMU Jacobians, residuals and cost partials are current; -1 = none
   // Speculative sweep: when the previous step was accepted the next one very likely is too, so its trial point is evaluated with the
@@ -382,8 +384,9 @@ struct cb2_problem {
     const bool graph = use_graphs && world == 1 && !kprof.on;
     if (graph && slot.exec) { CB2_CUDA(cudaGraphLaunch(slot.exec, stream)); stats.kernel_launches += slot.kernels; return; }
     const int64_t before = stats.kernel_launches;
-    if (graph) CB2_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    if (graph) { CB2_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal)); capturing = true; }
     body();
+    capturing = false;
     if (graph) {
       cudaGraph_t g = nullptr;
       CB2_CUDA(cudaStreamEndCapture(stream, &g));
@@ -884,10 +887,20 @@ struct cb2_problem {
   // Residual sweep over every sensor at parameter buffer `which`; scalars land in d_scal[slot], d_scal[slot + 1].
   template <int MODE>
   void launch_imu(cudaStream_t si, const SensorDesc* desc, const SensorState* st, const double* c, const int* nt) {
+    // Both IMU kernels are FP64-latency-bound single-warp CTAs at low occupancy: the gyroscope kernel runs beside the accelerometer kernel
+    // on the second stream (they touch disjoint buffers) instead of after it. (Not inside graph capture / the emulation build.)
+    cudaStream_t sg = si;
+#ifndef CB2_EMUL
+    const bool pair = imu_pair_streams && nt[1] && nt[2] && si == stream && !capturing;
+    if (pair) { CB2_CUDA(cudaEventRecord(ev_fork, stream)); CB2_CUDA(cudaStreamWaitEvent(stream_imu, ev_fork, 0)); sg = stream_imu; }
+#endif
     if (nt[2]) CB2_K((eval_kernel<kAccelerometer, MODE>), nt[2], eval_tile(kAccelerometer), smem_eval[2], si, desc, st, d_tiles.p + tile_off[2], c, d_knots.p, d_basis.p, d_pw.p,
                      d_frames.p, gravity[0], gravity[1], gravity[2], d_cost_partial.p + tile_off[2], d_invalid_partial.p + tile_off[2], 1);
-    if (nt[1]) CB2_K((eval_kernel<kGyroscope, MODE>), nt[1], eval_tile(kGyroscope), smem_eval[1], si, desc, st, d_tiles.p + tile_off[1], c, d_knots.p, d_basis.p, d_pw.p,
+    if (nt[1]) CB2_K((eval_kernel<kGyroscope, MODE>), nt[1], eval_tile(kGyroscope), smem_eval[1], sg, desc, st, d_tiles.p + tile_off[1], c, d_knots.p, d_basis.p, d_pw.p,
                      d_frames.p, gravity[0], gravity[1], gravity[2], d_cost_partial.p + tile_off[1], d_invalid_partial.p + tile_off[1], 1);
+#ifndef CB2_EMUL
+    if (pair) { CB2_CUDA(cudaEventRecord(ev_join, stream_imu)); CB2_CUDA(cudaStreamWaitEvent(stream, ev_join, 0)); }
+#endif
   }
   // imu: kImuSame = IMU sensors in MODE too; kImuJacobian = IMU sensors in Jacobian mode whatever MODE is (speculative Jacobians of
   // the trial point, see launch_step); kImuSkip = their Jacobians, residuals and cost partials of this point already exist.

@@ -593,47 +593,52 @@ __global__ void __launch_bounds__(kRedThreads) reduced_solve_smem_kernel(int N, 
   double* A = dyn_smem<double>();            // [N + 1][ld]
   double* PT = A + size_t(N + 1) * ld;       // [8][ldp] transposed panel of the current step, indexed by row - (p0 + pw)
   double* y = PT + kRsPanel * ldp;           // [N + 1]
-  __shared__ double Ld[kRsPanel * kRsPanel];
-  __shared__ double Linv[kRsPanel];
+  __shared__ double Ld[2][kRsPanel * kRsPanel];
+  __shared__ double Linv[2][kRsPanel];
   __shared__ int s_fail;
   if (t == 0) s_fail = 0;
   for (int e = t; e < ldg * ldg; e += kRedThreads) { const int r = e / ldg, c = e - r * ldg; A[r * ld + c] = Cw[e]; }
   __syncthreads();
-  for (int p0 = 0; p0 < N; p0 += kRsPanel) {
-    const int pw = min(kRsPanel, N - p0);
-    if (t == 0) {
-      double a[kRsPanel][kRsPanel];
+  // Factors the pw x pw diagonal block at (p0, p0) in registers (one thread) -> Ld[buf], Linv[buf], and in place.
+  auto factor_diag = [&](int p0, int pw, int buf) {
+    double a[kRsPanel][kRsPanel];
 #pragma unroll
-      for (int r = 0; r < kRsPanel; ++r)
+    for (int r = 0; r < kRsPanel; ++r)
 #pragma unroll
-        for (int c = 0; c <= r; ++c) a[r][c] = (r < pw) ? A[(p0 + r) * ld + p0 + c] : (r == c ? 1.0 : 0.0);
-      int fail = 0;
+      for (int c = 0; c <= r; ++c) a[r][c] = (r < pw) ? A[(p0 + r) * ld + p0 + c] : (r == c ? 1.0 : 0.0);
+    int fail = 0;
+#pragma unroll
+    for (int c = 0; c < kRsPanel; ++c) {
+      double d = a[c][c];
+      if (!(d > 0.0) || !isfinite(d)) { fail = 1; d = 1.0; }
+      const double inv = rsqrt(d);
+      a[c][c] = d * inv;
+      Linv[buf][c] = inv;
+#pragma unroll
+      for (int r = c + 1; r < kRsPanel; ++r) a[r][c] *= inv;
+#pragma unroll
+      for (int r = c + 1; r < kRsPanel; ++r)
+#pragma unroll
+        for (int k = c + 1; k <= r; ++k) a[r][k] -= a[r][c] * a[k][c];
+    }
+#pragma unroll
+    for (int r = 0; r < kRsPanel; ++r)
 #pragma unroll
       for (int c = 0; c < kRsPanel; ++c) {
-        double d = a[c][c];
-        if (!(d > 0.0) || !isfinite(d)) { fail = 1; d = 1.0; }
-        const double inv = rsqrt(d);
-        a[c][c] = d * inv;
-        Linv[c] = inv;
-#pragma unroll
-        for (int r = c + 1; r < kRsPanel; ++r) a[r][c] *= inv;
-#pragma unroll
-        for (int r = c + 1; r < kRsPanel; ++r)
-#pragma unroll
-          for (int k = c + 1; k <= r; ++k) a[r][k] -= a[r][c] * a[k][c];
+        Ld[buf][r * kRsPanel + c] = c <= r ? a[r][c] : 0.0;
+        if (c <= r && r < pw) A[(p0 + r) * ld + p0 + c] = a[r][c];
       }
-#pragma unroll
-      for (int r = 0; r < kRsPanel; ++r)
-#pragma unroll
-        for (int c = 0; c < kRsPanel; ++c) {
-          Ld[r * kRsPanel + c] = c <= r ? a[r][c] : 0.0;
-          if (c <= r && r < pw) A[(p0 + r) * ld + p0 + c] = a[r][c];
-        }
-      if (fail) s_fail = 1;
-    }
-    __syncthreads();
+    if (fail) s_fail = 1;
+  };
+  if (t == 0 && N > 0) factor_diag(0, min(kRsPanel, N), 0);
+  __syncthreads();
+  int cur = 0;
+  for (int p0 = 0; p0 < N; p0 += kRsPanel, cur ^= 1) {
+    const int pw = min(kRsPanel, N - p0);
     const int rbase = p0 + pw;               // first row below the diagonal block
     const int nrem = ldg - rbase;            // rows rbase .. N (the last one is the rhs row)
+    const double* Ldc = Ld[cur];
+    const double* Lic = Linv[cur];
     for (int rr = t; rr < nrem; rr += kRedThreads) {
       double* pr = A + (rbase + rr) * ld + p0;
       double x[kRsPanel];
@@ -641,8 +646,8 @@ __global__ void __launch_bounds__(kRedThreads) reduced_solve_smem_kernel(int N, 
       for (int c = 0; c < kRsPanel; ++c) {
         double sacc = c < pw ? pr[c] : 0.0;
 #pragma unroll
-        for (int k = 0; k < c; ++k) sacc -= x[k] * Ld[c * kRsPanel + k];
-        x[c] = sacc * Linv[c];
+        for (int k = 0; k < c; ++k) sacc -= x[k] * Ldc[c * kRsPanel + k];
+        x[c] = sacc * Lic[c];
       }
 #pragma unroll
       for (int c = 0; c < kRsPanel; ++c) { if (c < pw) pr[c] = x[c]; PT[c * ldp + rr] = c < pw ? x[c] : 0.0; }
@@ -651,34 +656,50 @@ __global__ void __launch_bounds__(kRedThreads) reduced_solve_smem_kernel(int N, 
 #pragma unroll
       for (int c = 0; c < kRsPanel; ++c) PT[c * ldp + rr] = 0.0;
     __syncthreads();
-    // trailing update: A(rbase + i, rbase + j) -= sum_k PT[k][i] PT[k][j] for i >= j, j < nrem - 1 (no rhs column)
-    const int TR = (nrem + 3) / 4, TC = (nrem - 1 + 3) / 4;
-    for (int e = t; e < TR * TC; e += kRedThreads) {
-      const int tr = e / TC, tc = e - tr * TC;
-      if (tc > tr) continue;
-      double acc[4][4];
+    // trailing update: A(rbase + i, rbase + j) -= sum_k PT[k][i] PT[k][j] for i >= j, j < nrem - 1 (no rhs column).
+    // Lookahead: warp 0 updates the NEXT diagonal block (i, j < 8) first and factors it while warps 1.. update everything else, so
+    // the one-thread 8x8 factorisation is off the critical path and a panel step needs two block barriers instead of three.
+    if (t < 32) {
+      for (int e = t; e < kRsPanel * kRsPanel; e += 32) {
+        const int i = e / kRsPanel, j = e - i * kRsPanel;
+        if (j <= i && i < nrem && j < nrem - 1) {
+          double sacc = 0.0;
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-#pragma unroll
-      for (int k = 0; k < kRsPanel; ++k) {
-        const double2 r01 = *reinterpret_cast<const double2*>(PT + k * ldp + 4 * tr), r23 = *reinterpret_cast<const double2*>(PT + k * ldp + 4 * tr + 2);
-        const double2 c01 = *reinterpret_cast<const double2*>(PT + k * ldp + 4 * tc), c23 = *reinterpret_cast<const double2*>(PT + k * ldp + 4 * tc + 2);
-        const double rv[4] = {r01.x, r01.y, r23.x, r23.y}, cv[4] = {c01.x, c01.y, c23.x, c23.y};
+          for (int k = 0; k < kRsPanel; ++k) sacc += PT[k * ldp + i] * PT[k * ldp + j];
+          A[(rbase + i) * ld + rbase + j] -= sacc;
+        }
+      }
+      __syncwarp();
+      if (t == 0 && rbase < N) factor_diag(rbase, min(kRsPanel, N - rbase), cur ^ 1);
+    } else {
+      const int TR = (nrem + 3) / 4, TC = (nrem - 1 + 3) / 4;
+      for (int e = t - 32; e < TR * TC; e += kRedThreads - 32) {
+        const int tr = e / TC, tc = e - tr * TC;
+        if (tc > tr || tr < 2) continue;       // tr < 2 (and hence tc < 2): the next diagonal block, owned by warp 0
+        double acc[4][4];
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
-          for (int b = 0; b < 4; ++b) acc[a][b] += rv[a] * cv[b];
-      }
+          for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const int i = 4 * tr + a;
-        if (i >= nrem) continue;
+        for (int k = 0; k < kRsPanel; ++k) {
+          const double2 r01 = *reinterpret_cast<const double2*>(PT + k * ldp + 4 * tr), r23 = *reinterpret_cast<const double2*>(PT + k * ldp + 4 * tr + 2);
+          const double2 c01 = *reinterpret_cast<const double2*>(PT + k * ldp + 4 * tc), c23 = *reinterpret_cast<const double2*>(PT + k * ldp + 4 * tc + 2);
+          const double rv[4] = {r01.x, r01.y, r23.x, r23.y}, cv[4] = {c01.x, c01.y, c23.x, c23.y};
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const int j = 4 * tc + b;
-          if (j <= i && j < nrem - 1) A[(rbase + i) * ld + rbase + j] -= acc[a][b];
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] += rv[a] * cv[b];
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const int i = 4 * tr + a;
+          if (i >= nrem) continue;
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const int j = 4 * tc + b;
+            if (j <= i && j < nrem - 1) A[(rbase + i) * ld + rbase + j] -= acc[a][b];
+          }
         }
       }
     }

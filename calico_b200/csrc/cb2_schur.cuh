@@ -377,10 +377,22 @@ __global__ void __launch_bounds__(256) border_gram_dmma_kernel(const BandSys* __
   const int wcols = nb * 8;
   for (int r0 = r_begin; r0 < r_end; r0 += kGramRows) {
     __syncthreads();
-    for (int e = t; e < kGramRows * wcols; e += 256) {
-      const int rr = e / wcols, cc = e - rr * wcols;
-      const int r = r0 + rr;
-      tile[rr * XS + cc] = (r < r_end && cc < nbw) ? Wg[size_t(r) * nbw + cc] : 0.0;
+    // 6 independent loads in flight per thread (clamped addresses, selects afterwards): the chunk load is pure latency otherwise.
+    for (int e0 = t; e0 < kGramRows * wcols; e0 += 6 * 256) {
+      double v[6];
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {
+        const int e = min(e0 + u * 256, kGramRows * wcols - 1);
+        const int rr = e / wcols, cc = e - rr * wcols;
+        const bool ok = r0 + rr < r_end && cc < nbw;
+        const double x = Wg[size_t(ok ? r0 + rr : r_begin) * nbw + (ok ? cc : 0)];
+        v[u] = ok ? x : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {
+        const int e = e0 + u * 256;
+        if (e < kGramRows * wcols) { const int rr = e / wcols; tile[rr * XS + (e - rr * wcols)] = v[u]; }
+      }
     }
     __syncthreads();
 #pragma unroll

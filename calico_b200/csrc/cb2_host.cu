@@ -288,6 +288,7 @@ struct cb2_problem {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool imu_side_stream = std::getenv("CB2_IMU_STREAM") != nullptr;
   bool imu_pair_streams = std::getenv("CB2_NO_IMU_PAIR") == nullptr;
+  bool debug_log = std::getenv("CB2_DEBUG") != nullptr;
   bool capturing = false;       // inside graphed(): stay on one stream
   bool speculative_imu = std::getenv("CB2_SPECULATIVE_IMU") != nullptr;   // measured neutral on C4 (Jacobian-mode IMU blocks cost +53 us over cost mode): off by default
   int imu_jac_point = -1;       // parameter buffer (0 / 1) whose IMU Jacobians, residuals and cost partials are current; -1 = none
@@ -1251,7 +1252,7 @@ struct cb2_problem {
         }
       }
       const bool solved = !(h_scal[kScSolveFail] > 0);
-      if (std::getenv("CB2_DEBUG"))
+      if (debug_log)
         std::fprintf(stderr, "[cb2 debug] iter %d radius %.3e solve_fail %.0f model_change %.6e step2 %.3e cand_cost %.6e cand_invalid %.0f\n", next_iter, radius,
                      h_scal[kScSolveFail], h_scal[kScModelChange], h_scal[kScStepNorm2], h_scal[kScCandCost], h_scal[kScCandInvalid]);
       it.step_is_valid = 0;

@@ -1034,7 +1034,7 @@ struct cb2_problem {
     }
     if (N_c > 0) {
       const long tot3 = long(N_c + 1) * (N_c + 1);
-      CB2_K(level3_build_kernel, int(std::min<long>((tot3 + 255) / 256, 1024)), 256, 0, stream, d_l1.p, PL, n_a, N_c, d_Cmat.p, d_grad.p, red_Cw,
+      CB2_K(level3_build_kernel, int(std::min<long>((tot3 * 8 + 255) / 256, 4096)), 256, 0, stream, d_l1.p, PL, n_a, N_c, d_Cmat.p, d_grad.p, red_Cw,
             d_rawdiag.p + std::max(h_l2.n, 1));
     }
     if (world > 1 && red_count > 0) comm->allreduce_sum(d_red.p, red_count, stream);   // THE data-path collective of an LM iteration

@@ -495,17 +495,35 @@ __global__ void level2_damp_kernel(BandSys l2, const double* __restrict__ dtil2)
 __global__ void __launch_bounds__(256) level3_build_kernel(const BandSys* __restrict__ chunks, int n_owned, long n_a, int N_c,
                                                            const double* __restrict__ Cmat, const double* __restrict__ grad,
                                                            double* __restrict__ Cw, double* __restrict__ rawdiag_c) {
+  // 8 lanes per entry: lane `sub` sums the Gram partials k = sub, sub + 8, ... of every owned chunk (the Gram kernel leaves up to 148
+  // row-split partials), then a fixed-order shuffle tree combines the 8 partial sums.
   const int ld = N_c + 1;
   const long total = long(ld) * ld;
-  for (long idx = long(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += long(gridDim.x) * blockDim.x) {
+  const int sub = threadIdx.x & 7;
+  for (long idx0 = (long(blockIdx.x) * blockDim.x + threadIdx.x) >> 3; idx0 < ((total + 31) & ~31L); idx0 += (long(gridDim.x) * blockDim.x) >> 3) {
+    const long idx = idx0 < total ? idx0 : total - 1;       // whole warps stay in the loop for the shuffles
     const int r = int(idx / ld), c = int(idx % ld);
-    double v = 0.0;
+    double part = 0.0;
     if (c < N_c) {
-      v = r == N_c ? grad[n_a + c] : Cmat[size_t(r) * N_c + c];
-      if (c == r) rawdiag_c[r] = v;
-      for (int p = 0; p < n_owned; ++p) { const int c0 = chunks[p].cal0; v -= gram_at(chunks[p], c0 + r, c0 + c); }
+      for (int p = 0; p < n_owned; ++p) {
+        const BandSys& sy = chunks[p];
+        const size_t stride = size_t(sy.nbw) * sy.nbw;
+        const double* __restrict__ T = sy.T + size_t(sy.cal0 + r) * sy.nbw + sy.cal0 + c;
+        for (int k = sub; k < sy.ksplit; k += 8) part += T[k * stride];
+      }
     }
-    Cw[idx] = v;
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    part += __shfl_xor_sync(0xffffffffu, part, 4);
+    if (sub == 0 && idx0 < total) {
+      double v = 0.0;
+      if (c < N_c) {
+        v = r == N_c ? grad[n_a + c] : Cmat[size_t(r) * N_c + c];
+        if (c == r) rawdiag_c[r] = v;
+        v -= part;
+      }
+      Cw[idx] = v;
+    }
   }
 }
 

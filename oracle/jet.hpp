@@ -2,6 +2,13 @@
 // product path (calico_b200/); only tests/, __graft_entry__.smoke() and bench.py's
 // cpu_baseline / --impl reference legs may use it.
 //
+// Pin status (tests/test_oracle_pins.py, tests/test_spline_fit.py; details in DESIGN.md §2): projections of OpenCv5 / OpenCv8 /
+// KannalaBrandt against OpenCV golden vectors, spline basis / fit / derivatives, SO(3) and IMU kinematics against the reference tests'
+// constants and tolerances, the trust-region radius schedule against the Ceres log stored in the reference's notebook, and the
+// reference's integration test acceptance. PARITY UNPINNED: DoubleSphere / FieldOfView / UnifiedCamera / ExtendedUnifiedCamera
+// projections (restated line by line, no independent golden source) and the per-iteration LM cost sequence (pinned to Ceres's
+// published semantics, not to a Ceres binary: Ceres / Eigen / Abseil are absent, the reference cannot be compiled here).
+//
 // Forward-mode dual numbers: the same mathematical object as ceres::Jet<double, N>
 // (Ceres is an un-vendored dependency of the reference: CMakeLists.txt:15, absent here).
 // The reference's cost functors are templated on T and are differentiated by

@@ -1354,22 +1354,43 @@ struct cb2_problem {
     launch_eval<kModeResiduals>(cur, kScCost);
     sync_scalars();
     int rc = CB2_OK;
-    for (auto& s : sensors) {
+    // Device -> host copies on this thread, the un-permutation (sorted position -> original observation) per sensor on host threads.
+    const int ns = int(sensors.size());
+    std::vector<std::vector<double>> rs(ns);
+    std::vector<std::vector<unsigned char>> vs(ns);
+    for (int si = 0; si < ns; ++si) {
+      sensors[si].d_r.download(rs[si], &stats.d2h_bytes);
+      sensors[si].d_valid.download(vs[si], &stats.d2h_bytes);
+    }
+    std::vector<char> bad(ns, 0);
+    auto unpermute = [&](int si) {
+      HostSensor& s = sensors[si];
       const int m = s.m();
       s.residuals.assign(size_t(s.n_obs()) * m, 0.0);
       s.residual_valid.assign(s.n_obs(), 0);
-      std::vector<double> r;
-      std::vector<unsigned char> valid;
-      s.d_r.download(r, &stats.d2h_bytes);
-      s.d_valid.download(valid, &stats.d2h_bytes);
-      bool bad = false;
+      const std::vector<double>& r = rs[si];
+      const std::vector<unsigned char>& valid = vs[si];
       for (int i = 0; i < s.n_active; ++i) {
         const int o = s.perm[i];
         for (int q = 0; q < m; ++q) s.residuals[size_t(o) * m + q] = r[size_t(i) * m + q];
         s.residual_valid[o] = valid[i];
-        bad |= !valid[i];
+        bad[si] |= !valid[i];
       }
-      if (bad && rc == CB2_OK) {
+    };
+#ifdef CB2_EMUL
+    for (int si = 0; si < ns; ++si) unpermute(si);
+#else
+    {
+      const int nth = std::max(1, std::min<int>(ns, int(std::thread::hardware_concurrency())));
+      std::atomic<int> next{0};
+      std::vector<std::thread> pool;
+      for (int th = 0; th < nth; ++th) pool.emplace_back([&] { for (int si = next++; si < ns; si = next++) unpermute(si); });
+      for (auto& th : pool) th.join();
+    }
+#endif
+    for (int si = 0; si < ns; ++si) {
+      const HostSensor& s = sensors[si];
+      if (bad[si] && rc == CB2_OK) {
         const char* kind = s.kind == kCamera ? "camera " : (s.kind == kGyroscope ? "gyroscope " : "accelerometer ");
         rc = fail(CB2_INTERNAL, std::string("Failed to update residual for ") + kind + s.name);
       }

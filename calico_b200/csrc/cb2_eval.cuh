@@ -121,7 +121,6 @@ __global__ void __launch_bounds__(eval_tile(KIND), (KIND == kCamera ? CB2_EVAL_M
     const int warp = t >> 5, lane = t & 31;
     const int nobs = min(32, tl.count - warp * 32);
     if (nobs > 0) {
-      const int total = nobs * rowlen;
       double* __restrict__ Jw = sd.J + (size_t(tl.start) + warp * 32) * rowlen;
       const double* __restrict__ rb = rec + warp * 32;
       if ((rowlen & 1) == 0) {

@@ -277,7 +277,8 @@ class CApi:
         self._check(rc)
         return summ, self.last_log
 
-    def evaluate_sensor(self, sid, want_jac=True):
+    def evaluate_sensor(self, sid, want_jac=True, raw_flags=False):
+        """raw_flags: return the uint8 flags of cb2_evaluate_sensor (bit 0 evaluated, bit 1 camera point behind the image plane) instead of a bool mask."""
         m = 2 if self.kind[sid] == CAMERA else 3
         n = self.n_obs[sid]
         W = 6 * self.k + self.n_intr[sid] + 7
@@ -285,7 +286,7 @@ class CApi:
         J = np.zeros((n, m, W)) if want_jac else None
         valid = np.zeros(n, dtype=np.uint8)
         self._check(self._f("evaluate_sensor")(self.h, sid, _d(r), _d(J), _u(valid)))
-        return r, J, valid.astype(bool)
+        return r, J, (valid if raw_flags else valid.astype(bool))
 
     def cost(self):
         c = C.c_double(0)
@@ -413,3 +414,19 @@ def fit_trajectory(stamps, q_xyzw, t_world_rig, knot_frequency=10.0, spline_orde
     knots, ctrl = np.zeros(nk.value), np.zeros((ncp.value, 6))
     _fit_check(lib, lib.cb2_fit_trajectory(stamps.size, _d(stamps), _d(q), _d(t), spline_order, knot_frequency, nk.value, _d(knots), ncp.value, _d(ctrl)))
     return knots, ctrl
+
+
+_num_intr_libs = {}
+
+
+def num_intrinsics(kind: int, model: int, lib_path: str = LIB_PATH) -> int:
+    """cb2_num_intrinsics: CameraModel::NumberOfParameters / the IMU models' parameter counts; -1 = unknown. Needs no GPU."""
+    lib = _num_intr_libs.get(lib_path)
+    if lib is None:
+        if not os.path.exists(lib_path):
+            raise ImportError(f"{lib_path} not found: the CUDA extension has not been built (there is no CPU fallback).")
+        lib = C.CDLL(lib_path)
+        lib.cb2_num_intrinsics.argtypes = [C.c_int, C.c_int]
+        lib.cb2_num_intrinsics.restype = C.c_int
+        _num_intr_libs[lib_path] = lib
+    return int(lib.cb2_num_intrinsics(int(kind), int(model)))

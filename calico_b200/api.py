@@ -57,8 +57,29 @@ class AccelerometerIntrinsicsModel(enum.IntEnum):   # accelerometer_models.h:16-
     kAccelerometerVectorNav = 3
 
 
-_CAMERA_PARAMS = {1: 8, 2: 11, 3: 7, 4: 6, 5: 5, 6: 4, 7: 5}
-_IMU_PARAMS = {1: 1, 2: 4, 3: 12}
+class _ParamTable:
+    """model -> number of intrinsics, defined ONCE behind the C ABI (cb2_num_intrinsics: camera_models.h:79,231,395,596,716,848,961;
+    accelerometer_models.h / gyroscope_models.h). Needs the library, not a GPU."""
+
+    def __init__(self, kind: int):
+        self._kind = kind
+
+    def _n(self, model: int) -> int:
+        return _capi.num_intrinsics(self._kind, int(model), **({"lib_path": _LIB} if _LIB else {}))
+
+    def __contains__(self, model) -> bool:
+        return self._n(model) >= 0
+
+    def __getitem__(self, model) -> int:
+        n = self._n(model)
+        if n < 0:
+            raise KeyError(model)
+        return n
+
+
+_CAMERA_PARAMS = _ParamTable(0)
+_IMU_PARAMS = _ParamTable(1)
+kLandmarkFrameId = -1                      # camera.h: landmarks are observed with model_id = -1
 
 
 _LIB = None   # None = the in-tree CUDA library; tests point this at the SIMT-emulation build of the same kernel sources
@@ -324,7 +345,10 @@ class Sensor:
         self._residuals = {mid: r[i].copy() for i, mid in enumerate(self._measurements) if valid[i]}
 
 
-def _push_world(api: _capi.CApi, trajectory: Trajectory, world_model: WorldModel):
+def _push_world(api: _capi.CApi, trajectory: Trajectory, world_model: WorldModel, landmarks_as_body: bool = False):
+    """landmarks_as_body (Camera::Project only, camera.cpp:169-184): the landmarks ride along as a constant pseudo rigid body with identity
+    pose and id kLandmarkFrameId. Optimize never pushes them: the reference rejects landmark observations (camera.cpp:125-131) and the
+    device path returns the same FailedPrecondition for their model_id."""
     if trajectory._spline is None:
         raise _capi.CalicoError(_capi.FAILED_PRECONDITION, "Trajectory has not been set.")
     api.set_trajectory(trajectory._spline.k, trajectory._spline.knots, trajectory._spline.ctrl)
@@ -334,6 +358,12 @@ def _push_world(api: _capi.CApi, trajectory: Trajectory, world_model: WorldModel
         pts = np.array([np.asarray(p, dtype=np.float64) for p in body.model_definition.values()]).reshape(-1, 3)
         api.add_rigid_body(rid, body.T_world_rigidbody._q_xyzw, body.T_world_rigidbody._t, ids, pts, body.world_pose_is_constant,
                            body.model_definition_is_constant)
+    if landmarks_as_body and world_model._landmarks:
+        if kLandmarkFrameId in world_model._rigidbodies:
+            raise _capi.CalicoError(_capi.INVALID_ARGUMENT, "Rigid body id -1 is reserved for landmarks (kLandmarkFrameId).")
+        ids = np.array(list(world_model._landmarks.keys()), dtype=np.int32)
+        pts = np.array([np.asarray(l.point, dtype=np.float64) for l in world_model._landmarks.values()]).reshape(-1, 3)
+        api.add_rigid_body(kLandmarkFrameId, np.array([0.0, 0.0, 0.0, 1.0]), np.zeros(3), ids, pts, True, True)
 
 
 class Camera(Sensor):                      # camera.{h,cpp}
@@ -382,24 +412,28 @@ class Camera(Sensor):                      # camera.{h,cpp}
         """camera.cpp:155-208 through the forward mode of the camera kernel (zero measurement, unit sigma, zero latency)."""
         api = _new_api()
         try:
-            _push_world(api, sensorrig_trajectory, world_model)
+            _push_world(api, sensorrig_trajectory, world_model, landmarks_as_body=True)
             sid = self._add_sensor(api, probe=True)
             times = np.asarray(interp_times, dtype=np.float64)
             stamp, image_id, model_id, feature_id = [], [], [], []
             for i, t in enumerate(times):
+                for lid in world_model._landmarks:                  # camera.cpp:169-184: landmarks first, model_id = kLandmarkFrameId
+                    stamp.append(t); image_id.append(i); model_id.append(kLandmarkFrameId); feature_id.append(lid)
                 for rid, body in world_model._rigidbodies.items():
                     for pid in body.model_definition:
                         stamp.append(t); image_id.append(i); model_id.append(rid); feature_id.append(pid)
             if not stamp:
                 return []
             api.add_camera_observations(sid, stamp, image_id, model_id, feature_id, np.zeros((len(stamp), 2)))
-            r, _, valid = api.evaluate_sensor(sid, want_jac=False)
+            r, _, flags = api.evaluate_sensor(sid, want_jac=False, raw_flags=True)
         except _capi.CalicoError as e:
             raise RuntimeError(str(e)) from None
         finally:
             api.close()
+        # flags == 1: projected and in front of the image plane. Points with z <= 0 are skipped (camera.cpp:172-174,186-188) for EVERY model,
+        # also those (DoubleSphere, Unified, ExtendedUnified) whose ProjectPoint accepts them.
         return [CameraMeasurement(-r[i], CameraObservationId(stamp[i] + self._latency, image_id[i], model_id[i], feature_id[i]))
-                for i in range(len(stamp)) if valid[i]]            # points with z <= 0 are skipped (camera.cpp:186-188)
+                for i in range(len(stamp)) if flags[i] == 1]
 
 
 class _Imu(Sensor):

@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(eval_tile(KIND), (KIND == kCamera ? CB2_EVAL_M
   double cost = 0.0;
   int bad = 0;
   bool ok = false;
+  double pc_z = 1.0;   // cameras, kModeResiduals: depth of the point in the camera frame (flag 2 of `valid`)
   if (active) {
     const SensorState S = states[tl.sensor];
     const long o = long(tl.start) + t;
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(eval_tile(KIND), (KIND == kCamera ? CB2_EVAL_M
       const int p = sd.pt[o];
       const double2 px = reinterpret_cast<const double2*>(sd.meas)[o];
       ok = camera_block_from_frame<MODE == kModeJacobian>(S, frames + size_t(sd.frame_base + sd.frm[o]) * FrameRec::kSize, px.x, px.y,
-                                                          v3(pw[3 * p], pw[3 * p + 1], pw[3 * p + 2]), rc);
+                                                          v3(pw[3 * p], pw[3 * p + 1], pw[3 * p + 2]), rc, MODE == kModeResiduals ? &pc_z : nullptr);
     } else {
       const double stamp = sd.stamp[o];
       const int seg = sd.seg[o];
@@ -93,7 +94,9 @@ __global__ void __launch_bounds__(eval_tile(KIND), (KIND == kCamera ? CB2_EVAL_M
     if (MODE == kModeJacobian) for (int q = 0; q < m; ++q) sd.r[o * m + q] = rc.get(q);
     if (MODE == kModeResiduals) {
       for (int q = 0; q < m; ++q) sd.r[o * m + q] = ok ? rc.get(q) : 0.0;
-      sd.valid[o] = ok ? 1 : 0;
+      // bit 0: the functor evaluated; bit 1 (cameras): the point lies behind the image plane, p_c.z <= 0 — Camera::Project skips those
+      // (camera.cpp:172-174,186-188) even for models that can project them.
+      sd.valid[o] = ok ? (pc_z > 0.0 ? 1 : 3) : 0;
     }
   }
   s_ok[t] = ok ? 1 : 0;

@@ -138,13 +138,15 @@ CB2_HD void camera_frame(const SensorState& S, const double* __restrict__ M, dou
 }
 
 template <bool kJac>
-CB2_HD bool camera_block_from_frame(const SensorState& S, const double* __restrict__ fr, double px, double py, const V3& p_w, const Rec& out) {
+CB2_HD bool camera_block_from_frame(const SensorState& S, const double* __restrict__ fr, double px, double py, const V3& p_w, const Rec& out,
+                                    double* pc_z = nullptr) {
   M3 R_rw, R_cr;
   for (int i = 0; i < 9; ++i) { R_rw.m[i] = fr[FrameRec::R_rw + i]; R_cr.m[i] = fr[FrameRec::R_cr + i]; }
   const V3 t_wr = v3(fr[FrameRec::t_wr], fr[FrameRec::t_wr + 1], fr[FrameRec::t_wr + 2]);
   const V3 a = R_rw * (p_w - t_wr);
   const V3 b = a - S.t;
   const V3 pc = R_cr * b;
+  if (pc_z) *pc_z = pc.z;
   double uv[2], dp[2][3], di[2][kMaxIntrinsics];
   if (!camera_project<kJac>(S.model, S.intr, pc, uv, dp, di)) return false;
   const double r0 = (px - uv[0]) * S.inv_sigma, r1 = (py - uv[1]) * S.inv_sigma;

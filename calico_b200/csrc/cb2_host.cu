@@ -67,7 +67,14 @@ struct DevBuf {
 #ifdef CB2_EMUL
     if (p) cudaFree(p);
 #else
-    if (p) cudaFreeAsync(p, nullptr);
+    if (p) {
+      const cudaError_t e = cudaFreeAsync(p, nullptr);
+      if (e != cudaSuccess) {   // a destructor cannot report through the status code: say it once on stderr and clear the sticky error
+        static std::atomic<bool> warned{false};
+        if (!warned.exchange(true)) std::fprintf(stderr, "[calico_b200] cudaFreeAsync failed: %s\n", cudaGetErrorString(e));
+        cudaGetLastError();
+      }
+    }
 #endif
     p = nullptr; n = 0;
   }
@@ -126,7 +133,7 @@ struct HostSensor {
   std::vector<int> perm;      // sorted position -> original observation index
   int n_active = 0;
   DevBuf<double> d_stamp, d_meas, d_r, d_J;
-  DevBuf<int> d_seg, d_pt, d_seg_start, d_frm, d_frame_obs, d_seg_frame;
+  DevBuf<int> d_seg, d_pt, d_seg_start, d_frm, d_frame_obs, d_seg_frame, d_perm;
   DevBuf<unsigned char> d_valid;
 };
 
@@ -184,9 +191,13 @@ struct KernelProfiler {
 // ----------------------------------------------------------------------------------------------------------------
 struct Comm {
   int world = 1, rank = 0;
+  bool dead = false;            // aborted after a failed / timed-out collective: every later use fails fast
   virtual ~Comm() {}
   virtual void allreduce_sum(double* buf, size_t n, cudaStream_t s) = 0;
   virtual void allreduce_max(double* buf, size_t n, cudaStream_t s) = 0;
+  virtual void allreduce_sum_u8(unsigned char* buf, size_t n, cudaStream_t s) = 0;
+  virtual bool async_error(std::string*) { return false; }   // an asynchronous failure of the communicator (peer died, ...)
+  virtual void abort() { dead = true; }                       // tears the communicator down so that stuck collectives return
 };
 
 #if !defined(CB2_EMUL)
@@ -198,6 +209,8 @@ struct NcclApi {
   int (*CommDestroy)(CommT) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, CommT, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
+  int (*CommGetAsyncError)(CommT, int*) = nullptr;
+  int (*CommAbort)(CommT) = nullptr;
   void* handle = nullptr;
   std::string error;
   bool load() {
@@ -214,6 +227,8 @@ struct NcclApi {
     CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(handle, "ncclCommDestroy"));
     AllReduce = reinterpret_cast<decltype(AllReduce)>(dlsym(handle, "ncclAllReduce"));
     GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(handle, "ncclGetErrorString"));
+    CommGetAsyncError = reinterpret_cast<decltype(CommGetAsyncError)>(dlsym(handle, "ncclCommGetAsyncError"));
+    CommAbort = reinterpret_cast<decltype(CommAbort)>(dlsym(handle, "ncclCommAbort"));
     if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce) { error = "libnccl is missing expected symbols"; return false; }
     return true;
   }
@@ -221,13 +236,28 @@ struct NcclApi {
 static NcclApi& nccl() { static NcclApi api; return api; }
 struct NcclComm : Comm {
   NcclApi::CommT comm = nullptr;
-  ~NcclComm() override { if (comm) nccl().CommDestroy(comm); }
+  ~NcclComm() override { if (comm && !dead) nccl().CommDestroy(comm); }
+  bool async_error(std::string* why) override {
+    if (!comm || dead || !nccl().CommGetAsyncError) return false;
+    int st = 0;
+    if (nccl().CommGetAsyncError(comm, &st) != 0 || st != 0) {   // ncclSuccess = 0; ncclInProgress only occurs for non-blocking communicators
+      if (why) *why = std::string("NCCL asynchronous error: ") + (nccl().GetErrorString ? nccl().GetErrorString(st) : "?");
+      return true;
+    }
+    return false;
+  }
+  void abort() override {
+    if (comm && !dead && nccl().CommAbort) nccl().CommAbort(comm);
+    dead = true; comm = nullptr;
+  }
   void check(int rc, const char* what) {
+    if (dead) throw CudaFail{"NCCL communicator was aborted after an earlier failure; create a new one (cb2_comm_init)."};
     if (rc != 0) throw CudaFail{std::string("NCCL error in ") + what + ": " + (nccl().GetErrorString ? nccl().GetErrorString(rc) : "?")};
   }
   // ncclFloat64 = 8; ncclSum = 0, ncclMax = 2
-  void allreduce_sum(double* buf, size_t n, cudaStream_t s) override { check(nccl().AllReduce(buf, buf, n, 8, 0, comm, s), "allreduce(sum)"); }
-  void allreduce_max(double* buf, size_t n, cudaStream_t s) override { check(nccl().AllReduce(buf, buf, n, 8, 2, comm, s), "allreduce(max)"); }
+  void allreduce_sum(double* buf, size_t n, cudaStream_t s) override { check(dead ? 0 : nccl().AllReduce(buf, buf, n, 8, 0, comm, s), "allreduce(sum)"); }
+  void allreduce_max(double* buf, size_t n, cudaStream_t s) override { check(dead ? 0 : nccl().AllReduce(buf, buf, n, 8, 2, comm, s), "allreduce(max)"); }
+  void allreduce_sum_u8(unsigned char* buf, size_t n, cudaStream_t s) override { check(dead ? 0 : nccl().AllReduce(buf, buf, n, 1 /* ncclUint8 */, 0, comm, s), "allreduce(sum, u8)"); }
 };
 #else
 // Test-only rendezvous: `world` host threads of one process, each driving its own handle, meet in every collective.
@@ -237,6 +267,8 @@ struct LocalGroup {
   int world = 0, arrived = 0, generation = 0;
   std::vector<double*> bufs;
   std::vector<double> result;
+  std::vector<unsigned char*> bufs8;
+  std::vector<unsigned char> result8;
 };
 static std::mutex g_groups_mu;
 static std::map<std::string, LocalGroup*>& local_groups() { static std::map<std::string, LocalGroup*> m; return m; }
@@ -264,6 +296,22 @@ struct LocalComm : Comm {
   }
   void allreduce_sum(double* buf, size_t n, cudaStream_t) override { reduce(buf, n, false); }
   void allreduce_max(double* buf, size_t n, cudaStream_t) override { reduce(buf, n, true); }
+  void allreduce_sum_u8(unsigned char* buf, size_t n, cudaStream_t) override {
+    std::unique_lock<std::mutex> lk(grp->mu);
+    const int gen = grp->generation;
+    if (grp->arrived == 0) grp->bufs8.assign(world, nullptr);
+    grp->bufs8[rank] = buf;
+    if (++grp->arrived == world) {
+      grp->result8.assign(n, 0);
+      for (size_t i = 0; i < n; ++i) { unsigned v = 0; for (int r = 0; r < world; ++r) v += grp->bufs8[r][i]; grp->result8[i] = (unsigned char)v; }
+      for (int r = 0; r < world; ++r) std::memcpy(grp->bufs8[r], grp->result8.data(), n);
+      grp->arrived = 0;
+      ++grp->generation;
+      grp->cv.notify_all();
+    } else {
+      grp->cv.wait(lk, [&] { return grp->generation != gen; });
+    }
+  }
 };
 #endif
 
@@ -360,7 +408,7 @@ struct cb2_problem {
   bool scaling_set = false;
 
   ~cb2_problem() {
-    if (stream) cudaStreamSynchronize(stream);       // device buffers are released (stream-ordered, default stream) after this body
+    if (stream) sync_stream(false);                   // device buffers are released (stream-ordered, default stream) after this body
     if (stream_imu) cudaStreamSynchronize(stream_imu);
     kprof.report();
     drop_graphs();
@@ -402,6 +450,40 @@ struct cb2_problem {
   }
 
   int fail(int code, const std::string& msg) { error = msg; return code; }
+
+  // Waits for the library's stream. With several ranks a collective that a peer never joins (crashed rank, mismatched call sequence)
+  // would block forever: the wait then polls with a deadline (CB2_COLLECTIVE_TIMEOUT_S, default 60 s) and the communicator's
+  // asynchronous error state (NCCL async error check); on either, the communicator is aborted — which makes the stuck kernel
+  // return — and the call fails with CB2_INTERNAL instead of hanging.
+  double collective_timeout_s = std::getenv("CB2_COLLECTIVE_TIMEOUT_S") ? std::atof(std::getenv("CB2_COLLECTIVE_TIMEOUT_S")) : 60.0;
+  void sync_stream(bool may_throw = true) {
+    if (world <= 1 || !comm) {
+      const cudaError_t e = cudaStreamSynchronize(stream);
+      if (e != cudaSuccess && may_throw) throw CudaFail{std::string("CUDA error: ") + cudaGetErrorString(e) + " at cudaStreamSynchronize"};
+      return;
+    }
+    const double t0 = now_s();
+    long spins = 0;
+    for (;;) {
+      const cudaError_t q = cudaStreamQuery(stream);
+      if (q == cudaSuccess) return;
+      if (q != cudaErrorNotReady) {
+        if (may_throw) throw CudaFail{std::string("CUDA error: ") + cudaGetErrorString(q) + " at cudaStreamQuery"};
+        return;
+      }
+      if ((++spins & 1023) != 0) continue;
+      std::string why;
+      const bool async = comm->async_error(&why);
+      if (!async && now_s() - t0 < collective_timeout_s) continue;
+      if (!async) why = "Cross-rank collective did not complete within " + std::to_string(collective_timeout_s) + " s (a peer rank is missing or the ranks' call sequences diverged)";
+      comm->abort();
+      cudaStreamSynchronize(stream);     // returns once the aborted collective has been torn down
+      cudaGetLastError();
+      uploaded = false;
+      if (may_throw) throw CudaFail{why + "; the communicator has been aborted."};
+      return;
+    }
+  }
 
   // ------------------------------------------------------------------------------------------------------------
   // Spline bookkeeping (host): BSpline::GetSplineIndex bspline.hpp:139-151, basis matrices bspline.hpp:192-244.
@@ -446,6 +528,8 @@ struct cb2_problem {
       return upload_impl();
     } catch (const CudaFail& f) {
       return fail(CB2_INTERNAL, f.msg);
+    } catch (const std::bad_alloc&) {
+      return fail(CB2_INTERNAL, "Out of host memory while packing the problem.");
     }
   }
 
@@ -480,7 +564,7 @@ struct cb2_problem {
 
   int upload_impl() {
     uploaded = false;
-    if (stream) CB2_CUDA(cudaStreamSynchronize(stream));
+    if (stream) sync_stream();
     drop_graphs();   // every device pointer baked into a captured solve phase is about to change
     if (knots.empty() || ctrl.empty()) return fail(CB2_FAILED_PRECONDITION, "Trajectory has not been set.");
     if (k != kK) return fail(CB2_UNIMPLEMENTED, "Only spline order 6 (calico::Trajectory::kSplineOrder, trajectory.h:28) is supported.");
@@ -623,6 +707,7 @@ struct cb2_problem {
       const std::vector<int>&seg = P.seg, &pt = P.pt, &frm = P.frm, &seg_start = P.seg_start;
       s.d_stamp.upload(stamp, h2d); s.d_meas.upload(meas, h2d); s.d_seg.upload(seg, h2d); s.d_pt.upload(pt, h2d); s.d_frm.upload(frm, h2d);
       s.d_seg_start.upload(seg_start, h2d);
+      s.d_perm.upload(s.perm, h2d);
       if (s.kind == kCamera) { s.d_frame_obs.upload(P.frame_obs, h2d); s.d_seg_frame.upload(P.seg_frame, h2d); }
       // Unknown layout of this sensor (constant or unreferenced blocks drop out, as in Ceres's reduced program).
       SensorDesc& d = h_desc[si];
@@ -1105,7 +1190,7 @@ struct cb2_problem {
 
   void sync_scalars() {
     CB2_CUDA(cudaMemcpyAsync(h_scal, d_scal.p, sizeof(double) * kScCount, cudaMemcpyDeviceToHost, stream));
-    CB2_CUDA(cudaStreamSynchronize(stream));
+    sync_stream();
     CB2_CUDA(cudaGetLastError());
     stats.d2h_bytes += sizeof(double) * kScCount;
     timer.resolve(phase_ms);
@@ -1168,7 +1253,6 @@ struct cb2_problem {
     double radius = opt.initial_trust_region_radius, decrease_factor = 2.0;
     double x_cost = 0, x_norm = 0, candidate_cost = 0, model_cost_change = 0, reference_cost = 0;
     int num_consecutive_invalid_steps = 0;
-    bool atleast_one_successful_step = false;
     cb2_iteration it{};
     timer.begin(kPhLoop, stream);
     const int blocks_tot = int(std::min<long>((n_tot + 255) / 256, 1024));
@@ -1275,13 +1359,13 @@ struct cb2_problem {
       }
       candidate_cost = h_scal[kScCandInvalid] > 0 ? std::numeric_limits<double>::max() : h_scal[kScCandCost];   // "Step failed to evaluate."
       it.step_norm = std::sqrt(h_scal[kScStepNorm2]);
-      if (atleast_one_successful_step && it.step_norm <= opt.parameter_tolerance * (x_norm + opt.parameter_tolerance)) {
+      if (it.step_norm <= opt.parameter_tolerance * (x_norm + opt.parameter_tolerance)) {
         S.termination_type = CB2_CONVERGENCE;
         msg("Parameter tolerance reached. Relative step_norm: %e <= %e.", it.step_norm / (x_norm + opt.parameter_tolerance), opt.parameter_tolerance);
         break;
       }
       it.cost_change = x_cost - candidate_cost;
-      if (atleast_one_successful_step && std::fabs(it.cost_change) <= opt.function_tolerance * x_cost) {
+      if (std::fabs(it.cost_change) <= opt.function_tolerance * x_cost) {
         S.termination_type = CB2_CONVERGENCE;
         msg("Function tolerance reached. |cost_change|/cost: %e <= %e", std::fabs(it.cost_change) / x_cost, opt.function_tolerance);
         break;
@@ -1305,7 +1389,6 @@ struct cb2_problem {
         radius = std::min(opt.max_trust_region_radius, radius);
         decrease_factor = 2.0;
         reference_cost = x_cost;
-        atleast_one_successful_step = true;
         ++S.num_successful_steps;
       } else {
         it.step_is_successful = 0;
@@ -1315,12 +1398,14 @@ struct cb2_problem {
         ++S.num_unsuccessful_steps;
       }
     }
+    // Ceres (solver.cc, SetSummaryFinalCost): the minimum over ALL recorded iterations, rejected ones included (their cost column is the
+    // candidate cost, trust_region_minimizer.cc HandleUnsuccessfulStep) — reproduced as is so that Summary::final_cost reads the same.
     S.final_cost = S.initial_cost;
     for (const auto& e : L) S.final_cost = std::min(S.final_cost, e.cost);
     S.num_iterations = int(L.size());
     stats.lm_iterations += int(L.size()) - 1;
     timer.end(kPhLoop, stream);
-    CB2_CUDA(cudaStreamSynchronize(stream));
+    sync_stream();
     timer.resolve(phase_ms);
     stats.lm_loop_ms = phase_ms[kPhLoop];
     S.total_time = now_s() - t_start;
@@ -1335,7 +1420,7 @@ struct cb2_problem {
       CB2_K(mask_ctrl_kernel, int(std::min<long>((n_a + 255) / 256, 1024)), 256, 0, stream, n_a, d_cp_own.p, rank == 0 ? 1 : 0, d_ctrl[cur].p, tmp);
       comm->allreduce_sum(tmp, size_t(n_a), stream);
       CB2_CUDA(cudaMemcpyAsync(d_ctrl[cur].p, tmp, sizeof(double) * n_a, cudaMemcpyDeviceToDevice, stream));
-      CB2_CUDA(cudaStreamSynchronize(stream));
+      sync_stream();
     }
     d_ctrl[cur].download(ctrl, &stats.d2h_bytes);
     d_state[cur].download(h_state, &stats.d2h_bytes);
@@ -1349,50 +1434,51 @@ struct cb2_problem {
     }
   }
 
-  // Sensor::UpdateResiduals (camera.cpp:70-80, gyroscope.cpp:171-182, accelerometer.cpp:58-69).
+  // Sensor::UpdateResiduals (camera.cpp:70-80, gyroscope.cpp:171-182, accelerometer.cpp:58-69): EVERY measurement's un-robustified residual.
+  // The sweep leaves residuals in the device order (sorted by spline segment, this rank's shard only); a scatter kernel puts them back into
+  // the caller's observation order on the device — all sensors in one buffer [r of sensor 0 | r of sensor 1 | ...] + a flag byte per observation —
+  // so that (i) with several ranks ONE sum over the ranks gives every rank every residual (an observation is evaluated by exactly one
+  // rank), and (ii) the host receives final-layout arrays: two device -> host copies, no host-side un-permutation.
+  DevBuf<double> d_rfull;
+  DevBuf<unsigned char> d_vfull;
   int refresh_residuals() {
     launch_eval<kModeResiduals>(cur, kScCost);
-    sync_scalars();
-    int rc = CB2_OK;
-    // Device -> host copies on this thread, the un-permutation (sorted position -> original observation) per sensor on host threads.
+    if (world > 1) comm->allreduce_sum(d_scal.p + kScCost, 2, stream);
     const int ns = int(sensors.size());
-    std::vector<std::vector<double>> rs(ns);
-    std::vector<std::vector<unsigned char>> vs(ns);
+    std::vector<size_t> roff(ns + 1, 0), voff(ns + 1, 0);
+    for (int si = 0; si < ns; ++si) { roff[si + 1] = roff[si] + size_t(sensors[si].n_obs()) * sensors[si].m(); voff[si + 1] = voff[si] + size_t(sensors[si].n_obs()); }
+    if (d_rfull.n != roff[ns] || d_vfull.n != voff[ns]) { d_rfull.alloc(roff[ns], false); d_vfull.alloc(voff[ns], false); CB2_CUDA(cudaDeviceSynchronize()); }
+    d_rfull.zero(stream); d_vfull.zero(stream);     // outliers (and, before the sum, the other ranks' observations) stay 0 / invalid
     for (int si = 0; si < ns; ++si) {
-      sensors[si].d_r.download(rs[si], &stats.d2h_bytes);
-      sensors[si].d_valid.download(vs[si], &stats.d2h_bytes);
-    }
-    std::vector<char> bad(ns, 0);
-    auto unpermute = [&](int si) {
       HostSensor& s = sensors[si];
-      const int m = s.m();
-      s.residuals.assign(size_t(s.n_obs()) * m, 0.0);
-      s.residual_valid.assign(s.n_obs(), 0);
-      const std::vector<double>& r = rs[si];
-      const std::vector<unsigned char>& valid = vs[si];
-      for (int i = 0; i < s.n_active; ++i) {
-        const int o = s.perm[i];
-        for (int q = 0; q < m; ++q) s.residuals[size_t(o) * m + q] = r[size_t(i) * m + q];
-        s.residual_valid[o] = valid[i];
-        bad[si] |= !valid[i];
-      }
-    };
-#ifdef CB2_EMUL
-    for (int si = 0; si < ns; ++si) unpermute(si);
-#else
-    {
-      const int nth = std::max(1, std::min<int>(ns, int(std::thread::hardware_concurrency())));
-      std::atomic<int> next{0};
-      std::vector<std::thread> pool;
-      for (int th = 0; th < nth; ++th) pool.emplace_back([&] { for (int si = next++; si < ns; si = next++) unpermute(si); });
-      for (auto& th : pool) th.join();
+      if (s.n_active > 0)
+        CB2_K(scatter_residuals_kernel, std::min((s.n_active + 255) / 256, 1184), 256, 0, stream, s.n_active, s.m(), s.d_perm.p, s.d_r.p, s.d_valid.p, d_rfull.p + roff[si],
+              d_vfull.p + voff[si]);
     }
-#endif
+    if (world > 1 && roff[ns] > 0) { comm->allreduce_sum(d_rfull.p, roff[ns], stream); comm->allreduce_sum_u8(d_vfull.p, voff[ns], stream); }
+    sync_scalars();
+    // Device -> host straight into the per-sensor result vectors (the totals are what Sensor::UpdateResiduals fills per measurement).
     for (int si = 0; si < ns; ++si) {
-      const HostSensor& s = sensors[si];
-      if (bad[si] && rc == CB2_OK) {
-        const char* kind = s.kind == kCamera ? "camera " : (s.kind == kGyroscope ? "gyroscope " : "accelerometer ");
-        rc = fail(CB2_INTERNAL, std::string("Failed to update residual for ") + kind + s.name);
+      HostSensor& s = sensors[si];
+      s.residuals.resize(size_t(s.n_obs()) * s.m());
+      s.residual_valid.resize(s.n_obs());
+      if (s.n_obs() == 0) continue;
+      CB2_CUDA(cudaMemcpyAsync(s.residuals.data(), d_rfull.p + roff[si], s.residuals.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
+      CB2_CUDA(cudaMemcpyAsync(s.residual_valid.data(), d_vfull.p + voff[si], s.residual_valid.size(), cudaMemcpyDeviceToHost, stream));
+      stats.d2h_bytes += int64_t(s.residuals.size() * sizeof(double) + s.residual_valid.size());
+    }
+    sync_stream();
+    int rc = CB2_OK;
+    if (h_scal[kScInvalid] > 0) {
+      // Some residual block could not be evaluated at the final point: the reference fails with kInternal on the first such sensor (camera.cpp:73-76).
+      for (int si = 0; si < ns && rc == CB2_OK; ++si) {
+        const HostSensor& s = sensors[si];
+        bool bad = false;
+        for (int o = 0; o < s.n_obs() && !bad; ++o) bad = !s.residual_valid[o] && !(s.kind == kCamera && !s.outlier.empty() && s.outlier[o]);
+        if (bad) {
+          const char* kind = s.kind == kCamera ? "camera " : (s.kind == kGyroscope ? "gyroscope " : "accelerometer ");
+          rc = fail(CB2_INTERNAL, std::string("Failed to update residual for ") + kind + s.name);
+        }
       }
     }
     return rc;
@@ -1402,6 +1488,22 @@ struct cb2_problem {
 // ================================================================================================================
 // C ABI
 // ================================================================================================================
+// No C++ exception may cross the C ABI: every entry point runs its body through one of these.
+template <class F>
+static int guarded(cb2_problem* p, F&& body) {
+  try {
+    return body();
+  } catch (const CudaFail& f) {
+    return p ? p->fail(CB2_INTERNAL, f.msg) : CB2_INTERNAL;
+  } catch (const std::bad_alloc&) {
+    try { return p ? p->fail(CB2_INTERNAL, "Out of host memory.") : CB2_INTERNAL; } catch (...) { return CB2_INTERNAL; }
+  } catch (const std::exception& e) {
+    try { return p ? p->fail(CB2_INTERNAL, std::string("Unexpected error: ") + e.what()) : CB2_INTERNAL; } catch (...) { return CB2_INTERNAL; }
+  } catch (...) {
+    return CB2_INTERNAL;
+  }
+}
+
 extern "C" {
 
 const char* cb2_version(void) {
@@ -1431,13 +1533,26 @@ void cb2_default_options(cb2_options* o) {
   o->use_cuda_graph = 0;
 }
 
-int cb2_problem_create(cb2_problem** out) { *out = new cb2_problem(); return CB2_OK; }
-void cb2_problem_destroy(cb2_problem* p) { delete p; }
+int cb2_problem_create(cb2_problem** out) {
+  if (!out) return CB2_INVALID_ARGUMENT;
+  *out = nullptr;
+  return guarded(nullptr, [&]() -> int { *out = new cb2_problem(); return CB2_OK; });
+}
+void cb2_problem_destroy(cb2_problem* p) { try { delete p; } catch (...) {} }
 const char* cb2_last_error(cb2_problem* p) { return p ? p->error.c_str() : ""; }
+
+// The number of intrinsics of a model: CameraModel::NumberOfParameters (camera_models.h:79,231,395,596,716,848,961) and the IMU
+// models' (accelerometer_models.h / gyroscope_models.h: 1, 4, 12); -1 for an unknown kind / model. One definition for every host layer.
+int cb2_num_intrinsics(int kind, int model) {
+  if (kind == kCamera) return camera_num_params(model);
+  if (kind == kGyroscope || kind == kAccelerometer) return imu_num_params(model);
+  return -1;
+}
 
 int cb2_set_device(int device) { return cudaSetDevice(device) == cudaSuccess ? CB2_OK : CB2_INTERNAL; }
 
 int cb2_set_trajectory(cb2_problem* p, int spline_order, int n_knots, const double* knots, int n_cp, const double* ctrl) {
+  return guarded(p, [&]() -> int {
   if (spline_order < 2) return p->fail(CB2_INVALID_ARGUMENT, "Spline order must be greater than 2.");   // bspline.hpp:27-30
   if (n_knots != n_cp + spline_order) return p->fail(CB2_INVALID_ARGUMENT, "Knot vector size must equal control points + spline order.");
   p->k = spline_order;
@@ -1445,11 +1560,13 @@ int cb2_set_trajectory(cb2_problem* p, int spline_order, int n_knots, const doub
   p->ctrl.assign(ctrl, ctrl + size_t(n_cp) * 6);
   p->uploaded = false;
   return CB2_OK;
+  });
 }
 int cb2_set_gravity(cb2_problem* p, const double* g) { std::memcpy(p->gravity, g, 24); p->uploaded = false; return CB2_OK; }
 
 int cb2_add_rigid_body(cb2_problem* p, int id, const double* q, const double* t, int n_pts, const int* feature_ids, const double* pts,
                        int pose_const, int model_const) {
+  return guarded(p, [&]() -> int {
   if (p->body_slot.count(id)) return p->fail(CB2_INVALID_ARGUMENT, "Rigid body with id " + std::to_string(id) + " already exists in world model.");   // world_model.cpp:32-35
   HostBody b;
   b.id = id; std::memcpy(b.q, q, 32); std::memcpy(b.t, t, 24);
@@ -1466,10 +1583,12 @@ int cb2_add_rigid_body(cb2_problem* p, int id, const double* q, const double* t,
   p->bodies.push_back(std::move(b));
   p->uploaded = false;
   return CB2_OK;
+  });
 }
 
 int cb2_add_sensor(cb2_problem* p, int kind, int model, const char* name, int n_intr, const double* intr, const double* q, const double* t,
                    double latency, double sigma, int loss_type, double loss_scale, int en_intr, int en_extr, int en_lat, int* sensor_id) {
+  return guarded(p, [&]() -> int {
   if (kind < 0 || kind > 2) return p->fail(CB2_INVALID_ARGUMENT, "Unknown sensor kind.");
   if (sigma <= 0.0) return p->fail(CB2_INVALID_ARGUMENT, "Sigma must be greater than 0.");   // camera.cpp:62-65
   p->sensors.emplace_back();
@@ -1482,17 +1601,18 @@ int cb2_add_sensor(cb2_problem* p, int kind, int model, const char* name, int n_
   *sensor_id = int(p->sensors.size()) - 1;
   p->uploaded = false;
   return CB2_OK;
+  });
 }
 
 int cb2_add_camera_observations(cb2_problem* p, int sid, int n, const double* stamp, const int* image_id, const int* model_id,
                                 const int* feature_id, const double* pixel, const uint8_t* outlier) {
   (void)image_id;
+  return guarded(p, [&]() -> int {
   if (sid < 0 || sid >= int(p->sensors.size()) || p->sensors[sid].kind != kCamera) return p->fail(CB2_INVALID_ARGUMENT, "Not a camera sensor id.");
+  if (n < 0) return p->fail(CB2_INVALID_ARGUMENT, "Negative observation count.");
   HostSensor& s = p->sensors[sid];
-  const size_t base = s.stamp.size();
-  s.stamp.insert(s.stamp.end(), stamp, stamp + n);
-  s.meas.insert(s.meas.end(), pixel, pixel + size_t(n) * 2);
-  s.body_slot.resize(base + n); s.feat_slot.resize(base + n); s.outlier.resize(base + n);
+  // All ids are resolved into local vectors first: a failed call leaves the sensor exactly as it was.
+  std::vector<int> bslot(n), fslot(n);
   int last_model = 0, last_bs = -2;   // consecutive observations almost always name the same rigid body
   for (int i = 0; i < n; ++i) {
     if (last_bs == -2 || model_id[i] != last_model) {
@@ -1509,30 +1629,41 @@ int cb2_add_camera_observations(cb2_problem* p, int sid, int n, const double* st
       else { auto f = b.slot.find(fid); fs = f != b.slot.end() ? f->second : -1; }
       if (fs < 0) return p->fail(CB2_INVALID_ARGUMENT, "Feature id not in rigid body model definition.");
     }
-    s.body_slot[base + i] = bs; s.feat_slot[base + i] = fs;
-    s.outlier[base + i] = outlier ? outlier[i] : 0;
+    bslot[i] = bs; fslot[i] = fs;
   }
+  const size_t base = s.stamp.size();
+  s.stamp.reserve(base + n); s.meas.reserve((base + n) * 2); s.body_slot.reserve(base + n); s.feat_slot.reserve(base + n); s.outlier.reserve(base + n);
+  s.stamp.insert(s.stamp.end(), stamp, stamp + n);
+  s.meas.insert(s.meas.end(), pixel, pixel + size_t(n) * 2);
+  s.body_slot.insert(s.body_slot.end(), bslot.begin(), bslot.end());
+  s.feat_slot.insert(s.feat_slot.end(), fslot.begin(), fslot.end());
+  if (outlier) s.outlier.insert(s.outlier.end(), outlier, outlier + n); else s.outlier.insert(s.outlier.end(), size_t(n), uint8_t(0));
   p->uploaded = false;
   return CB2_OK;
+  });
 }
 
 int cb2_add_imu_observations(cb2_problem* p, int sid, int n, const double* stamp, const int* seq, const double* xyz) {
   (void)seq;
+  return guarded(p, [&]() -> int {
   if (sid < 0 || sid >= int(p->sensors.size()) || p->sensors[sid].kind == kCamera) return p->fail(CB2_INVALID_ARGUMENT, "Not an IMU sensor id.");
+  if (n < 0) return p->fail(CB2_INVALID_ARGUMENT, "Negative observation count.");
   HostSensor& s = p->sensors[sid];
+  s.stamp.reserve(s.stamp.size() + n); s.meas.reserve(s.meas.size() + size_t(n) * 3); s.outlier.reserve(s.outlier.size() + n);
   s.stamp.insert(s.stamp.end(), stamp, stamp + n);
   s.meas.insert(s.meas.end(), xyz, xyz + size_t(n) * 3);
   s.outlier.insert(s.outlier.end(), n, 0);
   p->uploaded = false;
   return CB2_OK;
+  });
 }
 
-int cb2_upload(cb2_problem* p) { return p->uploaded ? CB2_OK : p->upload(); }
+int cb2_upload(cb2_problem* p) { return guarded(p, [&]() -> int { return p->uploaded ? CB2_OK : p->upload(); }); }
 
 int cb2_optimize(cb2_problem* p, const cb2_options* opts, cb2_summary* summary, cb2_iteration* log, int log_cap, int* n_log) {
   cb2_options o;
   if (opts) o = *opts; else cb2_default_options(&o);
-  try {
+  return guarded(p, [&]() -> int {
     if (!p->uploaded) { const int rc = p->upload(); if (rc != CB2_OK) return rc; }
     std::vector<cb2_iteration> L;
     cb2_summary S;
@@ -1543,13 +1674,11 @@ int cb2_optimize(cb2_problem* p, const cb2_options* opts, cb2_summary* summary, 
     if (rc != CB2_OK) return rc;
     p->download_parameters();
     return p->refresh_residuals();
-  } catch (const CudaFail& f) {
-    return p->fail(CB2_INTERNAL, f.msg);
-  }
+  });
 }
 
 int cb2_evaluate_sensor(cb2_problem* p, int sid, double* residuals, double* jacobians, uint8_t* valid) {
-  try {
+  return guarded(p, [&]() -> int {
     if (!p->uploaded) { const int rc = p->upload(); if (rc != CB2_OK) return rc; }
     if (sid < 0 || sid >= int(p->sensors.size())) return p->fail(CB2_INVALID_ARGUMENT, "Unknown sensor id.");
     HostSensor& s = p->sensors[sid];
@@ -1606,13 +1735,11 @@ int cb2_evaluate_sensor(cb2_problem* p, int sid, double* residuals, double* jaco
       if (jacobians) std::memcpy(jacobians + size_t(o) * m * W, hJ.data() + size_t(i) * m * W, sizeof(double) * m * W);
     }
     return CB2_OK;
-  } catch (const CudaFail& f) {
-    return p->fail(CB2_INTERNAL, f.msg);
-  }
+  });
 }
 
 int cb2_cost(cb2_problem* p, double* cost, int* ok) {
-  try {
+  return guarded(p, [&]() -> int {
     if (!p->uploaded) { const int rc = p->upload(); if (rc != CB2_OK) return rc; }
     p->launch_eval<kModeCost>(p->cur, kScCost);
     if (p->world > 1) p->comm->allreduce_sum(p->d_scal.p + kScCost, 2, p->stream);
@@ -1620,9 +1747,7 @@ int cb2_cost(cb2_problem* p, double* cost, int* ok) {
     *cost = p->h_scal[kScCost];
     *ok = p->h_scal[kScInvalid] > 0 ? 0 : 1;
     return CB2_OK;
-  } catch (const CudaFail& f) {
-    return p->fail(CB2_INTERNAL, f.msg);
-  }
+  });
 }
 
 int cb2_get_sensor(cb2_problem* p, int sid, double* intr, double* q, double* t, double* latency) {
@@ -1656,15 +1781,13 @@ int cb2_get_residuals(cb2_problem* p, int sid, double* out, uint8_t* valid) {
 
 int cb2_reset_parameters(cb2_problem* p) {
   if (!p->uploaded) return p->fail(CB2_FAILED_PRECONDITION, "Problem has not been uploaded.");
-  try {
+  return guarded(p, [&]() -> int {
     p->cur = 0;
     CB2_CUDA(cudaMemcpyAsync(p->d_ctrl[0].p, p->d_ctrl0.p, p->d_ctrl0.n * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
     CB2_CUDA(cudaMemcpyAsync(p->d_state[0].p, p->d_state0.p, p->d_state0.n * sizeof(SensorState), cudaMemcpyDeviceToDevice, p->stream));
     CB2_CUDA(cudaStreamSynchronize(p->stream));
     return CB2_OK;
-  } catch (const CudaFail& f) {
-    return p->fail(CB2_INTERNAL, f.msg);
-  }
+  });
 }
 
 int cb2_stats_reset(cb2_problem* p) { p->stats = cb2_stats{}; for (auto& v : p->phase_ms) v = 0.0; return CB2_OK; }
@@ -1746,6 +1869,8 @@ int cb2_fit_spline(int n, const double* times, const double* data6, int spline_o
     return CB2_OK;
   } catch (const CudaFail& f) {
     return fit_fail(CB2_INTERNAL, f.msg);
+  } catch (const std::exception& e) {
+    return fit_fail(CB2_INTERNAL, std::string("Unexpected error: ") + e.what());
   }
 }
 
@@ -1753,6 +1878,7 @@ int cb2_fit_trajectory(int n, const double* stamps, const double* q_xyzw, const 
                        double* knots_out, int n_cp, double* ctrl_out) {
   if (n <= 0 || !stamps || !q_xyzw || !t3) return fit_fail(CB2_INVALID_ARGUMENT, "Attempted to fit data on empty time vector.");
   // trajectory.cpp:19-24: timestamps sorted; :29-37: Eigen::AngleAxisd(rotation) -> axis * angle; :38 UnwrapPhaseLogMap (:81-93).
+  try {
   std::vector<int> order(n);
   for (int i = 0; i < n; ++i) order[i] = i;
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return stamps[a] < stamps[b]; });
@@ -1783,6 +1909,9 @@ int cb2_fit_trajectory(int n, const double* stamps, const double* q_xyzw, const 
     p[0] *= sc; p[1] *= sc; p[2] *= sc;
   }
   return cb2_fit_spline(n, ts.data(), data.data(), spline_order, knot_frequency, n_knots, knots_out, n_cp, ctrl_out);
+  } catch (const std::exception& e) {
+    return fit_fail(CB2_INTERNAL, std::string("Unexpected error: ") + e.what());
+  }
 }
 
 int cb2_comm_unique_id(uint8_t* id128) {
@@ -1819,6 +1948,8 @@ int cb2_comm_init(cb2_problem* p, int world_size, int rank, const uint8_t* id128
     return CB2_OK;
   } catch (const CudaFail& f) {
     return p->fail(CB2_INTERNAL, f.msg);
+  } catch (const std::exception& e) {
+    return p->fail(CB2_INTERNAL, std::string("Unexpected error: ") + e.what());
   }
 #endif
 }

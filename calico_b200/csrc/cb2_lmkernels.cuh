@@ -198,6 +198,18 @@ __global__ void unpack_norm_scalars_kernel(const double* __restrict__ buf, int w
     scal[kScGradMax] = m;
   }
 }
+// Sensor::UpdateResiduals: residuals from the device order (sorted by spline segment, this rank's shard) back into the caller's observation
+// order. perm[i] = original index of sorted position i; rfull / vfull were zeroed (outliers and other ranks' observations keep 0).
+__global__ void __launch_bounds__(256) scatter_residuals_kernel(int n_active, int m, const int* __restrict__ perm, const double* __restrict__ r,
+                                                                const unsigned char* __restrict__ valid, double* __restrict__ rfull,
+                                                                unsigned char* __restrict__ vfull) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_active; i += gridDim.x * blockDim.x) {
+    const long o = perm[i];
+    for (int q = 0; q < m; ++q) rfull[o * m + q] = r[long(i) * m + q];
+    vfull[o] = valid[i] ? 1 : 0;
+  }
+}
+
 // Final control-point exchange: keep what this rank is responsible for, zero the rest, then sum across ranks.
 __global__ void __launch_bounds__(256) mask_ctrl_kernel(long n_a, const unsigned char* __restrict__ cp_own, int count_shared,
                                                         const double* __restrict__ ctrl, double* __restrict__ out) {

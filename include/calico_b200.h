@@ -135,7 +135,8 @@ int cb2_optimize(cb2_problem* p, const cb2_options* opts, cb2_summary* summary, 
 /* Analogue of ceres::Problem::Evaluate as the reference tests use it (accelerometer_test.cpp:179-203): per sensor,
  * un-robustified residuals [n_obs][m] and Jacobians [n_obs][m][W] in the canonical column order
  * [control points 6k | intrinsics | extrinsic rotation (tangent 3) | extrinsic translation 3 | latency], W = 6k+n_intr+7,
- * valid[n_obs] = functor returned true. Any output may be NULL. Outlier observations are left untouched. */
+ * valid[n_obs] != 0 = functor returned true; for cameras bit 1 (value 2) is set in addition when the point lies behind the image plane
+ * (p_c.z <= 0), which Camera::Project skips (camera.cpp:172-174,186-188). Any output may be NULL. Outlier observations are left untouched. */
 int cb2_evaluate_sensor(cb2_problem* p, int sensor_id, double* residuals, double* jacobians, uint8_t* valid);
 /* 1/2 sum rho(|r|^2) over all non-outlier residual blocks at the current state; *ok = 0 if any functor fails. */
 int cb2_cost(cb2_problem* p, double* cost, int* ok);
@@ -156,7 +157,8 @@ int cb2_set_device(int device);
 int cb2_comm_clone(cb2_problem* dst, cb2_problem* src);
 /* Host-side shard plan (no device needed): the chunks [chunk_lo, chunk_hi) of n_chunks and the spline segments
  * [seg_lo, seg_hi) whose observations rank `rank` of `world_size` evaluates. Every rank is handed the whole problem and keeps
- * its shard; in multi-GPU mode cb2_get_residuals / cb2_evaluate_sensor cover the local shard only. */
+ * its shard; after cb2_optimize every rank holds EVERY observation's residual (cb2_get_residuals: one cross-rank sum of the scattered
+ * residual arrays, as Sensor::UpdateResiduals fills every measurement, camera.cpp:70-80); cb2_evaluate_sensor covers the local shard only. */
 int cb2_shard_plan(cb2_problem* p, int world_size, int rank, int* n_chunks, int* chunk_lo, int* chunk_hi, int* seg_lo, int* seg_hi);
 
 /* ---- trajectory spline fit, the step before the hot path (no problem handle; errors through cb2_fit_last_error) ----
@@ -183,6 +185,9 @@ int cb2_reset_parameters(cb2_problem* p);
 /* Upload now (otherwise done lazily by the first optimize/evaluate). */
 int cb2_upload(cb2_problem* p);
 const char* cb2_version(void);
+/* Number of intrinsics of a sensor model — CameraModel::NumberOfParameters (camera_models.h:79,231,395,596,716,848,961: 8, 11, 7, 5, 4,
+ * 4, 5) and the IMU models (accelerometer_models.h / gyroscope_models.h: 1, 4, 12); -1 for kNone / an unknown kind or model. */
+int cb2_num_intrinsics(int kind, int model);
 
 #ifdef __cplusplus
 }

@@ -162,8 +162,9 @@ namespace sensors {
 enum class CameraIntrinsicsModel : int { kNone, kOpenCv5, kOpenCv8, kKannalaBrandt, kDoubleSphere, kFieldOfView, kUnifiedCamera, kExtendedUnifiedCamera };   // camera_models.h:16-33
 enum class GyroscopeIntrinsicsModel : int { kNone, kGyroscopeScaleOnly, kGyroscopeScaleAndBias, kGyroscopeVectorNav };                                       // gyroscope_models.h:16-25
 enum class AccelerometerIntrinsicsModel : int { kNone, kAccelerometerScaleOnly, kAccelerometerScaleAndBias, kAccelerometerVectorNav };                       // accelerometer_models.h:16-25
-inline int NumberOfParameters(CameraIntrinsicsModel m) { static const int n[] = {-1, 8, 11, 7, 6, 5, 4, 5}; return n[int(m)]; }   // camera_models.h kNumberOfParameters
-inline int NumberOfImuParameters(int m) { static const int n[] = {-1, 1, 4, 12}; return (m >= 0 && m < 4) ? n[m] : -1; }          // {gyroscope,accelerometer}_models.h
+// camera_models.h kNumberOfParameters (:79,231,395,596,716,848,961) / {gyroscope,accelerometer}_models.h: defined once, behind the C ABI.
+inline int NumberOfParameters(CameraIntrinsicsModel m) { return cb2_num_intrinsics(CB2_CAMERA, int(m)); }
+inline int NumberOfImuParameters(int m) { return cb2_num_intrinsics(CB2_GYROSCOPE, m); }
 
 struct CameraObservationId {                                                                 // camera.h:24-50
   double stamp = 0; int image_id = 0, model_id = 0, feature_id = 0;
@@ -321,7 +322,10 @@ class SensorImpl : public Sensor {
 
 // *::Project at the sensor's current state (camera.cpp:155-208, gyroscope.cpp:56-82, accelerometer.cpp:76-123) through the device:
 // the residual of a zero measurement with unit sigma and zero latency is minus the projection.
-inline Status PushWorldAndTrajectory(cb2_problem* p, const Trajectory& trajectory, const WorldModel& world_model) {
+constexpr int kLandmarkFrameId = -1;   // camera.h: model_id of landmark observations
+// landmarks_as_body (Camera::Project only, camera.cpp:169-184): the landmarks ride along as a constant pseudo rigid body with identity pose and
+// id kLandmarkFrameId. Optimize never pushes them: the reference rejects landmark observations (camera.cpp:125-131) and so does cb2_upload.
+inline Status PushWorldAndTrajectory(cb2_problem* p, const Trajectory& trajectory, const WorldModel& world_model, bool landmarks_as_body = false) {
   int rc = cb2_set_trajectory(p, trajectory.spline_order(), int(trajectory.knots().size()), trajectory.knots().data(),
                               int(trajectory.control_points().size() / 6), trajectory.control_points().data());
   if (rc != CB2_OK) return calico::detail::FromCode(rc, cb2_last_error(p));
@@ -331,6 +335,14 @@ inline Status PushWorldAndTrajectory(cb2_problem* p, const Trajectory& trajector
     for (const auto& [pid, pt] : body->model_definition) { ids.push_back(pid); pts.insert(pts.end(), pt.begin(), pt.end()); }
     rc = cb2_add_rigid_body(p, id, body->T_world_rigidbody.q.data(), body->T_world_rigidbody.t.data(), int(ids.size()), ids.data(), pts.data(),
                             body->world_pose_is_constant, body->model_definition_is_constant);
+    if (rc != CB2_OK) return calico::detail::FromCode(rc, cb2_last_error(p));
+  }
+  if (landmarks_as_body && !world_model.landmarks().empty()) {
+    if (world_model.rigidbodies().count(kLandmarkFrameId)) return InvalidArgumentError("Rigid body id -1 is reserved for landmarks (kLandmarkFrameId).");
+    std::vector<int> ids; std::vector<double> pts;
+    for (const auto& [lid, lm] : world_model.landmarks()) { ids.push_back(lid); pts.insert(pts.end(), lm->point.begin(), lm->point.end()); }
+    const double q[4] = {0, 0, 0, 1}, t[3] = {0, 0, 0};
+    rc = cb2_add_rigid_body(p, kLandmarkFrameId, q, t, int(ids.size()), ids.data(), pts.data(), 1, 1);
     if (rc != CB2_OK) return calico::detail::FromCode(rc, cb2_last_error(p));
   }
   return OkStatus();
@@ -377,10 +389,10 @@ class Camera final : public detail::SensorImpl<Camera, CameraMeasurement, Camera
     if (rc != CB2_OK) return calico::detail::FromCode(rc, cb2_last_error(problem));
     return sid;
   }
-  // camera.cpp:155-208. Landmarks are not projected: the reference's own Optimize rejects landmark observations (camera.cpp:125-131).
+  // camera.cpp:155-208: per time all landmarks (model_id = kLandmarkFrameId), then every rigid body's points; points with z <= 0 are skipped.
   StatusOr<std::vector<CameraMeasurement>> Project(const std::vector<double>& interp_times, const Trajectory& trajectory, const WorldModel& world_model) const {
     detail::Handle h;
-    Status s = detail::PushWorldAndTrajectory(h.p, trajectory, world_model);
+    Status s = detail::PushWorldAndTrajectory(h.p, trajectory, world_model, /*landmarks_as_body=*/true);
     if (!s.ok()) return s;
     if (model_ <= 0) return FailedPreconditionError("Camera model has not been set!");
     int sid = -1;
@@ -389,12 +401,17 @@ class Camera final : public detail::SensorImpl<Camera, CameraMeasurement, Camera
     if (rc != CB2_OK) return calico::detail::FromCode(rc, cb2_last_error(h.p));
     std::vector<double> stamp, pixel;
     std::vector<int> image_id, model_id, feature_id;
-    for (size_t i = 0; i < interp_times.size(); ++i)
+    for (size_t i = 0; i < interp_times.size(); ++i) {
+      for (const auto& [lid, lm] : world_model.landmarks()) {
+        (void)lm;
+        stamp.push_back(interp_times[i]); image_id.push_back(int(i)); model_id.push_back(detail::kLandmarkFrameId); feature_id.push_back(lid);
+      }
       for (const auto& [rid, body] : world_model.rigidbodies())
         for (const auto& [pid, pt] : body->model_definition) {
           (void)pt;
           stamp.push_back(interp_times[i]); image_id.push_back(int(i)); model_id.push_back(rid); feature_id.push_back(pid);
         }
+    }
     pixel.assign(2 * stamp.size(), 0.0);
     const int n = int(stamp.size());
     std::vector<CameraMeasurement> out;
@@ -406,7 +423,7 @@ class Camera final : public detail::SensorImpl<Camera, CameraMeasurement, Camera
     rc = cb2_evaluate_sensor(h.p, sid, r.data(), nullptr, valid.data());
     if (rc != CB2_OK) return calico::detail::FromCode(rc, cb2_last_error(h.p));
     for (int i = 0; i < n; ++i) {
-      if (!valid[i]) continue;                                                               // point_camera.z() <= 0: skipped (camera.cpp:186-188)
+      if (valid[i] != 1) continue;   // bit 1 = point_camera.z() <= 0: skipped for every model (camera.cpp:172-174,186-188); 0 = projection failed
       out.push_back(CameraMeasurement{{-r[2 * i], -r[2 * i + 1]}, {stamp[i] + latency_, image_id[i], model_id[i], feature_id[i]}});
     }
     return out;

@@ -204,7 +204,7 @@ inline int __ldg(const int* p) { return *p; }
 
 // ---- runtime API subset ----
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaErrorEmul = 1 };
+enum { cudaSuccess = 0, cudaErrorEmul = 1, cudaErrorNotReady = 600 };
 typedef struct cb2emul_stream* cudaStream_t;
 struct cb2emul_event { std::chrono::steady_clock::time_point t; };
 typedef cb2emul_event* cudaEvent_t;
@@ -233,6 +233,7 @@ inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = nullptr; return cuda
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return cudaSuccess; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamQuery(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
 inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new cb2emul_event(); return cudaSuccess; }

@@ -62,6 +62,7 @@ class Config:
     n_frames: int
     corners_per_image: int   # 0 = all visible corners
     huber: bool = False
+    cauchy: bool = False       # ceres::CauchyLoss(1.0) on the cameras (optimization_utils.h:40-41; the reference's Kalibr demo uses it)
     outlier_fraction: float = 0.0
     frame_rate: float = 20.0
     imu_rate: float = 200.0
@@ -84,6 +85,9 @@ CONFIGS = {
     "small": Config("small", 2, 1, 1, 160, 10),
     "small_huber": Config("small_huber", 2, 1, 1, 160, 10, huber=True, outlier_fraction=0.03),
     "micro": Config("micro", 1, 1, 1, 24, 6),
+    "small_cauchy": Config("small_cauchy", 2, 1, 1, 160, 10, cauchy=True, outlier_fraction=0.03),
+    # the C5 shape (16 cameras + 2 IMUs, Huber, 2 % outliers: N_c = 279 calibration unknowns) on a short trajectory
+    "C5_like": Config("C5_like", 16, 1, 2, 300, 25, huber=True, outlier_fraction=0.02),
     # every camera and IMU intrinsics model once (Jacobian parity of the "next" models)
     "tiny_models": Config("tiny_models", 7, 1, 3, 30, 10, camera_models=(1, 2, 3, 4, 5, 6, 7), imu_models=(1, 2, 3)),
 }
@@ -227,6 +231,8 @@ def generate(cfg_name: str, api_factory: Callable, seed: int = SEED, noise: bool
                 ps.meas[bad] += rng.uniform(-20, 20, size=(int(bad.sum()), 2))
             if cfg.huber:
                 ps.loss_type, ps.loss_scale = 1, 1.0
+            if cfg.cauchy:
+                ps.loss_type, ps.loss_scale = 2, 1.0
         else:
             times = imu_t[imu_t + s.latency < last_valid]
             proj = project_sensor(api_factory, truth, si, times)

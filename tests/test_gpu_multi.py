@@ -34,25 +34,31 @@ def _worker(rank, world, port, lib, cfg, chunk, q):
     pa = prob.clone()
     ids = pa.push(a)
     a.comm_init_torch(world, rank)
+    # two calls with different iteration counts on the same handle: the ranks must stay in lockstep across calls
+    summ0, log0 = a.optimize(_capi.Options(minimizer_progress_to_stdout=0, max_num_iterations=2))
     summ, log = a.optimize(_capi.Options(minimizer_progress_to_stdout=0))
     pa.pull(a, ids)
     out = {"rank": rank, "term": summ.termination_type, "costs": [it.cost for it in log], "ok": [it.step_is_successful for it in log],
-           "ctrl": pa.spline.ctrl.copy(), "intr": [s.intr.copy() for s in pa.sensors], "launches": a.stats().kernel_launches}
+           "costs0": [it.cost for it in log0],
+           "ctrl": pa.spline.ctrl.copy(), "intr": [s.intr.copy() for s in pa.sensors], "launches": a.stats().kernel_launches,
+           "res": [a.get_residuals(sid) for sid in ids]}
     if rank == 0:
         o = oracle_py.oracle_api()
         po = prob.clone()
         ido = po.push(o)
+        so0, lo0 = o.optimize(oracle_py.OracleOptions(linear_solver=1, num_threads=os.cpu_count() or 1, max_num_iterations=2))
         so, lo = o.optimize(oracle_py.OracleOptions(linear_solver=1, num_threads=os.cpu_count() or 1))
         po.pull(o, ido)
         out["oracle"] = {"term": so.termination_type, "costs": [it.cost for it in lo], "ok": [it.step_is_successful for it in lo],
-                         "ctrl": po.spline.ctrl.copy(), "intr": [s.intr.copy() for s in po.sensors]}
+                         "costs0": [it.cost for it in lo0],
+                         "ctrl": po.spline.ctrl.copy(), "intr": [s.intr.copy() for s in po.sensors], "res": [o.get_residuals(sid) for sid in ido]}
     q.put(out)
     dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.skipif(_ngpus() < 2, reason="needs at least 2 GPUs")
-@pytest.mark.parametrize("world,cfg,chunk", [(2, "small", None), (2, "small", "9"), (2, "tiny", "6"), (4, "small", "7")])
+@pytest.mark.parametrize("world,cfg,chunk", [(2, "small", None), (2, "small", "9"), (2, "tiny", "6"), (4, "small", "7"), (8, "C2", None)])
 def test_multi_gpu_lm_matches_oracle(world, cfg, chunk, product_lib, oracle):
     if _ngpus() < world:
         pytest.skip(f"needs {world} GPUs")
@@ -72,7 +78,12 @@ def test_multi_gpu_lm_matches_oracle(world, cfg, chunk, product_lib, oracle):
         assert o["launches"] > 0
         assert o["term"] == ref["term"]
         assert o["ok"] == ref["ok"]
+        np.testing.assert_allclose(o["costs0"], ref["costs0"], rtol=1e-6)
         np.testing.assert_allclose(o["costs"], ref["costs"], rtol=1e-6)
+        # every rank holds EVERY measurement's residual (Sensor::UpdateResiduals, camera.cpp:70-80), not just its shard's
+        for (r1, v1), (r2, v2) in zip(o["res"], ref["res"]):
+            assert (v1 == v2).all() and v1.all()
+            np.testing.assert_allclose(r1, r2, rtol=1e-6, atol=1e-6 * max(1.0, np.abs(r2).max()))
         np.testing.assert_allclose(o["ctrl"], ref["ctrl"], rtol=1e-6, atol=1e-6)
         for a, b in zip(o["intr"], ref["intr"]):
             np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-9)

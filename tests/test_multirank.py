@@ -99,6 +99,9 @@ def test_emulated_multirank_lm_matches_oracle(world, cfg, iters, oracle, monkeyp
     ids_o = po.push(o)
     sum_o, log_o = o.optimize(oracle.OracleOptions(linear_solver=1, max_num_iterations=iters))
     po.pull(o, ids_o)
+    res_o = [o.get_residuals(sid) for sid in ids_o]
+    # a second call on the same handles with a different iteration count (ranks must stay in lockstep across calls)
+    sum_o2, log_o2 = o.optimize(oracle.OracleOptions(linear_solver=1, max_num_iterations=iters + 2))
     results, errors = [None] * world, []
 
     def run(rank):
@@ -109,7 +112,9 @@ def test_emulated_multirank_lm_matches_oracle(world, cfg, iters, oracle, monkeyp
             a.comm_init_local(world, rank, f"grp{world}")
             s, lg = a.optimize(_capi.Options(minimizer_progress_to_stdout=0, max_num_iterations=iters))
             pa.pull(a, ids)
-            results[rank] = (s, lg, pa)
+            res = [a.get_residuals(sid) for sid in ids]
+            s2, lg2 = a.optimize(_capi.Options(minimizer_progress_to_stdout=0, max_num_iterations=iters + 2))
+            results[rank] = (s, lg, pa, res, lg2)
         except Exception as e:   # noqa: BLE001
             errors.append(e)
     threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
@@ -118,8 +123,15 @@ def test_emulated_multirank_lm_matches_oracle(world, cfg, iters, oracle, monkeyp
     for t in threads:
         t.join()
     assert not errors, errors
-    for s, lg, pa in results:
+    for s, lg, pa, res, lg2 in results:
         assert s.num_residual_blocks == sum_o.num_residual_blocks
+        # Sensor::UpdateResiduals fills EVERY measurement's residual (camera.cpp:70-80): every rank holds all of them, not just its shard
+        for (r1, v1), (r2, v2) in zip(res, res_o):
+            assert v1.all() and (v1 == v2).all()
+            np.testing.assert_allclose(r1, r2, rtol=1e-7, atol=1e-7 * max(1.0, np.abs(r2).max()))
+        assert len(lg2) == len(log_o2)
+        for x, y in zip(lg2, log_o2):
+            assert abs(x.cost - y.cost) <= 1e-9 * y.cost
         assert len(lg) == len(log_o)
         for x, y in zip(lg, log_o):
             assert abs(x.cost - y.cost) <= 1e-9 * y.cost

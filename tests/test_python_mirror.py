@@ -156,3 +156,62 @@ def test_python_mirror_reference_integration_test(product_lib):
     right.MarkOutliersById([m.id for m, _ in pairs[:10]])
     with pytest.raises(RuntimeError, match="not within the measurement set"):
         right.MarkOutlierById(calico.CameraObservationId(-1.0, 0, 0, 0))
+
+
+def _every_model_project(n_poses=12):
+    """SetModel -> SetIntrinsics -> Project for every camera / IMU model (the reference's parameter counts: camera_models.h:79,231,395,596,716,
+    848,961), with a landmark in front of and a rigid-body point behind the camera (camera_test.cpp:113-237: 1 / 0 / 4 / 0 measurements)."""
+    from calico_b200 import synthetic
+    poses, all_stamps, _ = _fixture(2)
+    stamps = all_stamps[:n_poses]
+    trajectory = calico.Trajectory()
+    trajectory.FitSpline(poses)
+    world = calico.WorldModel()
+    body = calico.RigidBody()
+    body.id = 0
+    body.model_definition = {0: np.array([0.0, 0.0, 0.0]), 1: np.array([0.1, 0.0, 0.0]), 2: np.array([0.0, 0.1, 0.0]), 3: np.array([0.1, 0.1, 0.0]),
+                             4: np.array([0.0, 0.0, 5.0])}        # id 4 lies behind the camera (the rig looks down at z = 0 from z = 1)
+    world.AddRigidBody(body)
+    world.AddLandmark(calico.Landmark(np.array([0.05, 0.05, 0.0]), 7))
+    world.AddLandmark(calico.Landmark(np.array([0.0, 0.0, 3.0]), 8))      # behind
+    times = [t for t in stamps if 0.0 < t < stamps[-1]]
+    want = {1: 8, 2: 11, 3: 7, 4: 5, 5: 4, 6: 4, 7: 5}
+    for model in calico.CameraIntrinsicsModel:
+        if model == calico.CameraIntrinsicsModel.kNone:
+            continue
+        cam = calico.Camera()
+        cam.SetModel(model)
+        assert cam.GetIntrinsics().size == want[int(model)]
+        with pytest.raises(RuntimeError, match="Expected intrinsics size"):
+            cam.SetIntrinsics(np.zeros(want[int(model)] + 1))
+        cam.SetIntrinsics(synthetic.CAMERA_TRUTH[int(model)])
+        ms = cam.Project(times, trajectory, world)
+        ids = {(m.id.model_id, m.id.feature_id) for m in ms}
+        # in front: landmark 7 (model id -1) and body points 0..3; behind (z <= 0): landmark 8 and body point 4, skipped for EVERY model
+        assert ids == {(-1, 7), (0, 0), (0, 1), (0, 2), (0, 3)}, (model, ids)
+        assert len(ms) == 5 * len(times)
+        assert all(np.isfinite(m.pixel).all() for m in ms)
+    for cls, enum_cls in ((calico.Gyroscope, calico.GyroscopeIntrinsicsModel), (calico.Accelerometer, calico.AccelerometerIntrinsicsModel)):
+        for model in enum_cls:
+            if int(model) == 0:
+                continue
+            imu = cls()
+            imu.SetModel(model)
+            assert imu.GetIntrinsics().size == {1: 1, 2: 4, 3: 12}[int(model)]
+            imu.SetIntrinsics(synthetic.IMU_MODEL_TRUTH[int(model)])
+            assert len(imu.Project(times, trajectory, world)) == len(times)
+
+
+@pytest.mark.timeout(900)
+def test_every_model_through_the_mirror_on_emulated_kernels():
+    import build as emul_build
+    calico.set_library(emul_build.build())
+    try:
+        _every_model_project(n_poses=6)
+    finally:
+        calico.set_library(None)
+
+
+@pytest.mark.gpu
+def test_every_model_through_the_mirror(product_lib):
+    _every_model_project()

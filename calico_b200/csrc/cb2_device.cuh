@@ -40,7 +40,34 @@ struct SensorDesc {
   const int* frame_obs;         // cameras: [n_images + 1] first observation of every image (CSR over the sorted observations)
   const int* seg_frame;         // cameras: [n_seg + 1] first sensor-local image of every spline segment
   double* r; double* J; unsigned char* valid;
+  // Cameras with n_calib <= 16: the Jacobian sweep itself forms, per image group of a CTA, the COMPACT Gram matrix of the image's residual
+  // rows [g (6) | r | 0 | calibration (<= 16)] (24 x 24, six 8x8 DMMA tiles) and leaves
+  //   per (CTA, image): slot gslot_base + image + CTA-in-sensor, kGramSlot doubles = [ [g | r] x g : 8 x 6 | calib 0..7 x g : 8 x 6 |
+  //                     calib 8..15 x g : 8 x 6 | the image's basis weights w_0..w_5 | 1.0 (0.0 = unused slot) | pad ]  — everything
+  //                     whose expansion needs the basis weights, self-contained so that the consumer has no further indirection;
+  //   per (CTA, warp):  gcta[CTA-in-sensor][warp][kGramCta] = the calib x calib tiles (3 x 64) + the calibration gradient (16) summed over
+  //                     the rows of the warp's image groups.
+  // expand_gram_kernel / assemble_calib_kernel (cb2_normal.cuh) turn them into the normal equations, so the camera Jacobian is written
+  // once and never read back. gslots == nullptr: this sensor goes through accumulate_kernel.
+  double* gslots; int gslot_base;
+  double* gcta;
+  unsigned char gfield[2][24];  // record field of compact column c for residual row q (filled by the host with gram_field below)
 };
+constexpr int kGramSlot = 3 * 48 + 8;
+constexpr int kGramSlotW = 3 * 48, kGramSlotFlag = 3 * 48 + 6;
+constexpr int kGramCta = 3 * 64 + 16;
+
+// D(8x8) += A(8x4) B(4x8) in FP64 on the tensor pipe (mma.sync.m8n8k4.f64, SASS DMMA). Lane l holds a = A[l / 4][l % 4],
+// b = B[l % 4][l / 4], c0, c1 = D[l / 4][2 (l % 4) + {0, 1}].
+CB2_D void dmma_8x8x4(double& c0, double& c1, double a, double b) {
+#if defined(CB2_EMUL)
+  ::cb2emul::dmma_8x8x4(c0, c1, a, b);
+#else
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+#endif
+}
+
+
 
 struct EvalTile { int sensor, start, count; };
 

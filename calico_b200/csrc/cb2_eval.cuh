@@ -36,6 +36,9 @@ __global__ void __launch_bounds__(eval_tile(KIND), (KIND == kCamera ? CB2_EVAL_M
   __shared__ double s_red[kTile / 32];
   __shared__ int s_bad[kTile / 32];
   __shared__ unsigned char s_ok[kTile];
+  // fused compact Gram (cameras, Jacobian mode): image groups of this tile
+  __shared__ int s_gstart[(KIND == kCamera && MODE == kModeJacobian) ? kTile + 1 : 1], s_gfrm[(KIND == kCamera && MODE == kModeJacobian) ? kTile : 1];
+  __shared__ int s_wcount[kTile / 32], s_ng, s_hole;
   constexpr int m = (KIND == kCamera) ? 2 : 3;
   const EvalTile tl = tiles[blockIdx.x];
   const SensorDesc& sd = sensors[tl.sensor];
@@ -45,6 +48,21 @@ __global__ void __launch_bounds__(eval_tile(KIND), (KIND == kCamera ? CB2_EVAL_M
   int bad = 0;
   bool ok = false;
   double pc_z = 1.0;   // cameras, kModeResiduals: depth of the point in the camera frame (flag 2 of `valid`)
+  constexpr bool kGram = KIND == kCamera && MODE == kModeJacobian;
+  const bool do_gram = kGram && sd.gslots != nullptr;
+  int my_frm = -1, prev_frm = -2;
+  unsigned start_mask = 0;
+  bool is_start = false;
+  if (kGram && do_gram) {
+    // Image (frame) of every observation of the tile; an observation starts a group when its image differs from its predecessor's.
+    if (active) my_frm = sd.frm[long(tl.start) + t];
+    prev_frm = __shfl_up_sync(0xffffffffu, my_frm, 1);
+    if ((t & 31) == 0) prev_frm = (active && long(tl.start) + t > 0) ? sd.frm[long(tl.start) + t - 1] : -2;
+    is_start = active && (t == 0 || my_frm != prev_frm);
+    start_mask = __ballot_sync(0xffffffffu, is_start);
+    if ((t & 31) == 0) s_wcount[t >> 5] = __popc(start_mask);
+    if (t == 0) s_hole = (tl.start > 0 && my_frm != prev_frm) ? 1 : 0;   // the tile begins exactly at an image boundary: slot (first - 1) stays unused
+  }
   if (active) {
     const SensorState S = states[tl.sensor];
     const long o = long(tl.start) + t;
@@ -113,6 +131,12 @@ __global__ void __launch_bounds__(eval_tile(KIND), (KIND == kCamera ? CB2_EVAL_M
     cost_partial[blockIdx.x] = c;
     invalid_partial[blockIdx.x] = b;
   }
+  if (kGram && do_gram) {
+    int base = 0;
+    for (int w = 0; w < (t >> 5); ++w) base += s_wcount[w];
+    if (is_start) { const int gi = base + __popc(start_mask & ((1u << (t & 31)) - 1u)); s_gstart[gi] = t; s_gfrm[gi] = my_frm; }
+    if (t == 0) { int ng = 0; for (int w = 0; w < kTile / 32; ++w) ng += s_wcount[w]; s_ng = ng; }
+  }
   if (MODE == kModeJacobian) {
     // Phase 2. Every Jacobian entry is sum_q rec[fa_q] * rec[fb_q] with (fa, fb) depending only on the position inside the
     // m x jw row block. Each warp streams the CONTIGUOUS region holding the row blocks of its 32 observations, one observation
@@ -122,6 +146,68 @@ __global__ void __launch_bounds__(eval_tile(KIND), (KIND == kCamera ? CB2_EVAL_M
     const int rowlen = m * jw;
     __syncthreads();
     const int warp = t >> 5, lane = t & 31;
+    // Compact Gram of every image group of the tile on the FP64 tensor pipe, straight from the records in shared memory: rows are the
+    // residual rows (observation o, q in {0, 1}), columns [g_0..g_5 | r | 0 | calibration unknowns 0..15]. One k-step = 4 rows = 2
+    // observations; lane l supplies row (o + (l >> 1 & 1), q = l & 1) of column 8 b + (l >> 2) — a fixed record field per column block.
+    // The tiles that need the image's basis weights go to the image's slot; the calibration tiles are summed over the warp's groups.
+    double cgS[5][2];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) { cgS[i][0] = 0.0; cgS[i][1] = 0.0; }
+    auto gram_phase = [&]() {
+      const int q = lane & 1, oo = (lane >> 1) & 1, c = lane >> 2;
+      int fo[3];
+#pragma unroll
+      for (int b = 0; b < 3; ++b) fo[b] = int(sd.gfield[q][8 * b + c]) * kRecStride;
+      const int ng = s_ng;
+      const int cta_in_sensor = tl.start / kTile;
+      const int ri = lane >> 2, jp = lane & 3;          // accumulator fragment: row ri, columns 2 jp, 2 jp + 1
+      for (int g = warp; g < ng; g += kTile / 32) {
+        const int a = s_gstart[g], e = g + 1 < ng ? s_gstart[g + 1] : tl.count;
+        double cg[6][2];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { cg[i][0] = 0.0; cg[i][1] = 0.0; }
+        const double* ro = rec + a + oo;
+        const int npair = (e - a) >> 1;
+#pragma unroll 2
+        for (int kp = 0; kp < npair; ++kp, ro += 2) {
+          const double x0 = ro[fo[0]], x1 = ro[fo[1]], x2 = ro[fo[2]];
+          dmma_8x8x4(cg[0][0], cg[0][1], x0, x0);
+          dmma_8x8x4(cg[1][0], cg[1][1], x1, x0);
+          dmma_8x8x4(cg[2][0], cg[2][1], x1, x1);
+          dmma_8x8x4(cg[3][0], cg[3][1], x2, x0);
+          dmma_8x8x4(cg[4][0], cg[4][1], x2, x1);
+          dmma_8x8x4(cg[5][0], cg[5][1], x2, x2);
+        }
+        if ((e - a) & 1) {                              // odd group: the last k-step holds one observation (rows of lanes with oo == 1 are zero)
+          const double* rl = rec + (e - 1);
+          const double x0 = oo ? 0.0 : rl[fo[0]], x1 = oo ? 0.0 : rl[fo[1]], x2 = oo ? 0.0 : rl[fo[2]];
+          dmma_8x8x4(cg[0][0], cg[0][1], x0, x0);
+          dmma_8x8x4(cg[1][0], cg[1][1], x1, x0);
+          dmma_8x8x4(cg[2][0], cg[2][1], x1, x1);
+          dmma_8x8x4(cg[3][0], cg[3][1], x2, x0);
+          dmma_8x8x4(cg[4][0], cg[4][1], x2, x1);
+          dmma_8x8x4(cg[5][0], cg[5][1], x2, x2);
+        }
+        const int slot = sd.gslot_base + s_gfrm[g] + cta_in_sensor;
+        if (jp < 3) {                                   // columns 0..5 (g) of the tiles (0,0), (1,0), (2,0): rows of 6 doubles
+          double* __restrict__ S = sd.gslots + size_t(slot) * kGramSlot + ri * 6 + 2 * jp;
+          *reinterpret_cast<double2*>(S) = make_double2(cg[0][0], cg[0][1]);
+          *reinterpret_cast<double2*>(S + 48) = make_double2(cg[1][0], cg[1][1]);
+          *reinterpret_cast<double2*>(S + 96) = make_double2(cg[3][0], cg[3][1]);
+        }
+#pragma unroll
+        for (int i = 0; i < 5; ++i) { cgS[i][0] += cg[i + 1][0]; cgS[i][1] += cg[i + 1][1]; }
+        {
+          double* __restrict__ S = sd.gslots + size_t(slot) * kGramSlot;
+          if (lane < kK) S[kGramSlotW + lane] = rec[(CamRec::w0 + lane) * kRecStride + a];   // the image's basis weights (same for all its rows)
+          else if (lane == kK) S[kGramSlotFlag] = 1.0;
+          else if (lane == kK + 1 && g == 0 && s_hole) S[kGramSlotFlag - kGramSlot] = 0.0;    // the tile starts at an image boundary: slot - 1 is unused
+        }
+      }
+    };
+#ifdef CB2_GRAM_FIRST
+    if (kGram && do_gram) gram_phase();
+#endif
     const int nobs = min(32, tl.count - warp * 32);
     if (nobs > 0) {
       double* __restrict__ Jw = sd.J + (size_t(tl.start) + warp * 32) * rowlen;
@@ -211,6 +297,18 @@ __global__ void __launch_bounds__(eval_tile(KIND), (KIND == kCamera ? CB2_EVAL_M
             }
         }
       }
+    }
+    if (kGram && do_gram) {
+#ifndef CB2_GRAM_FIRST
+      gram_phase();                                     // the Jacobian stores of this warp drain while its Gram tiles are multiplied
+#endif
+      // Calibration tiles summed over this WARP's groups -> gcta[CTA][warp]: no block barrier, no atomics; assemble_calib_kernel sums the
+      // (CTA, warp) partials in a fixed order. Layout: [calib 0..7 x calib 0..7 | calib 8..15 x 0..7 | 8..15 x 8..15 | gradient 16].
+      double* __restrict__ out = sd.gcta + (size_t(tl.start / kTile) * (kTile / 32) + warp) * kGramCta;
+      *reinterpret_cast<double2*>(out + 2 * lane) = make_double2(cgS[1][0], cgS[1][1]);
+      *reinterpret_cast<double2*>(out + 64 + 2 * lane) = make_double2(cgS[3][0], cgS[3][1]);
+      *reinterpret_cast<double2*>(out + 128 + 2 * lane) = make_double2(cgS[4][0], cgS[4][1]);
+      if ((lane & 3) == 3) { out[192 + (lane >> 2)] = cgS[0][0]; out[200 + (lane >> 2)] = cgS[2][0]; }   // column 6 (r) of calib x [g | r]
     }
   }
 }

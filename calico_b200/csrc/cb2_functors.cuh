@@ -325,6 +325,16 @@ CB2_HD void jac_terms(int kind, int ni, int row, int col, int fa[3], int fb[3]) 
   if (col < 3) { if (kind != kGyroscope) fa[0] = (kind == kCamera ? int(CamRec::Jt) : int(AccRec::Jt)) + row * 3 + col; return; }
   fa[0] = (kind == kCamera ? int(CamRec::Jl) : (kind == kGyroscope ? int(GyrRec::Jl) : int(AccRec::Jl))) + row;
 }
+// Camera record field behind compact Gram column `col` of residual row q: [g_0..g_5 | r | 0 | calibration unknown col - 8] (SensorDesc::gslots).
+// canon_of_unknown[u] = canonical calibration column (0 .. ni + 6) of calibration-local unknown u, -1 = not stored.
+CB2_HD int gram_field(int ni, int q, int col, const int* canon_of_unknown, int n_unknowns) {
+  if (col < 6) return CamRec::G0 + q * 6 + col;
+  if (col == 6) return CamRec::r + q;
+  if (col < 8 || col - 8 >= n_unknowns || canon_of_unknown[col - 8] < 0) return CamRec::zero;
+  int fa[3], fb[3];
+  jac_terms(kCamera, ni, q, 6 * kK + canon_of_unknown[col - 8], fa, fb);
+  return fa[0];
+}
 CB2_HD double jac_entry(int kind, int ni, const Rec& rec, int row, int col) {
   int fa[3], fb[3];
   jac_terms(kind, ni, row, col, fa, fb);

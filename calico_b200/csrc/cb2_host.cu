@@ -395,7 +395,12 @@ struct cb2_problem {
   size_t smem_eval[3] = {0, 0, 0};
   int max_tilepairs1 = 0, max_ksplit1 = 1;
   bool gram_dmma1 = false;   // level-1 Gram product on the FP64 tensor pipe
-  bool acc_structured = std::getenv("CB2_ACC_STRUCTURED") != nullptr;   // image-wise Kronecker accumulation of camera rows (cb2_normal.cuh): opt-in
+  // Cameras with <= 16 calibration unknowns: compact per-image Gram slots written by the sweep, expanded by expand_gram_kernel (cb2_normal.cuh);
+  // their Jacobian is never read back. CB2_NO_SWEEP_GRAM=1 sends every sensor through accumulate_kernel (J re-read) instead.
+  bool sweep_gram = std::getenv("CB2_NO_SWEEP_GRAM") == nullptr;
+  DevBuf<double> d_gslots, d_gcta, d_segA2, d_segG2;
+  DevBuf<int> d_ext_tab, d_ext_dst;
+  int n_gram_sensors = 0, n_plain_sensors = 0;
   double* h_scal = nullptr;   // pinned
   double* h_param = nullptr;  // pinned: {radius, min_lm_diagonal, max_lm_diagonal} of the coming solve
   bool use_graphs = std::getenv("CB2_NO_GRAPHS") == nullptr;
@@ -603,6 +608,10 @@ struct cb2_problem {
     std::vector<std::vector<EvalTile>> tiles_by_kind(3);
     std::vector<int> frame_sensor, frame_seg;
     std::vector<double> frame_stamp;
+    size_t n_gslots = 0, n_gcta = 0;
+    std::vector<char> gram_sensor(std::max(ns, 1), 0);
+    std::vector<size_t> gcta_off(std::max(ns, 1), 0);
+    std::vector<int> gcta_cnt(std::max(ns, 1), 0);
     int64_t* h2d = &stats.h2d_bytes;
     // Phase A (one host thread per sensor): validation, segment lookup, counting sort by segment, SoA packing.
     struct Packed {
@@ -728,6 +737,19 @@ struct cb2_problem {
       if (d.u_trans >= 0 && s.kind != kGyroscope) for (int j = 0; j < 3; ++j) { d.jcanon[nj] = want + 3 + j; d.junk[nj] = d.u_trans + j; ++nj; }
       if (d.u_lat >= 0) { d.jcanon[nj] = want + 6; d.junk[nj] = d.u_lat; ++nj; }
       d.n_jcal = nj; d.jw = kCpCols + nj;
+      d.gslots = nullptr; d.gslot_base = 0;
+      if (sweep_gram && ns <= kAccMaxSensors && s.kind == kCamera && d.n_calib <= 16 && n_active > 0) {
+        d.gslot_base = int(n_gslots);
+        const size_t n_cta = size_t((n_active + eval_tile(kCamera) - 1) / eval_tile(kCamera));
+        n_gslots += P.frame_stamp.size() + n_cta;
+        const size_t n_part = n_cta * (eval_tile(kCamera) / 32);      // one calibration partial per (CTA, warp)
+        gram_sensor[si] = 1; gcta_off[si] = n_gcta; gcta_cnt[si] = int(n_part);
+        int canon_of_unknown[16];
+        for (int u = 0; u < 16; ++u) canon_of_unknown[u] = -1;
+        for (int j = 0; j < nj; ++j) canon_of_unknown[d.junk[j]] = d.jcanon[j];
+        for (int q = 0; q < 2; ++q) for (int col = 0; col < 24; ++col) d.gfield[q][col] = (unsigned char)gram_field(want, q, col, canon_of_unknown, 16);
+        n_gcta += n_part;
+      }
       s.d_r.alloc(size_t(n_active) * m);
       s.d_J.alloc(size_t(n_active) * m * d.jw);
       s.d_valid.alloc(n_active);
@@ -753,6 +775,15 @@ struct cb2_problem {
     d_frame_sensor.upload(frame_sensor, h2d); d_frame_seg.upload(frame_seg, h2d); d_frame_stamp.upload(frame_stamp, h2d);
     d_frames.alloc(size_t(std::max(n_frames, 1)) * FrameRec::kSize);
     d_cost_partial.alloc(std::max(n_tiles, 1)); d_invalid_partial.alloc(std::max(n_tiles, 1));
+    d_gslots.alloc(n_gslots * kGramSlot, false);
+    d_gcta.alloc(n_gcta * kGramCta);
+    { std::vector<int> tab(32 * kExpExt), dst(32 * kExpExt); expand_ext_table(tab.data(), dst.data()); d_ext_tab.upload(tab, h2d); d_ext_dst.upload(dst, h2d); }
+    n_gram_sensors = n_plain_sensors = 0;
+    for (int si = 0; si < ns; ++si) {
+      h_desc[si].gcta = nullptr;
+      if (gram_sensor[si]) { h_desc[si].gslots = d_gslots.p; h_desc[si].gcta = d_gcta.p + gcta_off[si] * kGramCta; ++n_gram_sensors; }
+      else if (h_desc[si].n_obs > 0) ++n_plain_sensors;
+    }
     d_desc.upload(h_desc, h2d);
     for (int b = 0; b < 2; ++b) d_state[b].upload(h_state, h2d);
     d_state0.upload(h_state, h2d);
@@ -773,15 +804,28 @@ struct cb2_problem {
     // Normal-equation storage.
     d_c2off.upload(c2off, h2d);
     std::vector<CalibEntry> ce;
+    const int nsl_ce = std::max(g_hi - g_lo, 0);
     for (int si = 0; si < ns; ++si) {
       const SensorDesc& d = h_desc[si];
-      for (int li = 0; li < d.n_calib; ++li) for (int lj = 0; lj <= li; ++lj) ce.push_back(CalibEntry{c2off[si] + li * d.n_calib + lj, d.calib_off + li, d.calib_off + lj});
-      for (int li = 0; li < d.n_calib; ++li) ce.push_back(CalibEntry{d.calib_off + li, d.calib_off + li, -1});
+      if (gram_sensor[si]) {
+        // per-(CTA, warp) partials of the sweep (SensorDesc::gcta): [calib 0..7 x 0..7 | 8..15 x 0..7 | 8..15 x 8..15 | gradient 0..15]
+        const long base = long(gcta_off[si]) * kGramCta;
+        for (int li = 0; li < d.n_calib; ++li) for (int lj = 0; lj <= li; ++lj) {
+          const int off = li < 8 ? li * 8 + lj : (lj < 8 ? 64 + (li - 8) * 8 + lj : 128 + (li - 8) * 8 + (lj - 8));
+          ce.push_back(CalibEntry{base + off, kGramCta, gcta_cnt[si], 2, d.calib_off + li, d.calib_off + lj});
+        }
+        for (int li = 0; li < d.n_calib; ++li) ce.push_back(CalibEntry{base + 192 + li, kGramCta, gcta_cnt[si], 2, d.calib_off + li, -1});
+      } else {
+        for (int li = 0; li < d.n_calib; ++li) for (int lj = 0; lj <= li; ++lj) ce.push_back(CalibEntry{long(c2off[si] + li * d.n_calib + lj), csz, nsl_ce, 0, d.calib_off + li, d.calib_off + lj});
+        for (int li = 0; li < d.n_calib; ++li) ce.push_back(CalibEntry{long(d.calib_off + li), N_c, nsl_ce, 1, d.calib_off + li, -1});
+      }
     }
     d_centries.upload(ce, h2d);
     d_cpartial.alloc(std::max<size_t>(ce.size(), 1) * kCalibSlices);
     const size_t nsl = size_t(std::max(g_hi - g_lo, 1));
     d_segA.alloc(nsl * 36 * 36); d_segG.alloc(nsl * 36);
+    const bool two_sources = n_gram_sensors > 0 && n_plain_sensors > 0;
+    d_segA2.alloc(two_sources ? nsl * 36 * 36 : 0); d_segG2.alloc(two_sources ? nsl * 36 : 0);
     d_segB.alloc(nsl * 36 * std::max(N_c, 1)); d_segC.alloc(nsl * std::max(csz, 1)); d_segGc.alloc(nsl * std::max(N_c, 1));
     d_Aband.alloc(size_t(n_a) * 36); d_Bmat.alloc(size_t(n_a) * std::max(N_c, 1)); d_Cmat.alloc(size_t(std::max(N_c, 1)) * std::max(N_c, 1));
     d_grad.alloc(n_tot); d_diag.alloc(n_tot); d_scaling.alloc(n_tot); d_dtil2.alloc(n_tot); d_ytil.alloc(n_tot);
@@ -935,8 +979,8 @@ struct cb2_problem {
     set(eval_kernel<kCamera, kModeCost>, ev_max[0]); set(eval_kernel<kCamera, kModeResiduals>, ev_max[0]); set(eval_kernel<kCamera, kModeJacobian>, ev_max[0]);
     set(eval_kernel<kGyroscope, kModeCost>, ev_max[1]); set(eval_kernel<kGyroscope, kModeResiduals>, ev_max[1]); set(eval_kernel<kGyroscope, kModeJacobian>, ev_max[1]);
     set(eval_kernel<kAccelerometer, kModeCost>, ev_max[2]); set(eval_kernel<kAccelerometer, kModeResiduals>, ev_max[2]); set(eval_kernel<kAccelerometer, kModeJacobian>, ev_max[2]);
-    set((accumulate_kernel<7, false>), acc_smem_bytes(false)); set((accumulate_kernel<8, false>), acc_smem_bytes(false));
-    set((accumulate_kernel<7, true>), acc_smem_bytes(true)); set((accumulate_kernel<8, true>), acc_smem_bytes(true));
+    set((accumulate_kernel<7>), acc_smem_bytes()); set((accumulate_kernel<8>), acc_smem_bytes());
+    set(expand_gram_kernel, expand_smem_bytes());
     int max_n1 = 0;
     for (const auto& sy : h_l1) max_n1 = std::max(max_n1, sy.n);
     const int nbw1 = h_l1[0].nbw, nbw2 = h_l2.nbw;
@@ -1040,22 +1084,34 @@ struct cb2_problem {
     const int ns = int(sensors.size());
     const int nsl = g_hi - g_lo;
     if (nsl > 0) {
-      int max_nc = 0;
-      for (const auto& d : h_desc) max_nc = std::max(max_nc, d.n_calib);
-#define CB2_ACC(NBV, STV) CB2_K((accumulate_kernel<NBV, STV>), nsl, kAccThreads, acc_smem_bytes(STV), stream, d_desc.p, ns, N_c, g_lo, d_c2off.p, csz, d_segA.p, \
-                                d_segG.p, d_segB.p, d_segC.p, d_segGc.p, d_frames.p)
-      const bool nb7 = kAccCal0 + max_nc <= 56;
-      if (acc_structured) { if (nb7) CB2_ACC(7, true); else CB2_ACC(8, true); }
-      else { if (nb7) CB2_ACC(7, false); else CB2_ACC(8, false); }
-#undef CB2_ACC
+      // IMU sensors (and cameras too wide for the compact slots) from their Jacobian rows; cameras from the Gram slots the sweep left.
+      // Both kernels are latency-bound at low occupancy and independent (separate control-point partials, disjoint calibration columns):
+      // they run side by side, accumulate_kernel on the second stream (a fork / join that a graph capture records as such).
+      const bool plain = n_plain_sensors > 0 || n_gram_sensors == 0, gram = n_gram_sensors > 0;
+      cudaStream_t s_acc = stream;
+#ifndef CB2_EMUL
+      if (plain && gram) { CB2_CUDA(cudaEventRecord(ev_fork, stream)); CB2_CUDA(cudaStreamWaitEvent(stream_imu, ev_fork, 0)); s_acc = stream_imu; }
+#endif
+      if (plain) {
+        int max_nc = 0;
+        for (const auto& d : h_desc) if (!d.gslots) max_nc = std::max(max_nc, d.n_calib);
+        if (kAccCal0 + max_nc <= 56) CB2_K((accumulate_kernel<7>), nsl, kAccThreads, acc_smem_bytes(), s_acc, d_desc.p, ns, N_c, g_lo, d_c2off.p, csz, d_segA.p, d_segG.p, d_segB.p, d_segC.p, d_segGc.p);
+        else CB2_K((accumulate_kernel<8>), nsl, kAccThreads, acc_smem_bytes(), s_acc, d_desc.p, ns, N_c, g_lo, d_c2off.p, csz, d_segA.p, d_segG.p, d_segB.p, d_segC.p, d_segGc.p);
+      }
+      if (gram)
+        CB2_K(expand_gram_kernel, nsl, kExpThreads, expand_smem_bytes(), stream, d_desc.p, ns, N_c, g_lo, d_ext_tab.p, d_ext_dst.p, plain ? d_segA2.p : d_segA.p,
+              plain ? d_segG2.p : d_segG.p, d_segB.p);
+#ifndef CB2_EMUL
+      if (plain && gram) { CB2_CUDA(cudaEventRecord(ev_join, stream_imu)); CB2_CUDA(cudaStreamWaitEvent(stream, ev_join, 0)); }
+#endif
     }
     const long total = n_a * 36 + n_a * N_c + n_a;
     CB2_K(assemble_band_kernel, int(std::min<long>((total + 255) / 256, 148 * 16)), 256, 0, stream, n_cp, g_lo, g_hi, N_c, d_segA.p, d_segG.p, d_segB.p,
-          d_Aband.p, d_Bmat.p, d_grad.p);
+          d_segA2.n ? d_segA2.p : nullptr, d_segG2.n ? d_segG2.p : nullptr, d_Aband.p, d_Bmat.p, d_grad.p);
     if (N_c > 0) {
       d_Cmat.zero(stream);
       const int ne = int(d_centries.n);
-      CB2_K(assemble_calib_kernel, dim3((ne + 31) / 32, kCalibSlices), dim3(32, 8), 0, stream, nsl, N_c, csz, ne, d_centries.p, d_segC.p, d_segGc.p, d_cpartial.p);
+      CB2_K(assemble_calib_kernel, dim3((ne + 31) / 32, kCalibSlices), dim3(32, 8), 0, stream, ne, d_centries.p, d_segC.p, d_segGc.p, d_gcta.p, d_cpartial.p);
       CB2_K(assemble_calib_final_kernel, (ne + 255) / 256, 256, 0, stream, N_c, ne, kCalibSlices, d_centries.p, d_cpartial.p, d_Cmat.p, d_grad.p + n_a);
     }
     CB2_K(hess_diag_kernel, int(std::min<long>((n_tot + 255) / 256, 1024)), 256, 0, stream, n_a, N_c, d_Aband.p, d_Cmat.p, d_diag.p);
@@ -1687,6 +1743,7 @@ int cb2_evaluate_sensor(cb2_problem* p, int sid, double* residuals, double* jaco
     if (na == 0) return CB2_OK;
     // Temporary descriptor storing every canonical column, un-robustified.
     SensorDesc d = d0;
+    d.gslots = nullptr; d.gcta = nullptr;
     d.n_jcal = ni + 7; d.jw = W;
     for (int j = 0; j < ni + 7; ++j) { d.jcanon[j] = j; d.junk[j] = j; }
     DevBuf<double> J, r;

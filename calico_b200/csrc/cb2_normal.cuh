@@ -15,12 +15,12 @@
 // == 4 mod 16: conflict-free fragment loads). The control-point block accumulates over all sensors of the warp and is
 // combined across warps in a fixed order at the end; the calibration blocks are flushed per sensor. No atomics.
 // Camera rows have more structure: all rows of one image share the basis weights w, and their control-point part is the Kronecker
-// product g (x) w (g = d r / d pose, 6 numbers per row). Per image the kernel therefore multiplies only the COMPACT rows
-// [g^ | r | calibration] (24 columns = 6 DMMA tiles instead of 28; g^ = g w_istar is read straight from the J columns of the control point
-// with the largest weight) and expands once per image:  H[cp_a, cp_b] += (w_a w_b / w_istar^2) G^[.,.],  H[cp_a, r|calib] += (w_a / w_istar) ...
-// This cuts the tensor work of K4 by ~4.7x, but measured on C4 it does not pay yet (378 us vs 361 us for the plain product): DRAM still
-// fetches every sector of the J rows, the tile pipeline is one tile deep per warp, and the two warps that also own an IMU sensor become
-// the critical path. It is therefore OPT-IN (CB2_ACC_STRUCTURED=1) until images are balanced across warps; parity-tested either way.
+// product g (x) w (g = d r / d pose, 6 numbers per row). For cameras with <= 16 calibration unknowns the Jacobian sweep itself (cb2_eval.cuh)
+// therefore leaves per (CTA, image) the COMPACT Gram matrix of the rows [g | r | 0 | calibration] (24 x 24 instead of 56 x 56: 6 DMMA tiles
+// instead of 28) while its Jacobian stores drain, and expand_gram_kernel below expands once per image:
+//     H[cp_a, cp_b] += w_a w_b G_gg,   H[cp_a, r | calib] += w_a G_g.,   H[calib, calib] += G_cc.
+// accumulate_kernel then only sees the IMU sensors (and cameras with more than 16 calibration unknowns): the camera Jacobian — 87 % of the
+// Jacobian bytes — is written once and never read back.
 // assemble_*_kernel: sums the <= 6 overlapping segment partials per control-point entry into the banded storage and
 // reduces the calibration blocks over all segments.
 #pragma once
@@ -35,12 +35,7 @@ constexpr int kAccStride = 68;     // doubles per tile row; 68 mod 16 == 4 -> th
 constexpr int kAccRcol = 36;       // local layout: cp 0..35 | r 36 | zeros 37..39 | calibration unknowns 40.. | zeros
 constexpr int kAccCal0 = 40;
 constexpr int kAccMaxSensors = 64;
-constexpr int kAccMaxSlots = 16;   // camera images of one spline segment handled by the structured path (more: plain product for that segment)
-constexpr int kAccSlot = 144;      // per image: G^gg 6x6 | sum r g^ (6) | sum c g^ (6 x 16) | w_a / w_istar (6)
-constexpr int kAccSlotGr = 36, kAccSlotGc = 42, kAccSlotRho = 138;
-CB2_HD constexpr size_t acc_smem_bytes(bool structured) {
-  return (size_t(kAccWarps) * 2 * (kAccRows * kAccStride + 4) + (structured ? size_t(kAccMaxSlots) * kAccSlot : 0)) * sizeof(double);
-}
+CB2_HD constexpr size_t acc_smem_bytes() { return size_t(kAccWarps) * 2 * (kAccRows * kAccStride + 4) * sizeof(double); }
 #ifndef CB2_ACC_MINBLOCKS
 #define CB2_ACC_MINBLOCKS 3
 #endif
@@ -66,22 +61,12 @@ CB2_D void cp_async_wait() {
 #endif
 }
 
-// D(8x8) += A(8x4) B(4x8) in FP64 on the tensor pipe. Lane l holds a = A[l / 4][l % 4], b = B[l % 4][l / 4],
-// c0, c1 = D[l / 4][2 (l % 4) + {0, 1}].
-CB2_D void dmma_8x8x4(double& c0, double& c1, double a, double b) {
-#if defined(CB2_EMUL)
-  ::cb2emul::dmma_8x8x4(c0, c1, a, b);
-#else
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-#endif
-}
-
 // NB = number of 8-column blocks of the local layout: 7 covers sensors with up to 16 calibration unknowns, 8 up to 20 (kMaxCalib).
-// kStruct = false compiles the structured camera path out entirely (the default build of the hot kernel carries none of its cost).
-template <int NB, bool kStruct>
+// Sensors whose Gram slots come from the sweep (sd.gslots != nullptr) are skipped here; the warps are dealt the remaining sensors.
+template <int NB>
 __global__ void __launch_bounds__(kAccThreads, (NB == 7 ? CB2_ACC_MINBLOCKS : 2)) accumulate_kernel(
     const SensorDesc* __restrict__ sensors, int n_sensors, int N_c, int g_lo, const int* __restrict__ c2off, int csz, double* __restrict__ segA,
-    double* __restrict__ segG, double* __restrict__ segB, double* __restrict__ segC, double* __restrict__ segGc, const double* __restrict__ frames) {
+    double* __restrict__ segG, double* __restrict__ segB, double* __restrict__ segC, double* __restrict__ segGc) {
   // dynamic shared memory: per warp two tile buffers of kAccRows x kAccStride (+ 4 doubles: the last fragment reads past a row end)
   typedef double TileBuf[2][kAccRows * kAccStride + 4];
   TileBuf* tiles = dyn_smem<TileBuf>();
@@ -95,158 +80,17 @@ __global__ void __launch_bounds__(kAccThreads, (NB == 7 ? CB2_ACC_MINBLOCKS : 2)
     for (int bj = 0; bj < NB; ++bj) { acc[bi][bj][0] = 0.0; acc[bi][bj][1] = 0.0; }
   double* const tb0 = tiles[warp][0];
   for (int i = lane; i < 2 * (kAccRows * kAccStride + 4); i += 32) tb0[i] = 0.0;   // padding columns stay zero for the whole kernel
-  bool dirty = false;
   __syncwarp();
-  // Per-image slots of the structured camera accumulation (shared memory behind the tile buffers) and their per-sensor offsets.
-  double* const slots = reinterpret_cast<double*>(tiles + kAccWarps);
-  __shared__ int s_slot_begin[kAccMaxSensors + 1];
-  __shared__ int s_use_struct;
-  if (kStruct && warp == 0) {   // lane-parallel: one sensor per lane and round, exclusive prefix sum by shuffles (no serial chain of dependent loads)
-    const bool ok = n_sensors <= kAccMaxSensors;
-    int base = 0;
-    for (int s0 = 0; ok && s0 < n_sensors; s0 += 32) {
-      const int s = s0 + lane;
-      int cnt = 0;
-      if (s < n_sensors) {
-        const SensorDesc& sd = sensors[s];
-        if (sd.kind == kCamera && sd.seg_frame != nullptr && sd.n_calib <= 16) cnt = sd.seg_frame[g + 1] - sd.seg_frame[g];
-      }
-      int incl = cnt;
-      for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += o; }
-      if (s < n_sensors) s_slot_begin[s] = base + incl - cnt;
-      base += __shfl_sync(0xffffffffu, incl, 31);
-    }
-    if (lane == 0) { s_slot_begin[n_sensors <= kAccMaxSensors ? n_sensors : 0] = base; s_use_struct = (ok && base <= kAccMaxSlots) ? 1 : 0; }
-  }
-  if (kStruct) __syncthreads();
-  const bool use_struct = kStruct && s_use_struct != 0;
-
-  for (int s = warp; s < n_sensors; s += kAccWarps) {
+  // The sensors this kernel handles are dealt round-robin to the warps by their rank among them (not by their global index).
+  int my_rank = 0;
+  for (int s = 0; s < n_sensors; ++s) {
     const SensorDesc& sd = sensors[s];
+    if (sd.gslots != nullptr) continue;
+    if ((my_rank++ % kAccWarps) != warp) continue;
     const int m = sd.m, jw = sd.jw, nc = sd.n_calib;
     const int o0 = sd.seg_start[g];
     const int rows = (sd.seg_start[g + 1] - o0) * m;
     if (rows == 0) continue;
-    if (kStruct && use_struct && sd.kind == kCamera && nc <= 16) {
-      // ---- camera rows, image by image (see the header comment): compact Gram of [g^ | r | calibration]; the Kronecker expansion of its
-      //      g^ rows is deferred to the end of the kernel (per-image slots in shared memory), the [r | calibration] square is summed here ----
-      constexpr int CS = 28, CR = 16;                         // compact tile: 16 rows x 24 columns, row stride 28 (== 12 mod 16: conflict-free fragments)
-      static_assert(CR * CS <= kAccRows * kAccStride + 4, "compact tile does not fit a tile buffer");
-      double* const cb[2] = {tiles[warp][0], tiles[warp][1]};
-      dirty = true;
-      for (int i = lane; i < CR * CS; i += 32) { cb[0][i] = 0.0; cb[1][i] = 0.0; }
-      __syncwarp();
-      // lane -> the one compact column it copies: 0..5 g^ (J columns 6 istar + lane), 6 r, 8 + junk[j] calibration column j
-      const int njc = jw - kCpCols;
-      const int my_cal = lane - 8;
-      const int dst_col = lane < 6 ? lane : (lane == 6 ? 6 : ((my_cal >= 0 && my_cal < njc) ? 8 + sd.junk[my_cal] : -1));
-      const int f_begin = sd.seg_frame[g], f_end = sd.seg_frame[g + 1];
-      // Per-image metadata is fetched once, up front (lane k: image f_begin + k), so that no dependent global load sits in the tile pipeline.
-      const int nfr = f_end - f_begin;
-      int my_obs0 = 0, my_rows = 0, my_istar = 0;
-      if (lane < nfr) {
-        my_obs0 = sd.frame_obs[f_begin + lane];
-        my_rows = (sd.frame_obs[f_begin + lane + 1] - my_obs0) * 2;
-        const double* w = frames + size_t(sd.frame_base + f_begin + lane) * FrameRec::kSize + FrameRec::w0;
-        double bv = fabs(w[0]);
-#pragma unroll
-        for (int a = 1; a < kK; ++a) { const double v = fabs(w[a]); if (v > bv) { bv = v; my_istar = a; } }
-      }
-      auto item_rows = [&](int f) { return __shfl_sync(0xffffffffu, my_rows, (f - f_begin) & 31); };
-      auto item_obs0 = [&](int f) { return __shfl_sync(0xffffffffu, my_obs0, (f - f_begin) & 31); };
-      auto frame_istar = [&](int f) { return __shfl_sync(0xffffffffu, my_istar, (f - f_begin) & 31); };
-      // flattened (image, pass) pipeline: the tile of the next item streams in while the current one is multiplied
-      auto issue = [&](int f, int pass, int buf) {
-        if (f < f_end) {
-          const int nrows = item_rows(f), r0 = pass * CR, nr = min(CR, nrows - r0), istar = frame_istar(f);
-          const size_t row0 = size_t(item_obs0(f)) * 2 + r0;                       // first J row of this tile
-          double* tb = cb[buf];
-          if (dst_col >= 0) {
-            const double* src = lane == 6 ? sd.r + row0 : sd.J + row0 * jw + (lane < 6 ? 6 * istar + lane : kCpCols + my_cal);
-            const int sstride = lane == 6 ? 1 : jw;
-#pragma unroll 4
-            for (int rr = 0; rr < nr; ++rr) cp_async8(tb + rr * CS + dst_col, src + size_t(rr) * sstride);
-          }
-          if (lane < 24) for (int rr = nr; rr < min(CR, (nr + 3) & ~3); ++rr) tb[rr * CS + lane] = 0.0;   // complete the last k-step with zero rows
-        }
-        cp_async_commit();
-      };
-      int cf = f_begin, cp = 0;                               // current item
-      issue(cf, cp, 0);
-      int buf = 0;
-      double cg[6][2], cgS[6][2];                             // compact Gram of the current image / summed over the sensor's images
-#pragma unroll
-      for (int q = 0; q < 6; ++q) { cgS[q][0] = 0.0; cgS[q][1] = 0.0; }
-      while (cf < f_end) {
-        const int nrows = item_rows(cf), npass = (nrows + CR - 1) / CR;
-        int nf = cf, np = cp + 1;
-        if (np >= npass) { nf = cf + 1; np = 0; }
-        issue(nf, np, buf ^ 1);
-        cp_async_wait<1>();
-        __syncwarp();
-        if (cp == 0) {
-#pragma unroll
-          for (int q = 0; q < 6; ++q) { cg[q][0] = 0.0; cg[q][1] = 0.0; }
-        }
-        const double* tb = cb[buf];
-        const int nr = min(CR, nrows - cp * CR);
-#pragma unroll
-        for (int ks = 0; ks < CR / 4; ++ks) {
-          if (4 * ks < nr) {
-            const double* row = tb + (4 * ks + fr) * CS + fc;
-            const double f0 = row[0], f1 = row[8], f2 = row[16];
-            dmma_8x8x4(cg[0][0], cg[0][1], f0, f0);
-            dmma_8x8x4(cg[1][0], cg[1][1], f1, f0);
-            dmma_8x8x4(cg[2][0], cg[2][1], f1, f1);
-            dmma_8x8x4(cg[3][0], cg[3][1], f2, f0);
-            dmma_8x8x4(cg[4][0], cg[4][1], f2, f1);
-            dmma_8x8x4(cg[5][0], cg[5][1], f2, f2);
-          }
-        }
-        __syncwarp();
-        if (cp == npass - 1) {
-          // image complete: its g^ rows go to the image's slot (expanded at the end of the kernel), the rest into the sensor sums
-          double* slot = slots + size_t(s_slot_begin[s] + (cf - f_begin)) * kAccSlot;
-          const double* w = frames + size_t(sd.frame_base + cf) * FrameRec::kSize + FrameRec::w0;
-          const int istar = frame_istar(cf);
-          if (lane < kK) slot[kAccSlotRho + lane] = w[lane] / w[istar];
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const int Jc = 2 * fr + i;                       // compact column of this accumulator entry (tiles (0,0), (1,0), (2,0))
-            if (Jc < 6) {
-              if (fc < 6) slot[fc * 6 + Jc] = cg[0][i];                           // G^gg[fc][Jc]
-              else if (fc == 6) slot[kAccSlotGr + Jc] = cg[0][i];                 // sum r g^
-              slot[kAccSlotGc + Jc * 16 + fc] = cg[1][i];                         // sum c_fc g^_Jc
-              slot[kAccSlotGc + Jc * 16 + 8 + fc] = cg[3][i];
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < 6; ++q) { cgS[q][0] += cg[q][0]; cgS[q][1] += cg[q][1]; }
-        }
-        cf = nf; cp = np; buf ^= 1;
-      }
-      cp_async_wait<0>();
-      __syncwarp();
-      // [r | calibration] x [r | calibration] of this sensor: calibration gradient and calibration block
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int Jc = 2 * fr + i;
-        if (Jc == 6) {                                        // column r of tiles (1,0), (2,0)
-          if (fc < nc) segGc[size_t(gl) * N_c + sd.calib_off + fc] = cgS[1][i];
-          if (8 + fc < nc) segGc[size_t(gl) * N_c + sd.calib_off + 8 + fc] = cgS[3][i];
-        }
-        // tiles (1,1): (li, lj) = (fc, Jc); (2,1): (8 + fc, Jc); (2,2): (8 + fc, 8 + Jc)
-        if (fc < nc && Jc <= fc) segC[size_t(gl) * csz + c2off[s] + fc * nc + Jc] = cgS[2][i];
-        if (8 + fc < nc && Jc < nc) segC[size_t(gl) * csz + c2off[s] + (8 + fc) * nc + Jc] = cgS[4][i];
-        if (8 + fc < nc && Jc <= fc) segC[size_t(gl) * csz + c2off[s] + (8 + fc) * nc + 8 + Jc] = cgS[5][i];
-      }
-      continue;
-    } else {
-    if (dirty) {   // a camera pass used these buffers with its own layout: restore the all-zero padding the generic path relies on
-      for (int i = lane; i < 2 * (kAccRows * kAccStride + 4); i += 32) tb0[i] = 0.0;
-      dirty = false;
-      __syncwarp();
-    }
     // Local column of every stored J column. The previous sensor's calibration columns are cleared first.
     if (lane < kAccStride - kAccCal0)
 #pragma unroll 4
@@ -301,7 +145,6 @@ __global__ void __launch_bounds__(kAccThreads, (NB == 7 ? CB2_ACC_MINBLOCKS : 2)
       __syncwarp();
     }
     cp_async_wait<0>();
-    }
     // Flush every entry that involves this sensor's calibration unknowns (blocks 5..NB-1), then reset them for the next sensor.
 #pragma unroll
     for (int bi = 5; bi < NB; ++bi) {
@@ -347,39 +190,163 @@ __global__ void __launch_bounds__(kAccThreads, (NB == 7 ? CB2_ACC_MINBLOCKS : 2)
     double v = 0.0;
 #pragma unroll
     for (int w = 0; w < kAccWarps; ++w) v += tiles[w][0][e];
-    if (kStruct && use_struct) {   // Kronecker expansion of the camera images: (w_a w_b / w_istar^2) G^gg[p][q], (w_b / w_istar) sum r g^_q
-      const int nslots = s_slot_begin[n_sensors];
-      const int a6 = I / 6, p6 = I - 6 * a6, b6 = Jx / 6, q6 = Jx - 6 * b6;
-      for (int k = 0; k < nslots; ++k) {
-        const double* slot = slots + size_t(k) * kAccSlot;
-        if (I < kCpCols) v += slot[kAccSlotRho + a6] * slot[kAccSlotRho + b6] * slot[p6 * 6 + q6];
-        else v += slot[kAccSlotRho + b6] * slot[kAccSlotGr + q6];
-      }
-    }
     if (I < kCpCols) segA[(size_t(gl) * kCpCols + I) * kCpCols + Jx] = v;
     else segG[size_t(gl) * kCpCols + Jx] = v;
   }
-  if (kStruct && use_struct) {     // control points x calibration of every structured camera: (w_a / w_istar) sum c g^_p over its images
-    for (int s = 0; s < n_sensors; ++s) {
-      const int k0 = s_slot_begin[s], k1 = s_slot_begin[s + 1];
-      if (k1 == k0) continue;
-      const SensorDesc& sd = sensors[s];
-      const int nc = sd.n_calib;
-      for (int e = t; e < kCpCols * 16; e += kAccThreads) {
-        const int Jx = e >> 4, li = e & 15, a6 = Jx / 6, p6 = Jx - 6 * a6;
-        if (li >= nc) continue;
-        double v = 0.0;
-        for (int k = k0; k < k1; ++k) { const double* slot = slots + size_t(k) * kAccSlot; v += slot[kAccSlotRho + a6] * slot[kAccSlotGc + p6 * 16 + li]; }
-        segB[(size_t(gl) * kCpCols + Jx) * N_c + sd.calib_off + li] = v;
+}
+
+// The camera part of the normal equations from the compact Gram slots the sweep left (see the header comment and SensorDesc::gslots).
+// One CTA per spline segment, one WARP per camera (round-robin): a warp walks its camera's slots of this segment on its own — no block
+// barrier until the end, so the dependent global loads (slot range -> image index -> basis weights -> slot data) of the warps overlap.
+// Slots are staged through per-warp shared memory with coalesced 16-byte loads; the expansion then follows the Kronecker structure
+//   H[cp_a, cp_b] += w_a w_b G (6 x 6):   lane l owns entry l of G for each of the 21 sub-blocks (a >= b) -> one load of G per slot, the six
+//                                         weights broadcast, 21 FMAs; the 4 entries 32..35 of every sub-block and the gradient row
+//                                         (w_b Gr) are "extra" entries, 4 per lane, described by ext_tab = (a << 16) | (b << 8) | offset;
+//   H[cp_a, calib]  += w_a Gc (16 x 6):   lane l owns entries l, l + 32, l + 64 of Gc for each a -> 18 accumulators, written per camera.
+// No atomics, fixed summation order. The warps' control-point partials are combined through shared memory at the end.
+// The calibration x calibration blocks and the calibration gradient need no basis weights: the sweep sums them per (CTA, warp)
+// (SensorDesc::gcta) and assemble_calib_kernel reduces them. The control-point block goes to its own per-segment buffer (accumulate_kernel
+// runs beside this kernel on a second stream); assemble_band_kernel adds the two.
+constexpr int kExpWarps = 8;
+constexpr int kExpThreads = 32 * kExpWarps;
+constexpr int kExpBatch = 4;                         // slots a warp stages at a time
+constexpr int kExpSub = 21;                          // 6 x 6 sub-blocks (a >= b) of the control-point block
+constexpr int kExpPart = kExpSub * 36 + 36;          // per-warp partial: 21 sub-blocks + the gradient row [b][q]
+constexpr int kExpExt = 4;                           // extra entries per lane: 21 x 4 leftovers + 36 gradient entries = 120 <= 128
+constexpr int kExpPerThread = (kExpPart + kExpThreads - 1) / kExpThreads;
+static_assert(kExpWarps * kExpBatch * kGramSlot >= (kExpWarps / 2) * kExpPart, "the staging area doubles as the reduction buffer");
+CB2_HD constexpr size_t expand_smem_bytes() { return size_t(kExpWarps) * kExpBatch * kGramSlot * sizeof(double); }
+// ext_tab[lane * kExpExt + j] = (a << 16) | (b << 8) | offset of the slot entry, a == 6: gradient row (weight 1); -1 = unused.
+// ext_dst[...] = index in the per-warp partial.
+inline void expand_ext_table(int* tab, int* dst) {
+  int n = 0;
+  for (int i = 0; i < 32 * kExpExt; ++i) { tab[i] = -1; dst[i] = 0; }
+  for (int a = 0; a < 6; ++a) for (int b = 0; b <= a; ++b) for (int e = 32; e < 36; ++e) { tab[n] = (a << 16) | (b << 8) | e; dst[n] = (a * (a + 1) / 2 + b) * 36 + e; ++n; }
+  for (int b = 0; b < 6; ++b) for (int q = 0; q < 6; ++q) { tab[n] = (6 << 16) | (b << 8) | (36 + q); dst[n] = kExpSub * 36 + b * 6 + q; ++n; }
+}
+__global__ void __launch_bounds__(kExpThreads, 2) expand_gram_kernel(const SensorDesc* __restrict__ sensors, int n_sensors, int N_c, int g_lo,
+                                                                     const int* __restrict__ ext_tab, const int* __restrict__ ext_dst,
+                                                                     double* __restrict__ segA, double* __restrict__ segG, double* __restrict__ segB) {
+  double* smem = dyn_smem<double>();
+  const int gl = blockIdx.x, g = g_lo + gl, t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  double* const s_slot = smem + size_t(warp) * kExpBatch * kGramSlot;                               // [kExpBatch][kGramSlot]
+  int et[kExpExt];
+#pragma unroll
+  for (int j = 0; j < kExpExt; ++j) et[j] = ext_tab[lane * kExpExt + j];
+  double va[kExpSub], ve[kExpExt];
+#pragma unroll
+  for (int i = 0; i < kExpSub; ++i) va[i] = 0.0;
+#pragma unroll
+  for (int j = 0; j < kExpExt; ++j) ve[j] = 0.0;
+  // Which sensors leave Gram slots: one ballot per 32 sensors (no chain of dependent descriptor loads); this warp takes every
+  // kExpWarps-th of them.
+  int my_rank = 0;
+  for (int s0 = 0; s0 < n_sensors; s0 += 32) {
+    unsigned mask = __ballot_sync(0xffffffffu, s0 + lane < n_sensors && sensors[s0 + lane].gslots != nullptr);
+    while (mask) {
+      const int s = s0 + __ffs(mask) - 1;
+      mask &= mask - 1;
+      if ((my_rank++ % kExpWarps) != warp) continue;
+    const SensorDesc& sd = sensors[s];
+    const int f_begin = sd.seg_frame[g], f_end = sd.seg_frame[g + 1];
+    const int o_first = sd.seg_start[g], o_last = sd.seg_start[g + 1] - 1;
+    if (f_end == f_begin) continue;
+    const int lo = sd.gslot_base + f_begin + o_first / eval_tile(kCamera);
+    const int n = sd.gslot_base + f_end - 1 + o_last / eval_tile(kCamera) - lo + 1;
+    const int nc = sd.n_calib, calib_off = sd.calib_off;
+    const double* __restrict__ slots = sd.gslots + size_t(lo) * kGramSlot;
+    for (int k0 = 0; k0 < n; k0 += kExpBatch) {
+      const int kn = min(kExpBatch, n - k0);
+      __syncwarp();
+      {
+        // the slots of a camera are contiguous: one coalesced copy, all loads of a lane issued before its first store
+        constexpr int NL = (kExpBatch * (kGramSlot / 2) + 31) / 32;
+        double2 buf[NL];
+        const double2* __restrict__ src = reinterpret_cast<const double2*>(slots + size_t(k0) * kGramSlot);
+        const int tot = kn * (kGramSlot / 2);
+#pragma unroll
+        for (int i = 0; i < NL; ++i) buf[i] = src[min(lane + 32 * i, tot - 1)];
+#pragma unroll
+        for (int i = 0; i < NL; ++i) if (lane + 32 * i < tot) reinterpret_cast<double2*>(s_slot)[lane + 32 * i] = buf[i];
       }
+      __syncwarp();
+      // control points x control points + gradient
+      for (int k = 0; k < kn; ++k) {
+        const double* __restrict__ S = s_slot + k * kGramSlot;
+        if (S[kGramSlotFlag] == 0.0) continue;                  // unused slot (stale data)
+        const double* __restrict__ w = S + kGramSlotW;          // w[6] is the flag = 1.0: the weight of the gradient row
+        double wv[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) wv[a] = w[a];
+        const double g0 = S[lane];                              // entry `lane` of [g | r] x g: row lane / 6, column lane % 6
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+          for (int b = 0; b <= a; ++b) va[a * (a + 1) / 2 + b] += (wv[a] * wv[b]) * g0;
+#pragma unroll
+        for (int j = 0; j < kExpExt; ++j)
+          if (et[j] >= 0) ve[j] += w[et[j] >> 16] * w[(et[j] >> 8) & 255] * S[et[j] & 255];
+      }
+      // control points x calibration: entry e = lane + 32 j of Gc [16][6] (li = e / 6, p = e % 6), j < 3, for each a < 6
+      double vb[18];
+#pragma unroll
+      for (int j = 0; j < 18; ++j) vb[j] = 0.0;
+      for (int k = 0; k < kn; ++k) {
+        const double* __restrict__ S = s_slot + k * kGramSlot;
+        if (S[kGramSlotFlag] == 0.0) continue;
+        const double c0 = S[48 + lane], c1 = S[48 + 32 + lane], c2 = S[48 + 64 + lane];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) { const double wa = S[kGramSlotW + a]; vb[3 * a] += wa * c0; vb[3 * a + 1] += wa * c1; vb[3 * a + 2] += wa * c2; }
+      }
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int e = lane + 32 * j, li = e / 6, p6 = e - 6 * li;
+          if (li < nc) {
+            double* dst = segB + (size_t(gl) * kCpCols + 6 * a + p6) * N_c + calib_off + li;
+            *dst = k0 == 0 ? vb[3 * a + j] : *dst + vb[3 * a + j];   // more than kExpBatch slots of one camera in one segment: rare
+          }
+        }
+    }
+    }
+  }
+  // fixed-order combination of the warps' partials in two rounds through the (now free) staging area: warp w + 4 -> warp w, then the four sums
+  double* const s_part = smem;                                      // [kExpWarps / 2][kExpPart]
+  auto put = [&](double* dst, bool add) {
+#pragma unroll
+    for (int i = 0; i < kExpSub; ++i) dst[i * 36 + lane] = add ? dst[i * 36 + lane] + va[i] : va[i];
+#pragma unroll
+    for (int j = 0; j < kExpExt; ++j) if (et[j] >= 0) { const int d = ext_dst[lane * kExpExt + j]; dst[d] = add ? dst[d] + ve[j] : ve[j]; }
+  };
+  __syncthreads();
+  if (warp >= kExpWarps / 2) put(s_part + size_t(warp - kExpWarps / 2) * kExpPart, false);
+  __syncthreads();
+  if (warp < kExpWarps / 2) put(s_part + size_t(warp) * kExpPart, true);
+  __syncthreads();
+  for (int k = t; k < kExpPart; k += kExpThreads) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < kExpWarps / 2; ++w) v += s_part[size_t(w) * kExpPart + k];
+    if (k < kExpSub * 36) {
+      const int sub = k / 36, e = k - 36 * sub;
+      int a = 0;
+      while ((a + 1) * (a + 2) / 2 <= sub) ++a;
+      const int bb = sub - a * (a + 1) / 2, p6 = e / 6, q6 = e - 6 * p6;
+      const int I = 6 * a + p6, Jx = 6 * bb + q6;
+      if (Jx <= I) segA[(size_t(gl) * kCpCols + I) * kCpCols + Jx] = v;   // (upper part of a diagonal sub-block: nothing to write)
+    } else {
+      segG[size_t(gl) * kCpCols + (k - kExpSub * 36)] = v;
     }
   }
 }
 
 // Banded A (lower band, A(i,j) at Aband[i*36 + 35 - (i-j)]), dense border Bmat[6 n_cp][N_c] and the control-point part of
 // the gradient, from the per-segment partials of this rank's segments [g_lo, g_hi). Control point c belongs to segments c-5..c.
+// segA2 / segG2: the cameras' control-point partials from expand_gram_kernel (nullptr when only one of the two kernels ran).
 __global__ void __launch_bounds__(256) assemble_band_kernel(int n_cp, int g_lo, int g_hi, int N_c, const double* __restrict__ segA,
                                                             const double* __restrict__ segG, const double* __restrict__ segB,
+                                                            const double* __restrict__ segA2, const double* __restrict__ segG2,
                                                             double* __restrict__ Aband, double* __restrict__ Bmat, double* __restrict__ grad) {
   const long n = 6L * n_cp;
   const long nA = n * kCpCols, nB = n * N_c;
@@ -393,6 +360,7 @@ __global__ void __launch_bounds__(256) assemble_band_kernel(int n_cp, int g_lo, 
         const int ci = i / 6, cj = j / 6;
         const int g0 = max(ci - 5, g_lo), g1 = min(cj, g_hi - 1);
         for (int g = g0; g <= g1; ++g) s += segA[(size_t(g - g_lo) * kCpCols + (i - 6 * g)) * kCpCols + (j - 6 * g)];
+        if (segA2) for (int g = g0; g <= g1; ++g) s += segA2[(size_t(g - g_lo) * kCpCols + (i - 6 * g)) * kCpCols + (j - 6 * g)];
       }
       Aband[idx] = s;
     } else if (idx < nA + nB) {
@@ -409,18 +377,22 @@ __global__ void __launch_bounds__(256) assemble_band_kernel(int n_cp, int g_lo, 
       const int g0 = max(ci - 5, g_lo), g1 = min(ci, g_hi - 1);
       double s = 0.0;
       for (int g = g0; g <= g1; ++g) s += segG[size_t(g - g_lo) * kCpCols + (i - 6 * g)];
+      if (segG2) for (int g = g0; g <= g1; ++g) s += segG2[size_t(g - g_lo) * kCpCols + (i - 6 * g)];
       grad[i] = s;
     }
   }
 }
 
-// Calibration block C (dense N_c x N_c storage, symmetric fill) and calibration gradient: reduction over all segments in two
-// deterministic stages. Stage 1: grid = (entries / 32, kCalibSlices), blockDim = (32, 8): x = entry, (blockIdx.y, y) = segment slice;
-// partial[slice][entry]. Stage 2: one thread per entry sums the slices in a fixed order and scatters.
-struct CalibEntry { int src; int dst_row, dst_col; };   // src: offset in a segment's segC (or segGc when dst_col < 0)
+// Calibration block C (dense N_c x N_c storage, symmetric fill) and calibration gradient: reduction over all partials in two
+// deterministic stages. An entry sums `count` partials `stride` doubles apart, starting at offset `src` of one of three buffers:
+// kind 0 per-segment segC, kind 1 per-segment segGc (accumulate_kernel's sensors), kind 2 the per-CTA calibration tiles the sweep
+// left for the cameras whose Gram is formed there (SensorDesc::gcta). Stage 1: grid = (entries / 32, kCalibSlices), blockDim = (32, 8):
+// x = entry, (blockIdx.y, y) = slice of the partials; partial[slice][entry]. Stage 2: one thread per entry sums the slices in a fixed
+// order and scatters.
+struct CalibEntry { long src; int stride, count, kind; int dst_row, dst_col; };   // dst_col < 0: gradient entry dst_row
 constexpr int kCalibSlices = 16;
-__global__ void __launch_bounds__(256) assemble_calib_kernel(int n_seg, int N_c, int csz, int n_entries, const CalibEntry* __restrict__ entries,
-                                                             const double* __restrict__ segC, const double* __restrict__ segGc,
+__global__ void __launch_bounds__(256) assemble_calib_kernel(int n_entries, const CalibEntry* __restrict__ entries, const double* __restrict__ segC,
+                                                             const double* __restrict__ segGc, const double* __restrict__ gcta,
                                                              double* __restrict__ partial) {
   __shared__ double part[8][33];
   const int e = blockIdx.x * 32 + threadIdx.x;
@@ -428,8 +400,14 @@ __global__ void __launch_bounds__(256) assemble_calib_kernel(int n_seg, int N_c,
   double s = 0.0;
   if (e < n_entries) {
     const CalibEntry ce = entries[e];
-    if (ce.dst_col >= 0) { for (int g = g0; g < n_seg; g += gs) s += segC[size_t(g) * csz + ce.src]; }
-    else { for (int g = g0; g < n_seg; g += gs) s += segGc[size_t(g) * N_c + ce.src]; }
+    const double* __restrict__ base = (ce.kind == 0 ? segC : (ce.kind == 1 ? segGc : gcta)) + ce.src;
+    int g = g0;
+    for (; g + 3 * gs < ce.count; g += 4 * gs) {        // 4 independent loads in flight, summed in index order
+      const double v0 = base[size_t(g) * ce.stride], v1 = base[size_t(g + gs) * ce.stride], v2 = base[size_t(g + 2 * gs) * ce.stride],
+                   v3 = base[size_t(g + 3 * gs) * ce.stride];
+      s += v0; s += v1; s += v2; s += v3;
+    }
+    for (; g < ce.count; g += gs) s += base[size_t(g) * ce.stride];
   }
   part[threadIdx.y][threadIdx.x] = s;
   __syncthreads();

@@ -172,6 +172,9 @@ inline unsigned __ballot_sync(unsigned, int pred) {
   if (nlanes < 32) out &= (1u << nlanes) - 1u;
   return out;
 }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffs(unsigned v) { return __builtin_ffs(int(v)); }
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
 inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
 inline int __all_sync(unsigned m, int pred) {
   const int tid = ::cb2emul::tls().linear_tid, w = tid / 32;

@@ -54,13 +54,13 @@ def test_emulated_sweep_matches_oracle(emul_lib, oracle):
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("schur,chunk", [("cr", None), ("cr", "6"), ("band", None), ("band", "6"), ("cr+structured", None), ("cr+plainloop", None)])
+@pytest.mark.parametrize("schur,chunk", [("cr", None), ("cr", "6"), ("band", None), ("band", "6"), ("cr+jreread", None), ("cr+plainloop", None)])
 def test_emulated_lm_iterations_match_oracle(schur, chunk, emul_lib, oracle, monkeypatch):
     """Three LM iterations through every kernel: level 1 by block cyclic reduction (default) and by the chunked band factor,
     single chunk and two chunks (+ separator level)."""
-    if schur.endswith("+structured"):      # image-wise Kronecker accumulation of the camera rows (opt-in path of accumulate_kernel)
+    if schur.endswith("+jreread"):         # every sensor through accumulate_kernel (J re-read) instead of the sweep's compact Gram slots
         schur = schur.split("+")[0]
-        monkeypatch.setenv("CB2_ACC_STRUCTURED", "1")
+        monkeypatch.setenv("CB2_NO_SWEEP_GRAM", "1")
     if schur.endswith("+plainloop"):       # no speculative trial sweep, no deferred host round trip: the textbook two-sync LM loop
         schur = schur.split("+")[0]
         monkeypatch.setenv("CB2_NO_SPECULATIVE_SWEEP", "1")

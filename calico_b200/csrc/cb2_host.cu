@@ -404,8 +404,10 @@ struct cb2_problem {
   double* h_scal = nullptr;   // pinned
   double* h_param = nullptr;  // pinned: {radius, min_lm_diagonal, max_lm_diagonal} of the coming solve
   bool use_graphs = std::getenv("CB2_NO_GRAPHS") == nullptr;
+  bool graph_collectives = std::getenv("CB2_NO_NCCL_GRAPHS") == nullptr;
+  bool ne_shared_pending = false;   // multi-rank: the shared-row sums of the current normal equations ride in the next solve's collective
   struct GraphSlot { cudaGraphExec_t exec = nullptr; int64_t kernels = 0; };
-  GraphSlot g_solve[2], g_trial[2], g_normal[2];   // LM phases as CUDA graphs, one per parameter buffer (cur = 0 / 1)
+  GraphSlot g_solve[4], g_trial[2], g_normal[4];   // LM phases as CUDA graphs, one per parameter buffer (cur = 0 / 1) [+ 2: multi-rank variant with the shared-row sums deferred into the solve]
   cb2_stats stats{};
   PhaseTimer timer;
   KernelProfiler kprof;
@@ -427,15 +429,17 @@ struct cb2_problem {
 
   void drop_graphs() {
 #ifndef CB2_EMUL
-    for (auto* set : {g_solve, g_trial, g_normal}) for (int i = 0; i < 2; ++i) { if (set[i].exec) cudaGraphExecDestroy(set[i].exec); set[i] = GraphSlot{}; }
+    for (int i = 0; i < 4; ++i) { for (auto* set : {g_solve, g_normal}) { if (set[i].exec) cudaGraphExecDestroy(set[i].exec); set[i] = GraphSlot{}; } }
+    for (int i = 0; i < 2; ++i) { if (g_trial[i].exec) cudaGraphExecDestroy(g_trial[i].exec); g_trial[i] = GraphSlot{}; }
 #endif
   }
   // Runs `body` (kernel launches and memsets on `stream` only) as a CUDA graph: captured and instantiated on first use, replayed afterwards.
-  // Only single-GPU (no NCCL inside) and not while the per-kernel profiler is on.
+  // With several ranks the cross-rank sums inside the body are captured too (NCCL collectives are graph-capturable); CB2_NO_NCCL_GRAPHS=1
+  // keeps multi-rank runs on plain launches. Not while the per-kernel profiler is on.
   template <class F>
   void graphed(GraphSlot& slot, F&& body) {
 #ifndef CB2_EMUL
-    const bool graph = use_graphs && world == 1 && !kprof.on;
+    const bool graph = use_graphs && !kprof.on && (world == 1 || graph_collectives);
     if (graph && slot.exec) { CB2_CUDA(cudaGraphLaunch(slot.exec, stream)); stats.kernel_launches += slot.kernels; return; }
     const int64_t before = stats.kernel_launches;
     if (graph) { CB2_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal)); capturing = true; }
@@ -830,7 +834,7 @@ struct cb2_problem {
     d_Aband.alloc(size_t(n_a) * 36); d_Bmat.alloc(size_t(n_a) * std::max(N_c, 1)); d_Cmat.alloc(size_t(std::max(N_c, 1)) * std::max(N_c, 1));
     d_grad.alloc(n_tot); d_diag.alloc(n_tot); d_scaling.alloc(n_tot); d_dtil2.alloc(n_tot); d_ytil.alloc(n_tot);
     d_Aband.zero(stream); d_Bmat.zero(stream); d_grad.zero(stream); d_ytil.zero(stream);
-    if (world > 1) { d_gradG.alloc(n_tot); d_normbuf.alloc(size_t(3 + world)); }
+    if (world > 1) d_gradG.alloc(n_tot);
     rc = plan_schur();
     if (rc != CB2_OK) return rc;
     set_kernel_attributes();
@@ -917,7 +921,7 @@ struct cb2_problem {
     for (int c = 0; c < N_c; ++c) colidx.push_back(int(n_a) + c);
     d_rowidx.upload(rowidx); d_colidx.upload(colidx);
     d_shared_idx.upload(shared_idx);
-    d_shared_buf.alloc(2 * size_t(std::max(n_shared, 1)));
+    d_shared_buf.alloc(shared_buf_size(std::max(n_shared, 1), world));
     d_L1.alloc(use_cr ? 1 : Lsz); d_W1.alloc(Wsz); d_T1.alloc(Tsz); d_Dinv.alloc(Dsz + size_t(std::max(n2, 1)));
     for (int l = 0; l < PL; ++l) {
       BandSys& sy = h_l1[l];
@@ -950,7 +954,7 @@ struct cb2_problem {
     h_l2.ksplit = std::max(1, std::min((n2 + 63) / 64, (148 + nt2 * (nt2 + 1) / 2 - 1) / (nt2 * (nt2 + 1) / 2)));
     // The separator system and the calibration system live in ONE buffer: it is what the ranks sum (one allreduce per LM solve).
     const size_t szL2 = size_t(n2) * 60, szW2 = size_t(n2) * nbw2, szCw = size_t(N_c + 1) * (N_c + 1);
-    d_red.alloc(szL2 + szW2 + szCw + 1);
+    d_red.alloc(szL2 + szW2 + szCw + shared_buf_size(std::max(n_shared, 1), world) + 1);   // tail: the deferred shared-row sums (see launch_step)
     d_T2.alloc(size_t(h_l2.ksplit) * nbw2 * nbw2);
     h_l2.row_gidx = d_rowidx.p + row_off2; h_l2.col_gidx = d_colidx.p + col_off2;
     h_l2.L = d_red.p; h_l2.W = d_red.p + szL2; h_l2.T = d_T2.p; h_l2.Dinv = d_Dinv.p + Dsz;
@@ -1063,7 +1067,9 @@ struct cb2_problem {
   }
 
   // K1-K3 at x, then K4: normal equations, Hessian diagonal, gradient norms.
-  void launch_jacobian_and_normal_equations() {
+  void launch_jacobian_and_normal_equations(bool defer_shared_sums = false) {
+    const bool defer_shared = defer_shared_sums && world > 1;
+    ne_shared_pending = defer_shared;
     sweep_skipped = jac_point == cur;          // the trial pass that led to this point's acceptance was a full sweep (launch_trial)
     if (!sweep_skipped) {
       timer.begin(kPhJacobian, stream);
@@ -1080,7 +1086,7 @@ struct cb2_problem {
       stats.camera_kernel_bytes += jacobian_bytes_per_sweep(kCamera);
     }
     timer.begin(kPhNormal, stream);
-    graphed(g_normal[cur], [&] {
+    graphed(g_normal[cur + (defer_shared ? 2 : 0)], [&] {
     const int ns = int(sensors.size());
     const int nsl = g_hi - g_lo;
     if (nsl > 0) {
@@ -1116,24 +1122,37 @@ struct cb2_problem {
     }
     CB2_K(hess_diag_kernel, int(std::min<long>((n_tot + 255) / 256, 1024)), 256, 0, stream, n_a, N_c, d_Aband.p, d_Cmat.p, d_diag.p);
     if (world > 1) {
-      // Separator rows and calibration receive contributions from several ranks: sum their gradient and Hessian diagonal
-      // (needed for the gradient norms, the Jacobi scaling and the LM damping); d_grad itself stays rank-local.
+      // Separator rows and calibration receive contributions from several ranks (lmkernels: pack_shared_kernel). d_grad itself stays
+      // rank-local; gradG carries the sums on the shared rows. When the host does not wait for this point's gradient norms (deferred
+      // round trip, see minimize) the sums are NOT exchanged here: they ride in the tail of the next solve's collective (launch_step).
       CB2_CUDA(cudaMemcpyAsync(d_gradG.p, d_grad.p, sizeof(double) * n_tot, cudaMemcpyDeviceToDevice, stream));
-      CB2_K(pack_shared_kernel, (n_shared + 255) / 256, 256, 0, stream, n_shared, d_shared_idx.p, d_gradG.p, d_diag.p, d_shared_buf.p);
-      comm->allreduce_sum(d_shared_buf.p, 2 * size_t(n_shared), stream);
-      CB2_K(unpack_shared_kernel, (n_shared + 255) / 256, 256, 0, stream, n_shared, d_shared_idx.p, d_shared_buf.p, d_gradG.p, d_diag.p);
-    }
-    CB2_K(gradient_norm_kernel, 1, kLmThreads, 0, stream, n_a, gradG(), d_cp_own.p, rank == 0 ? 1 : 0, d_desc.p, d_state[cur].p, ns, d_scal.p);
-    if (world > 1) {   // cost / invalid / |g|^2 (sums) and |g|_inf (max, as per-rank slots) in ONE collective
-      CB2_K(pack_norm_scalars_kernel, 1, 64, 0, stream, d_scal.p, world, rank, d_normbuf.p);
-      comm->allreduce_sum(d_normbuf.p, size_t(3 + world), stream);
-      CB2_K(unpack_norm_scalars_kernel, 1, 32, 0, stream, d_normbuf.p, world, d_scal.p);
+      CB2_K(gradient_norm_kernel, 1, kLmThreads, 0, stream, n_a, d_grad.p, d_cp_own.p, 1, 0, 0, d_desc.p, d_state[cur].p, ns, d_scal.p);   // owned part
+      if (!defer_shared) {
+        CB2_K(pack_shared_kernel, (n_shared + 255) / 256, 256, 0, stream, n_shared, d_shared_idx.p, d_grad.p, d_diag.p, d_scal.p, world, rank, d_shared_buf.p);
+        comm->allreduce_sum(d_shared_buf.p, shared_buf_size(n_shared, world), stream);
+        CB2_K(unpack_shared_kernel, (n_shared + 255) / 256, 256, 0, stream, n_shared, d_shared_idx.p, d_shared_buf.p, world, d_gradG.p, d_diag.p, d_scal.p);
+        CB2_K(gradient_norm_kernel, 1, kLmThreads, 0, stream, n_a, d_gradG.p, d_cp_own.p, 0, 1, 1, d_desc.p, d_state[cur].p, ns, d_scal.p);   // + shared part
+      }
+    } else {
+      CB2_K(gradient_norm_kernel, 1, kLmThreads, 0, stream, n_a, d_grad.p, d_cp_own.p, 1, 1, 0, d_desc.p, d_state[cur].p, ns, d_scal.p);
     }
     });
     timer.end(kPhNormal, stream);
   }
 
   const double* gradG() const { return world > 1 ? d_gradG.p : d_grad.p; }   // gradient with cross-rank sums on the shared rows
+
+  // The LM loop ends before another solve would have carried the deferred shared-row sums: exchange them now (every rank takes this
+  // branch together: it depends on the iteration count and the radius only).
+  void finish_shared_sums() {
+    if (!ne_shared_pending || world <= 1) return;
+    ne_shared_pending = false;
+    const int ns = int(sensors.size());
+    CB2_K(pack_shared_kernel, (n_shared + 255) / 256, 256, 0, stream, n_shared, d_shared_idx.p, d_grad.p, d_diag.p, d_scal.p, world, rank, d_shared_buf.p);
+    comm->allreduce_sum(d_shared_buf.p, shared_buf_size(n_shared, world), stream);
+    CB2_K(unpack_shared_kernel, (n_shared + 255) / 256, 256, 0, stream, n_shared, d_shared_idx.p, d_shared_buf.p, world, d_gradG.p, d_diag.p, d_scal.p);
+    CB2_K(gradient_norm_kernel, 1, kLmThreads, 0, stream, n_a, d_gradG.p, d_cp_own.p, 0, 1, 1, d_desc.p, d_state[cur].p, ns, d_scal.p);
+  }
 
   // One LM linear solve + candidate point + candidate cost. Everything is enqueued; the caller syncs once.
   void launch_step(double radius, const cb2_options& opt) {
@@ -1145,7 +1164,9 @@ struct cb2_problem {
     CB2_CUDA(cudaMemcpyAsync(d_scal.p + kScRadius, h_param, 3 * sizeof(double), cudaMemcpyHostToDevice, stream));
     stats.h2d_bytes += 3 * sizeof(double);
     // The solve phase is ~25 small latency-bound kernels: replayed as ONE CUDA graph per parameter buffer.
-    graphed(g_solve[cur], [&] {
+    const bool tail = ne_shared_pending && world > 1;
+    ne_shared_pending = false;
+    graphed(g_solve[cur + (tail ? 2 : 0)], [&] {
     CB2_K(damping_kernel, blocks, 256, 0, stream, n_tot, d_diag.p, d_scaling.p, d_scal.p, d_dtil2.p);
     CB2_CUDA(cudaMemsetAsync(d_scal.p + kScSolveFail, 0, sizeof(double), stream));
     const int nbw1 = h_l1[0].nbw;
@@ -1178,7 +1199,17 @@ struct cb2_problem {
       CB2_K(level3_build_kernel, int(std::min<long>((tot3 * 8 + 255) / 256, 4096)), 256, 0, stream, d_l1.p, PL, n_a, N_c, d_Cmat.p, d_grad.p, red_Cw,
             d_rawdiag.p + std::max(h_l2.n, 1));
     }
-    if (world > 1 && red_count > 0) comm->allreduce_sum(d_red.p, red_count, stream);   // THE data-path collective of an LM iteration
+    if (world > 1) {
+      // THE data-path collective of an LM iteration: separator + calibration system [+ the deferred shared-row sums of the normal equations].
+      double* tailp = d_red.p + red_count;
+      if (tail) CB2_K(pack_shared_kernel, (n_shared + 255) / 256, 256, 0, stream, n_shared, d_shared_idx.p, d_grad.p, d_diag.p, d_scal.p, world, rank, tailp);
+      comm->allreduce_sum(d_red.p, red_count + (tail ? shared_buf_size(n_shared, world) : 0), stream);
+      if (tail) {
+        CB2_K(unpack_shared_kernel, (n_shared + 255) / 256, 256, 0, stream, n_shared, d_shared_idx.p, tailp, world, d_gradG.p, d_diag.p, d_scal.p);
+        CB2_K(gradient_norm_kernel, 1, kLmThreads, 0, stream, n_a, d_gradG.p, d_cp_own.p, 0, 1, 1, d_desc.p, d_state[cur].p, ns, d_scal.p);
+        CB2_K(damping_shared_kernel, (n_shared + 255) / 256, 256, 0, stream, n_shared, d_shared_idx.p, d_diag.p, d_scaling.p, d_scal.p, d_dtil2.p);
+      }
+    }
     if (h_l2.n > 0) {
       CB2_K(level2_damp_kernel, (h_l2.n + 255) / 256, 256, 0, stream, h_l2, d_dtil2.p);
       const size_t smem_f2 = factor_smem_bytes(60, h_l2.nbw);
@@ -1305,7 +1336,7 @@ struct cb2_problem {
       S.total_time = now_s() - t_start;
       return CB2_OK;
     }
-    imu_jac_point = -1; jac_point = -1; speculate_next = true;
+    imu_jac_point = -1; jac_point = -1; speculate_next = true; ne_shared_pending = false;
     double radius = opt.initial_trust_region_radius, decrease_factor = 2.0;
     double x_cost = 0, x_norm = 0, candidate_cost = 0, model_cost_change = 0, reference_cost = 0;
     int num_consecutive_invalid_steps = 0;
@@ -1360,7 +1391,7 @@ struct cb2_problem {
       if (opt.minimizer_progress_to_stdout)
         std::printf("% 4d % 8e   % 3.2e   % 3.2e  % 3.2e  % 3.2e % 3.2e     % 4d   % 3.2e   % 3.2e\n", it.iteration, it.cost, it.cost_change,
                     it.gradient_max_norm, it.step_norm, it.relative_decrease, it.trust_region_radius, 1, it.iteration_time, now_s() - t_start);
-      if (pending_grad && (it.iteration >= opt.max_num_iterations || radius <= opt.min_trust_region_radius)) { sync_scalars(); resolve_pending_gradient(); }
+      if (pending_grad && (it.iteration >= opt.max_num_iterations || radius <= opt.min_trust_region_radius)) { finish_shared_sums(); sync_scalars(); resolve_pending_gradient(); }
       if (it.iteration >= opt.max_num_iterations) { S.termination_type = CB2_NO_CONVERGENCE; msg("Maximum number of iterations reached. Number of iterations: %.0f.", it.iteration); break; }
       if (!pending_grad && it.step_is_successful && it.gradient_max_norm <= opt.gradient_tolerance) {
         S.termination_type = CB2_CONVERGENCE; msg("Gradient tolerance reached. Gradient max norm: %e <= %e", it.gradient_max_norm, opt.gradient_tolerance); break;
@@ -1434,7 +1465,7 @@ struct cb2_problem {
         if (defer_normal_sync && jac_point == cur && !opt.minimizer_progress_to_stdout) {
           // The trial pass was a full sweep of this point: only the normal equations remain, and nothing the host must decide before the
           // next solve depends on them except the gradient-tolerance test, which is applied one round trip later (see above).
-          launch_jacobian_and_normal_equations();
+          launch_jacobian_and_normal_equations(/*defer_shared_sums=*/true);
           x_cost = candidate_cost;
           it.cost = x_cost;
           pending_grad = true;

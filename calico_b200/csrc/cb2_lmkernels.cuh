@@ -58,10 +58,12 @@ CB2_D void block_reduce(double (&v)[NV], double* sh) {
   }
 }
 
-// gradient_max_norm / gradient_norm^2 = |x - Plus(x, -g)|_inf / _2^2 over the part of the reduced parameter vector this rank
-// counts (ambient coordinates): owned control points everywhere, shared control points and calibration where count_shared.
+// gradient_max_norm / gradient_norm^2 = |x - Plus(x, -g)|_inf / _2^2 (ambient coordinates) over a part of the reduced parameter vector:
+// count_owned: the control points this rank owns; count_shared: the separator control points and the calibration blocks (whose gradient
+// entries are sums over the ranks). combine: fold the result into what scal[kScGradSq / kScGradMax] already hold (multi-rank: the
+// cross-rank sum / maximum of the ranks' owned parts) instead of overwriting them.
 __global__ void __launch_bounds__(kLmThreads) gradient_norm_kernel(long n_a, const double* __restrict__ grad, const unsigned char* __restrict__ cp_own,
-                                                                   int count_shared, const SensorDesc* __restrict__ sensors,
+                                                                   int count_owned, int count_shared, int combine, const SensorDesc* __restrict__ sensors,
                                                                    const SensorState* __restrict__ states, int n_sensors, double* __restrict__ scal) {
   __shared__ double sh[32];
   const int t = threadIdx.x;
@@ -72,7 +74,7 @@ __global__ void __launch_bounds__(kLmThreads) gradient_norm_kernel(long n_a, con
     for (int u = 0; u < 4; ++u) { const long i = min(i0 + long(u) * kLmThreads, n_a - 1); g[u] = grad[i]; own[u] = cp_own[i / 6]; }
 #pragma unroll
     for (int u = 0; u < 4; ++u)
-      if (i0 + long(u) * kLmThreads < n_a && (own[u] == kCpOwned || (own[u] == kCpShared && count_shared))) { mx = fmax(mx, fabs(g[u])); sq += g[u] * g[u]; }
+      if (i0 + long(u) * kLmThreads < n_a && ((own[u] == kCpOwned && count_owned) || (own[u] == kCpShared && count_shared))) { mx = fmax(mx, fabs(g[u])); sq += g[u] * g[u]; }
   }
   if (count_shared) for (int s = t; s < n_sensors; s += kLmThreads) {
     const SensorDesc& sd = sensors[s];
@@ -91,7 +93,10 @@ __global__ void __launch_bounds__(kLmThreads) gradient_norm_kernel(long n_a, con
   double vs[1] = {sq}, vm[1] = {mx};
   block_reduce<1, false>(vs, sh);
   block_reduce<1, true>(vm, sh);
-  if (t == 0) { scal[kScGradMax] = vm[0]; scal[kScGradSq] = vs[0]; }
+  if (t == 0) {
+    if (combine) { vm[0] = fmax(vm[0], scal[kScGradMax]); vs[0] += scal[kScGradSq]; }
+    scal[kScGradMax] = vm[0]; scal[kScGradSq] = vs[0];
+  }
 }
 
 // Candidate point x_cand = Plus(x, -ytil) (owned + shared control points and every non-constant sensor block), with the part
@@ -173,31 +178,45 @@ __global__ void __launch_bounds__(kLmThreads) apply_step_kernel(long n_a, const 
   }
 }
 
-// Multi-rank glue: pack / unpack the entries of (gradient, Hessian diagonal) that several ranks contribute to — separator rows
-// and calibration — around one cross-rank sum. idx[i] = global unknown index of packed entry i.
-__global__ void __launch_bounds__(256) pack_shared_kernel(int n, const int* __restrict__ idx, const double* __restrict__ grad,
-                                                          const double* __restrict__ diag, double* __restrict__ buf) {
+// Multi-rank glue. Separator rows and calibration receive contributions from several ranks: their gradient and Hessian-diagonal entries
+// (needed for the gradient norms, the Jacobi scaling and the LM damping), the cost / failure count of the sweep and the ranks' owned parts
+// of the gradient norms travel in ONE buffer through one cross-rank sum:
+//   buf = [grad(idx[0..n)) | diag(idx[0..n)) | cost, invalid, owned |g|^2 | one slot per rank holding that rank's owned |g|_inf, zero elsewhere].
+// idx[i] = global unknown index of shared entry i. After the sum every rank takes the maximum of the rank slots.
+CB2_HD constexpr size_t shared_buf_size(int n_shared, int world) { return 2 * size_t(n_shared) + 3 + size_t(world); }
+__global__ void __launch_bounds__(256) pack_shared_kernel(int n, const int* __restrict__ idx, const double* __restrict__ grad, const double* __restrict__ diag,
+                                                          const double* __restrict__ scal, int world, int rank, double* __restrict__ buf) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { buf[i] = grad[idx[i]]; buf[n + i] = diag[idx[i]]; }
+  if (blockIdx.x == 0) {
+    double* tail = buf + 2 * size_t(n);
+    const int t = threadIdx.x;
+    if (t < 3) tail[t] = scal[kScCost + t];             // kScCost, kScInvalid, kScGradSq are consecutive
+    for (int r = t; r < world; r += blockDim.x) tail[3 + r] = r == rank ? scal[kScGradMax] : 0.0;
+  }
 }
-__global__ void __launch_bounds__(256) unpack_shared_kernel(int n, const int* __restrict__ idx, const double* __restrict__ buf,
-                                                            double* __restrict__ grad, double* __restrict__ diag) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { grad[idx[i]] = buf[i]; diag[idx[i]] = buf[n + i]; }
-}
-// One SUM allreduce instead of a sum and a max: buf = [cost, invalid, gradient_norm^2 | one slot per rank holding that rank's local
-// gradient max norm, zero elsewhere]; after the sum every rank takes the maximum of the rank slots.
-__global__ void pack_norm_scalars_kernel(const double* __restrict__ scal, int world, int rank, double* __restrict__ buf) {
-  const int t = threadIdx.x;
-  if (t < 3) buf[t] = scal[kScCost + t];
-  for (int r = t; r < world; r += blockDim.x) buf[3 + r] = r == rank ? scal[kScGradMax] : 0.0;
-}
-__global__ void unpack_norm_scalars_kernel(const double* __restrict__ buf, int world, double* __restrict__ scal) {
-  if (threadIdx.x == 0) {
-    for (int q = 0; q < 3; ++q) scal[kScCost + q] = buf[q];
+// gradG = this rank's gradient with the summed entries on the shared rows; diag likewise; the scalar sums back into scal.
+__global__ void __launch_bounds__(256) unpack_shared_kernel(int n, const int* __restrict__ idx, const double* __restrict__ buf, int world,
+                                                            double* __restrict__ gradG, double* __restrict__ diag, double* __restrict__ scal) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { gradG[idx[i]] = buf[i]; diag[idx[i]] = buf[n + i]; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const double* tail = buf + 2 * size_t(n);
+    for (int q = 0; q < 3; ++q) scal[kScCost + q] = tail[q];
     double m = 0.0;
-    for (int r = 0; r < world; ++r) m = fmax(m, buf[3 + r]);
+    for (int r = 0; r < world; ++r) m = fmax(m, tail[3 + r]);
     scal[kScGradMax] = m;
   }
 }
+// LM damping of the shared rows once their summed diagonal is known (see damping_kernel).
+__global__ void __launch_bounds__(256) damping_shared_kernel(int n, const int* __restrict__ idx, const double* __restrict__ diag, const double* __restrict__ scaling,
+                                                             const double* __restrict__ scal, double* __restrict__ dtil2) {
+  const double radius = scal[kScRadius], lo = scal[kScLmLo], hi = scal[kScLmHi];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int j = idx[i];
+    const double s2 = scaling[j] * scaling[j];
+    dtil2[j] = fmin(fmax(diag[j] * s2, lo), hi) / (radius * s2);
+  }
+}
+
 // Sensor::UpdateResiduals: residuals from the device order (sorted by spline segment, this rank's shard) back into the caller's observation
 // order. perm[i] = original index of sorted position i; rfull / vfull were zeroed (outliers and other ranks' observations keep 0).
 __global__ void __launch_bounds__(256) scatter_residuals_kernel(int n_active, int m, const int* __restrict__ perm, const double* __restrict__ r,

@@ -35,6 +35,9 @@ constexpr int kCrLc = 32;           // row stride of the finished factor's copy 
 CB2_HD int cr_row_stride(int nbw) { const int M = 2 * kCrB + nbw; return ((M + 7) / 8 * 8 - 4 + 15) / 16 * 16 + 4; }   // >= M rounded to 8, == 4 mod 16
 CB2_HD size_t cr_smem_bytes(int nbw) { return (size_t(32) * cr_row_stride(nbw) + size_t(kCrB) * (kCrLs + kCrLc) + 34 + (nbw + 1) / 2) * sizeof(double); }
 CB2_HD size_t cr_u_size(int nbw) { return size_t(2 * kCrB) * (2 * kCrB + nbw); }
+// Staging area of the TMA load path of the non-first levels: [UL rows 30..59 | UR rows 0..29 | border rows of the block | diagonal block].
+CB2_HD size_t cr_stage_doubles(int nbw) { return size_t(2 * kCrB) * (2 * kCrB + nbw) + size_t(kCrB) * nbw + size_t(kCrB) * kCrB; }
+CB2_HD size_t cr_smem_bytes_tma(int nbw) { return (cr_smem_bytes(nbw) + 15) / 16 * 16 + cr_stage_doubles(nbw) * sizeof(double); }
 CB2_HD int cr_levels(int nblk) { int l = 0; while (((nblk + (1 << l) - 1) >> l) > 1) ++l; return l + 1; }
 
 #if defined(CB2_CR_CLOCKS) && !defined(CB2_EMUL)
@@ -59,7 +62,7 @@ template <bool kFirst>
 __global__ void __launch_bounds__(kCrThreads, (kFirst ? 2 : 1)) cr_level_kernel(const BandSys* __restrict__ systems, int level, long n_a, int N_c,
                                                              const double* __restrict__ Aband, const double* __restrict__ Bmat,
                                                              const double* __restrict__ Cmat, const double* __restrict__ grad,
-                                                             const double* __restrict__ dtil2, double* __restrict__ scal) {
+                                                             const double* __restrict__ dtil2, double* __restrict__ scal, int use_tma) {
   const BandSys sy = systems[blockIdx.y];
   const int stride = 1 << level;
   const int j = blockIdx.x, i = j * stride;
@@ -112,6 +115,47 @@ __global__ void __launch_bounds__(kCrThreads, (kFirst ? 2 : 1)) cr_level_kernel(
     return Aband + hi * kCpCols + (kCpCols - 1 - (ok ? d : 0));
   };
   // ---- 1. state of the block ----
+  // Non-first levels, TMA path (when the staging area fits beside the working set): everything the block needs is FOUR contiguous pieces of
+  // the previous level's output — rows 30..59 of the left update slot, rows 0..29 of the right one, the block's border rows and its diagonal
+  // block — fetched by four bulk asynchronous copies (cp.async.bulk + mbarrier: no registers, no per-element address arithmetic) and
+  // combined from shared memory. The slot rows carry the same column structure [E | F | border] as the working tile X.
+  const bool tma = !kFirst && use_tma != 0;
+  double* stA = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(dinv + 32) + (size_t(nbw + 1) / 2) * 8 + 15) & ~uintptr_t(15));
+  double* stB = stA + size_t(kCrB) * UW;
+  double* stC = stB + size_t(kCrB) * UW;
+  double* stD = stC + size_t(kCrB) * nbw;
+  __shared__ __align__(8) unsigned long long s_bar;
+  if (tma) {
+    if (t == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (t == 0) {
+      const unsigned bU = unsigned(sizeof(double) * kCrB * UW), bB = unsigned(sizeof(double) * kCrB * nbw), bD = unsigned(sizeof(double) * kCrB * kCrB);
+      mbar_expect_tx(&s_bar, (UL ? bU : 0u) + (UR ? bU : 0u) + bB + bD);
+      if (UL) bulk_g2s(stA, UL + size_t(kCrB) * UW, bU, &s_bar);
+      if (UR) bulk_g2s(stB, UR, bU, &s_bar);
+      bulk_g2s(stC, crBd, bB, &s_bar);
+      bulk_g2s(stD, crD, bD, &s_bar);
+    }
+    mbar_wait(&s_bar, 0);
+    for (int e = t; e < kCrB * kCrB; e += kCrThreads) {
+      const int r = e / kCrB, c = e - r * kCrB;
+      Dm[r * kCrLs + c] = stD[e] - (UL ? stA[size_t(r) * UW + kCrB + c] : 0.0) - (UR ? stB[size_t(r) * UW + c] : 0.0);
+    }
+    for (int e = t; e < kCrB * nbw; e += kCrThreads) {
+      const int r = e / nbw, c = e - r * nbw;
+      X[r * XS + 2 * kCrB + c] = stC[e] - (UL ? stA[size_t(r) * UW + 2 * kCrB + c] : 0.0) - (UR ? stB[size_t(r) * UW + 2 * kCrB + c] : 0.0);
+    }
+    if (elim) {
+      // couplings to the active neighbours: E = minus the E-part of the left slot's rows, F = minus the F-part of the right slot's rows
+      // (the 60 x 60 corner of a slot is symmetric: U[r][30 + c] == U[30 + c][r] bit for bit)
+      for (int e = t; e < kCrB * 2 * kCrB; e += kCrThreads) {
+        const int r = e / (2 * kCrB), c = e - r * (2 * kCrB);
+        const bool left = c < kCrB;
+        const double v = left ? ((has_a && UL) ? -stA[size_t(r) * UW + c] : 0.0) : ((has_b && UR) ? -stB[size_t(r) * UW + c] : 0.0);
+        X[r * XS + c] = v;
+      }
+    }
+  } else {
   cr_batched(kCrB * kCrB, t, [&](int e) -> double {
     const int r = e / kCrB, c = e - r * kCrB;
     if (kFirst) {
@@ -144,6 +188,7 @@ __global__ void __launch_bounds__(kCrThreads, (kFirst ? 2 : 1)) cr_level_kernel(
       return crBd[e] - ULz[size_t(kCrB + e / nbw) * UW + 2 * kCrB + e % nbw] - URz[size_t(e / nbw) * UW + 2 * kCrB + e % nbw];
     }, [&](int e, double v) { const int r = e / nbw; X[r * XS + 2 * kCrB + (e - r * nbw)] = v; });
   }
+  }
   if (!elim) {
     __syncthreads();
     for (int e = t; e < kCrB * kCrB; e += kCrThreads) sy.crD[size_t(i) * (kCrB * kCrB) + e] = Dm[(e / kCrB) * kCrLs + e % kCrB];
@@ -151,7 +196,7 @@ __global__ void __launch_bounds__(kCrThreads, (kFirst ? 2 : 1)) cr_level_kernel(
     return;
   }
   // couplings to the active neighbours: E = A(i, a) (rows of i, columns of a), F = A(i, b)
-  cr_batched(kCrB * 2 * kCrB, t, [&](int e) -> double {
+  if (!tma) cr_batched(kCrB * 2 * kCrB, t, [&](int e) -> double {
     const int r = e / (2 * kCrB), c = e - r * (2 * kCrB);
     const bool left = c < kCrB;
     const int cb = left ? c : c - kCrB;

@@ -57,6 +57,55 @@ constexpr int kGramSlot = 3 * 48 + 8;
 constexpr int kGramSlotW = 3 * 48, kGramSlotFlag = 3 * 48 + 6;
 constexpr int kGramCta = 3 * 64 + 16;
 
+// ---- TMA (bulk asynchronous copy engine) 1-D global -> shared copies, completion tracked by an mbarrier in shared memory ----
+// cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes (SASS UBLKCP): one thread issues the copy of a CONTIGUOUS block
+// (16-byte aligned address and size), the data lands in shared memory without passing through registers, and every thread that
+// needs it waits on the barrier's phase. The emulation build copies synchronously.
+CB2_D void mbar_init(unsigned long long* bar, int arrivals) {
+#if !defined(CB2_EMUL)
+  const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(arrivals));
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+#else
+  (void)bar; (void)arrivals;
+#endif
+}
+CB2_D void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+#if !defined(CB2_EMUL)
+  const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(a), "r"(bytes) : "memory");
+#else
+  (void)bar; (void)bytes;
+#endif
+}
+CB2_D void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+#if !defined(CB2_EMUL)
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(dst_smem)), a = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(d), "l"(src_gmem), "r"(bytes), "r"(a) : "memory");
+#else
+  (void)bar;
+  const unsigned char* s = static_cast<const unsigned char*>(src_gmem);
+  unsigned char* d = static_cast<unsigned char*>(dst_smem);
+  for (unsigned i = 0; i < bytes; ++i) d[i] = s[i];
+#endif
+}
+CB2_D void mbar_wait(unsigned long long* bar, unsigned parity) {
+#if !defined(CB2_EMUL)
+  const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(a), "r"(parity) : "memory");
+#else
+  (void)bar; (void)parity;
+#endif
+}
+
 // D(8x8) += A(8x4) B(4x8) in FP64 on the tensor pipe (mma.sync.m8n8k4.f64, SASS DMMA). Lane l holds a = A[l / 4][l % 4],
 // b = B[l % 4][l / 4], c0, c1 = D[l / 4][2 (l % 4) + {0, 1}].
 CB2_D void dmma_8x8x4(double& c0, double& c1, double a, double b) {

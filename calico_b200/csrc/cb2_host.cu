@@ -390,6 +390,7 @@ struct cb2_problem {
   // level 1 by block cyclic reduction (cb2_cr.cuh): the default; CB2_SCHUR=band selects the chunked left-to-right band factor
   bool use_cr = true;
   int cr_nlevels = 0, cr_max_nblk = 0;
+  bool cr_tma = false;              // non-first levels fetch their state with TMA bulk copies (cb2_cr.cuh)
   DevBuf<double> d_crD, d_crBd, d_crU, d_crWef, d_crL;
   int cur = 0;   // which of the two parameter buffers holds x
   size_t smem_eval[3] = {0, 0, 0};
@@ -989,7 +990,8 @@ struct cb2_problem {
     for (const auto& sy : h_l1) max_n1 = std::max(max_n1, sy.n);
     const int nbw1 = h_l1[0].nbw, nbw2 = h_l2.nbw;
     if (gram_dmma1) set(border_gram_dmma_kernel, gram_smem_bytes(nbw1));
-    if (use_cr) { set(cr_level_kernel<true>, cr_smem_bytes(nbw1)); set(cr_level_kernel<false>, cr_smem_bytes(nbw1)); }
+    cr_tma = use_cr && std::getenv("CB2_NO_TMA") == nullptr && cr_smem_bytes_tma(nbw1) <= 227 * 1024;   // staging area beside the working set
+    if (use_cr) { set(cr_level_kernel<true>, cr_smem_bytes(nbw1)); set(cr_level_kernel<false>, cr_tma ? cr_smem_bytes_tma(nbw1) : cr_smem_bytes(nbw1)); }
     else set(band_factor_kernel<6>, factor_smem_bytes(36, nbw1));
     set(band_factor_kernel<10>, factor_smem_bytes(60, nbw2));
     set(reduced_solve_kernel, size_t(N_c + 1) * (kRedPanel + 1) * 8);
@@ -1177,8 +1179,8 @@ struct cb2_problem {
       const size_t smem_cr = cr_smem_bytes(nbw1);
       for (int lv = 0; lv < cr_nlevels; ++lv) {
         const int nact = (cr_max_nblk + (1 << lv) - 1) >> lv;
-        if (lv == 0) CB2_K((cr_level_kernel<true>), dim3(nact, PL), kCrThreads, smem_cr, stream, d_l1.p, lv, n_a, N_c, d_Aband.p, d_Bmat.p, d_Cmat.p, d_grad.p, d_dtil2.p, d_scal.p);
-        else CB2_K((cr_level_kernel<false>), dim3(nact, PL), kCrThreads, smem_cr, stream, d_l1.p, lv, n_a, N_c, d_Aband.p, d_Bmat.p, d_Cmat.p, d_grad.p, d_dtil2.p, d_scal.p);
+        if (lv == 0) CB2_K((cr_level_kernel<true>), dim3(nact, PL), kCrThreads, smem_cr, stream, d_l1.p, lv, n_a, N_c, d_Aband.p, d_Bmat.p, d_Cmat.p, d_grad.p, d_dtil2.p, d_scal.p, 0);
+        else CB2_K((cr_level_kernel<false>), dim3(nact, PL), kCrThreads, cr_tma ? cr_smem_bytes_tma(nbw1) : smem_cr, stream, d_l1.p, lv, n_a, N_c, d_Aband.p, d_Bmat.p, d_Cmat.p, d_grad.p, d_dtil2.p, d_scal.p, cr_tma ? 1 : 0);
       }
     } else {
       CB2_K(gather_level1_kernel, dim3(std::max(1, std::min(64, (max_n1 * (36 + nbw1) + 255) / 256)), PL), 256, 0, stream, d_l1.p, n_a, N_c, d_Aband.p,

@@ -229,6 +229,127 @@ __global__ void __launch_bounds__(256) scatter_residuals_kernel(int n_active, in
   }
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// Freed world-model blocks (world_model.cpp:40-77: RigidBody::world_pose_is_constant / model_definition_is_constant = false). The rigid
+// body pose (quaternion with the left-multiplicative half-angle tangent of ceres::EigenQuaternionManifold + translation) and its model
+// points become unknowns appended to the calibration vector: body b: u_rot = body_u[2 b], u_trans = body_u[2 b + 1]; world point p:
+// pt_u[p]; -1 = constant. World points p_w = R_wm p_m + t_wm are recomputed from the current values (one table per parameter buffer).
+// ----------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) world_points_kernel(int n_points, const int* __restrict__ pt_body, const double* __restrict__ body_q,
+                                                           const double* __restrict__ body_t, const double* __restrict__ pm, double* __restrict__ pw) {
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_points; p += gridDim.x * blockDim.x) {
+    const int b = pt_body[p];
+    const M3 R = quat_matrix(Q4{body_q[4 * b], body_q[4 * b + 1], body_q[4 * b + 2], body_q[4 * b + 3]});
+    const V3 v = R * v3(pm[3 * p], pm[3 * p + 1], pm[3 * p + 2]);
+    pw[3 * p] = v.x + body_t[3 * b]; pw[3 * p + 1] = v.y + body_t[3 * b + 1]; pw[3 * p + 2] = v.z + body_t[3 * b + 2];
+  }
+}
+
+// Normal-equation contributions of the world unknowns of one camera's residual blocks, from the stored (robustified) Jacobian rows:
+//   d r / d p_w = - sum_i J[., 6 i + 3 .. 6 i + 5]   (p_w enters the residual only through p_w - t_wr; the basis weights sum to one), then
+//   d r / d t_wm = d r / d p_w,   d r / d delta_wm = 2 (v x d) per row with v = p_w - t_wm (left-multiplicative half-angle tangent),
+//   d r / d p_m = (d r / d p_w) R_wm.
+// Every product with a world column — against the control points of the block's segment, the camera's calibration columns, the other
+// world columns and the residual — is ADDED to the assembled Bmat / Cmat / gradient (after assemble_*_kernel wrote them). The pose columns
+// are shared by all observations of a body: a CTA sums them in shared memory (shared-memory atomics) and flushes once; the point columns go
+// straight to global atomics. Floating-point atomics make the summation order — and so the last bits of these entries — run-dependent:
+// this optional path trades the bitwise repeatability of the rest of the pipeline for simplicity.
+constexpr int kWorldMaxSeg = 8;    // spline segments one 128-observation tile may span in the shared-memory path (more: direct atomics)
+__global__ void __launch_bounds__(128) world_normal_kernel(const SensorDesc* __restrict__ sensors, const EvalTile* __restrict__ tiles, long n_a, int N_c,
+                                                           const int* __restrict__ pt_body, const int* __restrict__ body_u, const int* __restrict__ pt_u,
+                                                           const double* __restrict__ body_q, const double* __restrict__ body_t,
+                                                           const double* __restrict__ pw, double* __restrict__ Bmat, double* __restrict__ Cmat,
+                                                           double* __restrict__ grad) {
+  constexpr int kRow = 1 + 6 + kMaxCalib + kWorldMaxSeg * kCpCols;      // per pose column: gradient | pose columns | calibration | cp of up to 8 segments
+  __shared__ double s_acc[6 * kRow];
+  __shared__ int s_home[2];                                             // body and first segment of the tile's first observation
+  const EvalTile tl = tiles[blockIdx.x];
+  const SensorDesc& sd = sensors[tl.sensor];
+  const int t = threadIdx.x;
+  for (int e = t; e < 6 * kRow; e += blockDim.x) s_acc[e] = 0.0;
+  if (t == 0) { const long o0 = tl.start; s_home[0] = pt_body[sd.pt[o0]]; s_home[1] = sd.seg[o0]; }
+  __syncthreads();
+  const int home_b = s_home[0], seg0 = s_home[1];
+  const int jw = sd.jw, njc = sd.n_jcal;
+  if (t < tl.count) {
+    const long o = long(tl.start) + t;
+    const int p = sd.pt[o], b = pt_body[p], seg = sd.seg[o];
+    int uw[9];
+    uw[0] = uw[1] = uw[2] = body_u[2 * b]; uw[3] = uw[4] = uw[5] = body_u[2 * b + 1]; uw[6] = uw[7] = uw[8] = pt_u[p];
+#pragma unroll
+    for (int a = 0; a < 9; ++a) uw[a] = uw[a] < 0 ? -1 : uw[a] + a % 3;
+    if (uw[0] >= 0 || uw[3] >= 0 || uw[6] >= 0) {
+      const double* J0 = sd.J + size_t(o) * 2 * jw;
+      const double* J1 = J0 + jw;
+      const double r0 = sd.r[2 * o], r1 = sd.r[2 * o + 1];
+      double d0[3] = {0, 0, 0}, d1[3] = {0, 0, 0};
+      for (int i = 0; i < kK; ++i) for (int j = 0; j < 3; ++j) { d0[j] -= J0[6 * i + 3 + j]; d1[j] -= J1[6 * i + 3 + j]; }
+      const M3 R = quat_matrix(Q4{body_q[4 * b], body_q[4 * b + 1], body_q[4 * b + 2], body_q[4 * b + 3]});
+      const V3 v = v3(pw[3 * p] - body_t[3 * b], pw[3 * p + 1] - body_t[3 * b + 1], pw[3 * p + 2] - body_t[3 * b + 2]);
+      double w0[9], w1[9];                               // world columns of the two residual rows: [rotation 3 | translation 3 | point 3]
+      {
+        const V3 c0 = cross(v, v3(d0[0], d0[1], d0[2])), c1 = cross(v, v3(d1[0], d1[1], d1[2]));
+        w0[0] = 2.0 * c0.x; w0[1] = 2.0 * c0.y; w0[2] = 2.0 * c0.z; w1[0] = 2.0 * c1.x; w1[1] = 2.0 * c1.y; w1[2] = 2.0 * c1.z;
+        for (int j = 0; j < 3; ++j) {
+          w0[3 + j] = d0[j]; w1[3 + j] = d1[j];
+          w0[6 + j] = d0[0] * R.m[j] + d0[1] * R.m[3 + j] + d0[2] * R.m[6 + j];
+          w1[6 + j] = d1[0] * R.m[j] + d1[1] * R.m[3 + j] + d1[2] * R.m[6 + j];
+        }
+      }
+      const int ds = seg - seg0;
+      const bool in_smem = b == home_b && ds >= 0 && ds < kWorldMaxSeg;
+      for (int a = 0; a < 9; ++a) {
+        if (uw[a] < 0) continue;
+        const bool sm = in_smem && a < 6;
+        double* row = s_acc + a * kRow;                  // only used when sm
+        auto add = [&](int slot, double* gptr, double val) { if (sm) atomicAdd(row + slot, val); else atomicAdd(gptr, val); };
+        add(0, grad + n_a + uw[a], w0[a] * r0 + w1[a] * r1);
+        for (int c = 0; c <= a; ++c) {                   // world x world (lower triangle within the block's own 9 columns)
+          if (uw[c] < 0) continue;
+          const double val = w0[a] * w0[c] + w1[a] * w1[c];
+          if (sm && c < 6) atomicAdd(row + 1 + c, val);
+          else {
+            atomicAdd(Cmat + size_t(uw[a]) * N_c + uw[c], val);
+            if (c != a) atomicAdd(Cmat + size_t(uw[c]) * N_c + uw[a], val);
+          }
+        }
+        for (int j = 0; j < njc; ++j) {                  // world x the camera's calibration columns
+          const double val = w0[a] * J0[kCpCols + j] + w1[a] * J1[kCpCols + j];
+          const int uc = sd.calib_off + sd.junk[j];
+          if (sm) atomicAdd(row + 7 + j, val);
+          else { atomicAdd(Cmat + size_t(uw[a]) * N_c + uc, val); atomicAdd(Cmat + size_t(uc) * N_c + uw[a], val); }
+        }
+        for (int c = 0; c < kCpCols; ++c) {              // control points of the block's segment x world
+          const double val = w0[a] * J0[c] + w1[a] * J1[c];
+          if (sm) atomicAdd(row + 7 + kMaxCalib + ds * kCpCols + c, val);
+          else atomicAdd(Bmat + (size_t(6) * seg + c) * N_c + uw[a], val);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // flush the tile's pose sums
+  const int ur = body_u[2 * home_b], ut = body_u[2 * home_b + 1];
+  for (int e = t; e < 6 * kRow; e += blockDim.x) {
+    const double val = s_acc[e];
+    if (val == 0.0) continue;
+    const int a = e / kRow, k = e - a * kRow;
+    const int ua = (a < 3 ? ur : ut) + a % 3;
+    if (k == 0) atomicAdd(grad + n_a + ua, val);
+    else if (k < 7) {
+      const int c = k - 1, uc = (c < 3 ? ur : ut) + c % 3;
+      atomicAdd(Cmat + size_t(ua) * N_c + uc, val);
+      if (c != a) atomicAdd(Cmat + size_t(uc) * N_c + ua, val);
+    } else if (k < 7 + kMaxCalib) {
+      const int uc = sd.calib_off + sd.junk[k - 7];
+      atomicAdd(Cmat + size_t(ua) * N_c + uc, val); atomicAdd(Cmat + size_t(uc) * N_c + ua, val);
+    } else {
+      const int q = k - 7 - kMaxCalib, ds = q / kCpCols, c = q - ds * kCpCols;
+      atomicAdd(Bmat + (size_t(6) * (seg0 + ds) + c) * N_c + ua, val);
+    }
+  }
+}
+
 // Final control-point exchange: keep what this rank is responsible for, zero the rest, then sum across ranks.
 __global__ void __launch_bounds__(256) mask_ctrl_kernel(long n_a, const unsigned char* __restrict__ cp_own, int count_shared,
                                                         const double* __restrict__ ctrl, double* __restrict__ out) {

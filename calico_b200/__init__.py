@@ -8,7 +8,7 @@ not been built, and every device entry point fails with status 13 (Internal) whe
 C_ABI_SYMBOLS = [
     "cb2_default_options", "cb2_problem_create", "cb2_problem_destroy", "cb2_last_error", "cb2_set_trajectory", "cb2_set_gravity",
     "cb2_add_rigid_body", "cb2_add_sensor", "cb2_add_camera_observations", "cb2_add_imu_observations", "cb2_optimize",
-    "cb2_evaluate_sensor", "cb2_cost", "cb2_get_sensor", "cb2_set_sensor", "cb2_get_trajectory", "cb2_get_residuals",
+    "cb2_evaluate_sensor", "cb2_cost", "cb2_get_sensor", "cb2_set_sensor", "cb2_get_trajectory", "cb2_get_rigid_body", "cb2_get_residuals",
     "cb2_comm_unique_id", "cb2_comm_init", "cb2_comm_clone", "cb2_shard_plan", "cb2_set_device", "cb2_stats_reset", "cb2_stats_get", "cb2_reset_parameters",
     "cb2_upload", "cb2_version", "cb2_num_intrinsics", "cb2_fit_spline_size", "cb2_fit_spline", "cb2_fit_trajectory", "cb2_fit_last_error",
 ]

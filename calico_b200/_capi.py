@@ -186,6 +186,7 @@ class CApi:
             "cost": ([vp, _dp, _ip], C.c_int),
             "get_sensor": ([vp, C.c_int, _dp, _dp, _dp, _dp], C.c_int),
             "get_trajectory": ([vp, _dp], C.c_int),
+            "get_rigid_body": ([vp, C.c_int, _dp, _dp, _dp], C.c_int),
             "get_residuals": ([vp, C.c_int, _dp, _up], C.c_int),
         }
         if self.prefix == "cb2_":
@@ -300,6 +301,11 @@ class CApi:
         lat = C.c_double(0)
         self._check(self._f("get_sensor")(self.h, sid, _d(intr), _d(q), _d(t), C.byref(lat)))
         return intr, q, t, lat.value
+
+    def get_rigid_body(self, id, n_pts):
+        q, t, pts = np.zeros(4), np.zeros(3), np.zeros((n_pts, 3))
+        self._check(self._f("get_rigid_body")(self.h, id, _d(q), _d(t), _d(pts)))
+        return q, t, pts
 
     def get_trajectory(self):
         ctrl = np.zeros((self.n_cp, 6))

@@ -558,6 +558,13 @@ class BatchOptimizer:                      # batch_optimizer.{h,cpp}, calico.cpp
             except _capi.CalicoError as e:            # e.g. kInternal from the residual refresh: Ceres has already mutated the parameters
                 failure, summ = e, api.last_summary
             self._trajectory._spline.ctrl[...] = api.get_trajectory()
+            for rid, body in self._world_model._rigidbodies.items():      # freed world-model blocks are mutated in place too (world_model.cpp:52-70)
+                if body.world_pose_is_constant and body.model_definition_is_constant:
+                    continue
+                q, t, pts = api.get_rigid_body(rid, len(body.model_definition))
+                body.T_world_rigidbody._q_xyzw, body.T_world_rigidbody._t = np.array(q), np.array(t)
+                for pid, pt in zip(list(body.model_definition.keys()), pts):
+                    body.model_definition[pid] = np.array(pt)
             for s, sid in zip(self._sensors, ids):
                 try:
                     s._read_back(api, sid)

@@ -355,7 +355,15 @@ struct cb2_problem {
   std::vector<int> tile_off = std::vector<int>(4, 0);   // per kind offsets into the tile table
   DevBuf<SensorDesc> d_desc;
   DevBuf<SensorState> d_state[2], d_state0;
-  DevBuf<double> d_ctrl[2], d_ctrl0, d_knots, d_basis, d_pw;
+  DevBuf<double> d_ctrl[2], d_ctrl0, d_knots, d_basis;
+  // World model on the device: world points per parameter buffer; with freed rigid-body poses / model points (world_model.cpp:52-70) the
+  // body states are double-buffered unknowns like everything else and the world points are recomputed from them.
+  DevBuf<double> d_pw[2], d_body_q[2], d_body_t[2], d_pm[2], d_body_q0, d_body_t0, d_pm0;
+  DevBuf<int> d_pt_body, d_body_u, d_pt_u;
+  std::vector<int> h_body_u, h_pt_u;
+  bool world_free = false;
+  int n_points = 0, n_bodies = 0;
+  WorldRefs world_refs() const { return WorldRefs{n_bodies, n_points, d_body_u.p, d_pt_u.p}; }
   DevBuf<EvalTile> d_tiles;
   // camera images (frames): one record per (camera, stamp), shared by the residual blocks of that image
   int n_frames = 0;
@@ -578,9 +586,8 @@ struct cb2_problem {
     drop_graphs();   // every device pointer baked into a captured solve phase is about to change
     if (knots.empty() || ctrl.empty()) return fail(CB2_FAILED_PRECONDITION, "Trajectory has not been set.");
     if (k != kK) return fail(CB2_UNIMPLEMENTED, "Only spline order 6 (calico::Trajectory::kSplineOrder, trajectory.h:28) is supported.");
-    for (const auto& b : bodies)
-      if (!b.pose_const || !b.model_const)
-        return fail(CB2_UNIMPLEMENTED, "Estimating rigid-body poses or model definitions is not supported on the device path yet.");
+    world_free = false;
+    for (const auto& b : bodies) world_free = world_free || !b.pose_const || !b.model_const;
     int rc = ensure_device();
     if (rc != CB2_OK) return rc;
     n_cp = int(ctrl.size() / 6);
@@ -589,16 +596,23 @@ struct cb2_problem {
     n_a = 6L * n_cp;
     rc = plan_chunks();
     if (rc != CB2_OK) return rc;
-    // World points p_w = q_wm * p_m + t_wm.
-    std::vector<double> pw;
-    for (auto& b : bodies) {
+    // World points p_w = q_wm * p_m + t_wm; rigid-body states and the body of every point.
+    std::vector<double> pw, body_q, body_t, pm;
+    std::vector<int> pt_body;
+    for (size_t bi = 0; bi < bodies.size(); ++bi) {
+      HostBody& b = bodies[bi];
       b.pw0 = int(pw.size() / 3);
       const M3 R = quat_matrix(Q4{b.q[0], b.q[1], b.q[2], b.q[3]});
+      for (int j = 0; j < 4; ++j) body_q.push_back(b.q[j]);
+      for (int j = 0; j < 3; ++j) body_t.push_back(b.t[j]);
       for (size_t f = 0; f < b.feature_ids.size(); ++f) {
         const V3 p = R * v3(b.pts[3 * f], b.pts[3 * f + 1], b.pts[3 * f + 2]);
         pw.push_back(p.x + b.t[0]); pw.push_back(p.y + b.t[1]); pw.push_back(p.z + b.t[2]);
+        pm.push_back(b.pts[3 * f]); pm.push_back(b.pts[3 * f + 1]); pm.push_back(b.pts[3 * f + 2]);
+        pt_body.push_back(int(bi));
       }
     }
+    n_points = int(pt_body.size()); n_bodies = int(bodies.size());
     std::vector<double> basis(size_t(n_seg) * 36);
     for (int s = 0; s < n_seg; ++s) basis_matrix(knots, s + kK - 1, &basis[size_t(s) * 36]);
     // Sensors.
@@ -624,7 +638,7 @@ struct cb2_problem {
       int want = 0, n_active = 0; long blocks = 0, residuals = 0; bool ref_any = false;
       std::vector<int> seg_start, seg, pt, frm, frame_seg, frame_obs, seg_frame;
       std::vector<double> stamp, meas, frame_stamp;
-      std::vector<unsigned char> cp_ref;
+      std::vector<unsigned char> cp_ref, pt_ref;
     };
     std::vector<Packed> packed(ns);
     auto pack_sensor = [&](int si) {
@@ -637,6 +651,7 @@ struct cb2_problem {
       if (int(s.intr.size()) != want) return bad(CB2_INVALID_ARGUMENT, "Invalid number of intrinsics parameters.");
       const int m = s.m(), n = s.n_obs();
       P.cp_ref.assign(n_cp, 0);
+      if (world_free && s.kind == kCamera) P.pt_ref.assign(n_points, 0);
       // segment of each active observation; stable counting sort by segment
       std::vector<int> seg_of(n, -1);
       std::vector<int> count(n_seg + 1, 0);
@@ -648,6 +663,7 @@ struct cb2_problem {
         const int sg = spline_index(s.stamp[o]);
         if (sg < 0 || sg >= n_seg) return bad(CB2_INVALID_ARGUMENT, "Observation stamp is outside the valid knots of the trajectory.");
         for (int c = 0; c < kK; ++c) P.cp_ref[sg + c] = 1;        // referenced by some rank's residual block
+        if (!P.pt_ref.empty()) P.pt_ref[bodies[s.body_slot[o]].pw0 + s.feat_slot[o]] = 1;
         ++P.blocks; P.residuals += m;
         P.ref_any = true;
         if (sg < g_lo || sg >= g_hi) continue;                     // another rank's time range
@@ -770,8 +786,27 @@ struct cb2_problem {
       st.latency = s.latency; st.inv_sigma = 1.0 / s.sigma; st.loss_type = s.loss_type; st.loss_scale = s.loss_scale;
       smem_eval[s.kind] = std::max(smem_eval[s.kind], size_t(rec_size(s.kind, want)) * eval_rec_stride(s.kind) * sizeof(double));
     }
+    // Freed world-model blocks join the calibration vector after the sensors' blocks: per rigid body rotation (3, tangent) + translation (3)
+    // when its pose is estimated, 3 per model point when its definition is; like Ceres's reduced program, only blocks some residual
+    // block (of any rank) references.
+    n_sensor_unknowns = N_c;
+    h_body_u.assign(2 * std::max(n_bodies, 1), -1);
+    h_pt_u.assign(std::max(n_points, 1), -1);
+    n_world_pose_blocks = n_world_point_blocks = 0;
+    if (world_free) {
+      std::vector<unsigned char> pt_ref(n_points, 0);
+      for (int si = 0; si < ns; ++si) if (!packed[si].pt_ref.empty()) for (int p = 0; p < n_points; ++p) pt_ref[p] |= packed[si].pt_ref[p];
+      for (int bi = 0; bi < n_bodies; ++bi) {
+        const HostBody& b = bodies[bi];
+        bool ref = false;
+        for (size_t f = 0; f < b.feature_ids.size(); ++f) ref = ref || pt_ref[b.pw0 + f];
+        if (!ref) continue;
+        if (!b.pose_const) { h_body_u[2 * bi] = N_c; h_body_u[2 * bi + 1] = N_c + 3; N_c += 6; ++n_world_pose_blocks; }
+        if (!b.model_const) for (size_t f = 0; f < b.feature_ids.size(); ++f) if (pt_ref[b.pw0 + f]) { h_pt_u[b.pw0 + f] = N_c; N_c += 3; ++n_world_point_blocks; }
+      }
+    }
     n_tot = n_a + N_c;
-    if (N_c > kRedThreads) return fail(CB2_UNIMPLEMENTED, "More than 512 calibration unknowns are not supported.");
+    if (N_c > kRedThreads) return fail(CB2_UNIMPLEMENTED, "More than 512 calibration unknowns (sensor blocks + freed world-model blocks) are not supported.");
     tile_off[0] = 0;
     for (int kd = 0; kd < 3; ++kd) { tiles.insert(tiles.end(), tiles_by_kind[kd].begin(), tiles_by_kind[kd].end()); tile_off[kd + 1] = int(tiles.size()); }
     n_tiles = int(tiles.size());
@@ -794,7 +829,10 @@ struct cb2_problem {
     d_state0.upload(h_state, h2d);
     for (int b = 0; b < 2; ++b) d_ctrl[b].upload(ctrl, h2d);
     d_ctrl0.upload(ctrl, h2d);
-    d_knots.upload(knots, h2d); d_basis.upload(basis, h2d); d_pw.upload(pw, h2d);
+    d_knots.upload(knots, h2d); d_basis.upload(basis, h2d);
+    for (int b = 0; b < 2; ++b) { d_pw[b].upload(pw, h2d); d_body_q[b].upload(body_q, h2d); d_body_t[b].upload(body_t, h2d); d_pm[b].upload(pm, h2d); }
+    d_body_q0.upload(body_q, h2d); d_body_t0.upload(body_t, h2d); d_pm0.upload(pm, h2d);
+    d_pt_body.upload(pt_body, h2d); d_body_u.upload(h_body_u, h2d); d_pt_u.upload(h_pt_u, h2d);
     d_cp_ref.upload(cp_ref, h2d);
     n_cp_referenced = 0;
     for (auto v : cp_ref) n_cp_referenced += v;
@@ -1022,7 +1060,7 @@ struct cb2_problem {
 
   // Residual sweep over every sensor at parameter buffer `which`; scalars land in d_scal[slot], d_scal[slot + 1].
   template <int MODE>
-  void launch_imu(cudaStream_t si, const SensorDesc* desc, const SensorState* st, const double* c, const int* nt) {
+  void launch_imu(cudaStream_t si, const SensorDesc* desc, const SensorState* st, const double* c, const int* nt, const double* pwp) {
     // Both IMU kernels are FP64-latency-bound single-warp CTAs at low occupancy: the gyroscope kernel runs beside the accelerometer kernel
     // on the second stream (they touch disjoint buffers) instead of after it. (Not inside graph capture / the emulation build.)
     cudaStream_t sg = si;
@@ -1030,9 +1068,9 @@ struct cb2_problem {
     const bool pair = imu_pair_streams && nt[1] && nt[2] && si == stream && !capturing;
     if (pair) { CB2_CUDA(cudaEventRecord(ev_fork, stream)); CB2_CUDA(cudaStreamWaitEvent(stream_imu, ev_fork, 0)); sg = stream_imu; }
 #endif
-    if (nt[2]) CB2_K((eval_kernel<kAccelerometer, MODE>), nt[2], eval_tile(kAccelerometer), smem_eval[2], si, desc, st, d_tiles.p + tile_off[2], c, d_knots.p, d_basis.p, d_pw.p,
+    if (nt[2]) CB2_K((eval_kernel<kAccelerometer, MODE>), nt[2], eval_tile(kAccelerometer), smem_eval[2], si, desc, st, d_tiles.p + tile_off[2], c, d_knots.p, d_basis.p, pwp,
                      d_frames.p, gravity[0], gravity[1], gravity[2], d_cost_partial.p + tile_off[2], d_invalid_partial.p + tile_off[2], 1);
-    if (nt[1]) CB2_K((eval_kernel<kGyroscope, MODE>), nt[1], eval_tile(kGyroscope), smem_eval[1], sg, desc, st, d_tiles.p + tile_off[1], c, d_knots.p, d_basis.p, d_pw.p,
+    if (nt[1]) CB2_K((eval_kernel<kGyroscope, MODE>), nt[1], eval_tile(kGyroscope), smem_eval[1], sg, desc, st, d_tiles.p + tile_off[1], c, d_knots.p, d_basis.p, pwp,
                      d_frames.p, gravity[0], gravity[1], gravity[2], d_cost_partial.p + tile_off[1], d_invalid_partial.p + tile_off[1], 1);
 #ifndef CB2_EMUL
     if (pair) { CB2_CUDA(cudaEventRecord(ev_join, stream_imu)); CB2_CUDA(cudaStreamWaitEvent(stream, ev_join, 0)); }
@@ -1056,13 +1094,13 @@ struct cb2_problem {
     if (nt[0]) {
       launch_frames(which);
       if (MODE == kModeJacobian) timer.begin(kPhCamera, stream);
-      CB2_K((eval_kernel<kCamera, MODE>), nt[0], eval_tile(kCamera), smem_eval[0], stream, desc, st, d_tiles.p + tile_off[0], c, d_knots.p, d_basis.p, d_pw.p,
+      CB2_K((eval_kernel<kCamera, MODE>), nt[0], eval_tile(kCamera), smem_eval[0], stream, desc, st, d_tiles.p + tile_off[0], c, d_knots.p, d_basis.p, d_pw[which].p,
             d_frames.p, gravity[0], gravity[1], gravity[2], d_cost_partial.p + tile_off[0], d_invalid_partial.p + tile_off[0], 1);
       if (MODE == kModeJacobian) timer.end(kPhCamera, stream);
     }
     if (imu != kImuSkip) {
-      if (imu == kImuJacobian || MODE == kModeJacobian) launch_imu<kModeJacobian>(si, desc, st, c, nt);
-      else launch_imu<MODE>(si, desc, st, c, nt);
+      if (imu == kImuJacobian || MODE == kModeJacobian) launch_imu<kModeJacobian>(si, desc, st, c, nt, d_pw[which].p);
+      else launch_imu<MODE>(si, desc, st, c, nt, d_pw[which].p);
     }
     if (fork) { CB2_CUDA(cudaEventRecord(ev_join, stream_imu)); CB2_CUDA(cudaStreamWaitEvent(stream, ev_join, 0)); }
     CB2_K(reduce_cost_kernel, 1, 1024, 0, stream, d_cost_partial.p, d_invalid_partial.p, n_tiles, d_scal.p, slot);
@@ -1122,21 +1160,26 @@ struct cb2_problem {
       CB2_K(assemble_calib_kernel, dim3((ne + 31) / 32, kCalibSlices), dim3(32, 8), 0, stream, ne, d_centries.p, d_segC.p, d_segGc.p, d_gcta.p, d_cpartial.p);
       CB2_K(assemble_calib_final_kernel, (ne + 255) / 256, 256, 0, stream, N_c, ne, kCalibSlices, d_centries.p, d_cpartial.p, d_Cmat.p, d_grad.p + n_a);
     }
+    if (world_free && tile_off[1] > tile_off[0]) {   // freed world-model blocks: their rows / columns of the normal equations, from the cameras' Jacobian rows
+      if (N_c > n_sensor_unknowns) CB2_CUDA(cudaMemsetAsync(d_grad.p + n_a + n_sensor_unknowns, 0, sizeof(double) * (N_c - n_sensor_unknowns), stream));   // accumulated by atomics
+      CB2_K(world_normal_kernel, tile_off[1] - tile_off[0], 128, 0, stream, d_desc.p, d_tiles.p + tile_off[0], n_a, N_c, d_pt_body.p, d_body_u.p, d_pt_u.p,
+            d_body_q[cur].p, d_body_t[cur].p, d_pw[cur].p, d_Bmat.p, d_Cmat.p, d_grad.p);
+    }
     CB2_K(hess_diag_kernel, int(std::min<long>((n_tot + 255) / 256, 1024)), 256, 0, stream, n_a, N_c, d_Aband.p, d_Cmat.p, d_diag.p);
     if (world > 1) {
       // Separator rows and calibration receive contributions from several ranks (lmkernels: pack_shared_kernel). d_grad itself stays
       // rank-local; gradG carries the sums on the shared rows. When the host does not wait for this point's gradient norms (deferred
       // round trip, see minimize) the sums are NOT exchanged here: they ride in the tail of the next solve's collective (launch_step).
       CB2_CUDA(cudaMemcpyAsync(d_gradG.p, d_grad.p, sizeof(double) * n_tot, cudaMemcpyDeviceToDevice, stream));
-      CB2_K(gradient_norm_kernel, 1, kLmThreads, 0, stream, n_a, d_grad.p, d_cp_own.p, 1, 0, 0, d_desc.p, d_state[cur].p, ns, d_scal.p);   // owned part
+      CB2_K(gradient_norm_kernel, 1, kLmThreads, 0, stream, n_a, d_grad.p, d_cp_own.p, 1, 0, 0, d_desc.p, d_state[cur].p, ns, world_refs(), d_body_q[cur].p, d_scal.p);   // owned part
       if (!defer_shared) {
         CB2_K(pack_shared_kernel, (n_shared + 255) / 256, 256, 0, stream, n_shared, d_shared_idx.p, d_grad.p, d_diag.p, d_scal.p, world, rank, d_shared_buf.p);
         comm->allreduce_sum(d_shared_buf.p, shared_buf_size(n_shared, world), stream);
         CB2_K(unpack_shared_kernel, (n_shared + 255) / 256, 256, 0, stream, n_shared, d_shared_idx.p, d_shared_buf.p, world, d_gradG.p, d_diag.p, d_scal.p);
-        CB2_K(gradient_norm_kernel, 1, kLmThreads, 0, stream, n_a, d_gradG.p, d_cp_own.p, 0, 1, 1, d_desc.p, d_state[cur].p, ns, d_scal.p);   // + shared part
+        CB2_K(gradient_norm_kernel, 1, kLmThreads, 0, stream, n_a, d_gradG.p, d_cp_own.p, 0, 1, 1, d_desc.p, d_state[cur].p, ns, world_refs(), d_body_q[cur].p, d_scal.p);   // + shared part
       }
     } else {
-      CB2_K(gradient_norm_kernel, 1, kLmThreads, 0, stream, n_a, d_grad.p, d_cp_own.p, 1, 1, 0, d_desc.p, d_state[cur].p, ns, d_scal.p);
+      CB2_K(gradient_norm_kernel, 1, kLmThreads, 0, stream, n_a, d_grad.p, d_cp_own.p, 1, 1, 0, d_desc.p, d_state[cur].p, ns, world_refs(), d_body_q[cur].p, d_scal.p);
     }
     });
     timer.end(kPhNormal, stream);
@@ -1153,7 +1196,7 @@ struct cb2_problem {
     CB2_K(pack_shared_kernel, (n_shared + 255) / 256, 256, 0, stream, n_shared, d_shared_idx.p, d_grad.p, d_diag.p, d_scal.p, world, rank, d_shared_buf.p);
     comm->allreduce_sum(d_shared_buf.p, shared_buf_size(n_shared, world), stream);
     CB2_K(unpack_shared_kernel, (n_shared + 255) / 256, 256, 0, stream, n_shared, d_shared_idx.p, d_shared_buf.p, world, d_gradG.p, d_diag.p, d_scal.p);
-    CB2_K(gradient_norm_kernel, 1, kLmThreads, 0, stream, n_a, d_gradG.p, d_cp_own.p, 0, 1, 1, d_desc.p, d_state[cur].p, ns, d_scal.p);
+    CB2_K(gradient_norm_kernel, 1, kLmThreads, 0, stream, n_a, d_gradG.p, d_cp_own.p, 0, 1, 1, d_desc.p, d_state[cur].p, ns, world_refs(), d_body_q[cur].p, d_scal.p);
   }
 
   // One LM linear solve + candidate point + candidate cost. Everything is enqueued; the caller syncs once.
@@ -1208,7 +1251,7 @@ struct cb2_problem {
       comm->allreduce_sum(d_red.p, red_count + (tail ? shared_buf_size(n_shared, world) : 0), stream);
       if (tail) {
         CB2_K(unpack_shared_kernel, (n_shared + 255) / 256, 256, 0, stream, n_shared, d_shared_idx.p, tailp, world, d_gradG.p, d_diag.p, d_scal.p);
-        CB2_K(gradient_norm_kernel, 1, kLmThreads, 0, stream, n_a, d_gradG.p, d_cp_own.p, 0, 1, 1, d_desc.p, d_state[cur].p, ns, d_scal.p);
+        CB2_K(gradient_norm_kernel, 1, kLmThreads, 0, stream, n_a, d_gradG.p, d_cp_own.p, 0, 1, 1, d_desc.p, d_state[cur].p, ns, world_refs(), d_body_q[cur].p, d_scal.p);
         CB2_K(damping_shared_kernel, (n_shared + 255) / 256, 256, 0, stream, n_shared, d_shared_idx.p, d_diag.p, d_scaling.p, d_scal.p, d_dtil2.p);
       }
     }
@@ -1244,7 +1287,10 @@ struct cb2_problem {
       CB2_K(band_backsolve_kernel, PL, kBackThreads, backsolve_smem_bytes(max_n1, nbw1, 36), stream, d_l1.p, d_ytil.p);
     }
     CB2_K(apply_step_kernel, 1, kLmThreads, 0, stream, n_a, d_ytil.p, gradG(), d_dtil2.p, d_cp_ref.p, d_cp_own.p, rank == 0 ? 1 : 0, d_ctrl[cur].p,
-          d_ctrl[cur ^ 1].p, d_desc.p, d_state[cur].p, d_state[cur ^ 1].p, ns, N_c, d_scal.p);
+          d_ctrl[cur ^ 1].p, d_desc.p, d_state[cur].p, d_state[cur ^ 1].p, ns, N_c, world_refs(), d_body_q[cur].p, d_body_t[cur].p, d_pm[cur].p,
+          d_body_q[cur ^ 1].p, d_body_t[cur ^ 1].p, d_pm[cur ^ 1].p, d_scal.p);
+    if (world_free && n_points > 0)
+      CB2_K(world_points_kernel, (n_points + 255) / 256, 256, 0, stream, n_points, d_pt_body.p, d_body_q[cur ^ 1].p, d_body_t[cur ^ 1].p, d_pm[cur ^ 1].p, d_pw[cur ^ 1].p);
     });
     timer.end(kPhSchur, stream);
     launch_trial();
@@ -1319,11 +1365,13 @@ struct cb2_problem {
     }
     const int ncp_ref = n_cp_referenced;
     pbr += ncp_ref; pr += 6 * ncp_ref; per += 6 * ncp_ref;
+    pbr += 2 * n_world_pose_blocks + n_world_point_blocks;      // freed, referenced world-model blocks (pose = translation + quaternion block)
+    pr += 7 * n_world_pose_blocks + 3 * n_world_point_blocks; per += 6 * n_world_pose_blocks + 3 * n_world_point_blocks;
     S.num_residual_blocks = rb; S.num_residuals = rr;
     S.num_residual_blocks_reduced = rb; S.num_residuals_reduced = rr;
     S.num_parameter_blocks_reduced = pbr; S.num_parameters_reduced = pr; S.num_effective_parameters_reduced = per;
   }
-  int n_cp_referenced = 0;
+  int n_cp_referenced = 0, n_world_pose_blocks = 0, n_world_point_blocks = 0, n_sensor_unknowns = 0;
 
   int minimize(const cb2_options& opt, cb2_summary& S, std::vector<cb2_iteration>& L) {
     const double t_start = now_s();
@@ -1513,6 +1561,16 @@ struct cb2_problem {
     }
     d_ctrl[cur].download(ctrl, &stats.d2h_bytes);
     d_state[cur].download(h_state, &stats.d2h_bytes);
+    if (world_free) {   // the freed rigid-body poses / model points (world_model.cpp:52-70: Ceres mutates them in place)
+      std::vector<double> bq, bt, bp;
+      d_body_q[cur].download(bq, &stats.d2h_bytes); d_body_t[cur].download(bt, &stats.d2h_bytes); d_pm[cur].download(bp, &stats.d2h_bytes);
+      for (size_t bi = 0; bi < bodies.size(); ++bi) {
+        HostBody& b = bodies[bi];
+        for (int j = 0; j < 4; ++j) b.q[j] = bq[4 * bi + j];
+        for (int j = 0; j < 3; ++j) b.t[j] = bt[3 * bi + j];
+        for (size_t f = 0; f < b.feature_ids.size(); ++f) for (int j = 0; j < 3; ++j) b.pts[3 * f + j] = bp[3 * (b.pw0 + f) + j];
+      }
+    }
     for (size_t si = 0; si < sensors.size(); ++si) {
       HostSensor& s = sensors[si];
       const SensorState& st = h_state[si];
@@ -1801,7 +1859,7 @@ int cb2_evaluate_sensor(cb2_problem* p, int sid, double* residuals, double* jaco
     cb2_stats& stats = p->stats;
     KernelProfiler& kprof = p->kprof;
 #define CB2_EVAL(KIND, MODE)                                                                                                             \
-  CB2_K((eval_kernel<KIND, MODE>), nt, eval_tile(KIND), smem, stream, dd.p, st, dt.p, c, p->d_knots.p, p->d_basis.p, p->d_pw.p, p->d_frames.p, \
+  CB2_K((eval_kernel<KIND, MODE>), nt, eval_tile(KIND), smem, stream, dd.p, st, dt.p, c, p->d_knots.p, p->d_basis.p, p->d_pw[p->cur].p, p->d_frames.p, \
         p->gravity[0], p->gravity[1], p->gravity[2], cpart.p, ipart.p, 0)
     // residuals + validity (un-robustified), then the Jacobian pass if requested
     if (s.kind == kCamera) p->launch_frames(p->cur);
@@ -1859,6 +1917,16 @@ int cb2_set_sensor(cb2_problem* p, int sid, const double* intr, const double* q,
   p->uploaded = false;
   return CB2_OK;
 }
+// RigidBody write-back (world_model.h:41-69): pose and model definition after cb2_optimize; pts_xyz in the order the points were added.
+int cb2_get_rigid_body(cb2_problem* p, int id, double* q, double* t, double* pts) {
+  auto it = p->body_slot.find(id);
+  if (it == p->body_slot.end()) return p->fail(CB2_INVALID_ARGUMENT, "Unknown rigid body id.");
+  const HostBody& b = p->bodies[it->second];
+  if (q) std::memcpy(q, b.q, 32);
+  if (t) std::memcpy(t, b.t, 24);
+  if (pts) std::memcpy(pts, b.pts.data(), b.pts.size() * 8);
+  return CB2_OK;
+}
 int cb2_get_trajectory(cb2_problem* p, double* ctrl) { std::memcpy(ctrl, p->ctrl.data(), p->ctrl.size() * 8); return CB2_OK; }
 int cb2_get_residuals(cb2_problem* p, int sid, double* out, uint8_t* valid) {
   if (sid < 0 || sid >= int(p->sensors.size())) return p->fail(CB2_INVALID_ARGUMENT, "Unknown sensor id.");
@@ -1875,6 +1943,12 @@ int cb2_reset_parameters(cb2_problem* p) {
     p->cur = 0;
     CB2_CUDA(cudaMemcpyAsync(p->d_ctrl[0].p, p->d_ctrl0.p, p->d_ctrl0.n * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
     CB2_CUDA(cudaMemcpyAsync(p->d_state[0].p, p->d_state0.p, p->d_state0.n * sizeof(SensorState), cudaMemcpyDeviceToDevice, p->stream));
+    if (p->world_free && p->n_points > 0) {
+      CB2_CUDA(cudaMemcpyAsync(p->d_body_q[0].p, p->d_body_q0.p, p->d_body_q0.n * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+      CB2_CUDA(cudaMemcpyAsync(p->d_body_t[0].p, p->d_body_t0.p, p->d_body_t0.n * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+      CB2_CUDA(cudaMemcpyAsync(p->d_pm[0].p, p->d_pm0.p, p->d_pm0.n * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+      CB2_LAUNCH(world_points_kernel, (p->n_points + 255) / 256, 256, 0, p->stream, p->n_points, p->d_pt_body.p, p->d_body_q[0].p, p->d_body_t[0].p, p->d_pm[0].p, p->d_pw[0].p);
+    }
     CB2_CUDA(cudaStreamSynchronize(p->stream));
     return CB2_OK;
   });

@@ -58,13 +58,21 @@ CB2_D void block_reduce(double (&v)[NV], double* sh) {
   }
 }
 
+// Freed world-model blocks (see world_points_kernel below): where the rigid-body poses and model points sit in the calibration vector.
+struct WorldRefs {
+  int n_bodies, n_points;
+  const int* body_u;   // [2 n_bodies] offsets of (rotation, translation) in the calibration vector, -1 = constant
+  const int* pt_u;     // [n_points] offset of the model point, -1 = constant
+};
+
 // gradient_max_norm / gradient_norm^2 = |x - Plus(x, -g)|_inf / _2^2 (ambient coordinates) over a part of the reduced parameter vector:
 // count_owned: the control points this rank owns; count_shared: the separator control points and the calibration blocks (whose gradient
 // entries are sums over the ranks). combine: fold the result into what scal[kScGradSq / kScGradMax] already hold (multi-rank: the
 // cross-rank sum / maximum of the ranks' owned parts) instead of overwriting them.
 __global__ void __launch_bounds__(kLmThreads) gradient_norm_kernel(long n_a, const double* __restrict__ grad, const unsigned char* __restrict__ cp_own,
                                                                    int count_owned, int count_shared, int combine, const SensorDesc* __restrict__ sensors,
-                                                                   const SensorState* __restrict__ states, int n_sensors, double* __restrict__ scal) {
+                                                                   const SensorState* __restrict__ states, int n_sensors, WorldRefs world,
+                                                                   const double* __restrict__ body_q, double* __restrict__ scal) {
   __shared__ double sh[32];
   const int t = threadIdx.x;
   double mx = 0.0, sq = 0.0;
@@ -90,6 +98,23 @@ __global__ void __launch_bounds__(kLmThreads) gradient_norm_kernel(long n_a, con
       for (int k = 0; k < 4; ++k) { mx = fmax(mx, fabs(d[k])); sq += d[k] * d[k]; }
     }
   }
+  if (count_shared) {   // freed world-model blocks: pose rotation through the manifold, the rest directly
+    for (int b = t; b < world.n_bodies; b += kLmThreads) {
+      const int ur = world.body_u[2 * b], ut = world.body_u[2 * b + 1];
+      if (ur >= 0) {
+        const double* gc = grad + n_a + ur;
+        const Q4 q = Q4{body_q[4 * b], body_q[4 * b + 1], body_q[4 * b + 2], body_q[4 * b + 3]};
+        const Q4 p = quat_plus(q, v3(-gc[0], -gc[1], -gc[2]));
+        const double d[4] = {q.x - p.x, q.y - p.y, q.z - p.z, q.w - p.w};
+        for (int k = 0; k < 4; ++k) { mx = fmax(mx, fabs(d[k])); sq += d[k] * d[k]; }
+      }
+      if (ut >= 0) for (int k = 0; k < 3; ++k) { const double g = grad[n_a + ut + k]; mx = fmax(mx, fabs(g)); sq += g * g; }
+    }
+    for (int p = t; p < world.n_points; p += kLmThreads) {
+      const int u = world.pt_u[p];
+      if (u >= 0) for (int k = 0; k < 3; ++k) { const double g = grad[n_a + u + k]; mx = fmax(mx, fabs(g)); sq += g * g; }
+    }
+  }
   double vs[1] = {sq}, vm[1] = {mx};
   block_reduce<1, false>(vs, sh);
   block_reduce<1, true>(vm, sh);
@@ -110,7 +135,9 @@ __global__ void __launch_bounds__(kLmThreads) apply_step_kernel(long n_a, const 
                                                                 const double* __restrict__ ctrl, double* __restrict__ ctrl_cand,
                                                                 const SensorDesc* __restrict__ sensors, const SensorState* __restrict__ states,
                                                                 SensorState* __restrict__ states_cand, int n_sensors, int N_c,
-                                                                double* __restrict__ scal) {
+                                                                WorldRefs world, const double* __restrict__ body_q, const double* __restrict__ body_t,
+                                                                const double* __restrict__ pm, double* __restrict__ body_q_cand,
+                                                                double* __restrict__ body_t_cand, double* __restrict__ pm_cand, double* __restrict__ scal) {
   __shared__ double sh[5 * 32];
   const int t = threadIdx.x;
   double step2 = 0.0, x2 = 0.0, c2 = 0.0, model = 0.0, bad = 0.0;
@@ -169,6 +196,35 @@ __global__ void __launch_bounds__(kLmThreads) apply_step_kernel(long n_a, const 
       S.latency = xn; step2 += cs * (x - xn) * (x - xn); x2 += cs * x * x; c2 += cs * xn * xn;
     }
     states_cand[s] = S;
+  }
+  // freed world-model blocks (constant ones are copied so that the candidate tables are complete)
+  for (int b = t; b < world.n_bodies; b += kLmThreads) {
+    const int ur = world.body_u[2 * b], ut = world.body_u[2 * b + 1];
+    const Q4 q = Q4{body_q[4 * b], body_q[4 * b + 1], body_q[4 * b + 2], body_q[4 * b + 3]};
+    Q4 p = q;
+    if (ur >= 0) {
+      const double* y = ytil + n_a + ur;
+      p = quat_plus(q, v3(-y[0], -y[1], -y[2]));
+      step2 += cs * ((q.x - p.x) * (q.x - p.x) + (q.y - p.y) * (q.y - p.y) + (q.z - p.z) * (q.z - p.z) + (q.w - p.w) * (q.w - p.w));
+      x2 += cs * (q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+      c2 += cs * (p.x * p.x + p.y * p.y + p.z * p.z + p.w * p.w);
+    }
+    body_q_cand[4 * b] = p.x; body_q_cand[4 * b + 1] = p.y; body_q_cand[4 * b + 2] = p.z; body_q_cand[4 * b + 3] = p.w;
+    for (int k = 0; k < 3; ++k) {
+      const double x = body_t[3 * b + k];
+      double xn = x;
+      if (ut >= 0) { xn = x - ytil[n_a + ut + k]; step2 += cs * (x - xn) * (x - xn); x2 += cs * x * x; c2 += cs * xn * xn; }
+      body_t_cand[3 * b + k] = xn;
+    }
+  }
+  for (int p = t; p < world.n_points; p += kLmThreads) {
+    const int u = world.pt_u[p];
+    for (int k = 0; k < 3; ++k) {
+      const double x = pm[3 * p + k];
+      double xn = x;
+      if (u >= 0) { xn = x - ytil[n_a + u + k]; step2 += cs * (x - xn) * (x - xn); x2 += cs * x * x; c2 += cs * xn * xn; }
+      pm_cand[3 * p + k] = xn;
+    }
   }
   double red[5] = {step2, x2, c2, model, bad};
   block_reduce<5, false>(red, sh);

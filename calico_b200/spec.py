@@ -100,6 +100,9 @@ class ProblemSpec:
         """Write-back of the optimised state (the reference mutates the user's objects in place, camera.cpp:98-101)."""
         ids = ids if ids is not None else list(range(len(self.sensors)))
         self.spline.ctrl[...] = api.get_trajectory()
+        for b in self.bodies:
+            if not (b.pose_const and b.model_const):
+                b.q_xyzw, b.t, b.pts = api.get_rigid_body(b.id, np.asarray(b.pts).reshape(-1, 3).shape[0])
         for s, sid in zip(self.sensors, ids):
             intr, q, t, lat = api.get_sensor(sid)
             s.intr, s.q_xyzw, s.t, s.latency = intr, q, t, lat

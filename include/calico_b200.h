@@ -111,7 +111,9 @@ const char* cb2_last_error(cb2_problem* p);
 int cb2_set_trajectory(cb2_problem* p, int spline_order, int n_knots, const double* knots, int n_cp, const double* ctrl);
 /* WorldModel gravity (world_model.h:78,111); never estimated (world_model.cpp:79-81). */
 int cb2_set_gravity(cb2_problem* p, const double* g3);
-/* WorldModel::AddRigidBody (world_model.cpp:29-38, struct world_model.h:41-69). */
+/* WorldModel::AddRigidBody (world_model.cpp:29-38, struct world_model.h:41-69). With a false constness flag the block is estimated
+ * (world_model.cpp:52-70): the pose as translation + quaternion (EigenQuaternionManifold, optimization_utils.h:51-61), each model point
+ * as a 3-vector — extra unknowns of the reduced (calibration) system shared by all cameras. */
 int cb2_add_rigid_body(cb2_problem* p, int id, const double* q_xyzw, const double* t3, int n_pts, const int* feature_ids,
                        const double* pts_xyz, int world_pose_is_constant, int model_definition_is_constant);
 /* A sensor with its model, state and flags: Camera/Gyroscope/Accelerometer setters of sensor_base.h:27-101
@@ -145,6 +147,9 @@ int cb2_cost(cb2_problem* p, double* cost, int* ok);
 int cb2_get_sensor(cb2_problem* p, int sensor_id, double* intr, double* q_xyzw, double* t3, double* latency);
 int cb2_set_sensor(cb2_problem* p, int sensor_id, const double* intr, const double* q_xyzw, const double* t3, double latency);
 int cb2_get_trajectory(cb2_problem* p, double* ctrl);
+/* RigidBody write-back when world_pose_is_constant / model_definition_is_constant are false (world_model.cpp:52-70: the reference estimates
+ * those blocks and Ceres mutates them in place): q_xyzw[4], t3[3], pts_xyz[n_pts][3] in the order given to cb2_add_rigid_body. Any may be NULL. */
+int cb2_get_rigid_body(cb2_problem* p, int id, double* q_xyzw, double* t3, double* pts_xyz);
 /* Camera::GetMeasurementResidualPairs source (camera.cpp:258-279): residuals [n_obs][m] in observation order, valid mask. */
 int cb2_get_residuals(cb2_problem* p, int sensor_id, double* residuals, uint8_t* valid);
 

@@ -566,6 +566,13 @@ class BatchOptimizer {
     const int rc = cb2_optimize(h.p, &o, &cs, nullptr, 0, nullptr);
     // Parameters are written back even when the residual refresh failed, as Ceres has already mutated them in the reference.
     cb2_get_trajectory(h.p, trajectory_world_body_->control_points().data());
+    for (const auto& [rid, body] : world_model_->rigidbodies()) {   // freed world-model blocks are mutated in place too (world_model.cpp:52-70)
+      if (body->world_pose_is_constant && body->model_definition_is_constant) continue;
+      std::vector<double> pts(3 * body->model_definition.size());
+      if (cb2_get_rigid_body(h.p, rid, body->T_world_rigidbody.q.data(), body->T_world_rigidbody.t.data(), pts.data()) != CB2_OK) continue;
+      size_t k = 0;   // same iteration order as PushWorldAndTrajectory (the map is not modified in between)
+      for (auto& [pid, pt] : body->model_definition) { (void)pid; pt = {pts[3 * k], pts[3 * k + 1], pts[3 * k + 2]}; ++k; }
+    }
     for (size_t i = 0; i < sensors_.size(); ++i) {
       const Status rs = sensors_[i]->ReadBack(h.p, ids[i]);
       if (rc == CB2_OK && !rs.ok()) return rs;

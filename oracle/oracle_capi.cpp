@@ -189,6 +189,16 @@ int orc_get_sensor(void* hp, int sensor, double* intr, double* q_xyzw, double* t
   std::memcpy(intr, s.intr.data(), s.intr.size() * 8); std::memcpy(q_xyzw, s.q, 32); std::memcpy(t, s.t, 24); *latency = s.latency;
   return kOk;
 }
+int orc_get_rigid_body(void* hp, int id, double* q, double* t, double* pts) {
+  Handle* h = static_cast<Handle*>(hp);
+  auto it = h->body_slot.find(id);
+  if (it == h->body_slot.end()) return fail(h, kInvalidArgument, "Unknown rigid body id.");
+  const RigidBody& rb = h->p.bodies[it->second];
+  if (q) std::memcpy(q, rb.q, 32);
+  if (t) std::memcpy(t, rb.t, 24);
+  if (pts) std::memcpy(pts, rb.pts.data(), rb.pts.size() * 8);
+  return kOk;
+}
 int orc_get_trajectory(void* hp, double* ctrl) { Handle* h = static_cast<Handle*>(hp); std::memcpy(ctrl, h->p.ctrl.data(), h->p.ctrl.size() * 8); return kOk; }
 int orc_get_residuals(void* hp, int sensor, double* out, uint8_t* valid) {
   Handle* h = static_cast<Handle*>(hp);

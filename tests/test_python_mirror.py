@@ -45,10 +45,10 @@ def _fixture(samples_per_segment):
     return poses, sorted(poses.keys()), points
 
 
-def _toy_calibration(samples_per_segment, max_iterations):
+def _toy_calibration(samples_per_segment, max_iterations, free_world_pose=False):
     rng = np.random.default_rng(5)
     poses, stamps, points = _fixture(samples_per_segment)
-    planar_target = calico.RigidBody(world_pose_is_constant=True, model_definition_is_constant=True)
+    planar_target = calico.RigidBody(world_pose_is_constant=not free_world_pose, model_definition_is_constant=True)
     for i, p in enumerate(points):
         planar_target.model_definition[i] = p
     world_model = calico.WorldModel()
@@ -134,6 +134,11 @@ def test_python_mirror_on_emulated_kernels():
     try:
         summary, *_ = _toy_calibration(samples_per_segment=1, max_iterations=1)      # plumbing only; acceptance is the GPU test below
         assert summary.final_cost <= summary.initial_cost and summary.num_residual_blocks > 0
+        # world_pose_is_constant = false (world_model.cpp:66-70): the chart pose is estimated and written back into the RigidBody object
+        summary2, _, _, world_model, _ = _toy_calibration(samples_per_segment=1, max_iterations=6, free_world_pose=True)
+        body = next(iter(world_model._rigidbodies.values()))
+        assert summary2.num_parameters_reduced == summary.num_parameters_reduced + 7
+        assert np.abs(body.T_world_rigidbody.translation).max() > 0 or abs(body.T_world_rigidbody.rotation[0] - 1.0) > 0
     finally:
         calico.set_library(None)
 

@@ -1005,7 +1005,7 @@ struct cb2_problem {
     d_chunk_sys.upload(chunk_sys);
     d_rawdiag.alloc(size_t(std::max(n2, 1)) + std::max(N_c, 1));
     const size_t smem_f1 = factor_smem_bytes(36, nbw1), smem_f2 = factor_smem_bytes(60, nbw2);
-    if ((!use_cr && smem_f1 > 227 * 1024) || smem_f2 > 227 * 1024) return fail(CB2_UNIMPLEMENTED, "Too many calibration unknowns for the shared-memory Schur kernels.");
+    if ((!use_cr && smem_f1 > 227 * 1024) || (h_l2.n > 0 && smem_f2 > 227 * 1024)) return fail(CB2_UNIMPLEMENTED, "Too many calibration unknowns for the shared-memory Schur kernels.");
     return CB2_OK;
   }
   double* red_Cw = nullptr;
@@ -1031,7 +1031,7 @@ struct cb2_problem {
     cr_tma = use_cr && std::getenv("CB2_NO_TMA") == nullptr && cr_smem_bytes_tma(nbw1) <= 227 * 1024;   // staging area beside the working set
     if (use_cr) { set(cr_level_kernel<true>, cr_smem_bytes(nbw1)); set(cr_level_kernel<false>, cr_tma ? cr_smem_bytes_tma(nbw1) : cr_smem_bytes(nbw1)); }
     else set(band_factor_kernel<6>, factor_smem_bytes(36, nbw1));
-    set(band_factor_kernel<10>, factor_smem_bytes(60, nbw2));
+    if (h_l2.n > 0) set(band_factor_kernel<10>, factor_smem_bytes(60, nbw2));
     set(reduced_solve_kernel, size_t(N_c + 1) * (kRedPanel + 1) * 8);
     if (reduced_smem_bytes(N_c) <= 227 * 1024 - 256) set(reduced_solve_smem_kernel, reduced_smem_bytes(N_c));
     set(band_backsolve_kernel, std::max(use_cr ? size_t(0) : backsolve_smem_bytes(max_n1, nbw1, 36), backsolve_smem_bytes(h_l2.n, nbw2, 60)));

@@ -353,7 +353,7 @@ def main():
                                      "frac": sweep_achieved / peak, "algorithmic_bytes": sweep_bytes, "ms": sweep_ms}},
         "clocks": clocks,
         "e2e": {"value": iters2 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": st2.h2d_bytes / iters2, "d2h_bytes_per_step": st2.d2h_bytes / iters2,
-                "seconds": e2e_s, "ms_per_optimize_call": 1e3 * e2e_s, "iterations": iters2, "what": "assembly from host arrays (cb2_set_trajectory / cb2_add_*) + upload + cb2_optimize + parameter/residual write-back on a fresh problem handle"},
+                "seconds": e2e_s, "ms_per_optimize_call": 1e3 * e2e_s, "iterations": iters2, "termination": summ2.message.decode(errors="replace"), "what": "assembly from host arrays (cb2_set_trajectory / cb2_add_*) + upload + cb2_optimize + parameter/residual write-back on a fresh problem handle"},
         "gpu_launches": int(st.kernel_launches),
     }
     if not args.no_cpu_baseline:

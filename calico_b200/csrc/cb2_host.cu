@@ -22,6 +22,7 @@
 #include <vector>
 #include <map>
 #include <atomic>
+#include <mutex>
 #include <thread>
 #if defined(CB2_EMUL)
 #include <condition_variable>
@@ -102,6 +103,66 @@ struct DevBuf {
   }
 };
 
+// Process-wide pool of pinned (page-locked) host blocks for the staging of uploads and result downloads. Pinning is expensive (of the order
+// of 0.3 ms per MB), transfers from / to pinned memory run at the full PCIe / C2C rate and asynchronously; a calibration session creates a
+// problem per Optimize call (batch_optimizer.cpp:57), so blocks are kept for the life of the process and handed out by size.
+struct PinnedPool {
+  std::mutex mu;
+  std::multimap<size_t, void*> free_blocks;
+  void* get(size_t bytes, size_t* cap) {
+    bytes = std::max<size_t>(bytes, 256);
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      auto it = free_blocks.lower_bound(bytes);
+      if (it != free_blocks.end() && it->first <= 2 * bytes + (size_t(1) << 20)) { void* p = it->second; *cap = it->first; free_blocks.erase(it); return p; }
+    }
+    const size_t c = (bytes + (size_t(1) << 20) - 1) >> 20 << 20;
+    void* p = nullptr;
+    if (cudaMallocHost(&p, c) != cudaSuccess) { cudaGetLastError(); throw CudaFail{"cudaMallocHost failed (pinned staging memory)"}; }
+    *cap = c;
+    return p;
+  }
+  void put(void* p, size_t cap) { if (p) { std::lock_guard<std::mutex> lk(mu); free_blocks.emplace(cap, p); } }
+};
+static PinnedPool& pinned_pool() { static PinnedPool* pool = new PinnedPool(); return *pool; }   // never destroyed: outlives every handle
+struct PinnedBuf {
+  void* p = nullptr; size_t cap = 0;
+  PinnedBuf() = default;
+  PinnedBuf(const PinnedBuf&) = delete;
+  PinnedBuf& operator=(const PinnedBuf&) = delete;
+  PinnedBuf(PinnedBuf&& o) noexcept : p(o.p), cap(o.cap) { o.p = nullptr; o.cap = 0; }
+  PinnedBuf& operator=(PinnedBuf&& o) noexcept { if (this != &o) { release(); p = o.p; cap = o.cap; o.p = nullptr; o.cap = 0; } return *this; }
+  ~PinnedBuf() { release(); }
+  void acquire(size_t bytes) { if (cap < bytes) { release(); p = pinned_pool().get(bytes, &cap); } }
+  void release() { pinned_pool().put(p, cap); p = nullptr; cap = 0; }
+};
+
+// Growable host array backed by the pinned pool: the per-observation input copies of a problem (tens of MB) reuse warm, already-mapped
+// blocks from one Optimize call of a session to the next instead of paying fresh page faults for every std::vector.
+template <class T>
+struct PooledArray {
+  PinnedBuf buf;
+  size_t n = 0;
+  PooledArray() = default;
+  PooledArray(PooledArray&& o) noexcept : buf(std::move(o.buf)), n(o.n) { o.n = 0; }
+  PooledArray& operator=(PooledArray&& o) noexcept { buf = std::move(o.buf); n = o.n; o.n = 0; return *this; }
+  size_t size() const { return n; }
+  bool empty() const { return n == 0; }
+  T* data() { return static_cast<T*>(buf.p); }
+  const T* data() const { return static_cast<const T*>(buf.p); }
+  T& operator[](size_t i) { return data()[i]; }
+  const T& operator[](size_t i) const { return data()[i]; }
+  void reserve(size_t count) {
+    if (count * sizeof(T) <= buf.cap) return;
+    PinnedBuf nb;
+    nb.acquire(std::max(count * sizeof(T), 2 * buf.cap));
+    if (n) std::memcpy(nb.p, buf.p, n * sizeof(T));
+    std::swap(nb.p, buf.p); std::swap(nb.cap, buf.cap);
+  }
+  void append(const T* src, size_t count) { reserve(n + count); if (count) std::memcpy(data() + n, src, count * sizeof(T)); n += count; }
+  void append_fill(size_t count, T v) { reserve(n + count); for (size_t i = 0; i < count; ++i) data()[n + i] = v; n += count; }
+};
+
 struct HostBody {
   int id = 0;
   double q[4] = {0, 0, 0, 1}, t[3] = {0, 0, 0};
@@ -122,18 +183,20 @@ struct HostSensor {
   int loss_type = 0;
   double loss_scale = 1;
   bool en_intr = false, en_extr = false, en_lat = false;
-  std::vector<double> stamp, meas;
-  std::vector<int> body_slot, feat_slot;
-  std::vector<uint8_t> outlier;
-  std::vector<double> residuals;
-  std::vector<uint8_t> residual_valid;
+  PooledArray<double> stamp, meas;
+  PooledArray<int> body_slot, feat_slot;
+  PooledArray<uint8_t> outlier;
+  const double* residuals = nullptr;          // [n_obs][m] after cb2_optimize: points into the problem's pinned result block
+  const uint8_t* residual_valid = nullptr;    // [n_obs]
   int m() const { return kind == kCamera ? 2 : 3; }
   int n_obs() const { return int(stamp.size()); }
   // device-side bookkeeping
   std::vector<int> perm;      // sorted position -> original observation index
   int n_active = 0;
-  DevBuf<double> d_stamp, d_meas, d_r, d_J;
-  DevBuf<int> d_seg, d_pt, d_seg_start, d_frm, d_frame_obs, d_seg_frame, d_perm;
+  DevBuf<unsigned char> d_obs;   // ONE block per sensor: [stamp | measurement | segment | point | image | permutation], filled by one H2D copy
+  const int* d_perm = nullptr;   // (inside d_obs)
+  DevBuf<double> d_r, d_J;
+  DevBuf<int> d_seg_start, d_frame_obs, d_seg_frame;
   DevBuf<unsigned char> d_valid;
 };
 
@@ -534,8 +597,18 @@ struct cb2_problem {
     const double* vk = knots.data() + (kK - 1);
     const int nv = int(knots.size()) - 2 * (kK - 1);
     if (t == vk[nv - 1]) return nv - 2;
-    if (t < vk[nv - 1]) return int(std::upper_bound(vk, vk + nv, t) - vk) - 1;
-    return -1;
+    if (!(t < vk[nv - 1])) return -1;
+    // Same answer as upper_bound(valid knots, t) - 1 (bspline.hpp:139-151); the knots are (nearly always) uniform, so a linear guess
+    // corrected against the knot values replaces the binary search.
+    if (t >= vk[0] && nv >= 2) {
+      int i = int((t - vk[0]) / (vk[nv - 1] - vk[0]) * (nv - 1));
+      i = std::min(std::max(i, 0), nv - 2);
+      int steps = 0;
+      while (i > 0 && vk[i] > t && steps < 4) { --i; ++steps; }
+      while (i < nv - 2 && vk[i + 1] <= t && steps < 4) { ++i; ++steps; }
+      if (vk[i] <= t && t < vk[i + 1]) return i;
+    }
+    return int(std::upper_bound(vk, vk + nv, t) - vk) - 1;
   }
 
   // ------------------------------------------------------------------------------------------------------------
@@ -580,7 +653,9 @@ struct cb2_problem {
     return CB2_OK;
   }
 
+  bool timing_log = std::getenv("CB2_TIMING") != nullptr;
   int upload_impl() {
+    const double t_upload0 = now_s();
     uploaded = false;
     if (stream) sync_stream();
     drop_graphs();   // every device pointer baked into a captured solve phase is about to change
@@ -636,9 +711,12 @@ struct cb2_problem {
     struct Packed {
       int rc = CB2_OK; std::string err;
       int want = 0, n_active = 0; long blocks = 0, residuals = 0; bool ref_any = false;
-      std::vector<int> seg_start, seg, pt, frm, frame_seg, frame_obs, seg_frame;
-      std::vector<double> stamp, meas, frame_stamp;
+      std::vector<int> seg_start, frame_seg, frame_obs, seg_frame;
+      std::vector<double> frame_stamp;
       std::vector<unsigned char> cp_ref, pt_ref;
+      // the per-observation arrays, packed straight into ONE pinned staging block (offsets in bytes, 256-byte aligned)
+      PinnedBuf pin;
+      size_t off_stamp = 0, off_meas = 0, off_seg = 0, off_pt = 0, off_frm = 0, off_perm = 0, bytes = 0;
     };
     std::vector<Packed> packed(ns);
     auto pack_sensor = [&](int si) {
@@ -689,17 +767,34 @@ struct cb2_problem {
         }
       }
       s.n_active = P.n_active = n_active;
-      P.stamp.resize(n_active); P.meas.resize(size_t(n_active) * m); P.seg.resize(n_active);
-      if (s.kind == kCamera) { P.pt.resize(n_active); P.frm.resize(n_active); }
+      {
+        auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+        size_t off = 0;
+        P.off_stamp = off; off = al(off + size_t(n_active) * 8);
+        P.off_meas = off; off = al(off + size_t(n_active) * m * 8);
+        P.off_seg = off; off = al(off + size_t(n_active) * 4);
+        P.off_pt = off; off = al(off + (s.kind == kCamera ? size_t(n_active) * 4 : 0));
+        P.off_frm = off; off = al(off + (s.kind == kCamera ? size_t(n_active) * 4 : 0));
+        P.off_perm = off; off = al(off + size_t(n_active) * 4);
+        P.bytes = off;
+        P.pin.acquire(std::max<size_t>(off, 256));
+      }
+      unsigned char* base = static_cast<unsigned char*>(P.pin.p);
+      double* p_stamp = reinterpret_cast<double*>(base + P.off_stamp);
+      double* p_meas = reinterpret_cast<double*>(base + P.off_meas);
+      int* p_seg = reinterpret_cast<int*>(base + P.off_seg);
+      int* p_pt = reinterpret_cast<int*>(base + P.off_pt);
+      int* p_frm = reinterpret_cast<int*>(base + P.off_frm);
+      std::memcpy(base + P.off_perm, s.perm.data(), size_t(n_active) * 4);
       for (int i = 0; i < n_active; ++i) {
         const int o = s.perm[i];
-        P.stamp[i] = s.stamp[o];
-        P.seg[i] = seg_of[o];
-        for (int q = 0; q < m; ++q) P.meas[size_t(i) * m + q] = s.meas[size_t(o) * m + q];
+        p_stamp[i] = s.stamp[o];
+        p_seg[i] = seg_of[o];
+        for (int q = 0; q < m; ++q) p_meas[size_t(i) * m + q] = s.meas[size_t(o) * m + q];
         if (s.kind == kCamera) {
-          P.pt[i] = bodies[s.body_slot[o]].pw0 + s.feat_slot[o];
-          if (i == 0 || P.stamp[i] != P.stamp[i - 1]) { P.frame_seg.push_back(P.seg[i]); P.frame_stamp.push_back(P.stamp[i]); P.frame_obs.push_back(i); }
-          P.frm[i] = int(P.frame_stamp.size()) - 1;                // sensor-local image index; SensorDesc::frame_base makes it global
+          p_pt[i] = bodies[s.body_slot[o]].pw0 + s.feat_slot[o];
+          if (i == 0 || p_stamp[i] != p_stamp[i - 1]) { P.frame_seg.push_back(p_seg[i]); P.frame_stamp.push_back(p_stamp[i]); P.frame_obs.push_back(i); }
+          p_frm[i] = int(P.frame_stamp.size()) - 1;                // sensor-local image index; SensorDesc::frame_base makes it global
         }
       }
       if (s.kind == kCamera) {                                     // image CSR for the structured accumulation (cb2_normal.cuh)
@@ -720,6 +815,7 @@ struct cb2_problem {
       for (auto& th : pool) th.join();
     }
 #endif
+    const double t_packed = now_s();
     // Phase B (serial): unknown layout, device buffers, uploads.
     for (int si = 0; si < ns; ++si) {
       HostSensor& s = sensors[si];
@@ -733,11 +829,12 @@ struct cb2_problem {
       frame_sensor.insert(frame_sensor.end(), P.frame_stamp.size(), si);
       frame_seg.insert(frame_seg.end(), P.frame_seg.begin(), P.frame_seg.end());
       frame_stamp.insert(frame_stamp.end(), P.frame_stamp.begin(), P.frame_stamp.end());
-      const std::vector<double>&stamp = P.stamp, &meas = P.meas;
-      const std::vector<int>&seg = P.seg, &pt = P.pt, &frm = P.frm, &seg_start = P.seg_start;
-      s.d_stamp.upload(stamp, h2d); s.d_meas.upload(meas, h2d); s.d_seg.upload(seg, h2d); s.d_pt.upload(pt, h2d); s.d_frm.upload(frm, h2d);
+      const std::vector<int>& seg_start = P.seg_start;
+      // ONE asynchronous host -> device copy per sensor, from the pinned block its packing thread filled.
+      s.d_obs.alloc(std::max<size_t>(P.bytes, 256), false);
+      if (P.bytes) { CB2_CUDA(cudaMemcpyAsync(s.d_obs.p, P.pin.p, P.bytes, cudaMemcpyHostToDevice, nullptr)); *h2d += int64_t(P.bytes); }
+      s.d_perm = reinterpret_cast<const int*>(s.d_obs.p + P.off_perm);
       s.d_seg_start.upload(seg_start, h2d);
-      s.d_perm.upload(s.perm, h2d);
       if (s.kind == kCamera) { s.d_frame_obs.upload(P.frame_obs, h2d); s.d_seg_frame.upload(P.seg_frame, h2d); }
       // Unknown layout of this sensor (constant or unreferenced blocks drop out, as in Ceres's reduced program).
       SensorDesc& d = h_desc[si];
@@ -774,7 +871,9 @@ struct cb2_problem {
       s.d_r.alloc(size_t(n_active) * m);
       s.d_J.alloc(size_t(n_active) * m * d.jw);
       s.d_valid.alloc(n_active);
-      d.stamp = s.d_stamp.p; d.meas = s.d_meas.p; d.seg = s.d_seg.p; d.pt = s.d_pt.p; d.seg_start = s.d_seg_start.p; d.frm = s.d_frm.p;
+      d.stamp = reinterpret_cast<const double*>(s.d_obs.p + P.off_stamp); d.meas = reinterpret_cast<const double*>(s.d_obs.p + P.off_meas);
+      d.seg = reinterpret_cast<const int*>(s.d_obs.p + P.off_seg); d.pt = reinterpret_cast<const int*>(s.d_obs.p + P.off_pt);
+      d.frm = reinterpret_cast<const int*>(s.d_obs.p + P.off_frm); d.seg_start = s.d_seg_start.p;
       d.r = s.d_r.p; d.J = s.d_J.p; d.valid = s.d_valid.p;
       d.frame_obs = s.kind == kCamera ? s.d_frame_obs.p : nullptr; d.seg_frame = s.kind == kCamera ? s.d_seg_frame.p : nullptr;
       for (int o0 = 0, T = eval_tile(s.kind); o0 < n_active; o0 += T) tiles_by_kind[s.kind].push_back(EvalTile{si, o0, std::min(T, n_active - o0)});
@@ -878,6 +977,7 @@ struct cb2_problem {
     if (rc != CB2_OK) return rc;
     set_kernel_attributes();
     CB2_CUDA(cudaDeviceSynchronize());
+    if (timing_log) std::fprintf(stderr, "[cb2 timing] upload: pack %.2f ms, layout + alloc + H2D + plan %.2f ms\n", 1e3 * (t_packed - t_upload0), 1e3 * (now_s() - t_packed));
     uploaded = true;
     scaling_set = false;
     return CB2_OK;
@@ -1588,6 +1688,7 @@ struct cb2_problem {
   // rank), and (ii) the host receives final-layout arrays: two device -> host copies, no host-side un-permutation.
   DevBuf<double> d_rfull;
   DevBuf<unsigned char> d_vfull;
+  PinnedBuf h_res;
   int refresh_residuals() {
     launch_eval<kModeResiduals>(cur, kScCost);
     if (world > 1) comm->allreduce_sum(d_scal.p + kScCost, 2, stream);
@@ -1599,20 +1700,23 @@ struct cb2_problem {
     for (int si = 0; si < ns; ++si) {
       HostSensor& s = sensors[si];
       if (s.n_active > 0)
-        CB2_K(scatter_residuals_kernel, std::min((s.n_active + 255) / 256, 1184), 256, 0, stream, s.n_active, s.m(), s.d_perm.p, s.d_r.p, s.d_valid.p, d_rfull.p + roff[si],
+        CB2_K(scatter_residuals_kernel, std::min((s.n_active + 255) / 256, 1184), 256, 0, stream, s.n_active, s.m(), s.d_perm, s.d_r.p, s.d_valid.p, d_rfull.p + roff[si],
               d_vfull.p + voff[si]);
     }
     if (world > 1 && roff[ns] > 0) { comm->allreduce_sum(d_rfull.p, roff[ns], stream); comm->allreduce_sum_u8(d_vfull.p, voff[ns], stream); }
     sync_scalars();
-    // Device -> host straight into the per-sensor result vectors (the totals are what Sensor::UpdateResiduals fills per measurement).
+    // Device -> host: two asynchronous copies into the problem's pinned result block; cb2_get_residuals hands out slices of it.
+    const size_t rbytes = roff[ns] * sizeof(double);
+    h_res.acquire(std::max<size_t>(rbytes + voff[ns], 256));
+    unsigned char* hb = static_cast<unsigned char*>(h_res.p);
+    if (roff[ns]) {
+      CB2_CUDA(cudaMemcpyAsync(hb, d_rfull.p, rbytes, cudaMemcpyDeviceToHost, stream));
+      CB2_CUDA(cudaMemcpyAsync(hb + rbytes, d_vfull.p, voff[ns], cudaMemcpyDeviceToHost, stream));
+      stats.d2h_bytes += int64_t(rbytes + voff[ns]);
+    }
     for (int si = 0; si < ns; ++si) {
-      HostSensor& s = sensors[si];
-      s.residuals.resize(size_t(s.n_obs()) * s.m());
-      s.residual_valid.resize(s.n_obs());
-      if (s.n_obs() == 0) continue;
-      CB2_CUDA(cudaMemcpyAsync(s.residuals.data(), d_rfull.p + roff[si], s.residuals.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
-      CB2_CUDA(cudaMemcpyAsync(s.residual_valid.data(), d_vfull.p + voff[si], s.residual_valid.size(), cudaMemcpyDeviceToHost, stream));
-      stats.d2h_bytes += int64_t(s.residuals.size() * sizeof(double) + s.residual_valid.size());
+      sensors[si].residuals = reinterpret_cast<const double*>(hb) + roff[si];
+      sensors[si].residual_valid = hb + rbytes + voff[si];
     }
     sync_stream();
     int rc = CB2_OK;
@@ -1780,11 +1884,12 @@ int cb2_add_camera_observations(cb2_problem* p, int sid, int n, const double* st
   }
   const size_t base = s.stamp.size();
   s.stamp.reserve(base + n); s.meas.reserve((base + n) * 2); s.body_slot.reserve(base + n); s.feat_slot.reserve(base + n); s.outlier.reserve(base + n);
-  s.stamp.insert(s.stamp.end(), stamp, stamp + n);
-  s.meas.insert(s.meas.end(), pixel, pixel + size_t(n) * 2);
-  s.body_slot.insert(s.body_slot.end(), bslot.begin(), bslot.end());
-  s.feat_slot.insert(s.feat_slot.end(), fslot.begin(), fslot.end());
-  if (outlier) s.outlier.insert(s.outlier.end(), outlier, outlier + n); else s.outlier.insert(s.outlier.end(), size_t(n), uint8_t(0));
+  s.stamp.append(stamp, n);
+  s.meas.append(pixel, size_t(n) * 2);
+  s.body_slot.append(bslot.data(), n);
+  s.feat_slot.append(fslot.data(), n);
+  if (outlier) s.outlier.append(outlier, n); else s.outlier.append_fill(size_t(n), uint8_t(0));
+  s.residuals = nullptr; s.residual_valid = nullptr;   // the residuals of an earlier Optimize no longer match the measurement set
   p->uploaded = false;
   return CB2_OK;
   });
@@ -1797,9 +1902,10 @@ int cb2_add_imu_observations(cb2_problem* p, int sid, int n, const double* stamp
   if (n < 0) return p->fail(CB2_INVALID_ARGUMENT, "Negative observation count.");
   HostSensor& s = p->sensors[sid];
   s.stamp.reserve(s.stamp.size() + n); s.meas.reserve(s.meas.size() + size_t(n) * 3); s.outlier.reserve(s.outlier.size() + n);
-  s.stamp.insert(s.stamp.end(), stamp, stamp + n);
-  s.meas.insert(s.meas.end(), xyz, xyz + size_t(n) * 3);
-  s.outlier.insert(s.outlier.end(), n, 0);
+  s.stamp.append(stamp, n);
+  s.meas.append(xyz, size_t(n) * 3);
+  s.outlier.append_fill(size_t(n), uint8_t(0));
+  s.residuals = nullptr; s.residual_valid = nullptr;
   p->uploaded = false;
   return CB2_OK;
   });
@@ -1814,13 +1920,18 @@ int cb2_optimize(cb2_problem* p, const cb2_options* opts, cb2_summary* summary, 
     if (!p->uploaded) { const int rc = p->upload(); if (rc != CB2_OK) return rc; }
     std::vector<cb2_iteration> L;
     cb2_summary S;
+    const double t0 = now_s();
     int rc = p->minimize(o, S, L);
+    const double t1 = now_s();
     if (summary) *summary = S;
     if (n_log) *n_log = int(L.size());
     if (log) for (int i = 0; i < int(L.size()) && i < log_cap; ++i) log[i] = L[i];
     if (rc != CB2_OK) return rc;
     p->download_parameters();
-    return p->refresh_residuals();
+    const double t2 = now_s();
+    rc = p->refresh_residuals();
+    if (p->timing_log) std::fprintf(stderr, "[cb2 timing] optimize: LM loop %.2f ms, parameter write-back %.2f ms, residual refresh %.2f ms\n", 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (now_s() - t2));
+    return rc;
   });
 }
 
@@ -1931,9 +2042,9 @@ int cb2_get_trajectory(cb2_problem* p, double* ctrl) { std::memcpy(ctrl, p->ctrl
 int cb2_get_residuals(cb2_problem* p, int sid, double* out, uint8_t* valid) {
   if (sid < 0 || sid >= int(p->sensors.size())) return p->fail(CB2_INVALID_ARGUMENT, "Unknown sensor id.");
   const HostSensor& s = p->sensors[sid];
-  if (s.residuals.empty() && s.n_obs() > 0) return p->fail(CB2_FAILED_PRECONDITION, "Residuals have not been computed.");
-  if (out) std::memcpy(out, s.residuals.data(), s.residuals.size() * 8);
-  if (valid) std::memcpy(valid, s.residual_valid.data(), s.residual_valid.size());
+  if (!s.residuals && s.n_obs() > 0) return p->fail(CB2_FAILED_PRECONDITION, "Residuals have not been computed.");
+  if (out && s.n_obs() > 0) std::memcpy(out, s.residuals, size_t(s.n_obs()) * s.m() * 8);
+  if (valid && s.n_obs() > 0) std::memcpy(valid, s.residual_valid, size_t(s.n_obs()));
   return CB2_OK;
 }
 

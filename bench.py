@@ -96,8 +96,9 @@ def sample_config(name, frames):
 
 
 def bench_options(_capi_or_oracle_opts, iters, **kw):
-    """Tolerances disabled: exactly `iters` LM iterations are run."""
-    return _capi_or_oracle_opts(max_num_iterations=iters, function_tolerance=0.0, gradient_tolerance=0.0, parameter_tolerance=0.0,
+    """Tolerances disabled (negative: Ceres's tests are `<=`, so that an exactly-zero cost change at convergence does not stop the run either):
+    exactly `iters` LM iterations are run."""
+    return _capi_or_oracle_opts(max_num_iterations=iters, function_tolerance=-1.0, gradient_tolerance=-1.0, parameter_tolerance=-1.0,
                                 min_trust_region_radius=0.0, minimizer_progress_to_stdout=0, **kw)
 
 

@@ -239,3 +239,59 @@ def test_linear_solvers_agree(oracle):
         costs.append([it.cost for it in log])
     np.testing.assert_allclose(costs[1], costs[0], rtol=1e-9)
     np.testing.assert_allclose(costs[2], costs[0], rtol=1e-9)
+
+
+def test_wide_angle_models_round_trip_like_the_reference_test(oracle):
+    """The reference's own test of DoubleSphere / FieldOfView / UnifiedCamera / ExtendedUnifiedCamera (camera_models_test.cpp:170-253):
+    project the 61 x 61 ground grid seen from 1 m above its centre (fixture :71-101), invert with the model's closed-form inverse and compare
+    the bearing vectors — tolerance 1e-12, and 2e-2 for ExtendedUnifiedCamera whose projection (camera_models.h:995, `beta * norm`, not
+    squared) is not the inverse of its own UnprojectPixel. The inverses below are the published closed forms (Usenko et al. 2018 for the
+    double sphere / unified / extended unified models, Devernay & Faugeras 2001 for the field-of-view model) written independently in
+    numpy: this pins the oracle's ProjectPoint of the four models that have no OpenCV counterpart."""
+    R_wc = np.diag([1.0, -1.0, -1.0])
+    t_wc = np.array([0.75, 0.75, 1.0])
+    xs = np.arange(61) * 0.025
+    pts_w = np.array([[x, y, 0.0] for x in xs for y in xs])
+    pts_c = (pts_w - t_wc) @ R_wc          # R_wc^T (p - t), R_wc symmetric
+    bearing = pts_c / np.linalg.norm(pts_c, axis=1, keepdims=True)
+
+    def inv_double_sphere(intr, px):
+        f, cx, cy, xi, al = intr
+        mx, my = (px[0] - cx) / f, (px[1] - cy) / f
+        r2 = mx * mx + my * my
+        mz = (1 - al * al * r2) / (al * np.sqrt(1 - (2 * al - 1) * r2) + 1 - al)
+        k = (mz * xi + np.sqrt(mz * mz + (1 - xi * xi) * r2)) / (mz * mz + r2)
+        return np.array([k * mx, k * my, k * mz - xi])
+
+    def inv_fov(intr, px):
+        f, cx, cy, w = intr
+        mx, my = (px[0] - cx) / f, (px[1] - cy) / f
+        rd = np.hypot(mx, my)
+        eta = np.sin(rd * w) / (2 * rd * np.tan(w / 2)) if rd > 1e-8 else w / (2 * np.tan(w / 2))
+        return np.array([eta * mx, eta * my, np.cos(rd * w)])
+
+    def inv_unified(intr, px):
+        f, cx, cy, al = intr
+        mx, my = (1 - al) * (px[0] - cx) / f, (1 - al) * (px[1] - cy) / f
+        r2 = mx * mx + my * my
+        xi = al / (1 - al)
+        k = (xi + np.sqrt(1 + (1 - xi * xi) * r2)) / (1 + r2)
+        return np.array([k * mx, k * my, k - xi])
+
+    def inv_extended_unified(intr, px):
+        f, cx, cy, al, be = intr
+        mx, my = (px[0] - cx) / f, (px[1] - cy) / f
+        r2 = mx * mx + my * my
+        mz = (1 - be * al * al * r2) / (al * np.sqrt(1 - (2 * al - 1) * be * r2) + 1 - al)
+        return np.array([mx, my, mz])
+
+    cases = [(4, [785.0, 640, 400, 0.5, 0.5], inv_double_sphere, 1e-12), (5, [785.0, 640, 400, 0.05], inv_fov, 1e-12),
+             (6, [785.0, 640, 400, 0.5], inv_unified, 1e-12), (7, [785.0, 640, 400, 0.5, 0.5], inv_extended_unified, 2e-2)]
+    for model, intr, inverse, tol in cases:
+        worst = 0.0
+        for p, b in zip(pts_c, bearing):
+            ok, px = oracle.project_point(model, intr, p)
+            assert ok
+            v = inverse(intr, px)
+            worst = max(worst, np.abs(v / np.linalg.norm(v) - b).max())
+        assert worst <= tol, (model, worst)

@@ -62,7 +62,13 @@ template <bool kFirst>
 __global__ void __launch_bounds__(kCrThreads, (kFirst ? 2 : 1)) cr_level_kernel(const BandSys* __restrict__ systems, int level, long n_a, int N_c,
                                                              const double* __restrict__ Aband, const double* __restrict__ Bmat,
                                                              const double* __restrict__ Cmat, const double* __restrict__ grad,
-                                                             const double* __restrict__ dtil2, double* __restrict__ scal, int use_tma) {
+                                                             const double* __restrict__ dtil2, double* __restrict__ scal, int use_tma,
+                                                             int band_w = kCpCols, int b_stride = 0, int rhs_stride = 1, long src_row0 = -1) {
+  // Where the first level reads the system from: the assembled normal equations (band of width band_w = 36 in Aband, border rows in Bmat
+  // with stride b_stride = N_c, right-hand side grad, LM damping dtil2, rows src_row0 + i = the chunk's consecutive unknowns) or, for the
+  // SEPARATOR level between the chunks, the reduced separator system the ranks have just summed (band_w = 60, border + rhs rows of
+  // b_stride = N_c + 1 doubles, damping already added, src_row0 = 0).
+  if (b_stride == 0) b_stride = N_c;
   const BandSys sy = systems[blockIdx.y];
   const int stride = 1 << level;
   const int j = blockIdx.x, i = j * stride;
@@ -74,6 +80,15 @@ __global__ void __launch_bounds__(kCrThreads, (kFirst ? 2 : 1)) cr_level_kernel(
   const int nbw = sy.nbw, n = sy.n, t = threadIdx.x;
   const int M = 2 * kCrB + nbw;                                 // columns of X = [E | F | border]
   const int XS = cr_row_stride(nbw);
+  // Column split: gridDim.z CTAs work on one block. Everyone factors the (small) diagonal block and solves the 60 coupling columns [E | F]
+  // — they are the left operand of the Schur update — but solves, multiplies and stores only its own slice of 8-column blocks of
+  // X = [E | F | border]: the update U = [W_E W_F]^T W (80 % of the arithmetic, bound by the FP64 tensor pipe of ONE SM otherwise) and the
+  // forward substitution spread over gridDim.z SMs. Slice 0 also owns the per-block outputs (factor, [W_E | W_F]^T, failure flag).
+  const int nqb_all = (M + 7) / 8;
+  const int zid = blockIdx.z, nz = gridDim.z;
+  const int qb_lo = zid * nqb_all / nz, qb_hi = (zid + 1) * nqb_all / nz;
+  const int sl_lo = max(8 * qb_lo, 2 * kCrB), sl_hi = min(M, 8 * qb_hi);      // own columns beyond the coupling columns (solved by everyone)
+  const int n_extra = max(0, sl_hi - sl_lo);
   double* X = dyn_smem<double>();                               // [32][XS]; rows 30, 31 stay zero (k padding of the DMMA product)
   double* Dm = X + 32 * XS;                                     // [30][31]
   double* Lc = Dm + kCrB * kCrLs + (kCrB * kCrLs & 1);          // [30][32] copy of the factor, 16-byte aligned rows
@@ -99,7 +114,7 @@ __global__ void __launch_bounds__(kCrThreads, (kFirst ? 2 : 1)) cr_level_kernel(
   // latency-bound (one CTA per block, ~17 k doubles from L2), so memory-level parallelism is what sets their duration.
   const double* __restrict__ crD = sy.crD + size_t(i) * (kCrB * kCrB);
   const double* __restrict__ crBd = sy.crBd + size_t(i) * kCrB * nbw;
-  const long g0 = kFirst ? long(sy.row_gidx[0]) : 0;             // level-1 chunk rows are consecutive unknowns: row -> g0 + row
+  const long g0 = kFirst ? (src_row0 >= 0 ? src_row0 : long(sy.row_gidx[0])) : 0;   // level-1 chunk rows are consecutive unknowns: row -> g0 + row
   int* colg = reinterpret_cast<int*>(dinv + 32);                 // [nbw] global unknown of every border column (level 0 only)
   if (kFirst) {
     for (int c = t; c < nbw - 1; c += kCrThreads) colg[c] = sy.col_gidx[c];
@@ -111,8 +126,8 @@ __global__ void __launch_bounds__(kCrThreads, (kFirst ? 2 : 1)) cr_level_kernel(
   const double* __restrict__ URz = UR ? UR : sy.crZero;
   auto band_ptr = [&](long gi, long gj, bool& ok) -> const double* {   // &A(gi, gj) of the assembled band; ok = inside the block band
     const long hi = gi > gj ? gi : gj, d = gi > gj ? gi - gj : gj - gi;
-    ok = d < kCpCols;
-    return Aband + hi * kCpCols + (kCpCols - 1 - (ok ? d : 0));
+    ok = d < band_w;
+    return Aband + hi * band_w + (band_w - 1 - (ok ? d : 0));
   };
   // ---- 1. state of the block ----
   // Non-first levels, TMA path (when the staging area fits beside the working set): everything the block needs is FOUR contiguous pieces of
@@ -162,7 +177,7 @@ __global__ void __launch_bounds__(kCrThreads, (kFirst ? 2 : 1)) cr_level_kernel(
       const bool in = r0 + r < n && r0 + c < n;
       const long gi = g0 + min(r0 + r, n - 1), gj = g0 + min(r0 + c, n - 1);
       bool ok;
-      const double a = *band_ptr(gi, gj, ok), dd = dtil2[gi];
+      const double a = *band_ptr(gi, gj, ok), dd = dtil2 ? dtil2[gi] : 0.0;
       return in ? a + (r == c ? dd : 0.0) : (r == c ? 1.0 : 0.0);   // padding rows of a partial last block: identity
     }
     return crD[e] - ULz[size_t(kCrB + r) * UW + kCrB + c] - URz[size_t(r) * UW + c];
@@ -172,10 +187,10 @@ __global__ void __launch_bounds__(kCrThreads, (kFirst ? 2 : 1)) cr_level_kernel(
     const int cal0 = sy.cal0, ncal = nbw - 1 - cal0;
     cr_batched(kCrB * ncal, t, [&](int e) -> double {
       const int r = e / ncal, c = e - r * ncal;
-      const double v = Bmat[(g0 + min(r0 + r, n - 1)) * N_c + c];
+      const double v = Bmat[(g0 + min(r0 + r, n - 1)) * b_stride + c];
       return r0 + r < n ? v : 0.0;
     }, [&](int e, double v) { const int r = e / ncal; X[r * XS + 2 * kCrB + cal0 + (e - r * ncal)] = v; });
-    if (t < kCrB) X[t * XS + 2 * kCrB + nbw - 1] = r0 + t < n ? grad[g0 + r0 + t] : 0.0;
+    if (t < kCrB) X[t * XS + 2 * kCrB + nbw - 1] = r0 + t < n ? grad[(g0 + min(r0 + t, n - 1)) * rhs_stride] : 0.0;
     if (cal0 > 0) cr_batched(kCrB * cal0, t, [&](int e) -> double {
       const int r = e / cal0, c = e - r * cal0;
       const long gi = g0 + min(r0 + r, n - 1), gj = colg[c];
@@ -190,6 +205,7 @@ __global__ void __launch_bounds__(kCrThreads, (kFirst ? 2 : 1)) cr_level_kernel(
   }
   }
   if (!elim) {
+    if (zid != 0) return;                                        // a surviving block only carries its state over: one CTA does it
     __syncthreads();
     for (int e = t; e < kCrB * kCrB; e += kCrThreads) sy.crD[size_t(i) * (kCrB * kCrB) + e] = Dm[(e / kCrB) * kCrLs + e % kCrB];
     for (int e = t; e < kCrB * nbw; e += kCrThreads) sy.crBd[size_t(i) * kCrB * nbw + e] = X[(e / nbw) * XS + 2 * kCrB + e % nbw];
@@ -273,8 +289,9 @@ __global__ void __launch_bounds__(kCrThreads, (kFirst ? 2 : 1)) cr_level_kernel(
   for (int e = t; e < kCrB * kCrLc; e += kCrThreads) { const int r = e / kCrLc, c = e % kCrLc; Lc[e] = (c < r) ? Dm[r * kCrLs + c] : 0.0; }
   __syncthreads();
   CB2_CLK(2);
-  // ---- 2b. W = L^-1 X, one thread per column (L is read as a shared-memory broadcast) ----
-  for (int c = t; c < M; c += kCrThreads) {
+  // ---- 2b. W = L^-1 X for the coupling columns and the own slice, one thread per column (L is read as a shared-memory broadcast) ----
+  for (int idx = t; idx < 2 * kCrB + n_extra; idx += kCrThreads) {
+    const int c = idx < 2 * kCrB ? idx : sl_lo + (idx - 2 * kCrB);
     double w[kCrB];
 #pragma unroll
     for (int r = 0; r < kCrB; ++r) {
@@ -291,26 +308,28 @@ __global__ void __launch_bounds__(kCrThreads, (kFirst ? 2 : 1)) cr_level_kernel(
 #pragma unroll
     for (int r = 0; r < kCrB; ++r) X[r * XS + c] = w[r];
     if (c < 2 * kCrB) {
+      if (zid == 0) {
 #pragma unroll
-      for (int r = 0; r < kCrB; ++r) sy.crWef[size_t(i) * kCrB * (2 * kCrB) + c * kCrB + r] = w[r];   // transposed: [60][30]
+        for (int r = 0; r < kCrB; ++r) sy.crWef[size_t(i) * kCrB * (2 * kCrB) + c * kCrB + r] = w[r];   // transposed: [60][30]
+      }
     } else {
 #pragma unroll
       for (int r = 0; r < kCrB; ++r) if (r0 + r < n) sy.W[size_t(r0 + r) * nbw + (c - 2 * kCrB)] = w[r];
     }
   }
-  for (int e = t; e < kCrB * kCrB; e += kCrThreads) {
+  if (zid == 0) for (int e = t; e < kCrB * kCrB; e += kCrThreads) {
     const int r = e / kCrB, c = e % kCrB;
     sy.crL[size_t(i) * (kCrB * kCrB) + e] = c <= r ? Dm[r * kCrLs + c] : 0.0;
   }
   __syncthreads();
   CB2_CLK(3);
-  if (t == 0 && s_fail) atomicAdd(&scal[kScSolveFail], 1.0);
+  if (t == 0 && s_fail && zid == 0) atomicAdd(&scal[kScSolveFail], 1.0);
   if (nact == 1) return;                                         // last block of the chunk: nothing left to update
   // ---- 2c. U = [W_E W_F]^T W on the FP64 tensor pipe: 8x8 tiles, k = 32 (rows 30, 31 are zero) ----
   {
     double* U = sy.crU + size_t(level & 1) * sy.cr_uslots * usz + size_t(i / (2 * stride)) * usz;
     const int warp = t >> 5, lane = t & 31, fr = lane & 3, fc = lane >> 2;
-    const int nqb = (M + 7) / 8;
+    const int nqb = qb_hi;                                       // own slice of column blocks [qb_lo, qb_hi)
     // Warp w owns the 8 output rows p = 8 w .. 8 w + 7 (60 rows = 7.5 row blocks = the 8 warps): its A fragments (8 k-steps) stay in
     // registers, the B fragments stream from shared memory, 4 column blocks (independent accumulators) at a time.
     const int pb = warp;
@@ -318,7 +337,7 @@ __global__ void __launch_bounds__(kCrThreads, (kFirst ? 2 : 1)) cr_level_kernel(
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) af[ks] = X[(4 * ks + fr) * XS + 8 * pb + fc];
     const int p = 8 * pb + fc;
-    for (int qb0 = 0; qb0 < nqb; qb0 += 4) {
+    for (int qb0 = qb_lo; qb0 < nqb; qb0 += 4) {
       double acc[4][2];
 #pragma unroll
       for (int u = 0; u < 4; ++u) { acc[u][0] = 0.0; acc[u][1] = 0.0; }

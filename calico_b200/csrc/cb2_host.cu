@@ -118,7 +118,13 @@ struct PinnedPool {
     }
     const size_t c = (bytes + (size_t(1) << 20) - 1) >> 20 << 20;
     void* p = nullptr;
-    if (cudaMallocHost(&p, c) != cudaSuccess) { cudaGetLastError(); throw CudaFail{"cudaMallocHost failed (pinned staging memory)"}; }
+    if (cudaMallocHost(&p, c) != cudaSuccess) {
+      // No device (problem assembly and the shard plan work without one) or pinning refused: ordinary host memory — copies from it still
+      // work, only slower. Blocks are never returned to the system, so the two kinds can share the pool.
+      cudaGetLastError();
+      p = std::aligned_alloc(256, c);
+      if (!p) throw std::bad_alloc();
+    }
     *cap = c;
     return p;
   }
@@ -461,8 +467,13 @@ struct cb2_problem {
   // level 1 by block cyclic reduction (cb2_cr.cuh): the default; CB2_SCHUR=band selects the chunked left-to-right band factor
   bool use_cr = true;
   int cr_nlevels = 0, cr_max_nblk = 0;
+  int cr_zsplit = 1;                // CTAs per block of a cyclic-reduction level (column split of the forward substitution + Schur update)
   bool cr_tma = false;              // non-first levels fetch their state with TMA bulk copies (cb2_cr.cuh)
   DevBuf<double> d_crD, d_crBd, d_crU, d_crWef, d_crL;
+  // the separator level between the chunks by the same cyclic-reduction kernels (CB2_SEP_BAND=1: the single-CTA band factor instead)
+  bool sep_cr = false, gram_dmma2 = false;
+  int cr2_nlevels = 0;
+  DevBuf<double> d_cr2D, d_cr2Bd, d_cr2U, d_cr2Wef, d_cr2L;
   int cur = 0;   // which of the two parameter buffers holds x
   size_t smem_eval[3] = {0, 0, 0};
   int max_tilepairs1 = 0, max_ksplit1 = 1;
@@ -1099,13 +1110,26 @@ struct cb2_problem {
     h_l2.L = d_red.p; h_l2.W = d_red.p + szL2; h_l2.T = d_T2.p; h_l2.Dinv = d_Dinv.p + Dsz;
     red_Cw = d_red.p + szL2 + szW2;
     red_count = szL2 + szW2 + szCw;
+    sep_cr = use_cr && n2 > 0 && std::getenv("CB2_SEP_BAND") == nullptr && cr_smem_bytes(nbw2) <= 227 * 1024;
+    gram_dmma2 = sep_cr && nbw2 <= kGramMaxNbw && !std::getenv("CB2_GRAM_SIMT");
+    if (sep_cr) {
+      // separators = a block-tridiagonal chain of P - 1 blocks of 30 with the border [calibration | rhs]: cyclic reduction again
+      h_l2.nblk = n2 / kCrB; h_l2.cr_uslots = (h_l2.nblk + 1) / 2; h_l2.cal0 = 0;
+      cr2_nlevels = cr_levels(h_l2.nblk);
+      const size_t usz2 = cr_u_size(nbw2);
+      d_cr2D.alloc(size_t(h_l2.nblk) * kCrB * kCrB); d_cr2L.alloc(size_t(h_l2.nblk) * kCrB * kCrB); d_cr2Bd.alloc(size_t(h_l2.nblk) * kCrB * nbw2);
+      d_cr2Wef.alloc(size_t(h_l2.nblk) * kCrB * 2 * kCrB); d_cr2U.alloc(2 * size_t(h_l2.cr_uslots) * usz2 + usz2);
+      h_l2.crD = d_cr2D.p; h_l2.crL = d_cr2L.p; h_l2.crBd = d_cr2Bd.p; h_l2.crWef = d_cr2Wef.p; h_l2.crU = d_cr2U.p;
+      h_l2.crZero = d_cr2U.p + 2 * size_t(h_l2.cr_uslots) * usz2;
+      if (gram_dmma2) { h_l2.ksplit = std::max(1, std::min((n2 + kGramRows - 1) / kGramRows, 148)); d_T2.alloc(size_t(h_l2.ksplit) * nbw2 * nbw2); h_l2.T = d_T2.p; }
+    }
     d_l2.upload(std::vector<BandSys>(1, h_l2));
     std::vector<int> chunk_sys(P, -1);
     for (int l = 0; l < PL; ++l) chunk_sys[chunk_lo + l] = l;
     d_chunk_sys.upload(chunk_sys);
     d_rawdiag.alloc(size_t(std::max(n2, 1)) + std::max(N_c, 1));
     const size_t smem_f1 = factor_smem_bytes(36, nbw1), smem_f2 = factor_smem_bytes(60, nbw2);
-    if ((!use_cr && smem_f1 > 227 * 1024) || (h_l2.n > 0 && smem_f2 > 227 * 1024)) return fail(CB2_UNIMPLEMENTED, "Too many calibration unknowns for the shared-memory Schur kernels.");
+    if ((!use_cr && smem_f1 > 227 * 1024) || (h_l2.n > 0 && !sep_cr && smem_f2 > 227 * 1024)) return fail(CB2_UNIMPLEMENTED, "Too many calibration unknowns for the shared-memory Schur kernels.");
     return CB2_OK;
   }
   double* red_Cw = nullptr;
@@ -1128,10 +1152,12 @@ struct cb2_problem {
     for (const auto& sy : h_l1) max_n1 = std::max(max_n1, sy.n);
     const int nbw1 = h_l1[0].nbw, nbw2 = h_l2.nbw;
     if (gram_dmma1) set(border_gram_dmma_kernel, gram_smem_bytes(nbw1));
+    cr_zsplit = std::getenv("CB2_CR_ZSPLIT") ? std::max(1, std::atoi(std::getenv("CB2_CR_ZSPLIT"))) : std::max(1, std::min(4, (2 * kCrB + nbw1 + 7) / 8 / 6));
     cr_tma = use_cr && std::getenv("CB2_NO_TMA") == nullptr && cr_smem_bytes_tma(nbw1) <= 227 * 1024;   // staging area beside the working set
     if (use_cr) { set(cr_level_kernel<true>, cr_smem_bytes(nbw1)); set(cr_level_kernel<false>, cr_tma ? cr_smem_bytes_tma(nbw1) : cr_smem_bytes(nbw1)); }
     else set(band_factor_kernel<6>, factor_smem_bytes(36, nbw1));
-    if (h_l2.n > 0) set(band_factor_kernel<10>, factor_smem_bytes(60, nbw2));
+    if (h_l2.n > 0 && !sep_cr) set(band_factor_kernel<10>, factor_smem_bytes(60, nbw2));
+    if (gram_dmma2 && !gram_dmma1) set(border_gram_dmma_kernel, gram_smem_bytes(nbw2));
     set(reduced_solve_kernel, size_t(N_c + 1) * (kRedPanel + 1) * 8);
     if (reduced_smem_bytes(N_c) <= 227 * 1024 - 256) set(reduced_solve_smem_kernel, reduced_smem_bytes(N_c));
     set(band_backsolve_kernel, std::max(use_cr ? size_t(0) : backsolve_smem_bytes(max_n1, nbw1, 36), backsolve_smem_bytes(h_l2.n, nbw2, 60)));
@@ -1322,8 +1348,14 @@ struct cb2_problem {
       const size_t smem_cr = cr_smem_bytes(nbw1);
       for (int lv = 0; lv < cr_nlevels; ++lv) {
         const int nact = (cr_max_nblk + (1 << lv) - 1) >> lv;
-        if (lv == 0) CB2_K((cr_level_kernel<true>), dim3(nact, PL), kCrThreads, smem_cr, stream, d_l1.p, lv, n_a, N_c, d_Aband.p, d_Bmat.p, d_Cmat.p, d_grad.p, d_dtil2.p, d_scal.p, 0);
-        else CB2_K((cr_level_kernel<false>), dim3(nact, PL), kCrThreads, cr_tma ? cr_smem_bytes_tma(nbw1) : smem_cr, stream, d_l1.p, lv, n_a, N_c, d_Aband.p, d_Bmat.p, d_Cmat.p, d_grad.p, d_dtil2.p, d_scal.p, cr_tma ? 1 : 0);
+        // Column split (CTAs per block): as many as keep the level's eliminated blocks within one wave of the SMs (survivor blocks cost
+        // next to nothing); the wide first levels run one CTA per block.
+        const int n_elim = std::max(1, nact / 2) * PL;
+        const int nsm = 148;
+        int z = 1;
+        while (z < cr_zsplit && n_elim * (z * 2) <= nsm) z *= 2;
+        if (lv == 0) CB2_K((cr_level_kernel<true>), dim3(nact, PL, 1), kCrThreads, smem_cr, stream, d_l1.p, lv, n_a, N_c, d_Aband.p, d_Bmat.p, d_Cmat.p, d_grad.p, d_dtil2.p, d_scal.p, 0);
+        else CB2_K((cr_level_kernel<false>), dim3(nact, PL, z), kCrThreads, cr_tma ? cr_smem_bytes_tma(nbw1) : smem_cr, stream, d_l1.p, lv, n_a, N_c, d_Aband.p, d_Bmat.p, d_Cmat.p, d_grad.p, d_dtil2.p, d_scal.p, cr_tma ? 1 : 0);
       }
     } else {
       CB2_K(gather_level1_kernel, dim3(std::max(1, std::min(64, (max_n1 * (36 + nbw1) + 255) / 256)), PL), 256, 0, stream, d_l1.p, n_a, N_c, d_Aband.p,
@@ -1357,10 +1389,28 @@ struct cb2_problem {
     }
     if (h_l2.n > 0) {
       CB2_K(level2_damp_kernel, (h_l2.n + 255) / 256, 256, 0, stream, h_l2, d_dtil2.p);
-      const size_t smem_f2 = factor_smem_bytes(60, h_l2.nbw);
-      CB2_K((band_factor_kernel<10>), 1, kFacThreads, smem_f2, stream, d_l2.p, d_scal.p);
       const int nt2 = (h_l2.nbw + 63) / 64;
-      CB2_K(border_gram_kernel, dim3(nt2 * (nt2 + 1) / 2, 1, h_l2.ksplit), dim3(16, 16), 0, stream, d_l2.p);
+      if (sep_cr) {
+        // the separator chain by cyclic reduction: first level reads the summed separator system (band of width 60, border + rhs rows)
+        const int nbw2 = h_l2.nbw;
+        const bool tma2 = cr_tma && cr_smem_bytes_tma(nbw2) <= 227 * 1024;
+        for (int lv = 0; lv < cr2_nlevels; ++lv) {
+          const int nact = (h_l2.nblk + (1 << lv) - 1) >> lv;
+          const int n_elim = std::max(1, nact / 2);
+          int z = 1;
+          while (z < cr_zsplit && n_elim * (z * 2) <= 148) z *= 2;
+          if (lv == 0) CB2_K((cr_level_kernel<true>), dim3(nact, 1, z), kCrThreads, cr_smem_bytes(nbw2), stream, d_l2.p, lv, n_a, N_c, h_l2.L, h_l2.W, d_Cmat.p, h_l2.W + N_c,
+                             static_cast<const double*>(nullptr), d_scal.p, 0, 60, nbw2, nbw2, 0L);
+          else CB2_K((cr_level_kernel<false>), dim3(nact, 1, z), kCrThreads, tma2 ? cr_smem_bytes_tma(nbw2) : cr_smem_bytes(nbw2), stream, d_l2.p, lv, n_a, N_c, h_l2.L, h_l2.W,
+                     d_Cmat.p, h_l2.W + N_c, static_cast<const double*>(nullptr), d_scal.p, tma2 ? 1 : 0, 60, nbw2, nbw2, 0L);
+        }
+        if (gram_dmma2) CB2_K(border_gram_dmma_kernel, dim3(h_l2.ksplit, 1), 256, gram_smem_bytes(nbw2), stream, d_l2.p);
+        else CB2_K(border_gram_kernel, dim3(nt2 * (nt2 + 1) / 2, 1, h_l2.ksplit), dim3(16, 16), 0, stream, d_l2.p);
+      } else {
+        const size_t smem_f2 = factor_smem_bytes(60, h_l2.nbw);
+        CB2_K((band_factor_kernel<10>), 1, kFacThreads, smem_f2, stream, d_l2.p, d_scal.p);
+        CB2_K(border_gram_kernel, dim3(nt2 * (nt2 + 1) / 2, 1, h_l2.ksplit), dim3(16, 16), 0, stream, d_l2.p);
+      }
     }
     if (N_c > 0) {
       const long tot3 = long(N_c + 1) * (N_c + 1);
@@ -1370,7 +1420,15 @@ struct cb2_problem {
     }
     if (h_l2.n > 0) {
       CB2_K(border_matvec_kernel, dim3(std::max(1, std::min(148, (h_l2.n + 7) / 8)), 1), 256, size_t(h_l2.nbw) * sizeof(double), stream, d_l2.p, d_ytil.p);
-      CB2_K(band_backsolve_kernel, 1, kBackThreads, backsolve_smem_bytes(h_l2.n, h_l2.nbw, 60), stream, d_l2.p, d_ytil.p);
+      if (sep_cr) {
+        int lv = cr2_nlevels - 1, lo = lv;   // levels with <= 8 eliminated blocks share one launch
+        while (lo > 0 && std::max(1, ((h_l2.nblk + (1 << (lo - 1)) - 1) >> (lo - 1)) / 2) <= 8) --lo;
+        CB2_K(cr_back_kernel, dim3(1, 1), 256, 0, stream, d_l2.p, lv, lo, d_ytil.p);
+        for (lv = lo - 1; lv >= 0; --lv) {
+          const int nel = std::max(1, ((h_l2.nblk + (1 << lv) - 1) >> lv) / 2);
+          CB2_K(cr_back_kernel, dim3((nel + 7) / 8, 1), 256, 0, stream, d_l2.p, lv, lv, d_ytil.p);
+        }
+      } else CB2_K(band_backsolve_kernel, 1, kBackThreads, backsolve_smem_bytes(h_l2.n, h_l2.nbw, 60), stream, d_l2.p, d_ytil.p);
     }
     CB2_K(border_matvec_kernel, dim3(std::max(1, std::min(std::max(32, 592 / std::max(PL, 1)), (max_n1 + 7) / 8)), PL), 256, size_t(nbw1) * sizeof(double), stream, d_l1.p, d_ytil.p);
     if (use_cr) {

@@ -16,10 +16,32 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(_HERE, "liboracle.so")
 
 
+def _cpu_stamp() -> str:
+    """The host's instruction-set flags: the library is built with -march=native, so a binary built on another CPU model must be rebuilt."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    import hashlib
+                    return hashlib.sha1(line.encode()).hexdigest()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def build(force: bool = False):
     srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".hpp", ".cpp")) or f == "Makefile"]
-    if force or not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
-        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    stamp_path = os.path.join(_HERE, ".build_cpu")
+    stamp = _cpu_stamp()
+    try:
+        with open(stamp_path) as f:
+            same_cpu = f.read().strip() == stamp
+    except OSError:
+        same_cpu = False
+    if force or not same_cpu or not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
+        with open(stamp_path, "w") as f:
+            f.write(stamp)
     return LIB
 
 

@@ -483,6 +483,7 @@ struct cb2_problem {
   bool sweep_gram = std::getenv("CB2_NO_SWEEP_GRAM") == nullptr;
   DevBuf<double> d_gslots, d_gcta, d_segA2, d_segG2;
   DevBuf<int> d_ext_tab, d_ext_dst;
+  DevBuf<int2> d_gslot_tab, d_gram_meta;   // per (segment, slot-producing camera): {first slot, count}; per such camera: {calib_off, n_calib}
   int n_gram_sensors = 0, n_plain_sensors = 0;
   double* h_scal = nullptr;   // pinned
   double* h_param = nullptr;  // pinned: {radius, min_lm_diagonal, max_lm_diagonal} of the coming solve
@@ -928,6 +929,27 @@ struct cb2_problem {
     d_gslots.alloc(n_gslots * kGramSlot, false);
     d_gcta.alloc(n_gcta * kGramCta);
     { std::vector<int> tab(32 * kExpExt), dst(32 * kExpExt); expand_ext_table(tab.data(), dst.data()); d_ext_tab.upload(tab, h2d); d_ext_dst.upload(dst, h2d); }
+    {
+      // where expand_gram_kernel finds the slots of every (segment, camera): slot = gslot_base + image + CTA-in-sensor (see SensorDesc::gslots)
+      std::vector<int> gram_ids;
+      for (int si = 0; si < ns; ++si) if (gram_sensor[si]) gram_ids.push_back(si);
+      const int ng = int(gram_ids.size()), nsl_t = std::max(g_hi - g_lo, 0);
+      std::vector<int2> tab(size_t(std::max(nsl_t, 1)) * std::max(ng, 1), int2{0, 0}), meta(std::max(ng, 1), int2{0, 0});
+      for (int j = 0; j < ng; ++j) {
+        const int si = gram_ids[j];
+        const Packed& P = packed[si];
+        meta[j] = int2{h_desc[si].calib_off, h_desc[si].n_calib};
+        for (int gl = 0; gl < nsl_t; ++gl) {
+          const int g = g_lo + gl;
+          const int f_begin = P.seg_frame[g], f_end = P.seg_frame[g + 1];
+          if (f_end == f_begin) continue;
+          const int o_first = P.seg_start[g], o_last = P.seg_start[g + 1] - 1;
+          const int lo = h_desc[si].gslot_base + f_begin + o_first / eval_tile(kCamera);
+          tab[size_t(gl) * ng + j] = int2{lo, h_desc[si].gslot_base + f_end - 1 + o_last / eval_tile(kCamera) - lo + 1};
+        }
+      }
+      d_gslot_tab.upload(tab, h2d); d_gram_meta.upload(meta, h2d);
+    }
     n_gram_sensors = n_plain_sensors = 0;
     for (int si = 0; si < ns; ++si) {
       h_desc[si].gcta = nullptr;
@@ -1271,8 +1293,8 @@ struct cb2_problem {
         else CB2_K((accumulate_kernel<8>), nsl, kAccThreads, acc_smem_bytes(), s_acc, d_desc.p, ns, N_c, g_lo, d_c2off.p, csz, d_segA.p, d_segG.p, d_segB.p, d_segC.p, d_segGc.p);
       }
       if (gram)
-        CB2_K(expand_gram_kernel, nsl, kExpThreads, expand_smem_bytes(), stream, d_desc.p, ns, N_c, g_lo, d_ext_tab.p, d_ext_dst.p, plain ? d_segA2.p : d_segA.p,
-              plain ? d_segG2.p : d_segG.p, d_segB.p);
+        CB2_K(expand_gram_kernel, nsl, kExpThreads, expand_smem_bytes(), stream, d_gslot_tab.p, d_gram_meta.p, n_gram_sensors, d_gslots.p, N_c, d_ext_tab.p, d_ext_dst.p,
+              plain ? d_segA2.p : d_segA.p, plain ? d_segG2.p : d_segG.p, d_segB.p);
 #ifndef CB2_EMUL
       if (plain && gram) { CB2_CUDA(cudaEventRecord(ev_join, stream_imu)); CB2_CUDA(cudaStreamWaitEvent(stream, ev_join, 0)); }
 #endif

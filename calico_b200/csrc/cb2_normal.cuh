@@ -224,11 +224,15 @@ inline void expand_ext_table(int* tab, int* dst) {
   for (int a = 0; a < 6; ++a) for (int b = 0; b <= a; ++b) for (int e = 32; e < 36; ++e) { tab[n] = (a << 16) | (b << 8) | e; dst[n] = (a * (a + 1) / 2 + b) * 36 + e; ++n; }
   for (int b = 0; b < 6; ++b) for (int q = 0; q < 6; ++q) { tab[n] = (6 << 16) | (b << 8) | (36 + q); dst[n] = kExpSub * 36 + b * 6 + q; ++n; }
 }
-__global__ void __launch_bounds__(kExpThreads, 2) expand_gram_kernel(const SensorDesc* __restrict__ sensors, int n_sensors, int N_c, int g_lo,
+// slot_tab[(segment * n_gram + j)] = {first slot, slot count} of the j-th slot-producing camera in that segment and gram_meta[j] =
+// {calib_off, n_calib} (both built by the host at upload): a warp reaches its slots through ONE table load instead of a chain of
+// descriptor -> CSR -> slot-index loads.
+__global__ void __launch_bounds__(kExpThreads, 2) expand_gram_kernel(const int2* __restrict__ slot_tab, const int2* __restrict__ gram_meta, int n_gram,
+                                                                     const double* __restrict__ gslots, int N_c,
                                                                      const int* __restrict__ ext_tab, const int* __restrict__ ext_dst,
                                                                      double* __restrict__ segA, double* __restrict__ segG, double* __restrict__ segB) {
   double* smem = dyn_smem<double>();
-  const int gl = blockIdx.x, g = g_lo + gl, t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int gl = blockIdx.x, t = threadIdx.x, warp = t >> 5, lane = t & 31;
   double* const s_slot = smem + size_t(warp) * kExpBatch * kGramSlot;                               // [kExpBatch][kGramSlot]
   int et[kExpExt];
 #pragma unroll
@@ -238,23 +242,14 @@ __global__ void __launch_bounds__(kExpThreads, 2) expand_gram_kernel(const Senso
   for (int i = 0; i < kExpSub; ++i) va[i] = 0.0;
 #pragma unroll
   for (int j = 0; j < kExpExt; ++j) ve[j] = 0.0;
-  // Which sensors leave Gram slots: one ballot per 32 sensors (no chain of dependent descriptor loads); this warp takes every
-  // kExpWarps-th of them.
-  int my_rank = 0;
-  for (int s0 = 0; s0 < n_sensors; s0 += 32) {
-    unsigned mask = __ballot_sync(0xffffffffu, s0 + lane < n_sensors && sensors[s0 + lane].gslots != nullptr);
-    while (mask) {
-      const int s = s0 + __ffs(mask) - 1;
-      mask &= mask - 1;
-      if ((my_rank++ % kExpWarps) != warp) continue;
-    const SensorDesc& sd = sensors[s];
-    const int f_begin = sd.seg_frame[g], f_end = sd.seg_frame[g + 1];
-    const int o_first = sd.seg_start[g], o_last = sd.seg_start[g + 1] - 1;
-    if (f_end == f_begin) continue;
-    const int lo = sd.gslot_base + f_begin + o_first / eval_tile(kCamera);
-    const int n = sd.gslot_base + f_end - 1 + o_last / eval_tile(kCamera) - lo + 1;
-    const int nc = sd.n_calib, calib_off = sd.calib_off;
-    const double* __restrict__ slots = sd.gslots + size_t(lo) * kGramSlot;
+  for (int j = warp; j < n_gram; j += kExpWarps) {
+    {
+    const int2 rng = slot_tab[size_t(gl) * n_gram + j];
+    const int lo = rng.x, n = rng.y;
+    if (n == 0) continue;
+    const int2 meta = gram_meta[j];
+    const int nc = meta.y, calib_off = meta.x;
+    const double* __restrict__ slots = gslots + size_t(lo) * kGramSlot;
     for (int k0 = 0; k0 < n; k0 += kExpBatch) {
       const int kn = min(kExpBatch, n - k0);
       __syncwarp();

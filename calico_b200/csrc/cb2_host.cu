@@ -1168,7 +1168,7 @@ struct cb2_problem {
     set(eval_kernel<kCamera, kModeCost>, ev_max[0]); set(eval_kernel<kCamera, kModeResiduals>, ev_max[0]); set(eval_kernel<kCamera, kModeJacobian>, ev_max[0]);
     set(eval_kernel<kGyroscope, kModeCost>, ev_max[1]); set(eval_kernel<kGyroscope, kModeResiduals>, ev_max[1]); set(eval_kernel<kGyroscope, kModeJacobian>, ev_max[1]);
     set(eval_kernel<kAccelerometer, kModeCost>, ev_max[2]); set(eval_kernel<kAccelerometer, kModeResiduals>, ev_max[2]); set(eval_kernel<kAccelerometer, kModeJacobian>, ev_max[2]);
-    set((accumulate_kernel<7>), acc_smem_bytes()); set((accumulate_kernel<8>), acc_smem_bytes());
+    set((accumulate_kernel<6, 37>), acc_smem_bytes()); set((accumulate_kernel<7, kAccCal0>), acc_smem_bytes()); set((accumulate_kernel<8, kAccCal0>), acc_smem_bytes());
     set(expand_gram_kernel, expand_smem_bytes());
     int max_n1 = 0;
     for (const auto& sy : h_l1) max_n1 = std::max(max_n1, sy.n);
@@ -1289,8 +1289,9 @@ struct cb2_problem {
       if (plain) {
         int max_nc = 0;
         for (const auto& d : h_desc) if (!d.gslots) max_nc = std::max(max_nc, d.n_calib);
-        if (kAccCal0 + max_nc <= 56) CB2_K((accumulate_kernel<7>), nsl, kAccThreads, acc_smem_bytes(), s_acc, d_desc.p, ns, N_c, g_lo, d_c2off.p, csz, d_segA.p, d_segG.p, d_segB.p, d_segC.p, d_segGc.p);
-        else CB2_K((accumulate_kernel<8>), nsl, kAccThreads, acc_smem_bytes(), s_acc, d_desc.p, ns, N_c, g_lo, d_c2off.p, csz, d_segA.p, d_segG.p, d_segB.p, d_segC.p, d_segGc.p);
+        if (37 + max_nc <= 48) CB2_K((accumulate_kernel<6, 37>), nsl, kAccThreads, acc_smem_bytes(), s_acc, d_desc.p, ns, N_c, g_lo, d_c2off.p, csz, d_segA.p, d_segG.p, d_segB.p, d_segC.p, d_segGc.p);
+        else if (kAccCal0 + max_nc <= 56) CB2_K((accumulate_kernel<7, kAccCal0>), nsl, kAccThreads, acc_smem_bytes(), s_acc, d_desc.p, ns, N_c, g_lo, d_c2off.p, csz, d_segA.p, d_segG.p, d_segB.p, d_segC.p, d_segGc.p);
+        else CB2_K((accumulate_kernel<8, kAccCal0>), nsl, kAccThreads, acc_smem_bytes(), s_acc, d_desc.p, ns, N_c, g_lo, d_c2off.p, csz, d_segA.p, d_segG.p, d_segB.p, d_segC.p, d_segGc.p);
       }
       if (gram)
         CB2_K(expand_gram_kernel, nsl, kExpThreads, expand_smem_bytes(), stream, d_gslot_tab.p, d_gram_meta.p, n_gram_sensors, d_gslots.p, N_c, d_ext_tab.p, d_ext_dst.p,

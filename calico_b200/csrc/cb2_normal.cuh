@@ -32,8 +32,8 @@ constexpr int kAccWarps = 4;
 constexpr int kAccThreads = 32 * kAccWarps;
 constexpr int kAccRows = 16;       // J rows per shared-memory tile (4 DMMA k-steps)
 constexpr int kAccStride = 68;     // doubles per tile row; 68 mod 16 == 4 -> the 16 lanes of a half warp hit 16 distinct 8-byte banks
-constexpr int kAccRcol = 36;       // local layout: cp 0..35 | r 36 | zeros 37..39 | calibration unknowns 40.. | zeros
-constexpr int kAccCal0 = 40;
+constexpr int kAccRcol = 36;       // local layout: cp 0..35 | r 36 | zeros up to CAL0 | calibration unknowns CAL0.. | zeros
+constexpr int kAccCal0 = 40;       // CAL0 of the 7- and 8-block layouts; sensors with <= 11 calibration unknowns use CAL0 = 37 and 6 blocks (48 columns)
 constexpr int kAccMaxSensors = 64;
 CB2_HD constexpr size_t acc_smem_bytes() { return size_t(kAccWarps) * 2 * (kAccRows * kAccStride + 4) * sizeof(double); }
 #ifndef CB2_ACC_MINBLOCKS
@@ -61,10 +61,11 @@ CB2_D void cp_async_wait() {
 #endif
 }
 
-// NB = number of 8-column blocks of the local layout: 7 covers sensors with up to 16 calibration unknowns, 8 up to 20 (kMaxCalib).
+// NB = number of 8-column blocks of the local layout, CAL0 = first calibration column: (6, 37) covers sensors with up to 11 calibration
+// unknowns — the IMU models with 4 intrinsics: 21 DMMA tiles per k-step instead of 28 —, (7, 40) up to 16, (8, 40) up to 20 (kMaxCalib).
 // Sensors whose Gram slots come from the sweep (sd.gslots != nullptr) are skipped here; the warps are dealt the remaining sensors.
-template <int NB>
-__global__ void __launch_bounds__(kAccThreads, (NB == 7 ? CB2_ACC_MINBLOCKS : 2)) accumulate_kernel(
+template <int NB, int CAL0>
+__global__ void __launch_bounds__(kAccThreads, (NB <= 7 ? CB2_ACC_MINBLOCKS : 2)) accumulate_kernel(
     const SensorDesc* __restrict__ sensors, int n_sensors, int N_c, int g_lo, const int* __restrict__ c2off, int csz, double* __restrict__ segA,
     double* __restrict__ segG, double* __restrict__ segB, double* __restrict__ segC, double* __restrict__ segGc) {
   // dynamic shared memory: per warp two tile buffers of kAccRows x kAccStride (+ 4 doubles: the last fragment reads past a row end)
@@ -92,10 +93,10 @@ __global__ void __launch_bounds__(kAccThreads, (NB == 7 ? CB2_ACC_MINBLOCKS : 2)
     const int rows = (sd.seg_start[g + 1] - o0) * m;
     if (rows == 0) continue;
     // Local column of every stored J column. The previous sensor's calibration columns are cleared first.
-    if (lane < kAccStride - kAccCal0)
+    if (lane < kAccStride - CAL0)
 #pragma unroll 4
-      for (int rr = 0; rr < 2 * kAccRows; ++rr) tb0[(rr / kAccRows) * (kAccRows * kAccStride + 4) + (rr % kAccRows) * kAccStride + kAccCal0 + lane] = 0.0;
-    for (int c = lane; c < jw; c += 32) colpos[warp][c] = c < kCpCols ? c : kAccCal0 + sd.junk[c - kCpCols];
+      for (int rr = 0; rr < 2 * kAccRows; ++rr) tb0[(rr / kAccRows) * (kAccRows * kAccStride + 4) + (rr % kAccRows) * kAccStride + CAL0 + lane] = 0.0;
+    for (int c = lane; c < jw; c += 32) colpos[warp][c] = c < kCpCols ? c : CAL0 + sd.junk[c - kCpCols];
     __syncwarp();
     const double* __restrict__ Jg = sd.J + size_t(o0) * m * jw;
     const double* __restrict__ rg = sd.r + size_t(o0) * m;
@@ -145,22 +146,22 @@ __global__ void __launch_bounds__(kAccThreads, (NB == 7 ? CB2_ACC_MINBLOCKS : 2)
       __syncwarp();
     }
     cp_async_wait<0>();
-    // Flush every entry that involves this sensor's calibration unknowns (blocks 5..NB-1), then reset them for the next sensor.
+    // Flush every entry whose ROW is one of this sensor's calibration unknowns (local rows CAL0..), then reset them for the next sensor.
 #pragma unroll
-    for (int bi = 5; bi < NB; ++bi) {
-      const int li = 8 * (bi - 5) + fc;       // calibration-local unknown of this lane's accumulator row
+    for (int bi = CAL0 / 8; bi < NB; ++bi) {
+      const int li = 8 * bi + fc - CAL0;      // calibration-local unknown of this lane's accumulator row; < 0: a control-point / residual row
 #pragma unroll
       for (int bj = 0; bj <= bi; ++bj) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const int Jx = 8 * bj + 2 * fr + i;
           const double v = acc[bi][bj][i];
-          if (li < nc) {
+          if (li >= 0 && li < nc) {
             if (Jx < kCpCols) segB[(size_t(gl) * kCpCols + Jx) * N_c + sd.calib_off + li] = v;
             else if (Jx == kAccRcol) segGc[size_t(gl) * N_c + sd.calib_off + li] = v;
-            else if (Jx >= kAccCal0 && Jx - kAccCal0 <= li) segC[size_t(gl) * csz + c2off[s] + li * nc + (Jx - kAccCal0)] = v;
+            else if (Jx >= CAL0 && Jx - CAL0 <= li) segC[size_t(gl) * csz + c2off[s] + li * nc + (Jx - CAL0)] = v;
           }
-          acc[bi][bj][i] = 0.0;
+          if (li >= 0) acc[bi][bj][i] = 0.0;
         }
       }
     }

@@ -372,8 +372,20 @@ __global__ void __launch_bounds__(kCrThreads, (kFirst ? 2 : 1)) cr_level_kernel(
 // when every one of them fits one CTA (<= 8 eliminated blocks): the levels are then separated by a block barrier.
 // Everything a block needs is fetched with independent, coalesced loads up front (factor rows and [W_E | W_F]^T in registers), so the
 // 30 dependent steps of the triangular solve cost one shuffle + one FMA each.
-__global__ void __launch_bounds__(256) cr_back_kernel(const BandSys* __restrict__ systems, int level_hi, int level_lo, double* ytil) {
+// grid_sync != nullptr: ALL levels level_hi .. level_lo in one launch whatever their size — the CTAs (all co-resident: the host launches
+// at most one per SM) meet at a global barrier between levels (an arrival counter in HBM, zeroed before the launch), which removes one
+// kernel launch + drain per level from the dependent chain; ytil is then read around L1 (other SMs wrote it during this launch).
+__global__ void __launch_bounds__(256) cr_back_kernel(const BandSys* __restrict__ systems, int level_hi, int level_lo, double* ytil,
+                                                      unsigned* grid_sync = nullptr) {
   const BandSys sy = systems[blockIdx.y];
+  unsigned sync_round = 0;
+  auto yld = [&](int idx) -> double {
+#if defined(CB2_EMUL)
+    return ytil[idx];
+#else
+    return grid_sync ? __ldcg(ytil + idx) : ytil[idx];
+#endif
+  };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = sy.n;
   for (int level = level_hi; level >= level_lo; --level) {
@@ -395,9 +407,9 @@ __global__ void __launch_bounds__(256) cr_back_kernel(const BandSys* __restrict_
         // neighbour solutions: lane l holds x_a[l] and x_b[l]
         double xa = 0.0, xb = 0.0, rhs = 0.0;
         if (lane < kCrB) {
-          if (has_a && ra + lane < n) xa = ytil[sy.row_gidx[ra + lane]];
-          if (has_b && rb + lane < n) xb = ytil[sy.row_gidx[rb + lane]];
-          if (r0 + lane < n) rhs = ytil[sy.row_gidx[r0 + lane]];
+          if (has_a && ra + lane < n) xa = yld(sy.row_gidx[ra + lane]);
+          if (has_b && rb + lane < n) xb = yld(sy.row_gidx[rb + lane]);
+          if (r0 + lane < n) rhs = yld(sy.row_gidx[r0 + lane]);
         }
         if (has_a || has_b) {
           double wa[kCrB], wb[kCrB];
@@ -426,7 +438,22 @@ __global__ void __launch_bounds__(256) cr_back_kernel(const BandSys* __restrict_
         if (lane < kCrB && r0 + lane < n) ytil[sy.row_gidx[r0 + lane]] = x;
       }
     }
-    if (level > level_lo) { __threadfence_block(); __syncthreads(); }
+    if (level > level_lo) {
+      if (grid_sync) {
+#if !defined(CB2_EMUL)
+        // global barrier: every CTA of the grid arrives once per level
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          __threadfence();
+          const unsigned target = (++sync_round) * gridDim.x * gridDim.y;
+          atomicAdd(grid_sync, 1u);
+          while (atomicAdd(grid_sync, 0u) < target) { }
+          __threadfence();
+        }
+        __syncthreads();
+#endif
+      } else { __threadfence_block(); __syncthreads(); }
+    }
   }
 }
 

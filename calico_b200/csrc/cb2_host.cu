@@ -474,6 +474,7 @@ struct cb2_problem {
   bool sep_cr = false, gram_dmma2 = false;
   int cr2_nlevels = 0;
   DevBuf<double> d_cr2D, d_cr2Bd, d_cr2U, d_cr2Wef, d_cr2L;
+  DevBuf<unsigned> d_grid_sync;   // arrival counter of the fused back-substitution launch
   int cur = 0;   // which of the two parameter buffers holds x
   size_t smem_eval[3] = {0, 0, 0};
   int max_tilepairs1 = 0, max_ksplit1 = 1;
@@ -975,6 +976,7 @@ struct cb2_problem {
       d_cp_own.upload(own, h2d);
     }
     d_scal.alloc(kScCount);
+    d_grid_sync.alloc(4);
     cur = 0;
     // Normal-equation storage.
     d_c2off.upload(c2off, h2d);
@@ -1446,23 +1448,37 @@ struct cb2_problem {
       if (sep_cr) {
         int lv = cr2_nlevels - 1, lo = lv;   // levels with <= 8 eliminated blocks share one launch
         while (lo > 0 && std::max(1, ((h_l2.nblk + (1 << (lo - 1)) - 1) >> (lo - 1)) / 2) <= 8) --lo;
-        CB2_K(cr_back_kernel, dim3(1, 1), 256, 0, stream, d_l2.p, lv, lo, d_ytil.p);
+        CB2_K(cr_back_kernel, dim3(1, 1), 256, 0, stream, d_l2.p, lv, lo, d_ytil.p, static_cast<unsigned*>(nullptr));
         for (lv = lo - 1; lv >= 0; --lv) {
           const int nel = std::max(1, ((h_l2.nblk + (1 << lv) - 1) >> lv) / 2);
-          CB2_K(cr_back_kernel, dim3((nel + 7) / 8, 1), 256, 0, stream, d_l2.p, lv, lv, d_ytil.p);
+          CB2_K(cr_back_kernel, dim3((nel + 7) / 8, 1), 256, 0, stream, d_l2.p, lv, lv, d_ytil.p, static_cast<unsigned*>(nullptr));
         }
       } else CB2_K(band_backsolve_kernel, 1, kBackThreads, backsolve_smem_bytes(h_l2.n, h_l2.nbw, 60), stream, d_l2.p, d_ytil.p);
     }
     CB2_K(border_matvec_kernel, dim3(std::max(1, std::min(std::max(32, 592 / std::max(PL, 1)), (max_n1 + 7) / 8)), PL), 256, size_t(nbw1) * sizeof(double), stream, d_l1.p, d_ytil.p);
     if (use_cr) {
+      const int nel0 = std::max(1, cr_max_nblk / 2);
+      const int ctas0 = (nel0 + 7) / 8 * PL;
+#ifndef CB2_EMUL
+      // (opt-in: measured slower than one graph-captured launch per level on C4 — 57 us against ~45 us for the six launches)
+      const bool fused_back = ctas0 <= 148 && std::getenv("CB2_FUSED_BACK") != nullptr;
+#else
+      const bool fused_back = false;
+#endif
+      if (fused_back) {
+        // every level in ONE launch, the CTAs meeting at a global barrier between levels (all co-resident: at most one per SM)
+        CB2_CUDA(cudaMemsetAsync(d_grid_sync.p, 0, sizeof(unsigned), stream));
+        CB2_K(cr_back_kernel, dim3((nel0 + 7) / 8, PL), 256, 0, stream, d_l1.p, cr_nlevels - 1, 0, d_ytil.p, d_grid_sync.p);
+      } else {
       // Top levels with <= 8 eliminated blocks each share one launch (block barrier between levels); then one launch per level.
       int lv = cr_nlevels - 1, lo = lv;
       while (lo > 0 && std::max(1, ((cr_max_nblk + (1 << (lo - 1)) - 1) >> (lo - 1)) / 2) <= 8) --lo;
-      CB2_K(cr_back_kernel, dim3(1, PL), 256, 0, stream, d_l1.p, lv, lo, d_ytil.p);
+      CB2_K(cr_back_kernel, dim3(1, PL), 256, 0, stream, d_l1.p, lv, lo, d_ytil.p, static_cast<unsigned*>(nullptr));
       for (lv = lo - 1; lv >= 0; --lv) {
         const int nact = (cr_max_nblk + (1 << lv) - 1) >> lv;
         const int nel = std::max(1, nact / 2);
-        CB2_K(cr_back_kernel, dim3((nel + 7) / 8, PL), 256, 0, stream, d_l1.p, lv, lv, d_ytil.p);
+        CB2_K(cr_back_kernel, dim3((nel + 7) / 8, PL), 256, 0, stream, d_l1.p, lv, lv, d_ytil.p, static_cast<unsigned*>(nullptr));
+      }
       }
     } else {
       CB2_K(band_backsolve_kernel, PL, kBackThreads, backsolve_smem_bytes(max_n1, nbw1, 36), stream, d_l1.p, d_ytil.p);

@@ -106,7 +106,7 @@ class Stats(C.Structure):
         ("normal_eq_ms", C.c_double), ("schur_ms", C.c_double), ("cost_eval_ms", C.c_double),
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
         ("lm_loop_ms", C.c_double), ("lm_iterations", C.c_int64),
-        ("camera_kernel_ms", C.c_double), ("camera_kernel_bytes", C.c_double),
+        ("camera_kernel_ms", C.c_double), ("camera_kernel_bytes", C.c_double), ("camera_kernel_gram_bytes", C.c_double),
     ]
 
 

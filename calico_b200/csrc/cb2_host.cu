@@ -1274,6 +1274,7 @@ struct cb2_problem {
       stats.jacobian_blocks += last_sweep_imu ? num_active_blocks() : num_active_blocks() - num_active_blocks(true);
       stats.jacobian_bytes += last_sweep_imu ? jacobian_bytes_per_sweep() : jacobian_bytes_per_sweep(kCamera);
       stats.camera_kernel_bytes += jacobian_bytes_per_sweep(kCamera);
+      stats.camera_kernel_gram_bytes += gram_bytes_per_sweep();
     }
     timer.begin(kPhNormal, stream);
     graphed(g_normal[cur + (defer_shared ? 2 : 0)], [&] {
@@ -1508,6 +1509,7 @@ struct cb2_problem {
       stats.jacobian_blocks += num_active_blocks();
       stats.jacobian_bytes += jacobian_bytes_per_sweep();
       stats.camera_kernel_bytes += jacobian_bytes_per_sweep(kCamera);
+      stats.camera_kernel_gram_bytes += gram_bytes_per_sweep();
       return;
     }
     timer.begin(kPhCost, stream);
@@ -1541,6 +1543,7 @@ struct cb2_problem {
     }
     return total;
   }
+  double gram_bytes_per_sweep() const { return double(d_gslots.n + d_gcta.n) * sizeof(double); }
   long num_active_blocks(bool imu_only = false) const { long n = 0; for (const auto& d : h_desc) if (!imu_only || d.kind != kCamera) n += d.n_obs; return n; }
 
   // ------------------------------------------------------------------------------------------------------------

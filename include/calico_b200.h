@@ -94,6 +94,7 @@ typedef struct cb2_stats {
   int64_t lm_iterations;          /* LM iterations (accepted + rejected) run since reset */
   double camera_kernel_ms;        /* CUDA-event time of the camera residual+Jacobian kernel alone (the dominant kernel of the sweep) */
   double camera_kernel_bytes;     /* its algorithmic bytes (camera blocks only), same definition as jacobian_bytes */
+  double camera_kernel_gram_bytes; /* what the same kernel writes BESIDES the Jacobian: compact per-image Gram slots + per-warp calibration partials */
 } cb2_stats;
 
 void cb2_default_options(cb2_options* out);

@@ -87,3 +87,52 @@ def test_multi_gpu_lm_matches_oracle(world, cfg, chunk, product_lib, oracle):
         np.testing.assert_allclose(o["ctrl"], ref["ctrl"], rtol=1e-6, atol=1e-6)
         for a, b in zip(o["intr"], ref["intr"]):
             np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-9)
+
+
+def _timeout_worker(rank, world, port, lib, q):
+    """Rank 0 runs Optimize; rank 1 creates the communicator and then never joins a collective."""
+    import time
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["CB2_COLLECTIVE_TIMEOUT_S"] = "4"
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from oracle import oracle_py
+    truth, prob = synthetic.generate("tiny", oracle_py.oracle_api, noise=True)
+    a = _capi.CApi(lib)
+    a.set_device(rank)
+    prob.clone().push(a)
+    a.comm_init_torch(world, rank)
+    if rank == 0:
+        t0 = time.time()
+        try:
+            a.optimize(_capi.Options(minimizer_progress_to_stdout=0))
+            q.put(("no error", time.time() - t0, ""))
+        except _capi.CalicoError as e:
+            q.put((e.code, time.time() - t0, str(e)))
+    else:
+        time.sleep(12)       # never enters the solve: rank 0's first collective has no partner
+        q.put(("idle", 0.0, ""))
+    os._exit(0)              # the aborted communicator cannot take part in a clean process-group shutdown
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs at least 2 GPUs")
+def test_missing_rank_times_out_instead_of_hanging(product_lib, oracle):
+    """SURVEY §5 (NCCL failure detection): a collective a peer never joins ends with status 13 after CB2_COLLECTIVE_TIMEOUT_S, the
+    communicator aborted — not with a hang until an external watchdog kills the job (what happened to the round-1 N = 2 scaling run)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() + 7) % 2000
+    procs = [ctx.Process(target=_timeout_worker, args=(r, 2, port, product_lib, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    code, seconds, msg = next(o for o in outs if o[0] != "idle")
+    assert code == _capi.INTERNAL, (code, msg)
+    assert "collective" in msg.lower() or "nccl" in msg.lower()
+    assert 3.0 <= seconds <= 30.0

@@ -22,6 +22,7 @@
 #include <vector>
 #include <map>
 #include <atomic>
+#include <condition_variable>
 #include <mutex>
 #include <thread>
 #if defined(CB2_EMUL)
@@ -260,7 +261,10 @@ struct KernelProfiler {
 // ----------------------------------------------------------------------------------------------------------------
 struct Comm {
   int world = 1, rank = 0;
-  bool dead = false;            // aborted after a failed / timed-out collective: every later use fails fast
+  std::atomic<bool> dead{false};   // aborted after a failed / timed-out collective: every later use fails fast
+  double timeout_s = std::getenv("CB2_COLLECTIVE_TIMEOUT_S") ? std::atof(std::getenv("CB2_COLLECTIVE_TIMEOUT_S")) : 60.0;
+  virtual void arm() {}            // a region that may block on a peer begins / ends (watchdog deadline, see NcclComm)
+  virtual void disarm() {}
   virtual ~Comm() {}
   virtual void allreduce_sum(double* buf, size_t n, cudaStream_t s) = 0;
   virtual void allreduce_max(double* buf, size_t n, cudaStream_t s) = 0;
@@ -303,30 +307,68 @@ struct NcclApi {
   }
 };
 static NcclApi& nccl() { static NcclApi api; return api; }
+// A collective a peer never joins blocks either inside the NCCL call on the host (the first collective of a communicator sets up its
+// connections) or inside the kernel on the stream. Both are covered by a WATCHDOG thread per communicator: regions that may block arm a
+// deadline (CB2_COLLECTIVE_TIMEOUT_S, default 60 s); when it passes — or the communicator reports an asynchronous error — the watchdog calls
+// ncclCommAbort, which makes the blocked call / kernel return, and the caller reports status 13 instead of hanging.
 struct NcclComm : Comm {
   NcclApi::CommT comm = nullptr;
-  ~NcclComm() override { if (comm && !dead) nccl().CommDestroy(comm); }
-  bool async_error(std::string* why) override {
-    if (!comm || dead || !nccl().CommGetAsyncError) return false;
-    int st = 0;
-    if (nccl().CommGetAsyncError(comm, &st) != 0 || st != 0) {   // ncclSuccess = 0; ncclInProgress only occurs for non-blocking communicators
-      if (why) *why = std::string("NCCL asynchronous error: ") + (nccl().GetErrorString ? nccl().GetErrorString(st) : "?");
-      return true;
-    }
-    return false;
+  std::thread watchdog;
+  std::mutex wd_mu;
+  std::condition_variable wd_cv;
+  std::atomic<double> deadline{0.0};    // 0 = disarmed
+  std::atomic<bool> aborting{false};
+  bool stop = false;
+  std::string why;                      // set by the watchdog before `dead`
+  void start_watchdog() {
+    watchdog = std::thread([this] {
+      std::unique_lock<std::mutex> lk(wd_mu);
+      while (!stop) {
+        wd_cv.wait_for(lk, std::chrono::milliseconds(100));
+        if (stop || dead.load()) continue;
+        const double dl = deadline.load();
+        if (dl == 0.0) continue;
+        std::string reason;
+        bool fire = false;
+        if (now_s() > dl) { fire = true; reason = "Cross-rank collective did not complete within " + std::to_string(timeout_s) + " s (a peer rank is missing or the ranks' call sequences diverged)"; }
+        else if (nccl().CommGetAsyncError) {
+          int st = 0;
+          if (nccl().CommGetAsyncError(comm, &st) != 0 || (st != 0 && st != 7 /* ncclInProgress */)) { fire = true; reason = std::string("NCCL asynchronous error: ") + (nccl().GetErrorString ? nccl().GetErrorString(st) : "?"); }
+        }
+        if (fire) {
+          why = reason + "; the communicator has been aborted.";
+          aborting.store(true);            // before the abort: the call it unblocks reports `why`, not NCCL's post-abort error
+          if (nccl().CommAbort) nccl().CommAbort(comm);
+          dead.store(true);
+        }
+      }
+    });
   }
-  void abort() override {
-    if (comm && !dead && nccl().CommAbort) nccl().CommAbort(comm);
-    dead = true; comm = nullptr;
+  ~NcclComm() override {
+    { std::lock_guard<std::mutex> lk(wd_mu); stop = true; }
+    wd_cv.notify_all();
+    if (watchdog.joinable()) watchdog.join();
+    if (comm && !dead.load()) nccl().CommDestroy(comm);
   }
+  void arm() override { deadline.store(now_s() + timeout_s); }
+  void disarm() override { deadline.store(0.0); }
+  bool async_error(std::string* w) override { if (dead.load()) { if (w) *w = why; return true; } return false; }
+  void abort() override { dead.store(true); }
   void check(int rc, const char* what) {
-    if (dead) throw CudaFail{"NCCL communicator was aborted after an earlier failure; create a new one (cb2_comm_init)."};
+    if (dead.load() || aborting.load()) throw CudaFail{why.empty() ? std::string("NCCL communicator was aborted after an earlier failure; create a new one (cb2_comm_init).") : why};
     if (rc != 0) throw CudaFail{std::string("NCCL error in ") + what + ": " + (nccl().GetErrorString ? nccl().GetErrorString(rc) : "?")};
   }
+  int guarded_allreduce(void* buf, size_t n, int dtype, int op, cudaStream_t s) {
+    if (dead.load()) return 0;
+    arm();                               // the enqueue itself can block (connection set-up of the first collective)
+    const int rc = nccl().AllReduce(buf, buf, n, dtype, op, comm, s);
+    disarm();
+    return rc;
+  }
   // ncclFloat64 = 8; ncclSum = 0, ncclMax = 2
-  void allreduce_sum(double* buf, size_t n, cudaStream_t s) override { check(dead ? 0 : nccl().AllReduce(buf, buf, n, 8, 0, comm, s), "allreduce(sum)"); }
-  void allreduce_max(double* buf, size_t n, cudaStream_t s) override { check(dead ? 0 : nccl().AllReduce(buf, buf, n, 8, 2, comm, s), "allreduce(max)"); }
-  void allreduce_sum_u8(unsigned char* buf, size_t n, cudaStream_t s) override { check(dead ? 0 : nccl().AllReduce(buf, buf, n, 1 /* ncclUint8 */, 0, comm, s), "allreduce(sum, u8)"); }
+  void allreduce_sum(double* buf, size_t n, cudaStream_t s) override { check(guarded_allreduce(buf, n, 8, 0, s), "allreduce(sum)"); }
+  void allreduce_max(double* buf, size_t n, cudaStream_t s) override { check(guarded_allreduce(buf, n, 8, 2, s), "allreduce(max)"); }
+  void allreduce_sum_u8(unsigned char* buf, size_t n, cudaStream_t s) override { check(guarded_allreduce(buf, n, 1 /* ncclUint8 */, 0, s), "allreduce(sum, u8)"); }
 };
 #else
 // Test-only rendezvous: `world` host threads of one process, each driving its own handle, meet in every collective.
@@ -549,32 +591,30 @@ struct cb2_problem {
   // would block forever: the wait then polls with a deadline (CB2_COLLECTIVE_TIMEOUT_S, default 60 s) and the communicator's
   // asynchronous error state (NCCL async error check); on either, the communicator is aborted — which makes the stuck kernel
   // return — and the call fails with CB2_INTERNAL instead of hanging.
-  double collective_timeout_s = std::getenv("CB2_COLLECTIVE_TIMEOUT_S") ? std::atof(std::getenv("CB2_COLLECTIVE_TIMEOUT_S")) : 60.0;
   void sync_stream(bool may_throw = true) {
     if (world <= 1 || !comm) {
       const cudaError_t e = cudaStreamSynchronize(stream);
       if (e != cudaSuccess && may_throw) throw CudaFail{std::string("CUDA error: ") + cudaGetErrorString(e) + " at cudaStreamSynchronize"};
       return;
     }
-    const double t0 = now_s();
-    long spins = 0;
+    comm->arm();
     for (;;) {
       const cudaError_t q = cudaStreamQuery(stream);
-      if (q == cudaSuccess) return;
+      if (q == cudaSuccess) { comm->disarm(); return; }
       if (q != cudaErrorNotReady) {
+        comm->disarm();
         if (may_throw) throw CudaFail{std::string("CUDA error: ") + cudaGetErrorString(q) + " at cudaStreamQuery"};
         return;
       }
-      if ((++spins & 1023) != 0) continue;
-      std::string why;
-      const bool async = comm->async_error(&why);
-      if (!async && now_s() - t0 < collective_timeout_s) continue;
-      if (!async) why = "Cross-rank collective did not complete within " + std::to_string(collective_timeout_s) + " s (a peer rank is missing or the ranks' call sequences diverged)";
-      comm->abort();
-      cudaStreamSynchronize(stream);     // returns once the aborted collective has been torn down
+      if (!comm->dead.load()) continue;
+      // the watchdog aborted the communicator (deadline passed or asynchronous NCCL error): the stuck collective has been torn down
+      comm->disarm();
+      cudaStreamSynchronize(stream);
       cudaGetLastError();
       uploaded = false;
-      if (may_throw) throw CudaFail{why + "; the communicator has been aborted."};
+      std::string why;
+      comm->async_error(&why);
+      if (may_throw) throw CudaFail{why.empty() ? std::string("Cross-rank collective failed; the communicator has been aborted.") : why};
       return;
     }
   }
@@ -2318,6 +2358,7 @@ int cb2_comm_init(cb2_problem* p, int world_size, int rank, const uint8_t* id128
     NcclApi::UniqueId id;
     std::memcpy(&id, id128, sizeof id);
     c->check(nccl().CommInitRank(&c->comm, world_size, id, rank), "ncclCommInitRank");
+    c->start_watchdog();
     p->comm = std::shared_ptr<Comm>(c.release());
     p->world = world_size; p->rank = rank;
     return CB2_OK;

@@ -115,6 +115,8 @@ def _timeout_worker(rank, world, port, lib, q):
     else:
         time.sleep(12)       # never enters the solve: rank 0's first collective has no partner
         q.put(("idle", 0.0, ""))
+    q.close()
+    q.join_thread()          # the queue's feeder thread must flush before the hard exit below
     os._exit(0)              # the aborted communicator cannot take part in a clean process-group shutdown
 
 
@@ -129,10 +131,11 @@ def test_missing_rank_times_out_instead_of_hanging(product_lib, oracle):
     procs = [ctx.Process(target=_timeout_worker, args=(r, 2, port, product_lib, q)) for r in range(2)]
     for p in procs:
         p.start()
-    outs = [q.get(timeout=120) for _ in range(2)]
+    outs = [q.get(timeout=90) for _ in range(2)]
     for p in procs:
         p.join(timeout=60)
     code, seconds, msg = next(o for o in outs if o[0] != "idle")
+    print("rank 0:", code, "%.1f s" % seconds, msg)
     assert code == _capi.INTERNAL, (code, msg)
     assert "collective" in msg.lower() or "nccl" in msg.lower()
     assert 3.0 <= seconds <= 30.0

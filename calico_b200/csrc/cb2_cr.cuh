@@ -229,36 +229,39 @@ __global__ void __launch_bounds__(kCrThreads, (kFirst ? 2 : 1)) cr_level_kernel(
   for (int e = t; e < 2 * XS; e += kCrThreads) X[kCrB * XS + e] = 0.0;   // k-padding rows 30, 31
   __syncthreads();
   CB2_CLK(1);
-  // ---- 2a. Cholesky of the diagonal block, 6 columns per step: thread 0 factors the 6x6 pivot block, then panel + trailing update ----
-  for (int c0 = 0; c0 < kCrB; c0 += 6) {
-    if (t == 0) {
-      double a[6][6];
+  // ---- 2a. Cholesky of the diagonal block, 6 columns per step, with a one-step LOOKAHEAD: the one-thread factorisation of the 6x6 pivot
+  //      block — the only serial piece — is taken off the critical path: while warps 1..7 apply step s to the rest of the trailing matrix,
+  //      warp 0 updates the NEXT pivot block first and factors it. Two block barriers per step instead of three. ----
+  auto factor_pivot = [&](int c0) {                              // one thread
+    double a[6][6];
 #pragma unroll
-      for (int r = 0; r < 6; ++r)
+    for (int r = 0; r < 6; ++r)
 #pragma unroll
-        for (int c = 0; c <= r; ++c) a[r][c] = Dm[(c0 + r) * kCrLs + c0 + c];
-      int fail = 0;
+      for (int c = 0; c <= r; ++c) a[r][c] = Dm[(c0 + r) * kCrLs + c0 + c];
+    int fail = 0;
 #pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        double d = a[c][c];
-        if (!(d > 0.0) || !isfinite(d)) { fail = 1; d = 1.0; }
-        const double inv = rsqrt(d);
-        a[c][c] = d * inv;
-        dinv[c0 + c] = inv;
+    for (int c = 0; c < 6; ++c) {
+      double d = a[c][c];
+      if (!(d > 0.0) || !isfinite(d)) { fail = 1; d = 1.0; }
+      const double inv = rsqrt(d);
+      a[c][c] = d * inv;
+      dinv[c0 + c] = inv;
 #pragma unroll
-        for (int r = c + 1; r < 6; ++r) a[r][c] *= inv;
+      for (int r = c + 1; r < 6; ++r) a[r][c] *= inv;
 #pragma unroll
-        for (int r = c + 1; r < 6; ++r)
+      for (int r = c + 1; r < 6; ++r)
 #pragma unroll
-          for (int k = c + 1; k <= r; ++k) a[r][k] -= a[r][c] * a[k][c];
-      }
-#pragma unroll
-      for (int r = 0; r < 6; ++r)
-#pragma unroll
-        for (int c = 0; c <= r; ++c) Dm[(c0 + r) * kCrLs + c0 + c] = a[r][c];
-      if (fail) s_fail = 1;
+        for (int k = c + 1; k <= r; ++k) a[r][k] -= a[r][c] * a[k][c];
     }
-    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = 0; c <= r; ++c) Dm[(c0 + r) * kCrLs + c0 + c] = a[r][c];
+    if (fail) s_fail = 1;
+  };
+  if (t == 0) factor_pivot(0);
+  __syncthreads();
+  for (int c0 = 0; c0 < kCrB; c0 += 6) {
     const int rem = kCrB - c0 - 6;                               // rows below the pivot block
     if (t < rem) {                                               // panel row: forward-solve against the pivot block
       double* pr = Dm + (c0 + 6 + t) * kCrLs + c0;
@@ -274,15 +277,32 @@ __global__ void __launch_bounds__(kCrThreads, (kFirst ? 2 : 1)) cr_level_kernel(
       for (int c = 0; c < 6; ++c) pr[c] = x[c];
     }
     __syncthreads();
-    for (int e = t; e < rem * rem; e += kCrThreads) {            // trailing update (lower triangle)
-      const int rr = e / rem, cc = e % rem;
-      if (cc > rr) continue;
-      const double* lr = Dm + (c0 + 6 + rr) * kCrLs + c0;
-      const double* lc = Dm + (c0 + 6 + cc) * kCrLs + c0;
-      double s = 0.0;
+    if (rem > 0) {
+      if (t < 32) {                                              // warp 0: the next pivot block, then its factorisation
+        if (t < 21) {
+          int a6 = 0, r6 = t; while (r6 > a6) { r6 -= a6 + 1; ++a6; }
+          const int b6 = r6;                                     // entry (a6, b6), b6 <= a6
+          const double* lr = Dm + (c0 + 6 + a6) * kCrLs + c0;
+          const double* lc = Dm + (c0 + 6 + b6) * kCrLs + c0;
+          double sacc = 0.0;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) s += lr[k] * lc[k];
-      Dm[(c0 + 6 + rr) * kCrLs + c0 + 6 + cc] -= s;
+          for (int k = 0; k < 6; ++k) sacc += lr[k] * lc[k];
+          Dm[(c0 + 6 + a6) * kCrLs + c0 + 6 + b6] -= sacc;
+        }
+        __syncwarp();
+        if (t == 0) factor_pivot(c0 + 6);
+      } else {
+        for (int e = t - 32; e < rem * rem; e += kCrThreads - 32) {   // rest of the trailing update (lower triangle, rows beyond the next pivot block)
+          const int rr = e / rem, cc = e % rem;
+          if (cc > rr || rr < 6) continue;
+          const double* lr = Dm + (c0 + 6 + rr) * kCrLs + c0;
+          const double* lc = Dm + (c0 + 6 + cc) * kCrLs + c0;
+          double s = 0.0;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) s += lr[k] * lc[k];
+          Dm[(c0 + 6 + rr) * kCrLs + c0 + 6 + cc] -= s;
+        }
+      }
     }
     __syncthreads();
   }

@@ -485,7 +485,7 @@ struct cb2_problem {
   DevBuf<double> d_scal;
   DevBuf<unsigned char> d_cp_ref;
   // normal equations
-  DevBuf<int> d_c2off;
+  DevBuf<int> d_c2off, d_plain_idx;
   DevBuf<CalibEntry> d_centries;
   DevBuf<double> d_cpartial;
   DevBuf<double> d_segA, d_segG, d_segB, d_segC, d_segGc, d_Aband, d_Bmat, d_Cmat, d_grad, d_diag, d_scaling, d_dtil2, d_ytil;
@@ -509,6 +509,12 @@ struct cb2_problem {
   // level 1 by block cyclic reduction (cb2_cr.cuh): the default; CB2_SCHUR=band selects the chunked left-to-right band factor
   bool use_cr = true;
   int cr_nlevels = 0, cr_max_nblk = 0;
+  // Border Gram product split by reduction level (border_gram_dmma_kernel): part = {blk_res, blk_mod, k_off, k_cnt, level it follows (-1: the
+  // last one, after every level)}. Empty = one launch over all rows after the last level.
+  struct GramPart { int res, mod, k_off, k_cnt, after_level; };
+  std::vector<GramPart> gram_parts;
+  cudaStream_t stream_gram = nullptr;
+  cudaEvent_t ev_gram[4] = {nullptr, nullptr, nullptr, nullptr};
   int cr_zsplit = 1;                // CTAs per block of a cyclic-reduction level (column split of the forward substitution + Schur update)
   bool cr_tma = false;              // non-first levels fetch their state with TMA bulk copies (cb2_cr.cuh)
   DevBuf<double> d_crD, d_crBd, d_crU, d_crWef, d_crL;
@@ -528,6 +534,7 @@ struct cb2_problem {
   DevBuf<int> d_ext_tab, d_ext_dst;
   DevBuf<int2> d_gslot_tab, d_gram_meta;   // per (segment, slot-producing camera): {first slot, count}; per such camera: {calib_off, n_calib}
   int n_gram_sensors = 0, n_plain_sensors = 0;
+  int n_plain_idx = 0, acc_spc = 1;            // accumulate_kernel: its sensors (d_plain_idx) and the segments per CTA
   double* h_scal = nullptr;   // pinned
   double* h_param = nullptr;  // pinned: {radius, min_lm_diagonal, max_lm_diagonal} of the coming solve
   bool use_graphs = std::getenv("CB2_NO_GRAPHS") == nullptr;
@@ -544,12 +551,15 @@ struct cb2_problem {
   ~cb2_problem() {
     if (stream) sync_stream(false);                   // device buffers are released (stream-ordered, default stream) after this body
     if (stream_imu) cudaStreamSynchronize(stream_imu);
+    if (stream_gram) cudaStreamSynchronize(stream_gram);
     kprof.report();
     drop_graphs();
     if (h_scal) cudaFreeHost(h_scal);
     if (h_param) cudaFreeHost(h_param);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
+    for (auto& e : ev_gram) if (e) cudaEventDestroy(e);
+    if (stream_gram) cudaStreamDestroy(stream_gram);
     if (stream_imu) cudaStreamDestroy(stream_imu);
     if (stream) cudaStreamDestroy(stream);
   }
@@ -701,6 +711,8 @@ struct cb2_problem {
     }
     CB2_CUDA(cudaEventCreate(&ev_fork));
     CB2_CUDA(cudaEventCreate(&ev_join));
+    CB2_CUDA(cudaStreamCreateWithFlags(&stream_gram, cudaStreamNonBlocking));
+    for (auto& e : ev_gram) CB2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CB2_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_scal), sizeof(double) * kScCount));
     CB2_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_param), sizeof(double) * 4));
     return CB2_OK;
@@ -998,6 +1010,15 @@ struct cb2_problem {
       else if (h_desc[si].n_obs > 0) ++n_plain_sensors;
     }
     d_desc.upload(h_desc, h2d);
+    {
+      // accumulate_kernel's sensors and how many segments share one of its CTAs (one warp per (segment, sensor) pair)
+      std::vector<int> plain;
+      for (int si = 0; si < ns; ++si) if (!gram_sensor[si]) plain.push_back(si);
+      n_plain_idx = int(plain.size());
+      acc_spc = std::getenv("CB2_ACC_SPC1") ? 1 : (n_plain_idx <= 1 ? 4 : (n_plain_idx == 2 ? 2 : 1));
+      if (plain.empty()) plain.push_back(0);
+      d_plain_idx.upload(plain, h2d);
+    }
     for (int b = 0; b < 2; ++b) d_state[b].upload(h_state, h2d);
     d_state0.upload(h_state, h2d);
     for (int b = 0; b < 2; ++b) d_ctrl[b].upload(ctrl, h2d);
@@ -1112,6 +1133,22 @@ struct cb2_problem {
       sy.nblk = (sy.n + kCrB - 1) / kCrB;
       sy.ksplit = std::max(1, std::min((sy.n + 63) / 64, (296 + PL * max_tilepairs1 - 1) / (PL * max_tilepairs1)));
       if (gram_dmma1) sy.ksplit = std::max(1, std::min((sy.n + 63) / 64, std::max(1, 148 / PL)));
+      gram_parts.clear();
+      if (gram_dmma1 && use_cr && PL == 1 && world == 1 && !std::getenv("CB2_NO_EARLY_GRAM")) {
+        // The rows of the blocks the first levels eliminate (1/2, 1/4, 1/8 of the chunk) are multiplied beside the later levels.
+        const int L = std::min(3, cr_levels(sy.nblk) - 1);
+        int koff = 0;
+        for (int lv = 0; L >= 1 && lv <= L; ++lv) {
+          const bool last = lv == L;
+          const int res = last ? 0 : (1 << lv), mod = last ? (1 << L) : (1 << (lv + 1));
+          const int nsel = res < sy.nblk ? (sy.nblk - res + mod - 1) / mod : 0;
+          const int per = (last ? 1 : 4) * kGramRows;      // the last part is on the critical path: one row tile per CTA
+          const int kc = std::max(1, std::min(148, (nsel * kCrB + per - 1) / per));
+          gram_parts.push_back(GramPart{res, mod, koff, kc, last ? -1 : lv});
+          koff += kc;
+        }
+        if (!gram_parts.empty()) sy.ksplit = koff;
+      }
       max_ksplit1 = std::max(max_ksplit1, sy.ksplit);
       row_off[l] = rowidx.size();
       for (int i = 0; i < sy.n; ++i) rowidx.push_back(6 * chunks[p].a + i);
@@ -1332,9 +1369,10 @@ struct cb2_problem {
       if (plain) {
         int max_nc = 0;
         for (const auto& d : h_desc) if (!d.gslots) max_nc = std::max(max_nc, d.n_calib);
-        if (37 + max_nc <= 48) CB2_K((accumulate_kernel<6, 37>), nsl, kAccThreads, acc_smem_bytes(), s_acc, d_desc.p, ns, N_c, g_lo, d_c2off.p, csz, d_segA.p, d_segG.p, d_segB.p, d_segC.p, d_segGc.p);
-        else if (kAccCal0 + max_nc <= 56) CB2_K((accumulate_kernel<7, kAccCal0>), nsl, kAccThreads, acc_smem_bytes(), s_acc, d_desc.p, ns, N_c, g_lo, d_c2off.p, csz, d_segA.p, d_segG.p, d_segB.p, d_segC.p, d_segGc.p);
-        else CB2_K((accumulate_kernel<8, kAccCal0>), nsl, kAccThreads, acc_smem_bytes(), s_acc, d_desc.p, ns, N_c, g_lo, d_c2off.p, csz, d_segA.p, d_segG.p, d_segB.p, d_segC.p, d_segGc.p);
+        const int nacc = (nsl + acc_spc - 1) / acc_spc;
+        if (37 + max_nc <= 48) CB2_K((accumulate_kernel<6, 37>), nacc, kAccThreads, acc_smem_bytes(), s_acc, d_desc.p, d_plain_idx.p, n_plain_idx, nsl, acc_spc, N_c, g_lo, d_c2off.p, csz, d_segA.p, d_segG.p, d_segB.p, d_segC.p, d_segGc.p);
+        else if (kAccCal0 + max_nc <= 56) CB2_K((accumulate_kernel<7, kAccCal0>), nacc, kAccThreads, acc_smem_bytes(), s_acc, d_desc.p, d_plain_idx.p, n_plain_idx, nsl, acc_spc, N_c, g_lo, d_c2off.p, csz, d_segA.p, d_segG.p, d_segB.p, d_segC.p, d_segGc.p);
+        else CB2_K((accumulate_kernel<8, kAccCal0>), nacc, kAccThreads, acc_smem_bytes(), s_acc, d_desc.p, d_plain_idx.p, n_plain_idx, nsl, acc_spc, N_c, g_lo, d_c2off.p, csz, d_segA.p, d_segG.p, d_segB.p, d_segC.p, d_segGc.p);
       }
       if (gram)
         CB2_K(expand_gram_kernel, nsl, kExpThreads, expand_smem_bytes(), stream, d_gslot_tab.p, d_gram_meta.p, n_gram_sensors, d_gslots.p, N_c, d_ext_tab.p, d_ext_dst.p,
@@ -1422,6 +1460,14 @@ struct cb2_problem {
         while (z < cr_zsplit && n_elim * (z * 2) <= nsm) z *= 2;
         if (lv == 0) CB2_K((cr_level_kernel<true>), dim3(nact, PL, 1), kCrThreads, smem_cr, stream, d_l1.p, lv, n_a, N_c, d_Aband.p, d_Bmat.p, d_Cmat.p, d_grad.p, d_dtil2.p, d_scal.p, 0);
         else CB2_K((cr_level_kernel<false>), dim3(nact, PL, z), kCrThreads, cr_tma ? cr_smem_bytes_tma(nbw1) : smem_cr, stream, d_l1.p, lv, n_a, N_c, d_Aband.p, d_Bmat.p, d_Cmat.p, d_grad.p, d_dtil2.p, d_scal.p, cr_tma ? 1 : 0);
+        for (const GramPart& gp : gram_parts)
+          if (gp.after_level == lv) {     // this level's W rows are final: their share of the border Gram product, beside the next levels
+            cudaStream_t sg = stream;
+#ifndef CB2_EMUL
+            if (stream_gram) { CB2_CUDA(cudaEventRecord(ev_gram[lv], stream)); CB2_CUDA(cudaStreamWaitEvent(stream_gram, ev_gram[lv], 0)); sg = stream_gram; }
+#endif
+            CB2_K(border_gram_dmma_kernel, dim3(gp.k_cnt, PL), 256, gram_smem_bytes(nbw1), sg, d_l1.p, gp.res, gp.mod, gp.k_off, gp.k_cnt);
+          }
       }
     } else {
       CB2_K(gather_level1_kernel, dim3(std::max(1, std::min(64, (max_n1 * (36 + nbw1) + 255) / 256)), PL), 256, 0, stream, d_l1.p, n_a, N_c, d_Aband.p,
@@ -1429,7 +1475,13 @@ struct cb2_problem {
       const size_t smem_f1 = factor_smem_bytes(36, nbw1);
       CB2_K((band_factor_kernel<6>), PL, kFacThreads, smem_f1, stream, d_l1.p, d_scal.p);
     }
-    if (gram_dmma1) CB2_K(border_gram_dmma_kernel, dim3(max_ksplit1, PL), 256, gram_smem_bytes(nbw1), stream, d_l1.p);
+    if (gram_dmma1 && !gram_parts.empty()) {
+      const GramPart& gp = gram_parts.back();
+      CB2_K(border_gram_dmma_kernel, dim3(gp.k_cnt, PL), 256, gram_smem_bytes(nbw1), stream, d_l1.p, gp.res, gp.mod, gp.k_off, gp.k_cnt);
+#ifndef CB2_EMUL
+      if (stream_gram) { CB2_CUDA(cudaEventRecord(ev_gram[3], stream_gram)); CB2_CUDA(cudaStreamWaitEvent(stream, ev_gram[3], 0)); }   // join
+#endif
+    } else if (gram_dmma1) CB2_K(border_gram_dmma_kernel, dim3(max_ksplit1, PL), 256, gram_smem_bytes(nbw1), stream, d_l1.p, 0, 1, 0, -1);
     else CB2_K(border_gram_kernel, dim3(max_tilepairs1, PL, max_ksplit1), dim3(16, 16), 0, stream, d_l1.p);
     // Separator + calibration systems: rank-local direct terms minus the Schur terms of the owned chunks, summed across ranks.
     if (h_l2.n > 0) {

@@ -6,8 +6,8 @@
 // residual touches k consecutive control points (camera_cost_functor.cpp:52-60); B = H[cp,calib] couples a segment to
 // the sensors observed in it; C = H[calib,calib] is block-diagonal per sensor (no residual involves two sensors).
 //
-// accumulate_kernel: one CTA per spline segment, one WARP per sensor (round-robin). All residual rows of a segment touch the
-// same 36 control-point columns, so each warp forms the local Gram matrix X^T X of X = [J_cp | r | 0 0 0 | J_calib | 0..]
+// accumulate_kernel: one CTA per spline segment (per 2 / 4 segments when there are fewer sensors than warps), one WARP per
+// (segment, sensor) pair, round-robin. All residual rows of a segment touch the same 36 control-point columns, so each warp forms the local Gram matrix X^T X of X = [J_cp | r | 0 0 0 | J_calib | 0..]
 // (r as an extra column gives the gradient for free) on the FP64 TENSOR pipe: mma.sync.m8n8k4.f64 (SASS DMMA), 8x8
 // accumulator tiles in registers, lower block triangle only. For a Gram product the A and B fragments of a column block are
 // the same register (lane holds X[4 ks + lane % 4][8 b + lane / 4]), so a k-step of 4 rows costs NB shared loads for
@@ -66,13 +66,19 @@ CB2_D void cp_async_wait() {
 // Sensors whose Gram slots come from the sweep (sd.gslots != nullptr) are skipped here; the warps are dealt the remaining sensors.
 template <int NB, int CAL0>
 __global__ void __launch_bounds__(kAccThreads, (NB <= 7 ? CB2_ACC_MINBLOCKS : 2)) accumulate_kernel(
-    const SensorDesc* __restrict__ sensors, int n_sensors, int N_c, int g_lo, const int* __restrict__ c2off, int csz, double* __restrict__ segA,
-    double* __restrict__ segG, double* __restrict__ segB, double* __restrict__ segC, double* __restrict__ segGc) {
+    const SensorDesc* __restrict__ sensors, const int* __restrict__ plain_idx, int n_plain, int n_local_seg, int spc, int N_c, int g_lo,
+    const int* __restrict__ c2off, int csz, double* __restrict__ segA, double* __restrict__ segG, double* __restrict__ segB,
+    double* __restrict__ segC, double* __restrict__ segGc) {
   // dynamic shared memory: per warp two tile buffers of kAccRows x kAccStride (+ 4 doubles: the last fragment reads past a row end)
   typedef double TileBuf[2][kAccRows * kAccStride + 4];
   TileBuf* tiles = dyn_smem<TileBuf>();
   __shared__ int colpos[kAccWarps][kCpCols + kMaxCalib];
-  const int gl = blockIdx.x, g = g_lo + gl, t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  // spc segments per CTA (1, 2 or 4), kAccWarps / spc warps per segment: with fewer sensors than warps (C4: gyroscope + accelerometer) every
+  // warp still has a (segment, sensor) pair of its own instead of half the CTA waiting at the final barrier.
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int wps = kAccWarps / spc, lw = warp % wps;
+  const int gl = blockIdx.x * spc + warp / wps, g = g_lo + gl;
+  const bool live = gl < n_local_seg;
   const int fr = lane & 3, fc = lane >> 2;   // fragment row (k) and column of this lane
   double acc[NB][NB][2];                     // [bi][bj <= bi]: 8x8 tile of the local Gram matrix; the rest is dead code
 #pragma unroll
@@ -82,12 +88,10 @@ __global__ void __launch_bounds__(kAccThreads, (NB <= 7 ? CB2_ACC_MINBLOCKS : 2)
   double* const tb0 = tiles[warp][0];
   for (int i = lane; i < 2 * (kAccRows * kAccStride + 4); i += 32) tb0[i] = 0.0;   // padding columns stay zero for the whole kernel
   __syncwarp();
-  // The sensors this kernel handles are dealt round-robin to the warps by their rank among them (not by their global index).
-  int my_rank = 0;
-  for (int s = 0; s < n_sensors; ++s) {
+  // The sensors this kernel handles (plain_idx: those without Gram slots) are dealt round-robin to the warps of the segment.
+  for (int k = lw; live && k < n_plain; k += wps) {
+    const int s = plain_idx[k];
     const SensorDesc& sd = sensors[s];
-    if (sd.gslots != nullptr) continue;
-    if ((my_rank++ % kAccWarps) != warp) continue;
     const int m = sd.m, jw = sd.jw, nc = sd.n_calib;
     const int o0 = sd.seg_start[g];
     const int rows = (sd.seg_start[g + 1] - o0) * m;
@@ -182,7 +186,10 @@ __global__ void __launch_bounds__(kAccThreads, (NB <= 7 ? CB2_ACC_MINBLOCKS : 2)
   }
   __syncthreads();
   // tix -> (bi, bj) of the lower block triangle without a search loop: tix = bi (bi + 1) / 2 + bj, bi < 5.
-  for (int e = t; e < 15 * 64; e += kAccThreads) {
+  for (int e2 = t; e2 < spc * 15 * 64; e2 += kAccThreads) {
+    const int q = e2 / (15 * 64), e = e2 - q * (15 * 64);
+    const int gq = blockIdx.x * spc + q;                 // local segment of warps q wps .. (q + 1) wps - 1
+    if (gq >= n_local_seg) continue;
     const int tix = e >> 6, mrow = (e >> 3) & 7, ncol = e & 7;
     const int bi = tix >= 10 ? 4 : (tix >= 6 ? 3 : (tix >= 3 ? 2 : (tix >= 1 ? 1 : 0)));
     const int rem = tix - bi * (bi + 1) / 2;
@@ -190,9 +197,9 @@ __global__ void __launch_bounds__(kAccThreads, (NB <= 7 ? CB2_ACC_MINBLOCKS : 2)
     if (Jx > I || Jx >= kCpCols || I > kAccRcol) continue;
     double v = 0.0;
 #pragma unroll
-    for (int w = 0; w < kAccWarps; ++w) v += tiles[w][0][e];
-    if (I < kCpCols) segA[(size_t(gl) * kCpCols + I) * kCpCols + Jx] = v;
-    else segG[size_t(gl) * kCpCols + Jx] = v;
+    for (int w = 0; w < kAccWarps; ++w) if (w < wps) v += tiles[q * wps + w][0][e];
+    if (I < kCpCols) segA[(size_t(gq) * kCpCols + I) * kCpCols + Jx] = v;
+    else segG[size_t(gq) * kCpCols + Jx] = v;
   }
 }
 

@@ -360,16 +360,27 @@ CB2_D void gram_dmma(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 #endif
 }
-__global__ void __launch_bounds__(256) border_gram_dmma_kernel(const BandSys* __restrict__ systems) {
+// Row subsets (cyclic reduction only): blk_mod > 1 restricts the product to the 30-row blocks i = blk_res + m blk_mod — the blocks one
+// reduction level eliminates (blk_res = 2^lv, blk_mod = 2^(lv+1)) or all blocks of the levels >= L (0, 2^L) — whose W rows are final as
+// soon as that level's kernel has run: the host launches the early levels' products beside the later (latency-bound) levels. A launch
+// owns the partial matrices k_off .. k_off + k_cnt - 1 of T (k_cnt < 0: all sy.ksplit of them, every row).
+constexpr int kGramBlk = 30;
+__global__ void __launch_bounds__(256) border_gram_dmma_kernel(const BandSys* __restrict__ systems, int blk_res = 0, int blk_mod = 1, int k_off = 0,
+                                                               int k_cnt = -1) {
   const BandSys sy = systems[blockIdx.y];
-  if (int(blockIdx.x) >= sy.ksplit) return;
+  const int kc = k_cnt < 0 ? sy.ksplit : k_cnt;
+  if (int(blockIdx.x) >= kc) return;
   const int nbw = sy.nbw, nb = (nbw + 7) / 8, XS = gram_stride(nbw), ntile = nb * (nb + 1) / 2;
   double* tile = dyn_smem<double>();
   __shared__ unsigned char tbi[8 * kGramMaxTiles], tbj[8 * kGramMaxTiles];
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31, fr = lane & 3, fc = lane >> 2;
   for (int e = t; e < ntile; e += 256) { int bi = 0, rem = e; while (rem > bi) { rem -= bi + 1; ++bi; } tbi[e] = (unsigned char)bi; tbj[e] = (unsigned char)rem; }
-  const int rows_per = ((sy.n + sy.ksplit - 1) / sy.ksplit + kGramRows - 1) / kGramRows * kGramRows;
-  const int r_begin = blockIdx.x * rows_per, r_end = min(sy.n, r_begin + rows_per);
+  const int nblk30 = (sy.n + kGramBlk - 1) / kGramBlk;
+  const int nsel = blk_res < nblk30 ? (nblk30 - blk_res + blk_mod - 1) / blk_mod : 0;
+  const int nv = blk_mod == 1 ? sy.n : nsel * kGramBlk;      // rows of this launch, numbered consecutively ("virtual" rows)
+  auto row_of = [&](int v) { if (blk_mod == 1) return v; const int mb = v / kGramBlk; return (blk_res + mb * blk_mod) * kGramBlk + (v - mb * kGramBlk); };
+  const int rows_per = ((nv + kc - 1) / kc + kGramRows - 1) / kGramRows * kGramRows;
+  const int r_begin = blockIdx.x * rows_per, r_end = min(nv, r_begin + rows_per);
   double acc[kGramMaxTiles][2];
 #pragma unroll
   for (int i = 0; i < kGramMaxTiles; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
@@ -384,8 +395,9 @@ __global__ void __launch_bounds__(256) border_gram_dmma_kernel(const BandSys* __
       for (int u = 0; u < 6; ++u) {
         const int e = min(e0 + u * 256, kGramRows * wcols - 1);
         const int rr = e / wcols, cc = e - rr * wcols;
-        const bool ok = r0 + rr < r_end && cc < nbw;
-        const double x = Wg[size_t(ok ? r0 + rr : r_begin) * nbw + (ok ? cc : 0)];
+        const int ar = row_of(min(r0 + rr, nv - 1));
+        const bool ok = r0 + rr < r_end && ar < sy.n && cc < nbw;
+        const double x = Wg[size_t(ok ? ar : 0) * nbw + (ok ? cc : 0)];
         v[u] = ok ? x : 0.0;
       }
 #pragma unroll
@@ -405,7 +417,7 @@ __global__ void __launch_bounds__(256) border_gram_dmma_kernel(const BandSys* __
       }
     }
   }
-  double* T = sy.T + size_t(blockIdx.x) * nbw * nbw;
+  double* T = sy.T + size_t(k_off + blockIdx.x) * nbw * nbw;
 #pragma unroll
   for (int i = 0; i < kGramMaxTiles; ++i) {
     const int e = warp + 8 * i;

@@ -87,6 +87,28 @@ def test_emulated_lm_iterations_match_oracle(schur, chunk, emul_lib, oracle, mon
 
 
 @pytest.mark.timeout(900)
+@pytest.mark.parametrize("no_early_gram", [False, True])
+def test_emulated_single_plain_sensor_and_gram_variants(no_early_gram, emul_lib, oracle, monkeypatch):
+    """Camera + gyroscope only: accumulate_kernel packs FOUR segments into a CTA (one warp per (segment, sensor) pair; micro itself
+    runs two per CTA), and the border Gram product once split by reduction level (default) and once as a single launch."""
+    if no_early_gram:
+        monkeypatch.setenv("CB2_NO_EARLY_GRAM", "1")
+    truth, prob = synthetic.generate("micro", oracle.oracle_api, noise=True)
+    prob.sensors = prob.sensors[:-1]
+    assert [s.kind for s in prob.sensors] == [0, 1]
+    a, o = _capi.CApi(emul_lib), oracle.oracle_api()
+    prob.clone().push(a)
+    prob.clone().push(o)
+    sum_a, log_a = a.optimize(_capi.Options(minimizer_progress_to_stdout=0, max_num_iterations=3))
+    sum_o, log_o = o.optimize(oracle.OracleOptions(linear_solver=1, max_num_iterations=3))
+    assert len(log_a) == len(log_o) == 4
+    for x, y in zip(log_a, log_o):
+        assert abs(x.cost - y.cost) <= 1e-9 * abs(y.cost)
+        assert abs(x.step_norm - y.step_norm) <= 1e-7 * max(y.step_norm, 1e-12)
+        assert abs(x.gradient_max_norm - y.gradient_max_norm) <= 1e-7 * y.gradient_max_norm
+
+
+@pytest.mark.timeout(900)
 def test_emulated_lm_with_rejected_steps_matches_oracle(emul_lib, oracle):
     """The reference's toy stereo + IMU problem starts with three rejected steps (as in the stored Ceres log): exercises the
     reject -> accept transitions of the speculative trial sweep (the candidate buffer is reused by every new candidate)."""

@@ -42,6 +42,7 @@
 
 namespace cb2 {
 
+static int env_int(const char* name, int fallback) { const char* e = std::getenv(name); return e ? std::atoi(e) : fallback; }
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 struct CudaFail { std::string msg; };
@@ -509,8 +510,8 @@ struct cb2_problem {
   // level 1 by block cyclic reduction (cb2_cr.cuh): the default; CB2_SCHUR=band selects the chunked left-to-right band factor
   bool use_cr = true;
   int cr_nlevels = 0, cr_max_nblk = 0;
-  // Border Gram product split by reduction level (border_gram_dmma_kernel): part = {blk_res, blk_mod, k_off, k_cnt, level it follows (-1: the
-  // last one, after every level)}. Empty = one launch over all rows after the last level.
+  // Border Gram product in two parts (border_gram_dmma_kernel): part = {blk_res, blk_mod, k_off, k_cnt, level it follows (-1: after every
+  // level)}. Empty = one launch over all rows after the last level.
   struct GramPart { int res, mod, k_off, k_cnt, after_level; };
   std::vector<GramPart> gram_parts;
   cudaStream_t stream_gram = nullptr;
@@ -1135,17 +1136,26 @@ struct cb2_problem {
       if (gram_dmma1) sy.ksplit = std::max(1, std::min((sy.n + 63) / 64, std::max(1, 148 / PL)));
       gram_parts.clear();
       if (gram_dmma1 && use_cr && PL == 1 && world == 1 && !std::getenv("CB2_NO_EARLY_GRAM")) {
-        // The rows of the blocks the first levels eliminate (1/2, 1/4, 1/8 of the chunk) are multiplied beside the later levels.
-        const int L = std::min(3, cr_levels(sy.nblk) - 1);
+        // The rows of the blocks the first La levels eliminate (15/16 of the chunk for La = 4) are multiplied beside the LATER levels, from
+        // level Ls on: those levels are narrow (<= 16 blocks) and latency-bound, the product is bound by the FP64 tensor pipe and a CTA of
+        // it fills an SM's register file, so it takes the SMs the levels leave idle (all but `reserve` of them). What is left for the
+        // critical path after the last level is the 1/16 of the rows the late levels produce, one row tile per CTA.
+        // (Measured on C4, profiles/r02_variants.md: Schur phase 0.442 -> 0.400 ms; starting earlier or reserving fewer SMs slows the levels.)
+        static const int la_env = env_int("CB2_EARLY_GRAM_LEVELS", -1), ls_env = env_int("CB2_EARLY_GRAM_AFTER", -1), reserve = env_int("CB2_EARLY_GRAM_RESERVE", 64);
+        const int nlev = cr_levels(sy.nblk);
+        int ls_auto = 0;
+        while (ls_auto < nlev - 2 && ((sy.nblk + (2 << ls_auto) - 1) >> (ls_auto + 1)) > 16) ++ls_auto;   // first level followed by <= 16 active blocks
+        const int La = std::min(la_env >= 0 ? la_env : std::max(1, ls_auto), nlev - 1);
         int koff = 0;
-        for (int lv = 0; L >= 1 && lv <= L; ++lv) {
-          const bool last = lv == L;
-          const int res = last ? 0 : (1 << lv), mod = last ? (1 << L) : (1 << (lv + 1));
-          const int nsel = res < sy.nblk ? (sy.nblk - res + mod - 1) / mod : 0;
-          const int per = (last ? 1 : 4) * kGramRows;      // the last part is on the critical path: one row tile per CTA
-          const int kc = std::max(1, std::min(148, (nsel * kCrB + per - 1) / per));
-          gram_parts.push_back(GramPart{res, mod, koff, kc, last ? -1 : lv});
-          koff += kc;
+        if (La >= 1) {
+          const int Ls = std::max(La - 1, std::min(ls_env >= 0 ? ls_env : ls_auto, nlev - 2));
+          const int M = 1 << La, nmult = (sy.nblk + M - 1) / M;
+          const int rows_early = (sy.nblk - nmult) * kCrB, rows_last = nmult * kCrB;
+          const int k_early = std::max(1, std::min(std::max(1, 148 - reserve), (rows_early + kGramRows - 1) / kGramRows));
+          const int k_last = std::max(1, std::min(148, (rows_last + kGramRows - 1) / kGramRows));
+          gram_parts.push_back(GramPart{-1, M, 0, k_early, Ls});
+          gram_parts.push_back(GramPart{0, M, k_early, k_last, -1});
+          koff = k_early + k_last;
         }
         if (!gram_parts.empty()) sy.ksplit = koff;
       }
@@ -1461,10 +1471,10 @@ struct cb2_problem {
         if (lv == 0) CB2_K((cr_level_kernel<true>), dim3(nact, PL, 1), kCrThreads, smem_cr, stream, d_l1.p, lv, n_a, N_c, d_Aband.p, d_Bmat.p, d_Cmat.p, d_grad.p, d_dtil2.p, d_scal.p, 0);
         else CB2_K((cr_level_kernel<false>), dim3(nact, PL, z), kCrThreads, cr_tma ? cr_smem_bytes_tma(nbw1) : smem_cr, stream, d_l1.p, lv, n_a, N_c, d_Aband.p, d_Bmat.p, d_Cmat.p, d_grad.p, d_dtil2.p, d_scal.p, cr_tma ? 1 : 0);
         for (const GramPart& gp : gram_parts)
-          if (gp.after_level == lv) {     // this level's W rows are final: their share of the border Gram product, beside the next levels
+          if (gp.after_level == lv) {     // the W rows of the first levels' blocks are final: their share of the border Gram product, beside the next levels
             cudaStream_t sg = stream;
 #ifndef CB2_EMUL
-            if (stream_gram) { CB2_CUDA(cudaEventRecord(ev_gram[lv], stream)); CB2_CUDA(cudaStreamWaitEvent(stream_gram, ev_gram[lv], 0)); sg = stream_gram; }
+            if (stream_gram) { CB2_CUDA(cudaEventRecord(ev_gram[0], stream)); CB2_CUDA(cudaStreamWaitEvent(stream_gram, ev_gram[0], 0)); sg = stream_gram; }
 #endif
             CB2_K(border_gram_dmma_kernel, dim3(gp.k_cnt, PL), 256, gram_smem_bytes(nbw1), sg, d_l1.p, gp.res, gp.mod, gp.k_off, gp.k_cnt);
           }

@@ -360,9 +360,9 @@ CB2_D void gram_dmma(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 #endif
 }
-// Row subsets (cyclic reduction only): blk_mod > 1 restricts the product to the 30-row blocks i = blk_res + m blk_mod — the blocks one
-// reduction level eliminates (blk_res = 2^lv, blk_mod = 2^(lv+1)) or all blocks of the levels >= L (0, 2^L) — whose W rows are final as
-// soon as that level's kernel has run: the host launches the early levels' products beside the later (latency-bound) levels. A launch
+// Row subsets (cyclic reduction only): blk_mod > 1 restricts the product to the 30-row blocks i that are multiples of blk_mod = 2^L
+// (blk_res = 0: the blocks the reduction levels >= L eliminate) or to all the others (blk_res = -1: the blocks of the levels < L, whose W
+// rows are final once level L - 1 has run): the host launches the second kind beside the later, narrow, latency-bound levels. A launch
 // owns the partial matrices k_off .. k_off + k_cnt - 1 of T (k_cnt < 0: all sy.ksplit of them, every row).
 constexpr int kGramBlk = 30;
 __global__ void __launch_bounds__(256) border_gram_dmma_kernel(const BandSys* __restrict__ systems, int blk_res = 0, int blk_mod = 1, int k_off = 0,
@@ -376,9 +376,15 @@ __global__ void __launch_bounds__(256) border_gram_dmma_kernel(const BandSys* __
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31, fr = lane & 3, fc = lane >> 2;
   for (int e = t; e < ntile; e += 256) { int bi = 0, rem = e; while (rem > bi) { rem -= bi + 1; ++bi; } tbi[e] = (unsigned char)bi; tbj[e] = (unsigned char)rem; }
   const int nblk30 = (sy.n + kGramBlk - 1) / kGramBlk;
-  const int nsel = blk_res < nblk30 ? (nblk30 - blk_res + blk_mod - 1) / blk_mod : 0;
+  const int nmult = (nblk30 + blk_mod - 1) / blk_mod;          // multiples of blk_mod below nblk30
+  const int nsel = blk_res < 0 ? nblk30 - nmult : nmult;
   const int nv = blk_mod == 1 ? sy.n : nsel * kGramBlk;      // rows of this launch, numbered consecutively ("virtual" rows)
-  auto row_of = [&](int v) { if (blk_mod == 1) return v; const int mb = v / kGramBlk; return (blk_res + mb * blk_mod) * kGramBlk + (v - mb * kGramBlk); };
+  auto row_of = [&](int v) {
+    if (blk_mod == 1) return v;
+    const int mb = v / kGramBlk;
+    const int blk = blk_res < 0 ? (mb / (blk_mod - 1)) * blk_mod + mb % (blk_mod - 1) + 1 : mb * blk_mod;
+    return blk * kGramBlk + (v - mb * kGramBlk);
+  };
   const int rows_per = ((nv + kc - 1) / kc + kGramRows - 1) / kGramRows * kGramRows;
   const int r_begin = blockIdx.x * rows_per, r_end = min(nv, r_begin + rows_per);
   double acc[kGramMaxTiles][2];

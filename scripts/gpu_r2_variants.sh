@@ -1,7 +1,6 @@
-# A/B of the late round-2 changes on one B200: accumulate_kernel with several segments per CTA, border Gram split by reduction level.
+# A/B of the late round-2 changes on one B200: border Gram product of the early levels' rows beside the late reduction levels.
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" || exit 1
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_baseline_shapes.py tests/test_world_model.py -m gpu -q -x 2>&1 | tail -4
 run() {
   tag=$1; shift
   env "$@" timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/r2_var_$tag.json 2> gpurun_out/r2_var_$tag.err
@@ -11,10 +10,9 @@ d=json.load(open("gpurun_out/r2_var_$tag.json"))
 print("RESULT $tag it/s %.1f" % d["value"], "ms/step %.4f" % d["ms_per_step"], {k: round(v, 4) for k, v in d["phases_ms_per_iteration"].items()}, "e2e %.1f" % d["e2e"]["value"], "cost %.9g" % d["config"]["final_cost"])
 PY
 }
-run new CB2_DUMMY=1
-run noearly CB2_NO_EARLY_GRAM=1
-run spc1 CB2_ACC_SPC1=1
-run old CB2_NO_EARLY_GRAM=1 CB2_ACC_SPC1=1
-run new2 CB2_DUMMY=1
-CB2_PROFILE=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_kprof.json 2> gpurun_out/r2_kprof.txt
-grep "cb2 profile" gpurun_out/r2_kprof.txt | tail -26
+run a4r64 CB2_EARLY_GRAM_AFTER=4 CB2_EARLY_GRAM_RESERVE=64
+run a5r64 CB2_EARLY_GRAM_AFTER=5 CB2_EARLY_GRAM_RESERVE=64
+run a4r96 CB2_EARLY_GRAM_AFTER=4 CB2_EARLY_GRAM_RESERVE=96
+run l4a4r64 CB2_EARLY_GRAM_LEVELS=4 CB2_EARLY_GRAM_AFTER=4 CB2_EARLY_GRAM_RESERVE=64
+run l5a5r64 CB2_EARLY_GRAM_LEVELS=5 CB2_EARLY_GRAM_AFTER=5 CB2_EARLY_GRAM_RESERVE=64
+run l5a4r48 CB2_EARLY_GRAM_LEVELS=5 CB2_EARLY_GRAM_AFTER=4 CB2_EARLY_GRAM_RESERVE=48

@@ -514,6 +514,8 @@ struct cb2_problem {
   // level)}. Empty = one launch over all rows after the last level.
   struct GramPart { int res, mod, k_off, k_cnt, after_level; };
   std::vector<GramPart> gram_parts;
+  bool gram_prereduce = std::getenv("CB2_GRAM_PREREDUCE") != nullptr;   // opt-in: folding the early partials beside the late levels gained nothing (profiles/r02_variants.md)
+  bool calib_fork = std::getenv("CB2_NO_CALIB_FORK") == nullptr;
   cudaStream_t stream_gram = nullptr;
   cudaEvent_t ev_gram[4] = {nullptr, nullptr, nullptr, nullptr};
   int cr_zsplit = 1;                // CTAs per block of a cyclic-reduction level (column split of the forward substitution + Schur update)
@@ -524,6 +526,8 @@ struct cb2_problem {
   int cr2_nlevels = 0;
   DevBuf<double> d_cr2D, d_cr2Bd, d_cr2U, d_cr2Wef, d_cr2L;
   DevBuf<unsigned> d_grid_sync;   // arrival counter of the fused back-substitution launch
+  DevBuf<double> d_lm_partial;    // grid_reduce_last (lmkernels): per-CTA partial sums and arrival tickets of gradient_norm_kernel / apply_step_kernel
+  DevBuf<unsigned> d_lm_ticket;
   int cur = 0;   // which of the two parameter buffers holds x
   size_t smem_eval[3] = {0, 0, 0};
   int max_tilepairs1 = 0, max_ksplit1 = 1;
@@ -1039,6 +1043,7 @@ struct cb2_problem {
     }
     d_scal.alloc(kScCount);
     d_grid_sync.alloc(4);
+    d_lm_partial.alloc(16 * kLmMaxCtas); d_lm_ticket.alloc(4);   // grid_reduce_last: [gradient_norm | apply_step]
     cur = 0;
     // Normal-equation storage.
     d_c2off.upload(c2off, h2d);
@@ -1157,7 +1162,7 @@ struct cb2_problem {
           gram_parts.push_back(GramPart{0, M, k_early, k_last, -1});
           koff = k_early + k_last;
         }
-        if (!gram_parts.empty()) sy.ksplit = koff;
+        if (!gram_parts.empty()) { sy.ksplit = koff; sy.kfirst = gram_prereduce ? gram_parts[0].k_cnt - 1 : 0; }
       }
       max_ksplit1 = std::max(max_ksplit1, sy.ksplit);
       row_off[l] = rowidx.size();
@@ -1391,36 +1396,53 @@ struct cb2_problem {
       if (plain && gram) { CB2_CUDA(cudaEventRecord(ev_join, stream_imu)); CB2_CUDA(cudaStreamWaitEvent(stream, ev_join, 0)); }
 #endif
     }
+    // The calibration blocks (from segC / segGc / the sweep's per-warp partials) and the control-point band + border (from segA / segB /
+    // segG) are assembled from disjoint inputs into disjoint outputs (grad: calibration tail / control-point head): side by side.
+    cudaStream_t s_cal = stream;
+#ifndef CB2_EMUL
+    if (calib_fork && N_c > 0) { CB2_CUDA(cudaEventRecord(ev_fork, stream)); CB2_CUDA(cudaStreamWaitEvent(stream_imu, ev_fork, 0)); s_cal = stream_imu; }
+#endif
     const long total = n_a * 36 + n_a * N_c + n_a;
     CB2_K(assemble_band_kernel, int(std::min<long>((total + 255) / 256, 148 * 16)), 256, 0, stream, n_cp, g_lo, g_hi, N_c, d_segA.p, d_segG.p, d_segB.p,
           d_segA2.n ? d_segA2.p : nullptr, d_segG2.n ? d_segG2.p : nullptr, d_Aband.p, d_Bmat.p, d_grad.p);
     if (N_c > 0) {
-      d_Cmat.zero(stream);
+      d_Cmat.zero(s_cal);
       const int ne = int(d_centries.n);
-      CB2_K(assemble_calib_kernel, dim3((ne + 31) / 32, kCalibSlices), dim3(32, 8), 0, stream, ne, d_centries.p, d_segC.p, d_segGc.p, d_gcta.p, d_cpartial.p);
-      CB2_K(assemble_calib_final_kernel, (ne + 255) / 256, 256, 0, stream, N_c, ne, kCalibSlices, d_centries.p, d_cpartial.p, d_Cmat.p, d_grad.p + n_a);
+      CB2_K(assemble_calib_kernel, dim3((ne + 31) / 32, kCalibSlices), dim3(32, 8), 0, s_cal, ne, d_centries.p, d_segC.p, d_segGc.p, d_gcta.p, d_cpartial.p);
+      CB2_K(assemble_calib_final_kernel, (ne + 255) / 256, 256, 0, s_cal, N_c, ne, kCalibSlices, d_centries.p, d_cpartial.p, d_Cmat.p, d_grad.p + n_a);
     }
+#ifndef CB2_EMUL
+    if (s_cal != stream) { CB2_CUDA(cudaEventRecord(ev_join, s_cal)); CB2_CUDA(cudaStreamWaitEvent(stream, ev_join, 0)); }
+#endif
     if (world_free && tile_off[1] > tile_off[0]) {   // freed world-model blocks: their rows / columns of the normal equations, from the cameras' Jacobian rows
       if (N_c > n_sensor_unknowns) CB2_CUDA(cudaMemsetAsync(d_grad.p + n_a + n_sensor_unknowns, 0, sizeof(double) * (N_c - n_sensor_unknowns), stream));   // accumulated by atomics
       CB2_K(world_normal_kernel, tile_off[1] - tile_off[0], 128, 0, stream, d_desc.p, d_tiles.p + tile_off[0], n_a, N_c, d_pt_body.p, d_body_u.p, d_pt_u.p,
             d_body_q[cur].p, d_body_t[cur].p, d_pw[cur].p, d_Bmat.p, d_Cmat.p, d_grad.p);
     }
-    CB2_K(hess_diag_kernel, int(std::min<long>((n_tot + 255) / 256, 1024)), 256, 0, stream, n_a, N_c, d_Aband.p, d_Cmat.p, d_diag.p);
+    // Single rank: the Hessian diagonal (for the damping of the coming solve) beside the gradient norms — two small independent kernels.
+    cudaStream_t s_diag = stream;
+#ifndef CB2_EMUL
+    if (calib_fork && world == 1) { CB2_CUDA(cudaEventRecord(ev_fork, stream)); CB2_CUDA(cudaStreamWaitEvent(stream_imu, ev_fork, 0)); s_diag = stream_imu; }
+#endif
+    CB2_K(hess_diag_kernel, int(std::min<long>((n_tot + 255) / 256, 1024)), 256, 0, s_diag, n_a, N_c, d_Aband.p, d_Cmat.p, d_diag.p);
     if (world > 1) {
       // Separator rows and calibration receive contributions from several ranks (lmkernels: pack_shared_kernel). d_grad itself stays
       // rank-local; gradG carries the sums on the shared rows. When the host does not wait for this point's gradient norms (deferred
       // round trip, see minimize) the sums are NOT exchanged here: they ride in the tail of the next solve's collective (launch_step).
       CB2_CUDA(cudaMemcpyAsync(d_gradG.p, d_grad.p, sizeof(double) * n_tot, cudaMemcpyDeviceToDevice, stream));
-      CB2_K(gradient_norm_kernel, 1, kLmThreads, 0, stream, n_a, d_grad.p, d_cp_own.p, 1, 0, 0, d_desc.p, d_state[cur].p, ns, world_refs(), d_body_q[cur].p, d_scal.p);   // owned part
+      CB2_K(gradient_norm_kernel, lm_ctas(n_a), kLmThreads, 0, stream, n_a, d_grad.p, d_cp_own.p, 1, 0, 0, d_desc.p, d_state[cur].p, ns, world_refs(), d_body_q[cur].p, d_scal.p, d_lm_partial.p, d_lm_ticket.p);   // owned part
       if (!defer_shared) {
         CB2_K(pack_shared_kernel, (n_shared + 255) / 256, 256, 0, stream, n_shared, d_shared_idx.p, d_grad.p, d_diag.p, d_scal.p, world, rank, d_shared_buf.p);
         comm->allreduce_sum(d_shared_buf.p, shared_buf_size(n_shared, world), stream);
         CB2_K(unpack_shared_kernel, (n_shared + 255) / 256, 256, 0, stream, n_shared, d_shared_idx.p, d_shared_buf.p, world, d_gradG.p, d_diag.p, d_scal.p);
-        CB2_K(gradient_norm_kernel, 1, kLmThreads, 0, stream, n_a, d_gradG.p, d_cp_own.p, 0, 1, 1, d_desc.p, d_state[cur].p, ns, world_refs(), d_body_q[cur].p, d_scal.p);   // + shared part
+        CB2_K(gradient_norm_kernel, lm_ctas(n_a), kLmThreads, 0, stream, n_a, d_gradG.p, d_cp_own.p, 0, 1, 1, d_desc.p, d_state[cur].p, ns, world_refs(), d_body_q[cur].p, d_scal.p, d_lm_partial.p, d_lm_ticket.p);   // + shared part
       }
     } else {
-      CB2_K(gradient_norm_kernel, 1, kLmThreads, 0, stream, n_a, d_grad.p, d_cp_own.p, 1, 1, 0, d_desc.p, d_state[cur].p, ns, world_refs(), d_body_q[cur].p, d_scal.p);
+      CB2_K(gradient_norm_kernel, lm_ctas(n_a), kLmThreads, 0, stream, n_a, d_grad.p, d_cp_own.p, 1, 1, 0, d_desc.p, d_state[cur].p, ns, world_refs(), d_body_q[cur].p, d_scal.p, d_lm_partial.p, d_lm_ticket.p);
     }
+#ifndef CB2_EMUL
+    if (s_diag != stream) { CB2_CUDA(cudaEventRecord(ev_join, s_diag)); CB2_CUDA(cudaStreamWaitEvent(stream, ev_join, 0)); }
+#endif
     });
     timer.end(kPhNormal, stream);
   }
@@ -1436,7 +1458,7 @@ struct cb2_problem {
     CB2_K(pack_shared_kernel, (n_shared + 255) / 256, 256, 0, stream, n_shared, d_shared_idx.p, d_grad.p, d_diag.p, d_scal.p, world, rank, d_shared_buf.p);
     comm->allreduce_sum(d_shared_buf.p, shared_buf_size(n_shared, world), stream);
     CB2_K(unpack_shared_kernel, (n_shared + 255) / 256, 256, 0, stream, n_shared, d_shared_idx.p, d_shared_buf.p, world, d_gradG.p, d_diag.p, d_scal.p);
-    CB2_K(gradient_norm_kernel, 1, kLmThreads, 0, stream, n_a, d_gradG.p, d_cp_own.p, 0, 1, 1, d_desc.p, d_state[cur].p, ns, world_refs(), d_body_q[cur].p, d_scal.p);
+    CB2_K(gradient_norm_kernel, lm_ctas(n_a), kLmThreads, 0, stream, n_a, d_gradG.p, d_cp_own.p, 0, 1, 1, d_desc.p, d_state[cur].p, ns, world_refs(), d_body_q[cur].p, d_scal.p, d_lm_partial.p, d_lm_ticket.p);
   }
 
   // One LM linear solve + candidate point + candidate cost. Everything is enqueued; the caller syncs once.
@@ -1477,6 +1499,8 @@ struct cb2_problem {
             if (stream_gram) { CB2_CUDA(cudaEventRecord(ev_gram[0], stream)); CB2_CUDA(cudaStreamWaitEvent(stream_gram, ev_gram[0], 0)); sg = stream_gram; }
 #endif
             CB2_K(border_gram_dmma_kernel, dim3(gp.k_cnt, PL), 256, gram_smem_bytes(nbw1), sg, d_l1.p, gp.res, gp.mod, gp.k_off, gp.k_cnt);
+            if (gram_prereduce && gp.k_cnt > 1)      // ... and its partials folded into one, still off the critical path
+              CB2_K(gram_prereduce_kernel, dim3(std::min(148, (nbw1 * nbw1 + 255) / 256), PL), 256, 0, sg, d_l1.p, gp.k_off, gp.k_off + gp.k_cnt);
           }
       }
     } else {
@@ -1511,7 +1535,7 @@ struct cb2_problem {
       comm->allreduce_sum(d_red.p, red_count + (tail ? shared_buf_size(n_shared, world) : 0), stream);
       if (tail) {
         CB2_K(unpack_shared_kernel, (n_shared + 255) / 256, 256, 0, stream, n_shared, d_shared_idx.p, tailp, world, d_gradG.p, d_diag.p, d_scal.p);
-        CB2_K(gradient_norm_kernel, 1, kLmThreads, 0, stream, n_a, d_gradG.p, d_cp_own.p, 0, 1, 1, d_desc.p, d_state[cur].p, ns, world_refs(), d_body_q[cur].p, d_scal.p);
+        CB2_K(gradient_norm_kernel, lm_ctas(n_a), kLmThreads, 0, stream, n_a, d_gradG.p, d_cp_own.p, 0, 1, 1, d_desc.p, d_state[cur].p, ns, world_refs(), d_body_q[cur].p, d_scal.p, d_lm_partial.p, d_lm_ticket.p);
         CB2_K(damping_shared_kernel, (n_shared + 255) / 256, 256, 0, stream, n_shared, d_shared_idx.p, d_diag.p, d_scaling.p, d_scal.p, d_dtil2.p);
       }
     }
@@ -1586,9 +1610,9 @@ struct cb2_problem {
     } else {
       CB2_K(band_backsolve_kernel, PL, kBackThreads, backsolve_smem_bytes(max_n1, nbw1, 36), stream, d_l1.p, d_ytil.p);
     }
-    CB2_K(apply_step_kernel, 1, kLmThreads, 0, stream, n_a, d_ytil.p, gradG(), d_dtil2.p, d_cp_ref.p, d_cp_own.p, rank == 0 ? 1 : 0, d_ctrl[cur].p,
+    CB2_K(apply_step_kernel, lm_ctas(n_a), kLmThreads, 0, stream, n_a, d_ytil.p, gradG(), d_dtil2.p, d_cp_ref.p, d_cp_own.p, rank == 0 ? 1 : 0, d_ctrl[cur].p,
           d_ctrl[cur ^ 1].p, d_desc.p, d_state[cur].p, d_state[cur ^ 1].p, ns, N_c, world_refs(), d_body_q[cur].p, d_body_t[cur].p, d_pm[cur].p,
-          d_body_q[cur ^ 1].p, d_body_t[cur ^ 1].p, d_pm[cur ^ 1].p, d_scal.p);
+          d_body_q[cur ^ 1].p, d_body_t[cur ^ 1].p, d_pm[cur ^ 1].p, d_scal.p, d_lm_partial.p + 8 * kLmMaxCtas, d_lm_ticket.p + 1);
     if (world_free && n_points > 0)
       CB2_K(world_points_kernel, (n_points + 255) / 256, 256, 0, stream, n_points, d_pt_body.p, d_body_q[cur ^ 1].p, d_body_t[cur ^ 1].p, d_pm[cur ^ 1].p, d_pw[cur ^ 1].p);
     });

@@ -58,6 +58,36 @@ CB2_D void block_reduce(double (&v)[NV], double* sh) {
   }
 }
 
+// Grid-wide finish of a block_reduce: thread 0 of every CTA leaves its NV values in partial[blockIdx.x][NV]; the LAST CTA to arrive
+// (atomic ticket) gets true in its thread 0 with v[] = the CTAs' values combined in CTA order (fixed order -> deterministic), and resets
+// the ticket for the next launch / graph replay. max_mask bit q: value q is combined by maximum instead of sum.
+template <int NV>
+CB2_D bool grid_reduce_last(double (&v)[NV], unsigned max_mask, double* __restrict__ partial, unsigned* __restrict__ ticket) {
+  if (threadIdx.x != 0) return false;
+  if (gridDim.x == 1) return true;
+#pragma unroll
+  for (int q = 0; q < NV; ++q) partial[blockIdx.x * NV + q] = v[q];
+  __threadfence();
+  if (atomicAdd(ticket, 1u) != gridDim.x - 1) return false;
+  __threadfence();
+  const volatile double* pv = partial;
+#pragma unroll
+  for (int q = 0; q < NV; ++q) v[q] = pv[q];
+  for (unsigned b = 1; b < gridDim.x; ++b)
+#pragma unroll
+    for (int q = 0; q < NV; ++q) { const double o = pv[b * NV + q]; v[q] = (max_mask >> q & 1u) ? fmax(v[q], o) : v[q] + o; }
+  *ticket = 0u;
+  return true;
+}
+#ifdef CB2_EMUL
+constexpr int kLmMaxCtas = 2;       // emulation build: two CTAs even on the micro problems of the CPU tests (any grid size is valid)
+constexpr long kLmQuantum = 64;
+#else
+constexpr int kLmMaxCtas = 32;      // CTAs of gradient_norm_kernel / apply_step_kernel (4 x kLmThreads unknowns each)
+constexpr long kLmQuantum = 4L * kLmThreads;
+#endif
+CB2_HD int lm_ctas(long n_a) { const long c = (n_a + kLmQuantum - 1) / kLmQuantum; return int(c < 1 ? 1 : (c > kLmMaxCtas ? kLmMaxCtas : c)); }
+
 // Freed world-model blocks (see world_points_kernel below): where the rigid-body poses and model points sit in the calibration vector.
 struct WorldRefs {
   int n_bodies, n_points;
@@ -72,11 +102,13 @@ struct WorldRefs {
 __global__ void __launch_bounds__(kLmThreads) gradient_norm_kernel(long n_a, const double* __restrict__ grad, const unsigned char* __restrict__ cp_own,
                                                                    int count_owned, int count_shared, int combine, const SensorDesc* __restrict__ sensors,
                                                                    const SensorState* __restrict__ states, int n_sensors, WorldRefs world,
-                                                                   const double* __restrict__ body_q, double* __restrict__ scal) {
+                                                                   const double* __restrict__ body_q, double* __restrict__ scal,
+                                                                   double* __restrict__ partial, unsigned* __restrict__ ticket) {
   __shared__ double sh[32];
   const int t = threadIdx.x;
   double mx = 0.0, sq = 0.0;
-  for (long i0 = t; i0 < n_a; i0 += 4L * kLmThreads) {      // 4 independent loads in flight per thread (single CTA: latency-bound)
+  // 4 independent loads in flight per thread; lm_ctas(n_a) CTAs of 4 kLmThreads unknowns each (the kernel is pure latency: one round per CTA)
+  for (long i0 = blockIdx.x * 4L * kLmThreads + t; i0 < n_a; i0 += gridDim.x * 4L * kLmThreads) {
     double g[4]; int own[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) { const long i = min(i0 + long(u) * kLmThreads, n_a - 1); g[u] = grad[i]; own[u] = cp_own[i / 6]; }
@@ -84,7 +116,8 @@ __global__ void __launch_bounds__(kLmThreads) gradient_norm_kernel(long n_a, con
     for (int u = 0; u < 4; ++u)
       if (i0 + long(u) * kLmThreads < n_a && ((own[u] == kCpOwned && count_owned) || (own[u] == kCpShared && count_shared))) { mx = fmax(mx, fabs(g[u])); sq += g[u] * g[u]; }
   }
-  if (count_shared) for (int s = t; s < n_sensors; s += kLmThreads) {
+  const bool cal = count_shared && blockIdx.x == 0;       // the calibration blocks: first CTA only
+  if (cal) for (int s = t; s < n_sensors; s += kLmThreads) {
     const SensorDesc& sd = sensors[s];
     const double* gc = grad + n_a + sd.calib_off;
     for (int j = 0; j < sd.n_calib; ++j) {
@@ -98,7 +131,7 @@ __global__ void __launch_bounds__(kLmThreads) gradient_norm_kernel(long n_a, con
       for (int k = 0; k < 4; ++k) { mx = fmax(mx, fabs(d[k])); sq += d[k] * d[k]; }
     }
   }
-  if (count_shared) {   // freed world-model blocks: pose rotation through the manifold, the rest directly
+  if (cal) {   // freed world-model blocks: pose rotation through the manifold, the rest directly
     for (int b = t; b < world.n_bodies; b += kLmThreads) {
       const int ur = world.body_u[2 * b], ut = world.body_u[2 * b + 1];
       if (ur >= 0) {
@@ -118,9 +151,10 @@ __global__ void __launch_bounds__(kLmThreads) gradient_norm_kernel(long n_a, con
   double vs[1] = {sq}, vm[1] = {mx};
   block_reduce<1, false>(vs, sh);
   block_reduce<1, true>(vm, sh);
-  if (t == 0) {
-    if (combine) { vm[0] = fmax(vm[0], scal[kScGradMax]); vs[0] += scal[kScGradSq]; }
-    scal[kScGradMax] = vm[0]; scal[kScGradSq] = vs[0];
+  double both[2] = {vs[0], vm[0]};
+  if (grid_reduce_last<2>(both, 2u, partial, ticket)) {
+    if (combine) { both[1] = fmax(both[1], scal[kScGradMax]); both[0] += scal[kScGradSq]; }
+    scal[kScGradMax] = both[1]; scal[kScGradSq] = both[0];
   }
 }
 
@@ -137,11 +171,13 @@ __global__ void __launch_bounds__(kLmThreads) apply_step_kernel(long n_a, const 
                                                                 SensorState* __restrict__ states_cand, int n_sensors, int N_c,
                                                                 WorldRefs world, const double* __restrict__ body_q, const double* __restrict__ body_t,
                                                                 const double* __restrict__ pm, double* __restrict__ body_q_cand,
-                                                                double* __restrict__ body_t_cand, double* __restrict__ pm_cand, double* __restrict__ scal) {
+                                                                double* __restrict__ body_t_cand, double* __restrict__ pm_cand, double* __restrict__ scal,
+                                                                double* __restrict__ partial, unsigned* __restrict__ ticket) {
   __shared__ double sh[5 * 32];
   const int t = threadIdx.x;
   double step2 = 0.0, x2 = 0.0, c2 = 0.0, model = 0.0, bad = 0.0;
-  for (long i0 = t; i0 < n_a; i0 += 4L * kLmThreads) {      // 4 elements per thread per round, all loads issued before their first use
+  // 4 elements per thread per round, all loads issued before their first use; lm_ctas(n_a) CTAs, the calibration / world blocks in the first
+  for (long i0 = blockIdx.x * 4L * kLmThreads + t; i0 < n_a; i0 += gridDim.x * 4L * kLmThreads) {
     double xv[4], yv[4], gv[4], dv[4]; int own[4], ref[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -164,13 +200,14 @@ __global__ void __launch_bounds__(kLmThreads) apply_step_kernel(long n_a, const 
       }
     }
   }
-  for (long j = t; j < N_c; j += kLmThreads) {
+  const bool first = blockIdx.x == 0;
+  for (long j = t; first && j < N_c; j += kLmThreads) {
     const double y = ytil[n_a + j];
     if (!isfinite(y)) bad = 1.0;
     if (count_shared) model += y * (grad[n_a + j] + dtil2[n_a + j] * y);
   }
   const double cs = count_shared ? 1.0 : 0.0;
-  for (int s = t; s < n_sensors; s += kLmThreads) {
+  for (int s = t; first && s < n_sensors; s += kLmThreads) {
     const SensorDesc& sd = sensors[s];
     SensorState S = states[s];
     const double* y = ytil + n_a + sd.calib_off;
@@ -198,7 +235,7 @@ __global__ void __launch_bounds__(kLmThreads) apply_step_kernel(long n_a, const 
     states_cand[s] = S;
   }
   // freed world-model blocks (constant ones are copied so that the candidate tables are complete)
-  for (int b = t; b < world.n_bodies; b += kLmThreads) {
+  for (int b = t; first && b < world.n_bodies; b += kLmThreads) {
     const int ur = world.body_u[2 * b], ut = world.body_u[2 * b + 1];
     const Q4 q = Q4{body_q[4 * b], body_q[4 * b + 1], body_q[4 * b + 2], body_q[4 * b + 3]};
     Q4 p = q;
@@ -217,7 +254,7 @@ __global__ void __launch_bounds__(kLmThreads) apply_step_kernel(long n_a, const 
       body_t_cand[3 * b + k] = xn;
     }
   }
-  for (int p = t; p < world.n_points; p += kLmThreads) {
+  for (int p = t; first && p < world.n_points; p += kLmThreads) {
     const int u = world.pt_u[p];
     for (int k = 0; k < 3; ++k) {
       const double x = pm[3 * p + k];
@@ -228,7 +265,7 @@ __global__ void __launch_bounds__(kLmThreads) apply_step_kernel(long n_a, const 
   }
   double red[5] = {step2, x2, c2, model, bad};
   block_reduce<5, false>(red, sh);
-  if (t == 0) {
+  if (grid_reduce_last<5>(red, 0u, partial, ticket)) {
     scal[kScStepNorm2] = red[0]; scal[kScXNorm2] = red[1]; scal[kScCandXNorm2] = red[2]; scal[kScModelChange] = 0.5 * red[3];
     if (red[4] > 0.0) scal[kScSolveFail] += 1.0;
   }

@@ -22,6 +22,7 @@ namespace cb2 {
 struct BandSys {
   int n, hb, nbw;           // rows (multiple of 6), half bandwidth (hb + 1 = window size), border width (last column = rhs)
   int ksplit;               // row splits of the Gram product
+  int kfirst;               // first partial the consumers sum (> 0: gram_prereduce_kernel has folded the partials before it into it)
   const int* row_gidx;      // [n] global unknown index of each row
   const int* col_gidx;      // [nbw - 1] global unknown index of each border column, -1 = absent (zero column)
   double* L;                // [n][hb+1]: A on entry, Cholesky factor on exit; (i, j) at L[i*(hb+1) + hb - (i-j)]
@@ -442,13 +443,34 @@ __global__ void __launch_bounds__(256) border_gram_dmma_kernel(const BandSys* __
   }
 }
 
+// Folds the partial Gram matrices k_lo .. k_hi - 1 into partial k_hi - 1 (fixed order): run beside the late reduction levels on the partials
+// of the early launch, so that the consumers on the critical path (level3_build_kernel) sum 1 + k_last partials instead of ~115.
+__global__ void __launch_bounds__(256) gram_prereduce_kernel(const BandSys* __restrict__ systems, int k_lo, int k_hi) {
+  const BandSys sy = systems[blockIdx.y];
+  const size_t stride = size_t(sy.nbw) * sy.nbw;
+  for (size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x; e < stride; e += size_t(gridDim.x) * blockDim.x) {
+    double* __restrict__ T = sy.T + e;
+    double s = 0.0;
+    int k = k_lo;
+    for (; k + 8 <= k_hi; k += 8) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = T[(k + u) * stride];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; k < k_hi; ++k) s += T[k * stride];
+    T[(k_hi - 1) * stride] = s;
+  }
+}
+
 // Sum over the row splits of a system's Gram matrix.
 CB2_D double gram_at(const BandSys& sy, int a, int b) {
   const size_t stride = size_t(sy.nbw) * sy.nbw;
   const double* __restrict__ T = sy.T + size_t(a) * sy.nbw + b;
   double s = 0.0;
-  int k = 0;
-  for (; k + 8 <= sy.ksplit; k += 8) {   // 8 independent loads in flight, summed in the fixed order k = 0, 1, 2, ...
+  int k = sy.kfirst;
+  for (; k + 8 <= sy.ksplit; k += 8) {   // 8 independent loads in flight, summed in the fixed order k = kfirst, kfirst + 1, ...
     double v[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) v[u] = T[(k + u) * stride];
@@ -527,7 +549,7 @@ __global__ void __launch_bounds__(256) level3_build_kernel(const BandSys* __rest
         const BandSys& sy = chunks[p];
         const size_t stride = size_t(sy.nbw) * sy.nbw;
         const double* __restrict__ T = sy.T + size_t(sy.cal0 + r) * sy.nbw + sy.cal0 + c;
-        for (int k = sub; k < sy.ksplit; k += 8) part += T[k * stride];
+        for (int k = sy.kfirst + sub; k < sy.ksplit; k += 8) part += T[k * stride];
       }
     }
     part += __shfl_xor_sync(0xffffffffu, part, 1);

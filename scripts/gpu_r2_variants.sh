@@ -10,9 +10,9 @@ d=json.load(open("gpurun_out/r2_var_$tag.json"))
 print("RESULT $tag it/s %.1f" % d["value"], "ms/step %.4f" % d["ms_per_step"], {k: round(v, 4) for k, v in d["phases_ms_per_iteration"].items()}, "e2e %.1f" % d["e2e"]["value"], "cost %.9g" % d["config"]["final_cost"])
 PY
 }
-run a4r64 CB2_EARLY_GRAM_AFTER=4 CB2_EARLY_GRAM_RESERVE=64
-run a5r64 CB2_EARLY_GRAM_AFTER=5 CB2_EARLY_GRAM_RESERVE=64
-run a4r96 CB2_EARLY_GRAM_AFTER=4 CB2_EARLY_GRAM_RESERVE=96
-run l4a4r64 CB2_EARLY_GRAM_LEVELS=4 CB2_EARLY_GRAM_AFTER=4 CB2_EARLY_GRAM_RESERVE=64
-run l5a5r64 CB2_EARLY_GRAM_LEVELS=5 CB2_EARLY_GRAM_AFTER=5 CB2_EARLY_GRAM_RESERVE=64
-run l5a4r48 CB2_EARLY_GRAM_LEVELS=5 CB2_EARLY_GRAM_AFTER=4 CB2_EARLY_GRAM_RESERVE=48
+run default CB2_DUMMY=1
+run nocalibfork CB2_NO_CALIB_FORK=1
+run default2 CB2_DUMMY=1
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_baseline_shapes.py tests/test_world_model.py tests/test_edge_cases.py -m gpu -q -x 2>&1 | tail -2
+CB2_PROFILE=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_kprof.json 2> gpurun_out/r2_kprof.txt
+grep "cb2 profile" gpurun_out/r2_kprof.txt | tail -27

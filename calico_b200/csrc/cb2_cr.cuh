@@ -395,15 +395,17 @@ __global__ void __launch_bounds__(kCrThreads, (kFirst ? 2 : 1)) cr_level_kernel(
 // grid_sync != nullptr: ALL levels level_hi .. level_lo in one launch whatever their size — the CTAs (all co-resident: the host launches
 // at most one per SM) meet at a global barrier between levels (an arrival counter in HBM, zeroed before the launch), which removes one
 // kernel launch + drain per level from the dependent chain; ytil is then read around L1 (other SMs wrote it during this launch).
+// cluster != 0: the launch is ONE thread-block cluster per chunk (<= 8 CTAs = 64 eliminated blocks per level): the levels are separated by
+// the hardware cluster barrier (barrier.cluster, release / acquire) — C4: the levels with <= 64 eliminated blocks (8 of 10) in one launch.
 __global__ void __launch_bounds__(256) cr_back_kernel(const BandSys* __restrict__ systems, int level_hi, int level_lo, double* ytil,
-                                                      unsigned* grid_sync = nullptr) {
+                                                      unsigned* grid_sync = nullptr, int cluster = 0) {
   const BandSys sy = systems[blockIdx.y];
   unsigned sync_round = 0;
   auto yld = [&](int idx) -> double {
 #if defined(CB2_EMUL)
     return ytil[idx];
 #else
-    return grid_sync ? __ldcg(ytil + idx) : ytil[idx];
+    return (grid_sync || cluster) ? __ldcg(ytil + idx) : ytil[idx];
 #endif
   };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -459,7 +461,11 @@ __global__ void __launch_bounds__(256) cr_back_kernel(const BandSys* __restrict_
       }
     }
     if (level > level_lo) {
-      if (grid_sync) {
+      if (cluster) {
+#if !defined(CB2_EMUL)
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+#endif
+      } else if (grid_sync) {
 #if !defined(CB2_EMUL)
         // global barrier: every CTA of the grid arrives once per level
         __syncthreads();

@@ -516,6 +516,7 @@ struct cb2_problem {
   std::vector<GramPart> gram_parts;
   bool gram_prereduce = std::getenv("CB2_GRAM_PREREDUCE") != nullptr;   // opt-in: folding the early partials beside the late levels gained nothing (profiles/r02_variants.md)
   bool calib_fork = std::getenv("CB2_NO_CALIB_FORK") == nullptr;
+  bool back_cluster = std::getenv("CB2_NO_BACK_CLUSTER") == nullptr;   // back-substitution: the narrow levels in one thread-block-cluster launch
   cudaStream_t stream_gram = nullptr;
   cudaEvent_t ev_gram[4] = {nullptr, nullptr, nullptr, nullptr};
   int cr_zsplit = 1;                // CTAs per block of a cyclic-reduction level (column split of the forward substitution + Schur update)
@@ -1598,8 +1599,26 @@ struct cb2_problem {
         CB2_K(cr_back_kernel, dim3((nel0 + 7) / 8, PL), 256, 0, stream, d_l1.p, cr_nlevels - 1, 0, d_ytil.p, d_grid_sync.p);
       } else {
       // Top levels with <= 8 eliminated blocks each share one launch (block barrier between levels); then one launch per level.
+      // With thread-block clusters: the levels with <= 64 eliminated blocks share one launch of ONE cluster of <= 8 CTAs per chunk.
       int lv = cr_nlevels - 1, lo = lv;
-      while (lo > 0 && std::max(1, ((cr_max_nblk + (1 << (lo - 1)) - 1) >> (lo - 1)) / 2) <= 8) --lo;
+      const int fuse_cap = back_cluster ? 64 : 8;
+      while (lo > 0 && std::max(1, ((cr_max_nblk + (1 << (lo - 1)) - 1) >> (lo - 1)) / 2) <= fuse_cap) --lo;
+      const int cx = (std::max(1, ((cr_max_nblk + (1 << lo) - 1) >> lo) / 2) + 7) / 8;
+#ifndef CB2_EMUL
+      if (back_cluster && cx > 1) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(cx, PL); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cx; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        KernelProfiler::Rec pr{"cr_back_kernel(cluster)", nullptr, nullptr};
+        if (kprof.on) { cudaEventCreate(&pr.a); cudaEventCreate(&pr.b); cudaEventRecord(pr.a, stream); }
+        CB2_CUDA(cudaLaunchKernelEx(&cfg, cr_back_kernel, static_cast<const BandSys*>(d_l1.p), lv, lo, d_ytil.p, static_cast<unsigned*>(nullptr), 1));
+        if (kprof.on) { cudaEventRecord(pr.b, stream); kprof.open.push_back(pr); }
+        ++stats.kernel_launches;
+      } else
+#endif
       CB2_K(cr_back_kernel, dim3(1, PL), 256, 0, stream, d_l1.p, lv, lo, d_ytil.p, static_cast<unsigned*>(nullptr));
       for (lv = lo - 1; lv >= 0; --lv) {
         const int nact = (cr_max_nblk + (1 << lv) - 1) >> lv;

@@ -11,8 +11,6 @@ print("RESULT $tag it/s %.1f" % d["value"], "ms/step %.4f" % d["ms_per_step"], {
 PY
 }
 run default CB2_DUMMY=1
-run nocalibfork CB2_NO_CALIB_FORK=1
+run nobackcluster CB2_NO_BACK_CLUSTER=1
 run default2 CB2_DUMMY=1
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_baseline_shapes.py tests/test_world_model.py tests/test_edge_cases.py -m gpu -q -x 2>&1 | tail -2
-CB2_PROFILE=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_kprof.json 2> gpurun_out/r2_kprof.txt
-grep "cb2 profile" gpurun_out/r2_kprof.txt | tail -27
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_baseline_shapes.py tests/test_world_model.py -m gpu -q -x 2>&1 | tail -2

@@ -516,7 +516,7 @@ struct cb2_problem {
   std::vector<GramPart> gram_parts;
   bool gram_prereduce = std::getenv("CB2_GRAM_PREREDUCE") != nullptr;   // opt-in: folding the early partials beside the late levels gained nothing (profiles/r02_variants.md)
   bool calib_fork = std::getenv("CB2_NO_CALIB_FORK") == nullptr;
-  bool back_cluster = std::getenv("CB2_NO_BACK_CLUSTER") == nullptr;   // back-substitution: the narrow levels in one thread-block-cluster launch
+  bool back_cluster = std::getenv("CB2_BACK_CLUSTER") != nullptr;   // opt-in (measured neutral on C4, profiles/r02_variants.md): back-substitution of the narrow levels in one thread-block-cluster launch
   cudaStream_t stream_gram = nullptr;
   cudaEvent_t ev_gram[4] = {nullptr, nullptr, nullptr, nullptr};
   int cr_zsplit = 1;                // CTAs per block of a cyclic-reduction level (column split of the forward substitution + Schur update)

@@ -28,6 +28,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "lm_iterations_per_sec"
 UNIT = "LM iterations/s"
+E2E_CALLS = int(os.environ.get("CB2_BENCH_E2E_CALLS", "5"))   # end-to-end Optimize() calls per run; the median is reported
 FULL_FRAMES = {"C1": 50, "C2": 500, "C3": 2000, "C4": 5000, "C5": 10000}
 
 
@@ -285,31 +286,39 @@ def main():
     # A calibration session calls Optimize repeatedly (outlier marking -> re-optimise, camera.cpp:258-299); each call builds a new
     # problem from the caller's host arrays. The timed call below is such a repeat call: the handle of the kernel-timed run above has been
     # closed, so its device blocks sit in the library's memory pool. Every host->device byte of the problem is copied inside the timed region.
-    p2 = prob.clone()          # the caller's own host arrays (Python-side copy, not part of the API call)
-    api2 = gpu_api()
-    if world > 1:
-        api2.comm_clone(api)   # communicator creation is one-time process setup, not part of a solve
-    api.close()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    ids2 = p2.push(api2)
-    # Exactly --steps LM iterations in ONE Optimize() call: past convergence (~6 iterations on this problem) LM keeps producing steps whose
-    # model cost change is at rounding level; they are still solved and evaluated, so the invalid-step limit is lifted to let the call run on.
-    summ2, log2 = api2.optimize(bench_options(_capi.Options, args.steps, max_num_consecutive_invalid_steps=args.steps + 1))
-    p2.pull(api2, ids2)
-    for sid in ids2:
-        api2.get_residuals(sid)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    st2 = api2.stats()
-    iters2 = max(len(log2) - 1, 1)
-    if world > 1:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    api2.close()
+    # The call is made E2E_CALLS times, each on a fresh handle and a fresh copy of the caller's arrays, and the MEDIAN call is reported (all
+    # samples are in the line): a single call is at the mercy of the host (page faults of freshly cloned arrays, scheduling of the
+    # per-sensor packing threads) — single samples between 35 and 70 ms were seen on identical builds.
+    samples = []
+    api_prev = api
+    for _ in range(E2E_CALLS):
+        p2 = prob.clone()          # the caller's own host arrays (Python-side copy, not part of the API call)
+        api2 = gpu_api()
+        if world > 1:
+            api2.comm_clone(api_prev)   # communicator creation is one-time process setup, not part of a solve
+        api_prev.close()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        ids2 = p2.push(api2)
+        # Exactly --steps LM iterations in ONE Optimize() call: past convergence (~6 iterations on this problem) LM keeps producing steps whose
+        # model cost change is at rounding level; they are still solved and evaluated, so the invalid-step limit is lifted to let the call run on.
+        summ2, log2 = api2.optimize(bench_options(_capi.Options, args.steps, max_num_consecutive_invalid_steps=args.steps + 1))
+        p2.pull(api2, ids2)
+        for sid in ids2:
+            api2.get_residuals(sid)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        samples.append((dt, api2.stats(), max(len(log2) - 1, 1), summ2.message.decode(errors="replace")))
+        api_prev = api2
+    api_prev.close()
+    e2e_all_ms = [round(1e3 * x[0], 3) for x in samples]
+    e2e_s, st2, iters2, e2e_msg = sorted(samples, key=lambda x: x[0])[len(samples) // 2]
 
     if world > 1:
         dist.barrier()
@@ -359,7 +368,8 @@ def main():
                                      "frac": sweep_achieved / peak, "algorithmic_bytes": sweep_bytes, "ms": sweep_ms}},
         "clocks": clocks,
         "e2e": {"value": iters2 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": st2.h2d_bytes / iters2, "d2h_bytes_per_step": st2.d2h_bytes / iters2,
-                "seconds": e2e_s, "ms_per_optimize_call": 1e3 * e2e_s, "iterations": iters2, "termination": summ2.message.decode(errors="replace"), "what": "assembly from host arrays (cb2_set_trajectory / cb2_add_*) + upload + cb2_optimize + parameter/residual write-back on a fresh problem handle"},
+                "seconds": e2e_s, "ms_per_optimize_call": 1e3 * e2e_s, "iterations": iters2, "termination": e2e_msg, "calls_ms": e2e_all_ms,
+                "what": "assembly from host arrays (cb2_set_trajectory / cb2_add_*) + upload + cb2_optimize + parameter/residual write-back on a fresh problem handle; median of %d such calls (calls_ms lists them all)" % E2E_CALLS},
         "gpu_launches": int(st.kernel_launches),
     }
     if not args.no_cpu_baseline:

@@ -23,7 +23,7 @@ PY
 for tool in memcheck racecheck synccheck; do
   for cfg in "tiny" "tiny free_pose"; do
     tag=$(echo $cfg | tr ' ' '_')
-    timeout 1500 compute-sanitizer --tool $tool --error-exitcode 0 --print-limit 20 python /tmp/san_run.py $cfg > gpurun_out/sanitizer_${tool}_${tag}.log 2>&1
+    timeout 120 compute-sanitizer --tool $tool --error-exitcode 0 --print-limit 20 python /tmp/san_run.py $cfg > gpurun_out/sanitizer_${tool}_${tag}.log 2>&1
     echo "== $tool $cfg: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitizer_${tool}_${tag}.log | tail -1) $(grep 'solve ok' gpurun_out/sanitizer_${tool}_${tag}.log)"
   done
 done

@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(256) border_gram_dmma_kernel(const BandSys* __
       }
     }
     __syncthreads();
-#pragma unroll
+#pragma unroll 1
     for (int ks = 0; ks < kGramRows / 4; ++ks) {
       const double* trow = tile + (4 * ks + fr) * XS + fc;
 #pragma unroll

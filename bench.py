@@ -306,8 +306,7 @@ def main():
         # model cost change is at rounding level; they are still solved and evaluated, so the invalid-step limit is lifted to let the call run on.
         summ2, log2 = api2.optimize(bench_options(_capi.Options, args.steps, max_num_consecutive_invalid_steps=args.steps + 1))
         p2.pull(api2, ids2)
-        for sid in ids2:
-            api2.get_residuals(sid)
+        p2.residuals(api2, ids2)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if world > 1:

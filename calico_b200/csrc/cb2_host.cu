@@ -442,7 +442,7 @@ struct cb2_problem {
   std::string error;
 
   // ---- device state ----
-  bool uploaded = false;
+  std::atomic<bool> uploaded{false};   // atomic: cb2_add_*_observations may run concurrently on DIFFERENT sensors (each clears it)
   int device = -1;
   cudaStream_t stream = nullptr, stream_imu = nullptr;   // IMU sweeps overlap the camera sweep on a second stream
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -601,7 +601,8 @@ struct cb2_problem {
 #endif
   }
 
-  int fail(int code, const std::string& msg) { error = msg; return code; }
+  std::mutex error_mu;                 // concurrent observation uploads (one thread per sensor) may fail at the same time
+  int fail(int code, const std::string& msg) { std::lock_guard<std::mutex> lk(error_mu); error = msg; return code; }
 
   // Waits for the library's stream. With several ranks a collective that a peer never joins (crashed rank, mismatched call sequence)
   // would block forever: the wait then polls with a deadline (CB2_COLLECTIVE_TIMEOUT_S, default 60 s) and the communicator's
@@ -790,6 +791,12 @@ struct cb2_problem {
       size_t off_stamp = 0, off_meas = 0, off_seg = 0, off_pt = 0, off_frm = 0, off_perm = 0, bytes = 0;
     };
     std::vector<Packed> packed(ns);
+    // Sensors with many observations are packed by several threads each (the cores the one-thread-per-sensor scheme leaves idle).
+    const int pack_split_min = env_int("CB2_PACK_SPLIT_MIN", 65536);
+    int n_heavy = 0;
+    for (const auto& hs : sensors) n_heavy += hs.n_obs() >= pack_split_min ? 1 : 0;
+    const int hw_threads = std::max(1, int(std::thread::hardware_concurrency()));
+    const int sub_threads = std::max(1, env_int("CB2_PACK_SUB_THREADS", std::min(4, hw_threads / std::max(n_heavy, 1))));
     auto pack_sensor = [&](int si) {
       HostSensor& s = sensors[si];
       Packed& P = packed[si];
@@ -801,41 +808,80 @@ struct cb2_problem {
       const int m = s.m(), n = s.n_obs();
       P.cp_ref.assign(n_cp, 0);
       if (world_free && s.kind == kCamera) P.pt_ref.assign(n_points, 0);
-      // segment of each active observation; stable counting sort by segment
+      // Every pass below runs over T disjoint observation (or output) ranges: a large sensor is packed by T threads (sub_threads: the
+      // cores the per-sensor threads leave idle), a small one inline (T = 1). The result does not depend on T.
+      const int T = n >= pack_split_min ? std::max(1, sub_threads) : 1;
+      auto parallel = [&](auto&& fn) {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; ++t) th.emplace_back([&fn, t] { fn(t); });
+        fn(0);
+        for (auto& x : th) x.join();
+      };
+      auto lo_of = [&](long total, int t) { return int(total * t / T); };
+      // Pass 1: segment of each active observation, per-range histograms (-> stable counting sort by segment), reference marks.
       std::vector<int> seg_of(n, -1);
-      std::vector<int> count(n_seg + 1, 0);
+      std::vector<std::vector<int>> hist(T, std::vector<int>(n_seg + 1, 0));
+      std::vector<std::vector<unsigned char>> seg_seen(T, std::vector<unsigned char>(n_seg, 0));
+      std::vector<std::vector<unsigned char>> pt_seen(T);
+      struct RangeStat { int rc = CB2_OK; const char* err = nullptr; long blocks = 0; int n_active = 0, n_frames = 0; };
+      std::vector<RangeStat> rs(T);
+      parallel([&](int t) {
+        RangeStat& R = rs[t];
+        std::vector<int>& count = hist[t];
+        unsigned char* seen = seg_seen[t].data();
+        if (!P.pt_ref.empty()) pt_seen[t].assign(n_points, 0);
+        for (int o = lo_of(n, t), oe = lo_of(n, t + 1); o < oe; ++o) {
+          if (s.kind == kCamera && !s.outlier.empty() && s.outlier[o]) continue;   // camera.cpp:121-124
+          if (s.kind == kCamera && s.body_slot[o] < 0) {                            // camera.cpp:125-131
+            R.rc = CB2_FAILED_PRECONDITION; R.err = "Attempted to create cost function from an observation for a rigidbody that does not exist in the world model."; return;
+          }
+          const int sg = spline_index(s.stamp[o]);
+          if (sg < 0 || sg >= n_seg) { R.rc = CB2_INVALID_ARGUMENT; R.err = "Observation stamp is outside the valid knots of the trajectory."; return; }
+          seen[sg] = 1;                                              // referenced by some rank's residual block
+          if (!pt_seen[t].empty()) pt_seen[t][bodies[s.body_slot[o]].pw0 + s.feat_slot[o]] = 1;
+          ++R.blocks;
+          if (sg < g_lo || sg >= g_hi) continue;                     // another rank's time range
+          seg_of[o] = sg;
+          ++count[sg + 1];
+          ++R.n_active;
+        }
+      });
       int n_active = 0;
-      for (int o = 0; o < n; ++o) {
-        if (s.kind == kCamera && !s.outlier.empty() && s.outlier[o]) continue;   // camera.cpp:121-124
-        if (s.kind == kCamera && s.body_slot[o] < 0)
-          return bad(CB2_FAILED_PRECONDITION, "Attempted to create cost function from an observation for a rigidbody that does not exist in the world model.");   // camera.cpp:125-131
-        const int sg = spline_index(s.stamp[o]);
-        if (sg < 0 || sg >= n_seg) return bad(CB2_INVALID_ARGUMENT, "Observation stamp is outside the valid knots of the trajectory.");
-        for (int c = 0; c < kK; ++c) P.cp_ref[sg + c] = 1;        // referenced by some rank's residual block
-        if (!P.pt_ref.empty()) P.pt_ref[bodies[s.body_slot[o]].pw0 + s.feat_slot[o]] = 1;
-        ++P.blocks; P.residuals += m;
-        P.ref_any = true;
-        if (sg < g_lo || sg >= g_hi) continue;                     // another rank's time range
-        seg_of[o] = sg;
-        ++count[sg + 1];
-        ++n_active;
+      for (int t = 0; t < T; ++t) {
+        if (rs[t].rc != CB2_OK) return bad(rs[t].rc, rs[t].err);   // the first failing range in observation order
+        P.blocks += rs[t].blocks; n_active += rs[t].n_active;
+        for (int g = 0; g < n_seg; ++g) if (seg_seen[t][g]) for (int c = 0; c < kK; ++c) P.cp_ref[g + c] = 1;
+        if (!pt_seen[t].empty()) for (int q = 0; q < n_points; ++q) P.pt_ref[q] |= pt_seen[t][q];
       }
-      for (int g = 0; g < n_seg; ++g) count[g + 1] += count[g];
-      P.seg_start = count;
+      P.residuals = P.blocks * m;
+      P.ref_any = P.blocks > 0;
+      // seg_start = prefix sums of the summed histograms; hist[t] becomes range t's write cursor per segment (ranges in order: stable)
+      P.seg_start.assign(n_seg + 1, 0);
+      for (int g = 0; g < n_seg; ++g) {
+        int c = 0;
+        for (int t = 0; t < T; ++t) c += hist[t][g + 1];
+        P.seg_start[g + 1] = P.seg_start[g] + c;
+      }
+      for (int g = 0; g < n_seg; ++g) {
+        int at = P.seg_start[g];
+        for (int t = 0; t < T; ++t) { const int c = hist[t][g + 1]; hist[t][g + 1] = at; at += c; }
+      }
       const std::vector<int>& seg_start = P.seg_start;
       s.perm.assign(n_active, 0);
-      {
-        std::vector<int> cursor(count.begin(), count.end() - 1);
-        for (int o = 0; o < n; ++o) if (seg_of[o] >= 0) s.perm[cursor[seg_of[o]]++] = o;
-      }
+      parallel([&](int t) {
+        int* cursor = hist[t].data() + 1;
+        for (int o = lo_of(n, t), oe = lo_of(n, t + 1); o < oe; ++o) if (seg_of[o] >= 0) s.perm[cursor[seg_of[o]]++] = o;
+      });
       if (s.kind == kCamera) {
         // The corners of one image (same stamp) must be adjacent: order each segment's observations by stamp (stable; usually a no-op).
         auto by_stamp = [&](int a, int b) { return s.stamp[a] < s.stamp[b]; };
-        for (int g = 0; g < n_seg; ++g) {
-          int* b = s.perm.data() + seg_start[g];
-          int* e = s.perm.data() + seg_start[g + 1];
-          if (!std::is_sorted(b, e, by_stamp)) std::stable_sort(b, e, by_stamp);
-        }
+        parallel([&](int t) {
+          for (int g = lo_of(n_seg, t), ge = lo_of(n_seg, t + 1); g < ge; ++g) {
+            int* b = s.perm.data() + seg_start[g];
+            int* e = s.perm.data() + seg_start[g + 1];
+            if (!std::is_sorted(b, e, by_stamp)) std::stable_sort(b, e, by_stamp);
+          }
+        });
       }
       s.n_active = P.n_active = n_active;
       {
@@ -857,16 +903,35 @@ struct cb2_problem {
       int* p_pt = reinterpret_cast<int*>(base + P.off_pt);
       int* p_frm = reinterpret_cast<int*>(base + P.off_frm);
       std::memcpy(base + P.off_perm, s.perm.data(), size_t(n_active) * 4);
-      for (int i = 0; i < n_active; ++i) {
-        const int o = s.perm[i];
-        p_stamp[i] = s.stamp[o];
-        p_seg[i] = seg_of[o];
-        for (int q = 0; q < m; ++q) p_meas[size_t(i) * m + q] = s.meas[size_t(o) * m + q];
-        if (s.kind == kCamera) {
-          p_pt[i] = bodies[s.body_slot[o]].pw0 + s.feat_slot[o];
-          if (i == 0 || p_stamp[i] != p_stamp[i - 1]) { P.frame_seg.push_back(p_seg[i]); P.frame_stamp.push_back(p_stamp[i]); P.frame_obs.push_back(i); }
-          p_frm[i] = int(P.frame_stamp.size()) - 1;                // sensor-local image index; SensorDesc::frame_base makes it global
+      // Pass 3a: the SoA arrays in packed order; image starts (a new stamp) counted per range.
+      parallel([&](int t) {
+        int nf = 0;
+        for (int i = lo_of(n_active, t), ie = lo_of(n_active, t + 1); i < ie; ++i) {
+          const int o = s.perm[i];
+          p_stamp[i] = s.stamp[o];
+          p_seg[i] = seg_of[o];
+          for (int q = 0; q < m; ++q) p_meas[size_t(i) * m + q] = s.meas[size_t(o) * m + q];
+          if (s.kind == kCamera) {
+            p_pt[i] = bodies[s.body_slot[o]].pw0 + s.feat_slot[o];
+            if (i == 0 || s.stamp[o] != s.stamp[s.perm[i - 1]]) ++nf;
+          }
         }
+        rs[t].n_frames = nf;
+      });
+      if (s.kind == kCamera) {
+        // Pass 3b: per-image records (segment, stamp, first observation) and the sensor-local image index of every observation
+        // (SensorDesc::frame_base makes it global); range t's images start at the number of images before it.
+        int total_frames = 0;
+        std::vector<int> frame0(T);
+        for (int t = 0; t < T; ++t) { frame0[t] = total_frames; total_frames += rs[t].n_frames; }
+        P.frame_seg.resize(total_frames); P.frame_stamp.resize(total_frames); P.frame_obs.resize(total_frames);
+        parallel([&](int t) {
+          int f = frame0[t];                                       // images started before the current observation
+          for (int i = lo_of(n_active, t), ie = lo_of(n_active, t + 1); i < ie; ++i) {
+            if (i == 0 || p_stamp[i] != p_stamp[i - 1]) { P.frame_seg[f] = p_seg[i]; P.frame_stamp[f] = p_stamp[i]; P.frame_obs[f] = i; ++f; }
+            p_frm[i] = f - 1;
+          }
+        });
       }
       if (s.kind == kCamera) {                                     // image CSR for the structured accumulation (cb2_normal.cuh)
         P.frame_obs.push_back(n_active);

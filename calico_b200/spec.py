@@ -6,6 +6,7 @@ The reference keeps this state spread over `Trajectory`, `WorldModel` and `Senso
 from __future__ import annotations
 
 import copy
+from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass, field
 from typing import List, Optional
 
@@ -15,6 +16,7 @@ from . import _capi
 from .spline import Spline
 
 CAMERA, GYROSCOPE, ACCELEROMETER = _capi.CAMERA, _capi.GYROSCOPE, _capi.ACCELEROMETER
+PARALLEL_OBS = 100_000   # observations from which push() / residuals() use one thread per sensor
 
 # CameraIntrinsicsModel (camera_models.h:16-33) → number of intrinsics.
 CAMERA_NUM_PARAMS = {1: 8, 2: 11, 3: 7, 4: 5, 5: 4, 6: 4, 7: 5}
@@ -87,14 +89,36 @@ class ProblemSpec:
             sid = api.add_sensor(s.kind, s.model, s.name, s.intr, s.q_xyzw, s.t, s.latency, s.sigma, s.loss_type, s.loss_scale,
                                  s.en_intr, s.en_extr, s.en_lat)
             ids.append(sid)
+
+        def add_obs(pair):
+            s, sid = pair
             if s.n_obs == 0:
-                continue
+                return
             if s.kind == CAMERA:
                 api.add_camera_observations(sid, s.stamp, s.image_id, s.model_id, s.feature_id, s.meas, s.outlier)
             else:
                 seq = s.seq if s.seq is not None else np.arange(s.n_obs)
                 api.add_imu_observations(sid, s.stamp, seq, s.meas)
+
+        # The observation arrays of DIFFERENT sensors may be handed over concurrently (include/calico_b200.h); the calls are memory-bound
+        # copies that release the GIL, so large problems use one thread per sensor.
+        pairs = list(zip(self.sensors, ids))
+        if len(pairs) > 1 and sum(s.n_obs for s in self.sensors) >= PARALLEL_OBS:
+            with ThreadPoolExecutor(max_workers=min(len(pairs), 16)) as ex:
+                list(ex.map(add_obs, pairs))
+        else:
+            for pair in pairs:
+                add_obs(pair)
         return ids
+
+    def residuals(self, api: "_capi.CApi", ids=None):
+        """Residuals + validity flags of every sensor, in the caller's observation order (Sensor::UpdateResiduals, camera.cpp:70-80);
+        the per-sensor copies run concurrently on large problems."""
+        ids = ids if ids is not None else list(range(len(self.sensors)))
+        if len(ids) > 1 and sum(s.n_obs for s in self.sensors) >= PARALLEL_OBS:
+            with ThreadPoolExecutor(max_workers=min(len(ids), 16)) as ex:
+                return list(ex.map(api.get_residuals, ids))
+        return [api.get_residuals(sid) for sid in ids]
 
     def pull(self, api: "_capi.CApi", ids=None):
         """Write-back of the optimised state (the reference mutates the user's objects in place, camera.cpp:98-101)."""

@@ -123,7 +123,10 @@ int cb2_add_sensor(cb2_problem* p, int kind, int model, const char* name, int n_
                    const double* t3, double latency, double sigma, int loss_type, double loss_scale, int enable_intrinsics,
                    int enable_extrinsics, int enable_latency, int* sensor_id);
 /* Camera::AddMeasurements (camera.cpp:224-254) with the outlier set (camera.cpp:281-299) as a mask. id fields are
- * CameraObservationId (camera.h:24-50). model_id must name a rigid body (camera.cpp:125-131). */
+ * CameraObservationId (camera.h:24-50). model_id must name a rigid body (camera.cpp:125-131).
+ * Threading: a handle is single-caller, with two exceptions made for large problems — once every sensor and rigid body has been
+ * added, cb2_add_camera_observations / cb2_add_imu_observations may be called concurrently for DIFFERENT sensor ids, and after
+ * cb2_optimize cb2_get_residuals may be called concurrently (plain copies out of the result block). */
 int cb2_add_camera_observations(cb2_problem* p, int sensor_id, int n, const double* stamp, const int* image_id, const int* model_id,
                                 const int* feature_id, const double* pixel_xy, const uint8_t* outlier_mask);
 /* Gyroscope/Accelerometer::AddMeasurements (gyroscope.cpp, accelerometer.cpp); ids are {stamp, sequence}. */

@@ -19,7 +19,7 @@ for rep in range(3):
     api.upload(); t.append(time.perf_counter())
     summ, log = api.optimize(opts); t.append(time.perf_counter())
     p2.pull(api, ids); t.append(time.perf_counter())
-    for sid in ids: api.get_residuals(sid)
+    p2.residuals(api, ids)
     t.append(time.perf_counter())
     st = api.stats()
     api.close(); t.append(time.perf_counter())

@@ -109,6 +109,45 @@ def test_emulated_single_plain_sensor_and_gram_variants(no_early_gram, emul_lib,
 
 
 @pytest.mark.timeout(900)
+def test_host_packing_is_independent_of_its_thread_split(emul_lib, oracle, monkeypatch):
+    """upload() packs a large sensor with several host threads (ranges of observations): same packed problem — hence bitwise the same
+    cost, residuals (caller's order) and Jacobians — whatever the split, on shuffled input with flagged outliers, and through
+    concurrent cb2_add_*_observations calls (ProblemSpec.push with one thread per sensor)."""
+    from calico_b200 import spec as spec_mod
+    truth, prob = synthetic.generate("tiny", oracle.oracle_api, noise=True)
+    rng = np.random.default_rng(5)
+    for s in prob.sensors:                       # caller's order is arbitrary (absl::flat_hash_map iteration in the reference, camera.cpp:120)
+        order = rng.permutation(s.n_obs)
+        s.stamp, s.meas = s.stamp[order], s.meas[order]
+        if s.kind == 0:
+            s.image_id, s.model_id, s.feature_id = s.image_id[order], s.model_id[order], s.feature_id[order]
+            s.outlier = (rng.random(s.n_obs) < 0.1).astype(np.uint8)
+        elif s.seq is not None:
+            s.seq = s.seq[order]
+    results = []
+    for split, threads, par in (("1000000000", "1", 10**9), ("1", "4", 10**9), ("1", "3", 1)):
+        monkeypatch.setenv("CB2_PACK_SPLIT_MIN", split)
+        monkeypatch.setenv("CB2_PACK_SUB_THREADS", threads)
+        monkeypatch.setattr(spec_mod, "PARALLEL_OBS", par)
+        a = _capi.CApi(emul_lib)
+        p = prob.clone()
+        ids = p.push(a)
+        ev = [a.evaluate_sensor(sid) for sid in ids]
+        summ, log = a.optimize(_capi.Options(minimizer_progress_to_stdout=0, max_num_iterations=2))
+        res = p.residuals(a, ids)
+        results.append((ev, [x.cost for x in log], res, summ.num_residual_blocks))
+        a.close()
+    ev0, cost0, res0, nb0 = results[0]
+    assert nb0 == sum(int(s.n_obs - (s.outlier.sum() if s.outlier is not None else 0)) for s in prob.sensors)
+    for ev, cost, res, nb in results[1:]:
+        assert nb == nb0 and cost == cost0
+        for (r0, J0, v0), (r1, J1, v1) in zip(ev0, ev):
+            assert np.array_equal(r0, r1) and np.array_equal(J0, J1) and np.array_equal(v0, v1)
+        for (r0, v0), (r1, v1) in zip(res0, res):
+            assert np.array_equal(r0, r1) and np.array_equal(v0, v1)
+
+
+@pytest.mark.timeout(900)
 def test_emulated_lm_with_rejected_steps_matches_oracle(emul_lib, oracle):
     """The reference's toy stereo + IMU problem starts with three rejected steps (as in the stored Ceres log): exercises the
     reject -> accept transitions of the speculative trial sweep (the candidate buffer is reused by every new candidate)."""

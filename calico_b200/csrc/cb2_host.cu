@@ -791,12 +791,11 @@ struct cb2_problem {
       size_t off_stamp = 0, off_meas = 0, off_seg = 0, off_pt = 0, off_frm = 0, off_perm = 0, bytes = 0;
     };
     std::vector<Packed> packed(ns);
-    // Sensors with many observations are packed by several threads each (the cores the one-thread-per-sensor scheme leaves idle).
+    // A sensor with many observations can be packed by several threads (CB2_PACK_SUB_THREADS=n for sensors of at least CB2_PACK_SPLIT_MIN
+    // observations). Off by default: on C4 (8 cameras of 125 k observations, 16 host cores) two threads per camera on top of the one
+    // thread per sensor measured slower and erratic (pack 6-8 ms with spikes to 34 ms against 4.3-6.2 ms).
     const int pack_split_min = env_int("CB2_PACK_SPLIT_MIN", 65536);
-    int n_heavy = 0;
-    for (const auto& hs : sensors) n_heavy += hs.n_obs() >= pack_split_min ? 1 : 0;
-    const int hw_threads = std::max(1, int(std::thread::hardware_concurrency()));
-    const int sub_threads = std::max(1, env_int("CB2_PACK_SUB_THREADS", std::min(4, hw_threads / std::max(n_heavy, 1))));
+    const int sub_threads = std::max(1, env_int("CB2_PACK_SUB_THREADS", 1));
     auto pack_sensor = [&](int si) {
       HostSensor& s = sensors[si];
       Packed& P = packed[si];

@@ -331,16 +331,21 @@ __global__ void __launch_bounds__(32) camera_frame_kernel(int n_frames, const in
 
 // Sums the per-tile partials in a fixed order: scal[slot] = cost, scal[slot+1] = number of failed blocks. One CTA of 1024 threads,
 // 4 independent loads in flight per thread, shuffle reduction.
-__global__ void __launch_bounds__(1024) reduce_cost_kernel(const double* __restrict__ cost_partial, const int* __restrict__ invalid_partial,
+#ifdef CB2_EMUL
+constexpr int kRcThreads = 128;    // (emulation build: fewer OS threads)
+#else
+constexpr int kRcThreads = 1024;
+#endif
+__global__ void __launch_bounds__(kRcThreads) reduce_cost_kernel(const double* __restrict__ cost_partial, const int* __restrict__ invalid_partial,
                                                            int n, double* __restrict__ scal, int slot) {
   __shared__ double sc[32];
   __shared__ int sb[32];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   double c = 0.0; int b = 0;
-  for (int i0 = t; i0 < n; i0 += 4 * 1024) {
+  for (int i0 = t; i0 < n; i0 += 4 * kRcThreads) {
     double cv[4]; int bv[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { const int i = i0 + u * 1024; const int ic = min(i, n - 1); cv[u] = cost_partial[ic]; bv[u] = invalid_partial[ic]; if (i >= n) { cv[u] = 0.0; bv[u] = 0; } }
+    for (int u = 0; u < 4; ++u) { const int i = i0 + u * kRcThreads; const int ic = min(i, n - 1); cv[u] = cost_partial[ic]; bv[u] = invalid_partial[ic]; if (i >= n) { cv[u] = 0.0; bv[u] = 0; } }
 #pragma unroll
     for (int u = 0; u < 4; ++u) { c += cv[u]; b += bv[u]; }
   }
@@ -348,7 +353,7 @@ __global__ void __launch_bounds__(1024) reduce_cost_kernel(const double* __restr
   if (lane == 0) { sc[warp] = c; sb[warp] = b; }
   __syncthreads();
   if (warp == 0) {
-    c = sc[lane]; b = sb[lane];
+    c = lane < kRcThreads / 32 ? sc[lane] : 0.0; b = lane < kRcThreads / 32 ? sb[lane] : 0;
     for (int off = 16; off > 0; off >>= 1) { c += __shfl_down_sync(0xffffffffu, c, off); b += __shfl_down_sync(0xffffffffu, b, off); }
     if (lane == 0) { scal[slot] = c; scal[slot + 1] = double(b); }
   }

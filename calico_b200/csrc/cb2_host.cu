@@ -1410,7 +1410,7 @@ struct cb2_problem {
       else launch_imu<MODE>(si, desc, st, c, nt, d_pw[which].p);
     }
     if (fork) { CB2_CUDA(cudaEventRecord(ev_join, stream_imu)); CB2_CUDA(cudaStreamWaitEvent(stream, ev_join, 0)); }
-    CB2_K(reduce_cost_kernel, 1, 1024, 0, stream, d_cost_partial.p, d_invalid_partial.p, n_tiles, d_scal.p, slot);
+    CB2_K(reduce_cost_kernel, 1, kRcThreads, 0, stream, d_cost_partial.p, d_invalid_partial.p, n_tiles, d_scal.p, slot);
   }
 
   // K1-K3 at x, then K4: normal equations, Hessian diagonal, gradient norms.

@@ -5,7 +5,11 @@
 
 namespace cb2 {
 
+#ifdef CB2_EMUL
+constexpr int kLmThreads = 128;    // emulation build: one OS thread per CUDA thread, the barrier-heavy reductions get 8x fewer of them
+#else
 constexpr int kLmThreads = 1024;
+#endif
 
 // diag[j] = H(j, j): control points from the band, calibration from C.
 __global__ void __launch_bounds__(256) hess_diag_kernel(long n_a, int N_c, const double* __restrict__ Aband, const double* __restrict__ Cmat,
@@ -81,7 +85,7 @@ CB2_D bool grid_reduce_last(double (&v)[NV], unsigned max_mask, double* __restri
 }
 #ifdef CB2_EMUL
 constexpr int kLmMaxCtas = 2;       // emulation build: two CTAs even on the micro problems of the CPU tests (any grid size is valid)
-constexpr long kLmQuantum = 64;
+constexpr long kLmQuantum = 256;   // (micro / tiny problems: one CTA; the `small` ones: two)
 #else
 constexpr int kLmMaxCtas = 32;      // CTAs of gradient_norm_kernel / apply_step_kernel (4 x kLmThreads unknowns each)
 constexpr long kLmQuantum = 4L * kLmThreads;
